@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, read-only) in this CPU container.
+
+The reference has no tests or golden vectors of its own, so every
+expected value is produced here by importing its modules and calling its own
+functions; nothing from the reference is copied into the repo.  Recipe follows
+SURVEY.md Appendix C: stub `open3d`/`natsort` (unused on the hot path), run
+from a scratch CWD holding random-init checkpoints under the hard-coded
+`networks/logs/...` paths (optimizer.py:334,344), inject the reparameterisation
+noise so both sides see the same z0 (SeqConvVAE.py:159-169).
+
+Usage (container only; the GPU box never runs this):
+    python tests/golden/make_golden.py [--threads 1] [--only NAME ...]
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+REF = "/root/reference"
+OUT = os.path.join(REPO, "tests", "golden")
+sys.path.insert(0, REPO)
+sys.dont_write_bytecode = True
+
+from globalegomocap_b200 import synthetic as syn  # noqa: E402
+
+LOCAL_CKPT = "networks/logs/only_local_full_dataset_latent_2048_len_10_kl_0.5_2/checkpoints/19.pth.tar"
+GLOBAL_CKPT = "networks/logs/real_full_dataset_latent_2048_len_10_slide_window_step_1_kl_0.5/checkpoints/19.pth.tar"
+
+# CLI default weights as wired by main (optimizer.py:352-358, optimize_whole_sequence.py:14-19)
+W_LOCAL = dict(vae_weight=0.0, gmm_weight=0.0, smooth_weight=0.001 / 100, bone_length_weight=0.01,
+               weight_3d=0.01 / 10000, reproj_weight=0.01)
+W_GLOBAL = dict(vae_weight=0.0, gmm_weight=0.0, smooth_weight=0.001, bone_length_weight=0.01,
+                weight_3d=0.01, reproj_weight=0)
+# a set with every term switched on (incl. the default-0 E_vae)
+W_ALL = dict(vae_weight=0.003, gmm_weight=0.0, smooth_weight=0.02, bone_length_weight=0.05,
+             weight_3d=0.01, reproj_weight=0.04)
+
+
+def import_reference():
+    for name in ("open3d", "natsort"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            if name == "natsort":
+                m.natsorted = sorted
+            sys.modules[name] = m
+    sys.path[:0] = [REF, os.path.join(REF, "networks")]
+    import optimizer as ref_opt  # noqa
+    return ref_opt
+
+
+class Harness:
+    def __init__(self, scratch: str, clip, seeds=(11, 12), perturb_bn=True, pose_bias=True, cam="default"):
+        import torch
+        self.torch = torch
+        self.scratch = scratch
+        os.makedirs(os.path.join(scratch, "utils", "fisheye"), exist_ok=True)
+        link = os.path.join(scratch, "utils", "fisheye", "mean3D.mat")
+        if not os.path.exists(link):
+            os.symlink(os.path.join(REF, "utils", "fisheye", "mean3D.mat"), link)
+        bias = syn.mean_pose_bias(clip) if pose_bias else None
+        self.sd_local = syn.make_vae_state_dict(seeds[0], perturb_bn=perturb_bn, pose_bias=bias)
+        self.sd_global = syn.make_vae_state_dict(seeds[1], perturb_bn=perturb_bn, pose_bias=bias)
+        syn.save_checkpoint(self.sd_local, os.path.join(scratch, LOCAL_CKPT))
+        syn.save_checkpoint(self.sd_global, os.path.join(scratch, GLOBAL_CKPT))
+        self.camera_json = (os.path.join(REF, "utils/fisheye/fisheye.calibration.json") if cam == "default"
+                            else os.path.join(REF, "utils/fisheye/pose_fisheye_fisheye.calibration_new.json"))
+        os.chdir(scratch)
+        self.ref = import_reference()
+        self.clip = clip
+
+    def make_optimizer(self, which: str, weights: dict, max_iter=25):
+        torch = self.torch
+        est = np.asarray(self.clip["estimated_local_skeleton"])
+        opt = self.ref.BodyPoseOptimizer(
+            camera_model_path=self.camera_json, mean_skeleton=torch.from_numpy(est).float(),
+            vae_path=LOCAL_CKPT if which == "local" else GLOBAL_CKPT, latent_dim=2048, network_seq_len=10,
+            seq_len=10, windows_size=1, overlap_size=2, lr=2, max_iter=max_iter)
+        opt.set_weights(**weights)
+        return opt
+
+
+class EpsInjector:
+    """Replaces ConvVAE.reparameterize's torch.randn_like draw by queued noise."""
+
+    def __init__(self, ref):
+        from networks.models.SeqConvVAE import ConvVAE
+        self.cls = ConvVAE
+        self.queue = []
+        self.orig = ConvVAE.reparameterize
+        inj = self
+
+        def reparameterize(self_, mu, logvar):
+            import torch
+            std = torch.exp(0.5 * logvar)
+            eps = inj.queue.pop(0)
+            return eps * std + mu
+
+        ConvVAE.reparameterize = reparameterize
+
+    def push(self, eps):
+        import torch
+        self.queue.append(torch.from_numpy(np.asarray(eps, dtype=np.float32)).view(1, -1))
+
+    def restore(self):
+        self.cls.reparameterize = self.orig
+
+
+class LossTracer:
+    """Records (E, z) for every closure evaluation."""
+
+    def __init__(self, ref):
+        self.cls = ref.BodyPoseOptimizer
+        self.orig = self.cls.total_loss
+        self.records = []
+        tr = self
+
+        def total_loss(self_, hidden):
+            e = tr.orig(self_, hidden)
+            tr.records.append((float(e), hidden.detach().clone().numpy().reshape(-1)))
+            return e
+
+        self.cls.total_loss = total_loss
+
+    def take(self):
+        r, self.records = self.records, []
+        return r
+
+    def restore(self):
+        self.cls.total_loss = self.orig
+
+
+def gen_fisheye(h: Harness):
+    torch = h.torch
+    out = {}
+    for tag, cam in (("default", "fisheye.calibration.json"), ("new", "pose_fisheye_fisheye.calibration_new.json")):
+        from utils.fisheye.FishEyeCalibrated import FishEyeCameraCalibrated
+        model = FishEyeCameraCalibrated(os.path.join(REF, "utils/fisheye", cam))
+        rng = np.random.default_rng(5)
+        pts = rng.uniform([-0.6, -0.6, 0.05], [0.6, 0.6, 1.5], size=(64, 3))
+        pts[:2] = [[0.1, 0.2, 0.8], [-0.3, 0.1, 0.5]]          # SURVEY.md A.5 sanity points
+        pts[2] = [0.2, -0.1, -0.3]                               # behind the camera plane (theta > 0)
+        pts[3] = [1e-4, 0.0, 1.0]                                # almost on the optical axis
+        x = torch.from_numpy(pts).float().requires_grad_(True)
+        uv = model.world2camera_pytorch(x)
+        ju = torch.autograd.grad(uv[:, 0].sum(), x, retain_graph=True)[0]
+        jv = torch.autograd.grad(uv[:, 1].sum(), x)[0]
+        out[f"{tag}_points"] = pts.astype(np.float32)
+        out[f"{tag}_uv"] = uv.detach().numpy()
+        out[f"{tag}_du"] = ju.numpy()
+        out[f"{tag}_dv"] = jv.numpy()
+    np.savez_compressed(os.path.join(OUT, "fisheye.npz"), **out)
+    print("fisheye:", {k: v.shape for k, v in out.items()})
+
+
+def energy_cases(h: Harness):
+    """Poses at which the terms are evaluated with the decoder bypassed."""
+    est = np.asarray(h.clip["estimated_local_skeleton"])
+    rng = np.random.default_rng(77)
+    cases = []
+    w0 = est[0:10].astype(np.float32)
+    cases.append(("at_x0_plus_noise", 0, w0 + 0.004 * rng.standard_normal(w0.shape).astype(np.float32)))
+    w1 = est[8:18].astype(np.float32)
+    cases.append(("shifted", 8, w1 + np.float32(0.03)))
+    far = w1.copy()
+    far[:, :, 0] *= np.float32(3.0)          # many joints leave the heatmap (zero padding region)
+    cases.append(("outside", 8, far))
+    poly, cx, cy = syn.load_camera()
+    edge = w0.copy()
+    border = [(-0.3, 20.0), (63.2, 10.0), (31.5, -0.5), (12.25, 63.4), (0.0, 0.0), (63.0, 63.0), (62.999, 5.5),
+              (-1.01, 30.0), (64.2, 30.0), (30.0, -1.2), (5.0, 62.0), (0.5, 0.5), (63.0, 31.0), (17.0, 0.0)]
+    for k, (ix, iy) in enumerate(border):               # frame 0, joints 0..13 sit on / just off the borders
+        edge[0, k] = syn.point_for_heat_pixel(ix, iy, 0.5, poly, cx, cy).astype(np.float32)
+    edge[1, 0] = edge[1, 4]                  # zero-length bones 1,4 at frame 1 (norm subgradient 0)
+    edge[1, 1] = edge[1, 4]
+    cases.append(("edges", 0, edge))
+    cases.append(("dense_near", 0, w0 + 0.004 * rng.standard_normal(w0.shape).astype(np.float32)))
+    return cases
+
+
+def gen_energy(h: Harness):
+    torch = h.torch
+    heat_all = np.asarray(h.clip["heatmap_list"])
+    out = {}
+    names = []
+    for wname, weights in (("local", W_LOCAL), ("global", W_GLOBAL), ("all", W_ALL)):
+        opt = h.make_optimizer("local", weights)
+        for cname, start, xnp in energy_cases(h):
+            x0 = np.asarray(h.clip["estimated_local_skeleton"])[start:start + 10]
+            heat = syn.dense_heat_window(1) if cname in ("edges", "dense_near") else heat_all[start:start + 10]
+            opt.initial_pose = torch.from_numpy(x0).float()
+            hs = torch.from_numpy(heat).float().permute((0, 3, 1, 2)).contiguous()
+            opt.heatmap_seq = hs.view(-1, hs.shape[-2], hs.shape[-1])
+            key = f"{wname}__{cname}"
+            names.append(key)
+            terms = [("e3d", opt.pose_energy_3d), ("smooth", opt.smooth_accelerate), ("bone", opt.bone_length_energy),
+                     ("vae", opt.vae_energy), ("reproj", opt.reprojection_energy_heatmap_fast)]
+            for tname, fn in terms:
+                x = torch.from_numpy(xnp).float().requires_grad_(True)
+                e = fn(x)
+                g = torch.autograd.grad(e, x, allow_unused=True)[0]
+                out[f"{key}__E_{tname}"] = np.float32(e.item())
+                out[f"{key}__G_{tname}"] = (g if g is not None else torch.zeros_like(x)).numpy()
+            # total exactly as total_loss combines it (optimizer.py:229-240), decoder bypassed
+            x = torch.from_numpy(xnp).float().requires_grad_(True)
+            e_r = 0 if opt.reproj_weight == 0 else opt.reprojection_energy_heatmap_fast(x)
+            tot = (opt.weight_3d * opt.pose_energy_3d(x) + opt.smooth_weight * opt.smooth_accelerate(x)
+                   + opt.bone_length_weight * opt.bone_length_energy(x) + opt.vae_weight * opt.vae_energy(x)
+                   + opt.reproj_weight * e_r)
+            g = torch.autograd.grad(tot, x)[0]
+            out[f"{key}__E_total"] = np.float32(tot.item())
+            out[f"{key}__G_total"] = g.numpy()
+            out[f"{key}__x"] = xnp
+            out[f"{key}__start"] = np.int64(start)
+        out[f"{wname}__weights"] = np.asarray([weights["weight_3d"], weights["smooth_weight"],
+                                               weights["bone_length_weight"], weights["vae_weight"],
+                                               weights["reproj_weight"]], dtype=np.float64)
+        out["mean_bone_length"] = opt.mean_bone_length.numpy()
+    out["names"] = np.asarray(names)
+    np.savez_compressed(os.path.join(OUT, "energy.npz"), **out)
+    print("energy:", len(names), "cases")
+
+
+def gen_vae(h: Harness):
+    torch = h.torch
+    opt = h.make_optimizer("local", W_LOCAL)
+    net = opt.network
+    rng = np.random.default_rng(3)
+    W = 3
+    z = rng.standard_normal((W, 2048)).astype(np.float32)
+    zt = torch.from_numpy(z).requires_grad_(True)
+    pose = net.decode_to_bodypose(zt)                       # (W,10,15,3)
+    up = rng.standard_normal((W, 10, 15, 3)).astype(np.float32)
+    dz = torch.autograd.grad((pose * torch.from_numpy(up)).sum(), zt)[0]
+    x = np.asarray(h.clip["estimated_local_skeleton"])[:30].reshape(3, 10, 45).astype(np.float32)
+    with torch.no_grad():
+        mu, logvar = net.encode(torch.from_numpy(x).permute(0, 2, 1).contiguous())
+        std = torch.exp(0.5 * logvar)
+    np.savez_compressed(os.path.join(OUT, "vae.npz"), z=z, pose=pose.detach().numpy(), upstream=up, dz=dz.numpy(),
+                        enc_in=x, mu=mu.numpy(), std=std.numpy(), vae_seed=np.int64(11))
+    print("vae: pose", pose.shape, "dz", dz.shape)
+
+
+def gen_traces(h: Harness):
+    torch = h.torch
+    inj = EpsInjector(h.ref)
+    tracer = LossTracer(h.ref)
+    est = np.asarray(h.clip["estimated_local_skeleton"])
+    heat_all = np.asarray(h.clip["heatmap_list"])
+    cams = np.asarray(h.clip["camera_pose_list"])
+    out = {}
+    rng = np.random.default_rng(2024)
+    starts = [0, 8, 16]
+    eps_all = rng.standard_normal((len(starts), 2, 2048)).astype(np.float32)
+    out["starts"] = np.asarray(starts)
+    out["eps"] = eps_all
+    for max_iter in (1, 2, 3, 5, 25):
+        lopt = h.make_optimizer("local", W_LOCAL, max_iter=max_iter)
+        gopt = h.make_optimizer("global", W_GLOBAL, max_iter=max_iter)
+        for wi, s in enumerate(starts):
+            x0 = est[s:s + 10]
+            heat = heat_all[s:s + 10]
+            inj.push(eps_all[wi, 0])
+            # optimizer.py:386 — the third argument is ignored by the energy
+            res_l = lopt.optimize_pose_seq_pytorch_LBFGS(x0, heat, x0.copy())
+            rec = tracer.take()
+            tag = f"mi{max_iter}_w{wi}_local"
+            out[tag + "_E"] = np.asarray([r[0] for r in rec], dtype=np.float64)
+            out[tag + "_z"] = np.stack([r[1] for r in rec]).astype(np.float32)
+            out[tag + "_pose"] = res_l
+            rel = h.ref.get_relative_global_pose_with_camera_matrix(res_l, cams[s:s + 10])
+            out[tag + "_relglobal"] = rel
+            inj.push(eps_all[wi, 1])
+            res_g = gopt.optimize_pose_seq_pytorch_LBFGS(rel, heat, rel.copy())
+            rec = tracer.take()
+            tag = f"mi{max_iter}_w{wi}_global"
+            out[tag + "_E"] = np.asarray([r[0] for r in rec], dtype=np.float64)
+            out[tag + "_z"] = np.stack([r[1] for r in rec]).astype(np.float32)
+            out[tag + "_pose"] = res_g
+            print(f"trace max_iter={max_iter} w{wi}: evals L/G = {len(out[f'mi{max_iter}_w{wi}_local_E'])}/{len(rec)}")
+    out["mean_bone_length"] = lopt.mean_bone_length.numpy()
+    tracer.restore()
+    inj.restore()
+    np.savez_compressed(os.path.join(OUT, "traces.npz"), **out)
+
+
+def gen_main(h: Harness, max_iter=3):
+    """End-to-end optimizer.main on the clip with a fixed small iteration count.
+    main hard-codes max_iter=25 (optimizer.py:340,350); it is a constructor
+    argument, so the constructor is wrapped to override it — the reference's
+    code itself is untouched."""
+    torch = h.torch
+    inj = EpsInjector(h.ref)
+    data_dir = os.path.join(h.scratch, "data", "synth", "clip0")
+    syn.write_clip_pickle(h.clip, data_dir)
+    n = len(h.clip["estimated_local_skeleton"])
+    W = len(syn.window_starts(n))
+    rng = np.random.default_rng(4242)
+    eps = rng.standard_normal((W, 2, 2048)).astype(np.float32)
+    for w in range(W):                      # call order: local(w0), global(w0), local(w1), ...
+        inj.push(eps[w, 0])
+        inj.push(eps[w, 1])
+    orig_init = h.ref.BodyPoseOptimizer.__init__
+
+    def patched(self_, *a, **kw):
+        kw["max_iter"] = max_iter
+        return orig_init(self_, *a, **kw)
+
+    h.ref.BodyPoseOptimizer.__init__ = patched
+    try:
+        errors, est_seq, mid_local, opt_seq, gt_seq = h.ref.main(
+            data_dir, camera_model_path=h.camera_json, vae_weight=0.0, gmm_weight=0.0, smoothness_weight=0.001,
+            bone_length_weight=0.01, weight_3d=0.01, reproj_weight=0.01, visualization=False, save=False,
+            merge=True, final_smooth=True)
+    finally:
+        h.ref.BodyPoseOptimizer.__init__ = orig_init
+        inj.restore()
+    out = {"eps": eps, "max_iter": np.int64(max_iter), "n_frames": np.int64(n),
+           "final_estimated_seq": np.asarray(est_seq), "mid_local_pose_seq": np.asarray(mid_local),
+           "final_optimized_seq": np.asarray(opt_seq), "final_gt_seq": np.asarray(gt_seq)}
+    for k, v in errors.items():
+        out["err__" + k] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, f"main_mi{max_iter}.npz"), **out)
+    print("main:", {k: np.asarray(v).shape for k, v in out.items() if not k.startswith("err__")})
+    print({k: float(np.mean(v)) for k, v in errors.items()})
+
+
+def gen_clip_fixture(clip):
+    """The clip itself (heatmaps compress well: compact bumps)."""
+    np.savez_compressed(os.path.join(OUT, "clip58.npz"), **{k: np.asarray(v) for k, v in clip.items()})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--threads", type=int, default=1)
+    ap.add_argument("--only", nargs="*", default=None)
+    args = ap.parse_args()
+    import torch
+    torch.set_num_threads(args.threads)
+    clip = syn.make_clip(58, seed=7)
+    scratch = tempfile.mkdtemp(prefix="gem_golden_")
+    h = Harness(scratch, clip)
+    todo = args.only or ["clip", "fisheye", "energy", "vae", "traces", "main"]
+    if "clip" in todo:
+        gen_clip_fixture(clip)
+    if "fisheye" in todo:
+        gen_fisheye(h)
+    if "energy" in todo:
+        gen_energy(h)
+    if "vae" in todo:
+        gen_vae(h)
+    if "traces" in todo:
+        gen_traces(h)
+    if "main" in todo:
+        gen_main(h, 3)
+    print("done; scratch =", scratch)
+
+
+if __name__ == "__main__":
+    main()
