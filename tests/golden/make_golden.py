@@ -57,7 +57,7 @@ def import_reference():
 
 
 class Harness:
-    def __init__(self, scratch: str, clip, seeds=(11, 12), perturb_bn=True, pose_bias=True, cam="default"):
+    def __init__(self, scratch: str, clip, seeds=(11, 12), perturb_bn=True, pose_bias=True, cam="default", gain=1.0):
         import torch
         self.torch = torch
         self.scratch = scratch
@@ -66,8 +66,8 @@ class Harness:
         if not os.path.exists(link):
             os.symlink(os.path.join(REF, "utils", "fisheye", "mean3D.mat"), link)
         bias = syn.mean_pose_bias(clip) if pose_bias else None
-        self.sd_local = syn.make_vae_state_dict(seeds[0], perturb_bn=perturb_bn, pose_bias=bias)
-        self.sd_global = syn.make_vae_state_dict(seeds[1], perturb_bn=perturb_bn, pose_bias=bias)
+        self.sd_local = syn.make_vae_state_dict(seeds[0], perturb_bn=perturb_bn, pose_bias=bias, gain=gain)
+        self.sd_global = syn.make_vae_state_dict(seeds[1], perturb_bn=perturb_bn, pose_bias=bias, gain=gain)
         syn.save_checkpoint(self.sd_local, os.path.join(scratch, LOCAL_CKPT))
         syn.save_checkpoint(self.sd_global, os.path.join(scratch, GLOBAL_CKPT))
         self.camera_json = (os.path.join(REF, "utils/fisheye/fisheye.calibration.json") if cam == "default"
@@ -248,7 +248,7 @@ def gen_vae(h: Harness):
     print("vae: pose", pose.shape, "dz", dz.shape)
 
 
-def gen_traces(h: Harness):
+def gen_traces(h: Harness, max_iters=(1, 2, 3, 5, 25), fname="traces.npz"):
     torch = h.torch
     inj = EpsInjector(h.ref)
     tracer = LossTracer(h.ref)
@@ -261,7 +261,7 @@ def gen_traces(h: Harness):
     eps_all = rng.standard_normal((len(starts), 2, 2048)).astype(np.float32)
     out["starts"] = np.asarray(starts)
     out["eps"] = eps_all
-    for max_iter in (1, 2, 3, 5, 25):
+    for max_iter in max_iters:
         lopt = h.make_optimizer("local", W_LOCAL, max_iter=max_iter)
         gopt = h.make_optimizer("global", W_GLOBAL, max_iter=max_iter)
         for wi, s in enumerate(starts):
@@ -288,7 +288,7 @@ def gen_traces(h: Harness):
     out["mean_bone_length"] = lopt.mean_bone_length.numpy()
     tracer.restore()
     inj.restore()
-    np.savez_compressed(os.path.join(OUT, "traces.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, fname), **out)
 
 
 def gen_main(h: Harness, max_iter=3):
@@ -347,7 +347,7 @@ def main():
     clip = syn.make_clip(58, seed=7)
     scratch = tempfile.mkdtemp(prefix="gem_golden_")
     h = Harness(scratch, clip)
-    todo = args.only or ["clip", "fisheye", "energy", "vae", "traces", "main"]
+    todo = args.only or ["clip", "fisheye", "energy", "vae", "traces", "main", "traces_g2"]
     if "clip" in todo:
         gen_clip_fixture(clip)
     if "fisheye" in todo:
@@ -360,6 +360,12 @@ def main():
         gen_traces(h)
     if "main" in todo:
         gen_main(h, 3)
+    if "traces_g2" in todo:
+        # weights drawn with twice PyTorch's default bound: larger decoder Jacobian, the energy
+        # drops by orders of magnitude and most 25-iteration trajectories are well conditioned
+        os.chdir(REPO)
+        h2 = Harness(tempfile.mkdtemp(prefix="gem_golden_g2_"), clip, gain=2.0)
+        gen_traces(h2, max_iters=(5, 25), fname="traces_g2.npz")
     print("done; scratch =", scratch)
 
 

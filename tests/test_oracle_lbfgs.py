@@ -1,0 +1,147 @@
+"""oracle/lbfgs_np.py pinned against the installed torch.optim.LBFGS (the
+third-party code the reference calls, torch 2.11) on toy problems, and against
+the reference's own per-evaluation traces (tests/golden/traces.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import energy_np as en
+from oracle.lbfgs_np import lbfgs_minimize
+from oracle.pipeline_np import StageSolver, relative_global_pose
+
+W_LOCAL = (0.01 / 10000, 0.001 / 100, 0.01, 0.0, 0.01)
+W_GLOBAL = (0.01, 0.001, 0.01, 0.0, 0)
+
+
+def _torch_run(fn, x0, max_iter):
+    x = torch.nn.Parameter(torch.tensor(x0, dtype=torch.float32))
+    opt = torch.optim.LBFGS([x], lr=2, max_iter=max_iter, tolerance_change=1e-6, line_search_fn="strong_wolfe")
+    trace = []
+
+    def closure():
+        opt.zero_grad()
+        loss = fn(x)
+        loss.backward()
+        trace.append((float(loss), x.detach().clone().numpy()))
+        return loss
+
+    opt.step(closure)
+    st = opt.state[x]
+    return x.detach().numpy(), trace, st["n_iter"], st["func_evals"]
+
+
+def _np_closure(fn):
+    def closure(z):
+        x = torch.tensor(z, dtype=torch.float32, requires_grad=True)
+        loss = fn(x)
+        loss.backward()
+        return float(loss), x.grad.numpy().copy()
+    return closure
+
+
+def rosenbrock(x):
+    return (100 * (x[1:] - x[:-1] ** 2) ** 2 + (1 - x[:-1]) ** 2).sum()
+
+
+def quartic(x):
+    i = torch.arange(1, x.numel() + 1, dtype=torch.float32)
+    return (i * (x - 0.5) ** 2).sum() + 0.1 * (x ** 4).sum() + torch.sin(3 * x).sum()
+
+
+def flat(x):            # tiny gradients: first-iteration t = min(1, 1/|g|_1)*lr stays a Python float
+    return 1e-3 * (x ** 2).sum()
+
+
+@pytest.mark.parametrize("fn,n,seed", [(rosenbrock, 16, 0), (rosenbrock, 64, 1), (quartic, 32, 2), (quartic, 200, 3),
+                                        (flat, 8, 4)])
+@pytest.mark.parametrize("max_iter", [1, 3, 7, 25])
+def test_matches_torch_lbfgs(fn, n, seed, max_iter):
+    rng = np.random.default_rng(seed)
+    x0 = rng.standard_normal(n).astype(np.float32)
+    xt, trace_t, n_iter_t, evals_t = _torch_run(fn, x0, max_iter)
+    xn, info = lbfgs_minimize(_np_closure(fn), x0, lr=2, max_iter=max_iter, tolerance_change=1e-6)
+    assert info["n_iter"] == n_iter_t
+    assert info["func_evals"] == evals_t == len(info["trace"])
+    # same evaluation points and losses, evaluation by evaluation (fp32 dot-product
+    # order differs between numpy and ATen, so allow round-off growth)
+    for (ft, zt), (fnp, zn) in zip(trace_t, info["trace"]):
+        np.testing.assert_allclose(zn, zt, rtol=2e-3, atol=2e-4)
+        assert abs(ft - fnp) <= 2e-3 * max(1.0, abs(ft))
+    np.testing.assert_allclose(xn, xt, rtol=2e-3, atol=2e-4)
+
+
+def _solver(which, clip58, vae_weights, camera, max_iter):
+    mb = en.mean_bone_length(clip58["estimated_local_skeleton"])
+    sd = vae_weights[0] if which == "local" else vae_weights[1]
+    return StageSolver(sd, camera, mb, W_LOCAL if which == "local" else W_GLOBAL, max_iter=max_iter)
+
+
+def test_teacher_forced_energy_matches_reference_trace(golden_dir, clip58, vae_weights, camera):
+    """Every closure evaluation of the reference's max_iter=25 runs, replayed at
+    the reference's own z: energy within 1e-4 relative (north-star bar)."""
+    g = np.load(os.path.join(golden_dir, "traces.npz"))
+    for wi, s in enumerate(g["starts"]):
+        heat = clip58["heatmap_list"][s:s + 10]
+        x0 = clip58["estimated_local_skeleton"][s:s + 10]
+        loc = _solver("local", clip58, vae_weights, camera, 25).closure_for(x0, heat)
+        glo = _solver("global", clip58, vae_weights, camera, 25).closure_for(g[f"mi25_w{wi}_local_relglobal"], heat)
+        for stage, cl in (("local", loc), ("global", glo)):
+            E, Z = g[f"mi25_w{wi}_{stage}_E"], g[f"mi25_w{wi}_{stage}_z"]
+            for k in range(0, len(E), 3):
+                e, _ = cl(Z[k])
+                assert abs(e - E[k]) <= 1e-4 * abs(E[k]), (wi, stage, k, e, E[k])
+
+
+# Free-running trajectories.  torch's strong-Wolfe search is ill-conditioned on this problem:
+# the first trial step is tiny (t = min(1, 1/|g|_1)*lr), the ray is almost linear over it, and the
+# cubic extrapolation's discriminant d1^2 - g1*g2 is then a difference of two nearly equal numbers
+# (relative gap 1e-5..1e-2, see oracle.lbfgs_np events).  Round-off in the loss / in g.d is amplified
+# by 1/gap per decision, and a sign flip switches between bisection and a jump to the 10x bound.  The
+# reference itself differs by 9.6 mm (local) / 238 mm (global) between 1 and 8 CPU threads at
+# max_iter=25.  So: every run must agree with the reference on its first
+# evaluations, runs with max_iter <= 2 must agree completely, and over all longer runs a clear majority
+# must meet the north-star bar (energy 1e-4 relative at EVERY evaluation, final joints 0.5 mm).
+def agreement(E, E_ref, pose, pose_ref):
+    n = min(len(E), len(E_ref))
+    rel = np.abs(np.asarray(E[:n]) - np.asarray(E_ref[:n])) / np.abs(E_ref).max()
+    lead = int(np.argmax(rel > 1e-4)) if (rel > 1e-4).any() else n
+    err_mm = float(np.abs(pose - pose_ref).max() * 1000)
+    strict = lead == n and len(E) == len(E_ref) and err_mm < 0.5
+    return lead, err_mm, strict
+
+
+def _free_running_cases(g, clip58, weights, camera, max_iter):
+    cams = clip58["camera_pose_list"]
+    out = []
+    for wi, s in enumerate(g["starts"]):
+        heat = clip58["heatmap_list"][s:s + 10]
+        rel = relative_global_pose(g[f"mi{max_iter}_w{wi}_local_pose"], cams[s:s + 10])
+        np.testing.assert_allclose(rel, g[f"mi{max_iter}_w{wi}_local_relglobal"], rtol=0, atol=1e-12)
+        for stage, x0, e in (("local", clip58["estimated_local_skeleton"][s:s + 10], 0), ("global", rel, 1)):
+            pose, info = _solver(stage, clip58, weights, camera, max_iter).solve(x0, heat, g["eps"][wi, e])
+            E = np.array([t[0] for t in info["trace"]])
+            out.append(((max_iter, wi, stage),) + agreement(E, g[f"mi{max_iter}_w{wi}_{stage}_E"], pose,
+                                                            g[f"mi{max_iter}_w{wi}_{stage}_pose"]))
+    return out
+
+
+def test_free_running_matches_reference(golden_dir, clip58, vae_weights, vae_weights_g2, camera):
+    g1 = np.load(os.path.join(golden_dir, "traces.npz"))
+    g2 = np.load(os.path.join(golden_dir, "traces_g2.npz"))
+    cases = []
+    for mi in (1, 2, 3, 5, 25):
+        cases += _free_running_cases(g1, clip58, vae_weights, camera, mi)
+    for mi in (5, 25):
+        cases += [(("g2",) + c[0],) + c[1:] for c in _free_running_cases(g2, clip58, vae_weights_g2, camera, mi)]
+    for key, lead, err_mm, strict in cases:
+        print(key, "leading evals in agreement:", lead, "final joints mm: %.4f" % err_mm, "strict" if strict else "")
+        assert lead >= 2, key
+        if key[-3] <= 2:
+            assert strict, key
+    long_runs = [c for c in cases if c[0][-3] >= 3]
+    n_strict = sum(c[3] for c in long_runs)
+    assert n_strict >= 0.6 * len(long_runs), (n_strict, len(long_runs))
+    full = [c for c in cases if c[0][-3] == 25 and c[3]]
+    assert len(full) >= 4          # complete 25-iteration solves that track the reference to 0.5 mm
