@@ -1,0 +1,422 @@
+// C ABI of libgem_b200.so (declared in include/gem_b200.h): context, scratch ownership and the
+// per-stage pipeline that strings the kernels together without host synchronisation.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace gem {
+
+// ---- error plumbing ------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_last_error = buf;
+    return GEM_ERR_CUDA;
+}
+
+}  // namespace gem
+
+using namespace gem;
+
+struct gem_ctx {
+    int device = 0;
+    int Wmax = 0, n = 0, T = 0, J = 0, H = 0, Wd = 0, m = 0;
+    int gemm_mode = 0;
+    bool have_camera = false, have_skeleton = false;
+    bool have_vae[2] = {false, false};
+    gem_vae_weights vae[2];
+    int64_t scratch_bytes = 0;
+    std::vector<void*> allocs;
+
+    // decoder activations (token-major [W*T][C]) and their gradients
+    float *act[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *pose = nullptr;
+    float *gact[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *gpose = nullptr;
+    // encoder activations, fc output
+    float *eact[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *fc = nullptr, *z0 = nullptr;
+    // closure outputs
+    float *f_new = nullptr, *g_new = nullptr;
+    LbfgsBuffers lb;
+    gem_lbfgs_params lb_params;
+    bool lb_started = false;
+    void* tc_workspace = nullptr;
+    size_t tc_workspace_bytes = 0;
+};
+
+static const int kDecC[6] = {256, 128, 64, 64, 64, 0};   // channels after dec[0..4]; dec[5] -> J*3
+static const int kEncC[5] = {64, 64, 128, 256, 512};
+
+template <typename T>
+static int ctx_alloc(gem_ctx* c, T** p, size_t count) {
+    void* q = nullptr;
+    const size_t bytes = count * sizeof(T);
+    GEM_CUDA(cudaMalloc(&q, bytes ? bytes : 16));
+    c->allocs.push_back(q);
+    c->scratch_bytes += (int64_t)bytes;
+    *p = static_cast<T*>(q);
+    return GEM_OK;
+}
+
+#define GEM_TRY(expr)            \
+    do {                         \
+        int _rc = (expr);        \
+        if (_rc != GEM_OK) return _rc; \
+    } while (0)
+
+extern "C" {
+
+int gem_version(void) { return 100; }
+const char* gem_last_error(void) { return g_last_error.c_str(); }
+
+int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, int seq_len, int num_joints, int heat_h,
+                   int heat_w, int max_history) {
+    GEM_REQUIRE(out != nullptr, "out is NULL");
+    GEM_REQUIRE(max_windows > 0 && latent_dim > 0 && latent_dim % 4 == 0 && latent_dim <= 2048,
+                "latent_dim must be a multiple of 4 in (0, 2048]");
+    GEM_REQUIRE(seq_len >= 3 && seq_len <= 32 && num_joints > 0 && num_joints <= kMaxJoints &&
+                    seq_len * num_joints <= 160,
+                "window geometry out of range");
+    GEM_REQUIRE(max_history >= 1 && max_history <= 64, "max_history must be in [1, 64]");
+    GEM_CUDA(cudaSetDevice(device));
+    gem_ctx* c = new gem_ctx();
+    c->device = device, c->Wmax = max_windows, c->n = latent_dim, c->T = seq_len, c->J = num_joints;
+    c->H = heat_h, c->Wd = heat_w, c->m = max_history;
+    const size_t W = (size_t)max_windows, tok = W * seq_len, n = latent_dim;
+    const size_t Weven = (W + 1) & ~(size_t)1;   // energy kernel copies window pairs
+    int rc = GEM_OK;
+    auto A = [&](float** p, size_t cnt) { if (rc == GEM_OK) rc = ctx_alloc(c, p, cnt); };
+    for (int i = 0; i < 5; ++i) A(&c->act[i], tok * kDecC[i]), A(&c->gact[i], tok * kDecC[i]);
+    A(&c->pose, Weven * seq_len * num_joints * 3), A(&c->gpose, Weven * seq_len * num_joints * 3);
+    for (int i = 0; i < 5; ++i) A(&c->eact[i], tok * kEncC[i]);
+    A(&c->fc, W * 2 * n), A(&c->z0, W * n), A(&c->f_new, W), A(&c->g_new, W * n);
+    LbfgsBuffers& b = c->lb;
+    memset(&b, 0, sizeof(b));
+    A(&b.X, W * n), A(&b.D, W * n), A(&b.G, W * n), A(&b.PG, W * n), A(&b.GP, W * n), A(&b.BG0, W * n),
+        A(&b.BG1, W * n), A(&b.ZT, W * n);
+    A(&b.Y, W * max_history * n), A(&b.S, W * max_history * n), A(&b.RO, W * max_history);
+    if (rc == GEM_OK) {
+        void* st = nullptr;
+        cudaError_t e = cudaMalloc(&st, W * lbfgs_state_bytes());
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(lbfgs state)", __FILE__, __LINE__);
+        else c->allocs.push_back(st), c->scratch_bytes += (int64_t)(W * lbfgs_state_bytes()), b.st = (LbfgsWin*)st;
+    }
+    b.n = latent_dim, b.m = max_history;
+    if (rc != GEM_OK) {
+        gem_ctx_destroy(c);
+        return rc;
+    }
+    c->gemm_mode = tc_gemm_available() ? 1 : 0;
+    // default skeleton: the reference's 15-joint kinematic tree (optimizer.py:34)
+    if (num_joints == 15) {
+        static const int32_t parents[15] = {0, 0, 1, 2, 0, 4, 5, 1, 7, 8, 9, 4, 11, 12, 13};
+        rc = gem_ctx_set_skeleton(c, parents, 15);
+        if (rc != GEM_OK) {
+            gem_ctx_destroy(c);
+            return rc;
+        }
+    }
+    *out = c;
+    return GEM_OK;
+}
+
+int gem_ctx_destroy(gem_ctx* c) {
+    if (!c) return GEM_OK;
+    cudaSetDevice(c->device);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->tc_workspace) cudaFree(c->tc_workspace);
+    delete c;
+    return GEM_OK;
+}
+
+int64_t gem_ctx_scratch_bytes(const gem_ctx* c) { return c ? c->scratch_bytes : 0; }
+
+int gem_ctx_set_gemm_mode(gem_ctx* c, int mode) {
+    GEM_REQUIRE(c != nullptr, "ctx is NULL");
+    GEM_REQUIRE(mode == 0 || mode == 1, "mode must be 0 or 1");
+    if (mode == 1 && !tc_gemm_available()) {
+        set_error("tcgen05 GEMM path not available in this build");
+        return GEM_ERR_STATE;
+    }
+    c->gemm_mode = mode;
+    return GEM_OK;
+}
+
+int gem_ctx_set_camera(gem_ctx* c, const double* poly_h, int n_poly, double cx, double cy) {
+    GEM_REQUIRE(c && poly_h && n_poly >= 1 && n_poly <= kMaxPoly, "bad camera polynomial");
+    CameraConst cam;
+    memset(&cam, 0, sizeof(cam));
+    for (int i = 0; i < n_poly; ++i) cam.poly[i] = (float)poly_h[i];   // python scalars are cast to the tensor dtype
+    cam.n_poly = n_poly, cam.cx = (float)cx, cam.cy = (float)cy;
+    GEM_CUDA(cudaSetDevice(c->device));
+    GEM_TRY(upload_camera(cam));
+    c->have_camera = true;
+    return GEM_OK;
+}
+
+int gem_ctx_set_skeleton(gem_ctx* c, const int32_t* parents_h, int num_joints) {
+    GEM_REQUIRE(c && parents_h && num_joints == c->J, "skeleton size must match the ctx");
+    SkeletonConst sk;
+    memset(&sk, 0, sizeof(sk));
+    for (int j = 0; j < num_joints; ++j) {
+        GEM_REQUIRE(parents_h[j] >= 0 && parents_h[j] < num_joints, "parent index out of range");
+        sk.parent[j] = parents_h[j];
+    }
+    sk.num_joints = num_joints;
+    GEM_CUDA(cudaSetDevice(c->device));
+    GEM_TRY(upload_skeleton(sk));
+    c->have_skeleton = true;
+    return GEM_OK;
+}
+
+int gem_ctx_set_vae(gem_ctx* c, int which, const gem_vae_weights* w) {
+    GEM_REQUIRE(c && w && (which == 0 || which == 1), "bad arguments");
+    const int T = c->T, n = c->n, P = c->J * 3;
+    const int dk[6] = {n, 256, 128, 64, 64, 64}, dn[6] = {T * 256, 128, 64, 64, 64, P}, dt[6] = {1, 3, 3, 3, 3, 3};
+    const int bk[6] = {P, 64, 64, 64, 128, T * 256}, bn[6] = {64, 64, 64, 128, 256, n}, bt[6] = {3, 3, 3, 3, 3, 1};
+    const int ek[6] = {P, 64, 64, 128, 256, T * 512}, en_[6] = {64, 64, 128, 256, 512, 2 * n},
+              et[6] = {3, 3, 3, 3, 3, 1};
+    for (int i = 0; i < 6; ++i) {
+        GEM_REQUIRE(w->dec[i].w_d && w->dec[i].k == dk[i] && w->dec[i].n == dn[i] && w->dec[i].taps == dt[i],
+                    "decoder layer shape mismatch");
+        GEM_REQUIRE(w->dec_bwd[i].w_d && w->dec_bwd[i].k == bk[i] && w->dec_bwd[i].n == bn[i] &&
+                        w->dec_bwd[i].taps == bt[i],
+                    "decoder bwd layer shape mismatch");
+        GEM_REQUIRE(w->enc[i].w_d && w->enc[i].k == ek[i] && w->enc[i].n == en_[i] && w->enc[i].taps == et[i],
+                    "encoder layer shape mismatch");
+    }
+    c->vae[which] = *w;
+    c->have_vae[which] = true;
+    return GEM_OK;
+}
+
+}  // extern "C"
+
+// ---- layer runner ----------------------------------------------------------------------------
+static int run_layer(gem_ctx* c, cudaStream_t s, const gem_layer& L, const float* A, int lda, int M, float* C, int ldc,
+                     int epi, const float* aux) {
+    TapGemmArgs g;
+    g.A = A, g.B = L.w_d, g.bias = L.bias_d, g.aux = aux, g.C = C;
+    g.M = M, g.N = L.n, g.K = L.k, g.taps = L.taps, g.T = c->T;
+    g.lda = lda, g.ldb = (L.n + 3) & ~3, g.ldc = ldc, g.ldaux = L.n, g.epi = epi;
+    if (c->gemm_mode == 1 && L.taps == 1)
+        return launch_tap_gemm_tc(s, g, c->tc_workspace, c->tc_workspace_bytes);
+    return launch_tap_gemm_simt(s, g);
+}
+
+static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const float* z, float* pose_out) {
+    const gem_vae_weights& v = c->vae[which];
+    const int T = c->T, M = W * T, P = c->J * 3;
+    GEM_TRY(run_layer(c, s, v.dec[0], z, c->n, W, c->act[0], T * 256, EPI_LRELU, nullptr));
+    const float* in = c->act[0];
+    for (int i = 1; i <= 4; ++i) {
+        GEM_TRY(run_layer(c, s, v.dec[i], in, v.dec[i].k, M, c->act[i], v.dec[i].n, EPI_LRELU, nullptr));
+        in = c->act[i];
+    }
+    return run_layer(c, s, v.dec[5], in, 64, M, pose_out, P, EPI_NONE, nullptr);
+}
+
+static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const float* dpose, float* dz) {
+    const gem_vae_weights& v = c->vae[which];
+    const int T = c->T, M = W * T, P = c->J * 3;
+    // dec_bwd[i] is the bwd-data of dec[5-i]; its output is d(pre-activation of dec[4-i])
+    const float* in = dpose;
+    int lda = P;
+    for (int i = 0; i < 5; ++i) {
+        const int a = 4 - i;   // activation whose LeakyReLU derivative masks this output
+        GEM_TRY(run_layer(c, s, v.dec_bwd[i], in, lda, M, c->gact[a], v.dec_bwd[i].n, EPI_MASK, c->act[a]));
+        in = c->gact[a];
+        lda = v.dec_bwd[i].n;
+    }
+    return run_layer(c, s, v.dec_bwd[5], c->gact[0], T * 256, W, dz, c->n, EPI_NONE, nullptr);
+}
+
+static int encode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const float* pose, const float* eps, float* z0,
+                       float* mu, float* sd) {
+    const gem_vae_weights& v = c->vae[which];
+    const int T = c->T, M = W * T, P = c->J * 3;
+    const float* in = pose;
+    int lda = P;
+    for (int i = 0; i < 5; ++i) {
+        GEM_TRY(run_layer(c, s, v.enc[i], in, lda, M, c->eact[i], v.enc[i].n, EPI_LRELU, nullptr));
+        in = c->eact[i];
+        lda = v.enc[i].n;
+    }
+    GEM_TRY(run_layer(c, s, v.enc[5], in, T * 512, W, c->fc, 2 * c->n, EPI_NONE, nullptr));
+    return launch_reparam(s, c->fc, eps, z0, mu, sd, W, c->n);
+}
+
+#define GEM_ENTER(c, W)                                                          \
+    GEM_REQUIRE((c) != nullptr, "ctx is NULL");                                  \
+    if ((W) > (c)->Wmax) {                                                       \
+        set_error("more windows than the ctx was created for");                  \
+        return GEM_ERR_CAPACITY;                                                 \
+    }                                                                            \
+    GEM_REQUIRE((W) >= 0, "W must be >= 0");                                      \
+    GEM_CUDA(cudaSetDevice((c)->device))
+
+extern "C" {
+
+int gem_energy_grad(gem_ctx* c, void* stream, int W, const float* pose_d, const float* pose0_d, const float* heat_d,
+                    const int64_t* frame_base_d, const int32_t* clip_d, const float* mean_bone_d,
+                    const gem_energy_weights* wt, float* energy_d, float* terms_d, float* grad_d, uint32_t* status_d) {
+    GEM_ENTER(c, W);
+    GEM_REQUIRE(pose_d && pose0_d && clip_d && mean_bone_d && wt && energy_d && grad_d, "NULL argument");
+    if (wt->reproj != 0.f && !c->have_camera) {
+        set_error("camera not set");
+        return GEM_ERR_STATE;
+    }
+    return launch_energy_grad((cudaStream_t)stream, W, c->T, c->J, c->H, c->Wd, pose_d, pose0_d, heat_d, frame_base_d,
+                              clip_d, mean_bone_d, *wt, energy_d, terms_d, grad_d, status_d);
+}
+
+int gem_decode(gem_ctx* c, void* stream, int which, int W, const float* z_d, float* pose_d) {
+    GEM_ENTER(c, W);
+    GEM_REQUIRE((which == 0 || which == 1) && z_d && pose_d, "bad arguments");
+    if (!c->have_vae[which]) {
+        set_error("VAE weights not set");
+        return GEM_ERR_STATE;
+    }
+    return decode_impl(c, (cudaStream_t)stream, which, W, z_d, pose_d);
+}
+
+int gem_decode_vjp(gem_ctx* c, void* stream, int which, int W, const float* dpose_d, float* dz_d) {
+    GEM_ENTER(c, W);
+    GEM_REQUIRE((which == 0 || which == 1) && dpose_d && dz_d, "bad arguments");
+    if (!c->have_vae[which]) {
+        set_error("VAE weights not set");
+        return GEM_ERR_STATE;
+    }
+    return decode_vjp_impl(c, (cudaStream_t)stream, which, W, dpose_d, dz_d);
+}
+
+int gem_encode(gem_ctx* c, void* stream, int which, int W, const float* pose_d, const float* eps_d, float* z0_d,
+               float* mu_d, float* std_d) {
+    GEM_ENTER(c, W);
+    GEM_REQUIRE((which == 0 || which == 1) && pose_d && eps_d && z0_d, "bad arguments");
+    if (!c->have_vae[which]) {
+        set_error("VAE weights not set");
+        return GEM_ERR_STATE;
+    }
+    return encode_impl(c, (cudaStream_t)stream, which, W, pose_d, eps_d, z0_d, mu_d, std_d);
+}
+
+static int lbfgs_configure(gem_ctx* c, const gem_lbfgs_params* p, float* trace, int trace_stride) {
+    GEM_REQUIRE(p && p->max_iter >= 1 && p->max_eval >= 1 && p->lr > 0, "bad L-BFGS parameters");
+    GEM_REQUIRE(p->max_iter - 1 <= c->m, "max_iter - 1 exceeds the ctx's max_history");
+    c->lb.lr = p->lr, c->lb.tol_grad = p->tolerance_grad, c->lb.tol_change = p->tolerance_change;
+    c->lb.max_iter = p->max_iter, c->lb.max_eval = p->max_eval;
+    c->lb.trace = trace, c->lb.trace_stride = trace_stride;
+    c->lb_params = *p;
+    return GEM_OK;
+}
+
+int gem_lbfgs_begin(gem_ctx* c, void* stream, int W, const float* z0_d, const gem_lbfgs_params* params_h) {
+    GEM_ENTER(c, W);
+    GEM_REQUIRE(z0_d != nullptr, "z0 is NULL");
+    GEM_TRY(lbfgs_configure(c, params_h, nullptr, 0));
+    c->lb_started = true;
+    return launch_lbfgs_begin((cudaStream_t)stream, c->lb, z0_d, W);
+}
+
+const float* gem_lbfgs_trial(gem_ctx* c) { return c ? c->lb.ZT : nullptr; }
+const float* gem_lbfgs_x(gem_ctx* c) { return c ? c->lb.X : nullptr; }
+
+int gem_lbfgs_advance(gem_ctx* c, void* stream, int W, const float* loss_d, const float* grad_d) {
+    GEM_ENTER(c, W);
+    GEM_REQUIRE(loss_d && grad_d, "NULL argument");
+    if (!c->lb_started) {
+        set_error("gem_lbfgs_begin has not been called");
+        return GEM_ERR_STATE;
+    }
+    return launch_lbfgs_advance((cudaStream_t)stream, c->lb, loss_d, grad_d, W);
+}
+
+__global__ void copy_trace_kernel(const float* src, int src_stride, float* dst, int dst_stride, int W, int cols) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)W * cols) return;
+    const int w = (int)(i / cols), k = (int)(i - (size_t)w * cols);
+    dst[(size_t)w * dst_stride + k] = src[(size_t)w * src_stride + k];
+}
+
+int gem_lbfgs_stats(gem_ctx* c, void* stream, int W, int32_t* n_iter_d, int32_t* func_evals_d, int32_t* finished_d,
+                    double* t_d, double* loss_d, float* trace_d, int trace_stride) {
+    GEM_ENTER(c, W);
+    if (trace_d && c->lb.trace && W > 0) {
+        const int cols = trace_stride < c->lb.trace_stride ? trace_stride : c->lb.trace_stride;
+        const size_t total = (size_t)W * cols;
+        copy_trace_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            c->lb.trace, c->lb.trace_stride, trace_d, trace_stride, W, cols);
+        GEM_CHECK_LAUNCH();
+    }
+    return launch_lbfgs_stats((cudaStream_t)stream, c->lb, W, n_iter_d, func_evals_d, finished_d, t_d, loss_d);
+}
+
+int gem_solve_stage(gem_ctx* c, void* stream, int which, int W, const float* pose0_d, const float* heat_d,
+                    const int64_t* frame_base_d, const int32_t* clip_d, const float* mean_bone_d, const float* eps_d,
+                    const gem_energy_weights* wt, const gem_lbfgs_params* params_h, float* pose_out_d,
+                    float* energy_trace_d, int32_t* n_iter_d, int32_t* func_evals_d, uint32_t* status_d) {
+    GEM_ENTER(c, W);
+    GEM_REQUIRE((which == 0 || which == 1) && pose0_d && clip_d && mean_bone_d && eps_d && wt && params_h && pose_out_d,
+                "bad arguments");
+    if (!c->have_vae[which] || (wt->reproj != 0.f && !c->have_camera)) {
+        set_error("VAE weights / camera not set");
+        return GEM_ERR_STATE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (W == 0) return GEM_OK;
+    GEM_TRY(lbfgs_configure(c, params_h, energy_trace_d, energy_trace_d ? params_h->max_eval + 1 : 0));
+    if (status_d) GEM_CUDA(cudaMemsetAsync(status_d, 0, (size_t)W * sizeof(uint32_t), s));
+    if (energy_trace_d)
+        GEM_CUDA(cudaMemsetAsync(energy_trace_d, 0xff, (size_t)W * (params_h->max_eval + 1) * sizeof(float), s));   // NaN
+    // z0 = mu + eps * std                                   optimizer.py:255-259
+    GEM_TRY(encode_impl(c, s, which, W, pose0_d, eps_d, c->z0, nullptr, nullptr));
+    GEM_TRY(launch_lbfgs_begin(s, c->lb, c->z0, W));
+    c->lb_started = true;
+    // LBFGS.step: at most max_eval + 1 closure evaluations per window (lbfgs.py:478-487, App. B)
+    for (int round = 0; round <= params_h->max_eval; ++round) {
+        GEM_TRY(decode_impl(c, s, which, W, c->lb.ZT, c->pose));
+        GEM_TRY(launch_energy_grad(s, W, c->T, c->J, c->H, c->Wd, c->pose, pose0_d, heat_d, frame_base_d, clip_d,
+                                   mean_bone_d, *wt, c->f_new, nullptr, c->gpose, status_d));
+        GEM_TRY(decode_vjp_impl(c, s, which, W, c->gpose, c->g_new));
+        GEM_TRY(launch_lbfgs_advance(s, c->lb, c->f_new, c->g_new, W));
+    }
+    // final decode of the optimum                           optimizer.py:273-276
+    GEM_TRY(decode_impl(c, s, which, W, c->lb.X, pose_out_d));
+    c->lb.trace = nullptr;   // the caller's buffer is not retained
+    c->lb.trace_stride = 0;
+    return launch_lbfgs_stats(s, c->lb, W, n_iter_d, func_evals_d, nullptr, nullptr, nullptr);
+}
+
+int gem_relative_global(gem_ctx* c, void* stream, int W, const void* pose_d, int pose_is_f64, const double* cams_d,
+                        double* out_f64_d, float* out_f32_d) {
+    GEM_ENTER(c, W);
+    GEM_REQUIRE(pose_d && cams_d && (out_f64_d || out_f32_d), "NULL argument");
+    return launch_transform((cudaStream_t)stream, W, c->T, c->J, pose_d, pose_is_f64, cams_d, out_f64_d, out_f32_d, 0);
+}
+
+int gem_to_global(gem_ctx* c, void* stream, int W, const void* pose_d, int pose_is_f64, const double* cams_d,
+                  double* out_f64_d) {
+    GEM_ENTER(c, W);
+    GEM_REQUIRE(pose_d && cams_d && out_f64_d, "NULL argument");
+    return launch_transform((cudaStream_t)stream, W, c->T, c->J, pose_d, pose_is_f64, cams_d, out_f64_d, nullptr, 1);
+}
+
+int gem_merge_windows(gem_ctx* c, void* stream, int W, int overlap, const double* windows_d, double* out_d) {
+    GEM_REQUIRE(c != nullptr && W >= 0, "bad arguments");
+    GEM_REQUIRE(windows_d && out_d, "NULL argument");
+    GEM_CUDA(cudaSetDevice(c->device));
+    return launch_merge((cudaStream_t)stream, W, c->T, overlap, c->J * 3, windows_d, out_d);
+}
+
+int gem_gaussian_smooth(gem_ctx* c, void* stream, int N, int row, double sigma, const double* seq_d, double* out_d) {
+    GEM_REQUIRE(c != nullptr && N >= 0 && row > 0, "bad arguments");
+    GEM_REQUIRE(seq_d && out_d, "NULL argument");
+    GEM_CUDA(cudaSetDevice(c->device));
+    return launch_gauss((cudaStream_t)stream, N, row, sigma, seq_d, out_d);
+}
+
+}  // extern "C"

@@ -1,0 +1,281 @@
+// Fused energy + analytic gradient for W independent windows (one launch).
+//
+// Replaces, per closure evaluation, the reference's pose_energy_3d / smooth_accelerate /
+// bone_length_energy / vae_energy / reprojection_energy_heatmap_fast (optimizer.py:139-149,
+// 172-177, 202-218, 226-240), FishEyeCameraCalibrated.world2camera_pytorch
+// (FishEyeCalibrated.py:96-129), grid_sample(bilinear, zeros, align_corners=True) and the
+// autograd backward of all of them (~70 tiny ATen kernels + one host sync) by ONE kernel:
+//   * a CTA owns two consecutive windows (2 x T x J joints, one thread per joint);
+//   * the windows' pose and anchor tiles (2 x 1800 B each) are staged into shared memory by
+//     the TMA engine (cp.async.bulk + mbarrier) and the gradient tile leaves the same way;
+//   * the heatmaps are gathered in place from the pickle's HWC layout: 4 texels per joint,
+//     never the 2.4 MB of maps per window;
+//   * per-term energies are reduced with warp shuffles, combined in the reference's order.
+// Compiled with --fmad=false: the pixel-coordinate chain must round like ATen's separate
+// fp32 ops, because floor() of the pixel coordinate selects the texels.
+#include "kernels.cuh"
+
+namespace gem {
+
+__constant__ CameraConst c_cam;
+__constant__ SkeletonConst c_skel;
+
+int upload_camera(const CameraConst& cam) {
+    GEM_CUDA(cudaMemcpyToSymbol(c_cam, &cam, sizeof(cam)));
+    return GEM_OK;
+}
+int upload_skeleton(const SkeletonConst& sk) {
+    GEM_CUDA(cudaMemcpyToSymbol(c_skel, &sk, sizeof(sk)));
+    return GEM_OK;
+}
+
+constexpr int kSlot = 160;             // threads per window (>= T*J, multiple of 32)
+constexpr int kWinPerCta = 2;
+constexpr int kThreads = kSlot * kWinPerCta;
+
+struct EnergyArgs {
+    const float* pose;
+    const float* pose0;
+    const float* heat;
+    const int64_t* frame_base;
+    const int32_t* clip;
+    const float* mean_bone;
+    float* energy;
+    float* terms;
+    float* grad;
+    uint32_t* status;
+    int W, T, J, H, Wd;
+    float w3d, ws, wb, wv, wr;
+    int use_bulk;
+};
+
+__device__ __forceinline__ float texel(const float* __restrict__ heat, int64_t frame, int y, int x, int j, int H,
+                                       int Wd, int J) {
+    if (x < 0 || x >= Wd || y < 0 || y >= H) return 0.f;     // padding_mode='zeros'
+    return __ldg(heat + ((frame * H + y) * (int64_t)Wd + x) * J + j);
+}
+
+__global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
+    __shared__ __align__(16) float s_x[kWinPerCta * kSlot * 3];
+    __shared__ __align__(16) float s_x0[kWinPerCta * kSlot * 3];
+    __shared__ __align__(16) float s_g[kWinPerCta * kSlot * 3];
+    __shared__ float s_red[kThreads / 32][5];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x;
+    const int TJ = a.T * a.J;
+    const int n = TJ * 3;                         // floats per window
+    const int w0 = blockIdx.x * kWinPerCta;
+    const int nwin = min(kWinPerCta, a.W - w0);
+    const bool bulk = a.use_bulk && nwin == kWinPerCta;
+
+    // ---- stage pose / anchor tiles -----------------------------------------------------------
+    if (bulk) {
+        // windows are contiguous in memory: one bulk copy covers both (2*n*4 bytes, 16-B multiple)
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(kWinPerCta * n * sizeof(float));
+            mbar_arrive_expect_tx(&s_bar, 2 * bytes);
+            bulk_g2s(s_x, a.pose + (size_t)w0 * n, bytes, &s_bar);
+            bulk_g2s(s_x0, a.pose0 + (size_t)w0 * n, bytes, &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+    } else {
+        for (int i = tid; i < nwin * n; i += kThreads) {
+            s_x[i] = a.pose[(size_t)w0 * n + i];
+            s_x0[i] = a.pose0[(size_t)w0 * n + i];
+        }
+        __syncthreads();
+    }
+    // with the bulk path both windows sit back to back (stride n); keep the same packing otherwise
+    const int wl = tid / kSlot;                   // window slot inside the CTA
+    const int k = tid - wl * kSlot;               // joint-frame index t*J + j
+    const bool active = wl < nwin && k < TJ;
+    const int w = w0 + wl;
+    const float* X = s_x + wl * n;
+    const float* X0 = s_x0 + wl * n;
+
+    float e3d = 0.f, esm = 0.f, ebn = 0.f, eva = 0.f, erp = 0.f;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (active) {
+        const int t = k / a.J, j = k - t * a.J;
+        const float x = X[k * 3 + 0], y = X[k * 3 + 1], z = X[k * 3 + 2];
+
+        // E_3d = sum (x - x0)^2                                     optimizer.py:210-213
+        {
+            const float dx = x - X0[k * 3 + 0], dy = y - X0[k * 3 + 1], dz = z - X0[k * 3 + 2];
+            e3d = dx * dx + dy * dy + dz * dz;
+            gx += a.w3d * (2.f * dx), gy += a.w3d * (2.f * dy), gz += a.w3d * (2.f * dz);
+        }
+        // E_vae = sum x^2 on the decoded pose                        optimizer.py:215-218,238
+        {
+            eva = x * x + y * y + z * z;
+            gx += a.wv * (2.f * x), gy += a.wv * (2.f * y), gz += a.wv * (2.f * z);
+        }
+        // E_smooth: a_s = (x_s - x_{s+1}) - (x_{s+1} - x_{s+2}), s = 0..T-3   optimizer.py:202-208
+        {
+            float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {        // q = 0: a_t (coef 1), 1: a_{t-1} (coef -2), 2: a_{t-2} (coef 1)
+                const int s = t - q;
+                if (s < 0 || s > a.T - 3) continue;
+                const float coef = (q == 1) ? -2.f : 1.f;
+                const float* p0 = X + ((s)*a.J + j) * 3;
+                const float* p1 = X + ((s + 1) * a.J + j) * 3;
+                const float* p2 = X + ((s + 2) * a.J + j) * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float ac = (p0[c] - p1[c]) - (p1[c] - p2[c]);
+                    acc[c] += coef * ac;
+                    if (q == 0) esm += ac * ac;
+                }
+            }
+            gx += a.ws * (2.f * acc[0]), gy += a.ws * (2.f * acc[1]), gz += a.ws * (2.f * acc[2]);
+        }
+        // E_bone = sum (|x_j - x_parent| - Lbar_j)^2                 optimizer.py:172-177, 89-94
+        {
+            const float* mb = a.mean_bone + (size_t)a.clip[w] * a.J;
+            const int p = c_skel.parent[j];
+            const float bx = x - X[(t * a.J + p) * 3 + 0], by = y - X[(t * a.J + p) * 3 + 1],
+                        bz = z - X[(t * a.J + p) * 3 + 2];
+            const float len = sqrtf(bx * bx + by * by + bz * bz);
+            const float diff = len - mb[j];
+            ebn = diff * diff;
+            if (len > 0.f) {                        // torch.norm's subgradient at 0 is 0
+                const float c = a.wb * (2.f * diff) / len;
+                gx += c * bx, gy += c * by, gz += c * bz;
+            }
+            for (int cj = 0; cj < a.J; ++cj) {      // this joint as the parent of cj
+                if (cj == j || c_skel.parent[cj] != j) continue;
+                const float cx = X[(t * a.J + cj) * 3 + 0] - x, cy = X[(t * a.J + cj) * 3 + 1] - y,
+                            cz = X[(t * a.J + cj) * 3 + 2] - z;
+                const float cl = sqrtf(cx * cx + cy * cy + cz * cz);
+                if (cl > 0.f) {
+                    const float c = a.wb * (2.f * (cl - mb[cj])) / cl;
+                    gx -= c * cx, gy -= c * cy, gz -= c * cz;
+                }
+            }
+        }
+        // E_reproj = -sum bilinear(H_tj; pix(project(x)))            optimizer.py:139-149
+        if (a.wr != 0.f) {
+            const float zn = -z;
+            const float r = sqrtf(x * x + y * y);
+            if (r == 0.f) {
+                if (a.status) atomicOr(a.status + w, GEM_WIN_NORM_ZERO);
+            } else {
+                const float theta = atanf(zn / r);
+                float rho = c_cam.poly[0], drho = 0.f, ti = 1.f;
+                for (int i = 1; i < c_cam.n_poly; ++i) {          // power accumulation, not Horner
+                    drho += (float)i * c_cam.poly[i] * ti;
+                    ti *= theta;
+                    rho += ti * c_cam.poly[i];
+                }
+                const float inv = 1.0f / r;
+                const float u = x * inv * rho + c_cam.cx;
+                const float v = y * inv * rho + c_cam.cy;
+                // pose_2d[:,0] -= 128; (pose_2d - 512)/512; grid_sample unnormalise (align_corners)
+                const float gxn = ((u - 128.f) - 512.f) / 512.f;
+                const float gyn = (v - 512.f) / 512.f;
+                const float ix = ((gxn + 1.f) / 2.f) * (float)(a.Wd - 1);
+                const float iy = ((gyn + 1.f) / 2.f) * (float)(a.H - 1);
+                const float fx0 = floorf(ix), fy0 = floorf(iy);
+                // Anything further than one texel outside contributes exactly 0.
+                if (fx0 >= -1.f && fx0 <= (float)a.Wd && fy0 >= -1.f && fy0 <= (float)a.H) {
+                    const int x0 = (int)fx0, y0 = (int)fy0;
+                    const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix;
+                    const float wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
+                    const int64_t frame = a.frame_base[w] + t;
+                    const float nw = texel(a.heat, frame, y0, x0, j, a.H, a.Wd, a.J);
+                    const float ne = texel(a.heat, frame, y0, x0 + 1, j, a.H, a.Wd, a.J);
+                    const float sw = texel(a.heat, frame, y0 + 1, x0, j, a.H, a.Wd, a.J);
+                    const float se = texel(a.heat, frame, y0 + 1, x0 + 1, j, a.H, a.Wd, a.J);
+                    erp = -(nw * (wx0 * wy0) + ne * (wx1 * wy0) + sw * (wx0 * wy1) + se * (wx1 * wy1));
+                    const float ds_dix = -nw * wy0 + ne * wy0 - sw * wy1 + se * wy1;
+                    const float ds_diy = -nw * wx0 - ne * wx1 + sw * wx0 + se * wx1;
+                    const float du = ds_dix * ((float)(a.Wd - 1) * 0.5f / 512.f);   // dS/du
+                    const float dv = ds_diy * ((float)(a.H - 1) * 0.5f / 512.f);    // dS/dv
+                    // fisheye Jacobian
+                    const float r2 = r * r, q = r2 + z * z, r3 = r2 * r;
+                    const float dth_dx = z * x / (r * q), dth_dy = z * y / (r * q), dth_dz = -r / q;
+                    const float xr = x / r, yr = y / r;
+                    const float du_dx = rho / r - x * x * rho / r3 + xr * drho * dth_dx;
+                    const float du_dy = -x * y * rho / r3 + xr * drho * dth_dy;
+                    const float du_dz = xr * drho * dth_dz;
+                    const float dv_dx = -x * y * rho / r3 + yr * drho * dth_dx;
+                    const float dv_dy = rho / r - y * y * rho / r3 + yr * drho * dth_dy;
+                    const float dv_dz = yr * drho * dth_dz;
+                    gx -= a.wr * (du * du_dx + dv * dv_dx);
+                    gy -= a.wr * (du * du_dy + dv * dv_dy);
+                    gz -= a.wr * (du * du_dz + dv * dv_dz);
+                }
+            }
+        }
+    }
+    if (wl < kWinPerCta && k < TJ) {
+        float* G = s_g + wl * n;
+        G[k * 3 + 0] = gx, G[k * 3 + 1] = gy, G[k * 3 + 2] = gz;
+    }
+
+    // ---- per-window energy reduction: shuffle inside each warp, then kSlot/32 partials --------
+    const float r0 = warp_sum(e3d), r1 = warp_sum(esm), r2 = warp_sum(ebn), r3 = warp_sum(eva), r4 = warp_sum(erp);
+    if ((tid & 31) == 0) {
+        float* d = s_red[tid >> 5];
+        d[0] = r0, d[1] = r1, d[2] = r2, d[3] = r3, d[4] = r4;
+    }
+    if (bulk) fence_proxy_async_smem();           // make s_g visible to the bulk-copy engine
+    __syncthreads();
+
+    if (tid < kWinPerCta && tid < nwin) {
+        constexpr int wpw = kSlot / 32;
+        float t5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int q = 0; q < wpw; ++q)
+#pragma unroll
+            for (int c = 0; c < 5; ++c) t5[c] += s_red[tid * wpw + q][c];
+        const int ww = w0 + tid;
+        if (a.terms) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) a.terms[(size_t)ww * 5 + c] = t5[c];
+        }
+        // optimizer.py:239-240 (left to right; the reproj product is skipped when its weight is 0)
+        float E = a.w3d * t5[0] + a.ws * t5[1] + a.wb * t5[2] + a.wv * t5[3];
+        if (a.wr != 0.f) E += a.wr * t5[4];
+        a.energy[ww] = E;
+    }
+    if (bulk) {
+        if (tid == 0) {
+            bulk_s2g(a.grad + (size_t)w0 * n, s_g, (uint32_t)(kWinPerCta * n * sizeof(float)));
+            bulk_commit();
+            bulk_wait_read0();
+        }
+    } else {
+        for (int i = tid; i < nwin * n; i += kThreads) a.grad[(size_t)w0 * n + i] = s_g[i];
+    }
+}
+
+int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, const float* pose,
+                       const float* pose0, const float* heat, const int64_t* frame_base, const int32_t* clip,
+                       const float* mean_bone, const gem_energy_weights& wt, float* energy, float* terms,
+                       float* grad, uint32_t* status) {
+    if (W <= 0) return GEM_OK;
+    GEM_REQUIRE(T * J <= kSlot, "T*J must be <= 160");
+    GEM_REQUIRE(T >= 3, "seq_len must be >= 3");
+    GEM_REQUIRE(wt.reproj == 0.f || (heat != nullptr && frame_base != nullptr), "heatmaps required when reproj != 0");
+    EnergyArgs a;
+    a.pose = pose, a.pose0 = pose0, a.heat = heat, a.frame_base = frame_base, a.clip = clip, a.mean_bone = mean_bone;
+    a.energy = energy, a.terms = terms, a.grad = grad, a.status = status;
+    a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd;
+    a.w3d = wt.w3d, a.ws = wt.smooth, a.wb = wt.bone, a.wv = wt.vae, a.wr = wt.reproj;
+    const size_t pair_bytes = (size_t)kWinPerCta * T * J * 3 * sizeof(float);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    a.use_bulk = (pair_bytes % 16 == 0) && al16(pose) && al16(pose0) && al16(grad);
+    const int grid = (W + kWinPerCta - 1) / kWinPerCta;
+    energy_grad_kernel<<<grid, kThreads, 0, stream>>>(a);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+}  // namespace gem

@@ -1,0 +1,51 @@
+// Launch wrappers shared between the translation units of libgem_b200.so.
+#pragma once
+#include "common.cuh"
+
+namespace gem {
+
+int upload_camera(const CameraConst& cam);
+int upload_skeleton(const SkeletonConst& sk);
+int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, const float* pose, const float* pose0,
+                       const float* heat, const int64_t* frame_base, const int32_t* clip, const float* mean_bone,
+                       const gem_energy_weights& wt, float* energy, float* terms, float* grad, uint32_t* status);
+
+enum { EPI_NONE = 0, EPI_LRELU = 1, EPI_MASK = 2 };
+struct TapGemmArgs {
+    const float* A;      // [M][lda]
+    const float* B;      // [taps][K][ldb]
+    const float* bias;   // [N] or NULL
+    const float* aux;    // [M][ldaux] saved activation for EPI_MASK
+    float* C;            // [M][ldc]
+    int M, N, K, taps, T;
+    int lda, ldb, ldc, ldaux;   // ldb = row stride of B[tap][k][:] (N rounded up to a multiple of 4, zero padded)
+    int epi;
+};
+int launch_tap_gemm_simt(cudaStream_t stream, const TapGemmArgs& g);
+int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* workspace, size_t workspace_bytes);
+bool tc_gemm_available();
+
+struct LbfgsWin;
+struct LbfgsBuffers {
+    LbfgsWin* st;
+    float *X, *D, *G, *PG, *GP, *BG0, *BG1, *ZT;   // [W][n]
+    float *Y, *S;                                   // [W][m][n]
+    float* RO;                                      // [W][m]
+    float* trace;                                   // [W][trace_stride] or NULL
+    int n, m, trace_stride;
+    double lr, tol_grad, tol_change;
+    int max_iter, max_eval;
+};
+size_t lbfgs_state_bytes();
+int launch_lbfgs_begin(cudaStream_t stream, const LbfgsBuffers& b, const float* z0, int W);
+int launch_lbfgs_advance(cudaStream_t stream, const LbfgsBuffers& b, const float* loss, const float* grad, int W);
+int launch_lbfgs_stats(cudaStream_t stream, const LbfgsBuffers& b, int W, int32_t* n_iter, int32_t* evals,
+                       int32_t* finished, double* t, double* loss);
+
+int launch_reparam(cudaStream_t stream, const float* fc, const float* eps, float* z0, float* mu, float* sd, int W, int n);
+int launch_transform(cudaStream_t stream, int W, int T, int J, const void* pose, int pose_is_f64, const double* cams,
+                     double* out64, float* out32, int mode);
+int launch_merge(cudaStream_t stream, int W, int T, int overlap, int row, const double* win, double* out);
+int launch_gauss(cudaStream_t stream, int N, int row, double sigma, const double* seq, double* out);
+
+}  // namespace gem

@@ -1,0 +1,190 @@
+"""Drop-in mirror of the reference's optimiser surface (reference optimizer.py):
+
+    BodyPoseOptimizer(camera_model_path, mean_skeleton, vae_path, seq_len, network_seq_len,
+                      latent_dim, windows_size=5, overlap_size=1, slide_window=False, lr=2, max_iter=25)
+        .set_weights(vae_weight, gmm_weight, smooth_weight, bone_length_weight, weight_3d, reproj_weight)
+        .optimize_pose_seq_pytorch_LBFGS(relative_global_pose, heatmap_seq, smoothed_pose) -> (10,15,3) fp32
+        .total_loss(hidden_parameter) -> scalar
+    main(data_id, camera_model_path, vae_weight, gmm_weight, smoothness_weight, bone_length_weight,
+         weight_3d, reproj_weight, visualization=False, final_smooth=False, merge=True, save=False,
+         save_pose=False) -> (errors, final_estimated_seq, mid_local_pose_seq, final_optimized_seq, final_gt_seq)
+
+Same names, argument meaning, pickle / checkpoint / camera formats and error behaviour
+("norm is zero!").  What differs is the execution: every window of the clip is optimised in one
+batch on the GPU through libgem_b200.so; there is no CPU path.  Arguments the reference accepts and
+never reads (gmm_weight, merge, windows_size, slide_window, smoothed_pose, ...) are
+accepted and ignored here too.  Extra keyword arguments (max_iter, eps, engine) are additions.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+
+import numpy as np
+import torch
+
+from .engine import Engine, GemError, energy_weights, lbfgs_params
+from .metrics import calculate_errors
+from .pipeline import SequenceOptimizer
+from .vae_prep import PreparedVae
+
+LOCAL_VAE_PATH = "networks/logs/only_local_full_dataset_latent_2048_len_10_kl_0.5_2/checkpoints/19.pth.tar"
+GLOBAL_VAE_PATH = "networks/logs/real_full_dataset_latent_2048_len_10_slide_window_step_1_kl_0.5/checkpoints/19.pth.tar"
+GEM_WIN_NORM_ZERO = 1
+
+_vae_cache = {}
+_engine_cache = {}
+
+
+def load_vae(vae_path, device, seq_len=10, latent_dim=2048):
+    """torch.load(vae_path)['state_dict'] (optimizer.py:59), prepared once per (path, mtime):
+    the reference re-reads both 130 MB checkpoints for every clip."""
+    key = (os.path.abspath(vae_path), os.path.getmtime(vae_path), str(device), seq_len, latent_dim)
+    if key not in _vae_cache:
+        sd = torch.load(vae_path, map_location="cpu")["state_dict"]
+        _vae_cache[key] = PreparedVae(sd, device, seq_len=seq_len, latent_dim=latent_dim)
+    return _vae_cache[key]
+
+
+def shared_engine(max_windows, max_history=24, latent_dim=2048, seq_len=10):
+    """One Engine per process, grown when a clip needs more windows / a longer history."""
+    key = (latent_dim, seq_len, torch.cuda.current_device() if torch.cuda.is_available() else -1)
+    eng = _engine_cache.get(key)
+    if eng is None or eng.max_windows < max_windows or eng.max_history < max_history:
+        if eng is not None:
+            max_windows, max_history = max(max_windows, eng.max_windows), max(max_history, eng.max_history)
+            eng.close()
+        eng = Engine(max_windows=max(max_windows, 128), latent_dim=latent_dim, seq_len=seq_len,
+                     max_history=max_history)
+        _engine_cache[key] = eng
+    return eng
+
+
+def _raise_on_status(status):
+    if int((status & GEM_WIN_NORM_ZERO).sum()) != 0:
+        raise Exception("norm is zero!")          # FishEyeCalibrated.py:124-127
+
+
+class BodyPoseOptimizer:
+    kinematic_parents = [0, 0, 1, 2, 0, 4, 5, 1, 7, 8, 9, 4, 11, 12, 13]
+
+    def __init__(self, camera_model_path, mean_skeleton, vae_path, seq_len, network_seq_len, latent_dim,
+                 windows_size=5, overlap_size=1, slide_window=False, lr=2, max_iter=25, engine=None,
+                 max_windows=128):
+        self.seq_len, self.network_seq_len = seq_len, network_seq_len
+        self.windows_size, self.slide_window, self.overlap_size = windows_size, slide_window, overlap_size
+        self.lr, self.max_iter = lr, max_iter
+        self.engine = engine if engine is not None else Engine(max_windows=max_windows, latent_dim=latent_dim,
+                                                               seq_len=seq_len, max_history=max(max_iter - 1, 1))
+        self.device = self.engine.device
+        # mean over all frames of the bone lengths of `mean_skeleton` (optimizer.py:42-43, 89-94)
+        sk = torch.as_tensor(np.asarray(mean_skeleton) if not isinstance(mean_skeleton, torch.Tensor)
+                             else mean_skeleton).float().to(self.device).view(-1, 15, 3)
+        bones = torch.linalg.vector_norm(sk - sk[:, self.kinematic_parents, :], dim=-1)
+        self.mean_bone_length = torch.mean(bones, 0)
+        self.engine.set_vae(0, load_vae(vae_path, self.device, seq_len, latent_dim))
+        self.engine.set_camera_json(camera_model_path)
+        self.vae_weight = self.gmm_weight = self.smooth_weight = None
+        self.bone_length_weight = self.reproj_weight = self.weight_3d = None
+        self.initial_pose = None
+        self.heatmap_seq = None
+
+    def set_weights(self, vae_weight, gmm_weight, smooth_weight, bone_length_weight, weight_3d, reproj_weight):
+        self.vae_weight, self.gmm_weight, self.smooth_weight = vae_weight, gmm_weight, smooth_weight
+        self.bone_length_weight, self.weight_3d, self.reproj_weight = bone_length_weight, weight_3d, reproj_weight
+
+    def _weights(self):
+        return energy_weights(self.weight_3d, self.smooth_weight, self.bone_length_weight, self.vae_weight,
+                              self.reproj_weight)
+
+    def optimize_windows(self, poses, heatmaps, eps=None, want_trace=False):
+        """Batched form: poses [W,T,15,3], heatmaps [W,T,H,Wd,15] (HWC, as in the pickle)."""
+        poses = torch.as_tensor(np.asarray(poses)).float()
+        W = poses.shape[0]
+        heat = fb = None
+        if self.reproj_weight != 0:
+            heat = torch.as_tensor(np.asarray(heatmaps)).float()
+            heat = heat.reshape(W * self.seq_len, *heat.shape[-3:])
+            fb = torch.arange(W, dtype=torch.int64) * self.seq_len
+        if eps is None:
+            eps = torch.randn(W, self.engine.n)               # one draw per stage call, SeqConvVAE.py:159-169
+        res = self.engine.solve_stage(0, poses, heat, fb, torch.zeros(W, dtype=torch.int32),
+                                      self.mean_bone_length, eps, self._weights(),
+                                      lbfgs_params(lr=self.lr, max_iter=self.max_iter), want_trace=want_trace)
+        _raise_on_status(res["status"])
+        return res
+
+    def optimize_pose_seq_pytorch_LBFGS(self, relative_global_pose, heatmap_seq, smoothed_pose, eps=None):
+        res = self.optimize_windows(np.asarray(relative_global_pose)[None], np.asarray(heatmap_seq)[None],
+                                    None if eps is None else np.asarray(eps).reshape(1, -1))
+        self.initial_pose = torch.as_tensor(np.asarray(relative_global_pose)).float()
+        if self.reproj_weight != 0:
+            self.heatmap_seq = torch.as_tensor(np.asarray(heatmap_seq)).float()
+        return res["pose"][0].cpu().numpy()
+
+    def total_loss(self, hidden_parameter):
+        """E(z) at the state left by the last optimize call (initial pose / heatmaps), optimizer.py:226-240."""
+        if self.initial_pose is None:
+            raise GemError("total_loss needs a previous optimize_pose_seq_pytorch_LBFGS call (initial_pose unset)")
+        z = torch.as_tensor(hidden_parameter).detach().float().reshape(1, -1)
+        pose = self.engine.decode(0, z)
+        heat = fb = None
+        if self.reproj_weight != 0:
+            heat, fb = self.heatmap_seq, torch.zeros(1, dtype=torch.int64)
+        E, _, _, status = self.engine.energy_grad(pose, self.initial_pose[None], heat, fb,
+                                                  torch.zeros(1, dtype=torch.int32), self.mean_bone_length,
+                                                  self._weights(), want_terms=False)
+        _raise_on_status(status)
+        return E[0]
+
+
+def load_clip(data_id):
+    """'<data_id>/test_data.pkl' -> dict of ndarrays (optimizer.py:315-324); extra keys are ignored."""
+    with open("{}/test_data.pkl".format(data_id), "rb") as f:
+        data = pickle.load(f)
+    return {k: np.asarray(data[k]) for k in ("estimated_local_skeleton", "gt_global_skeleton", "camera_pose_list",
+                                             "heatmap_list")}
+
+
+def main(data_id, camera_model_path, vae_weight, gmm_weight, smoothness_weight, bone_length_weight, weight_3d,
+         reproj_weight, visualization=False, final_smooth=False, merge=True, save=False, save_pose=False,
+         max_iter=25, eps=None, local_vae_path=LOCAL_VAE_PATH, global_vae_path=GLOBAL_VAE_PATH, engine=None):
+    clip = load_clip(data_id)
+    seq_len, overlap = 10, 2
+    n_windows = len(range(0, len(clip["estimated_local_skeleton"]) - seq_len + 1, seq_len - overlap))
+    eng = engine if engine is not None else shared_engine(n_windows, max(max_iter - 1, 1))
+    eng.set_camera_json(camera_model_path)
+    eng.set_vae(0, load_vae(local_vae_path, eng.device))
+    eng.set_vae(1, load_vae(global_vae_path, eng.device))
+    seq_opt = SequenceOptimizer(eng, vae_weight=vae_weight, smoothness_weight=smoothness_weight,
+                                bone_length_weight=bone_length_weight, weight_3d=weight_3d,
+                                reproj_weight=reproj_weight, lr=2, max_iter=max_iter)
+    if eps is None:
+        # the reference draws torch.randn_like(std) of shape (1, 2048) in the order local(w0),
+        # global(w0), local(w1), ... from the global generator; one CPU draw of (W, 2, 2048)
+        # consumes the same stream
+        eps = torch.randn(n_windows, 2, eng.n)
+    batch, sol, merged = seq_opt.run([clip], eps=eps, final_smooth=final_smooth is True)
+    _raise_on_status(sol["local"]["status"])
+    m = merged[0]
+    if m is None:
+        raise ValueError("clip shorter than one window ({} frames)".format(seq_len))
+    final_estimated_seq = list(m["final_estimated_seq"].cpu().numpy())
+    mid_estimated_seq = list(m["mid_estimated_seq"].cpu().numpy())
+    mid_local_pose_seq = list(m["mid_local_pose_seq"].cpu().numpy())
+    final_gt_seq = list(m["final_gt_seq"].cpu().numpy())
+    final_optimized_seq = m["final_optimized_seq"].cpu().numpy()
+    if final_smooth is not True:
+        final_optimized_seq = list(final_optimized_seq)
+    if visualization is True or save:
+        raise NotImplementedError("mesh visualisation / .ply export need open3d and are outside this path")
+    if save_pose:
+        dataset_dir, seq_name = os.path.split(data_id)
+        dataset_name = os.path.split(dataset_dir)[1]
+        out_dir = "out/{}/{}".format(dataset_name, seq_name)
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, "result_pose.pkl"), "wb") as f:
+            pickle.dump({"estimated_pose": final_estimated_seq, "optimized_pose": final_optimized_seq,
+                         "mid_optimized_pose": mid_estimated_seq, "gt_pose": final_gt_seq}, f)
+    errors = calculate_errors(final_estimated_seq, mid_estimated_seq, final_optimized_seq, final_gt_seq)
+    return errors, final_estimated_seq, mid_local_pose_seq, final_optimized_seq, final_gt_seq

@@ -1,0 +1,135 @@
+"""Batched per-sequence pipeline: every window of every clip goes through the
+local stage, the SLAM camera transform and the global stage together, then the
+clips are stitched (reference optimizer.py:370-450, which loops window by window).
+
+Host logic only: window partition, index bookkeeping and buffer placement.  All
+arithmetic runs in libgem_b200.so through ``Engine``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .engine import KINEMATIC_PARENTS, Engine, energy_weights, lbfgs_params
+
+SEQ_LEN = 10
+OVERLAP = 2
+
+
+def window_starts(n_frames, seq_len=SEQ_LEN, overlap=OVERLAP):
+    """range(0, N - seq_len + 1, seq_len - overlap), reference optimizer.py:370: the trailing
+    (N - seq_len) mod (seq_len - overlap) frames are dropped."""
+    return list(range(0, n_frames - seq_len + 1, seq_len - overlap))
+
+
+def stage_weights(vae_weight, smoothness_weight, bone_length_weight, weight_3d, reproj_weight):
+    """(local, global) energy weights exactly as main wires them (optimizer.py:352-358): the global
+    stage hard-codes bone_length_weight=0.01 and reproj_weight=0, the local stage scales the
+    smoothness weight by 1/100 and weight_3d by 1/10000."""
+    local = energy_weights(weight_3d / 10000, smoothness_weight / 100, bone_length_weight, vae_weight, reproj_weight)
+    glob = energy_weights(weight_3d, smoothness_weight, 0.01, vae_weight, 0)
+    return local, glob
+
+
+class WindowBatch:
+    """Device-resident inputs of all windows of a list of clips."""
+
+    def __init__(self, engine: Engine, clips, pinned=False):
+        dev = engine.device
+        self.n_frames = [len(c["estimated_local_skeleton"]) for c in clips]
+        self.starts = [window_starts(n, engine.T, OVERLAP) for n in self.n_frames]
+        self.n_windows = [len(s) for s in self.starts]
+        offs = np.concatenate([[0], np.cumsum(self.n_frames)])
+        self.frame_offsets = offs
+        fb = np.concatenate([np.asarray(s, dtype=np.int64) + offs[i] for i, s in enumerate(self.starts)]
+                            or [np.zeros(0, np.int64)])
+        self.W = int(fb.shape[0])
+        clip_idx = np.concatenate([np.full(len(s), i, dtype=np.int32) for i, s in enumerate(self.starts)]
+                                  or [np.zeros(0, np.int32)])
+
+        def cat(key, dtype):
+            arrs = [torch.as_tensor(np.asarray(c[key])) for c in clips]
+            t = torch.cat(arrs, dim=0) if len(arrs) > 1 else arrs[0]
+            return t.to(device=dev, dtype=dtype, non_blocking=True)
+
+        self.est = cat("estimated_local_skeleton", torch.float64)          # [F,15,3]
+        self.cams = cat("camera_pose_list", torch.float64)                 # [F,4,4]
+        self.gt = cat("gt_global_skeleton", torch.float64) if "gt_global_skeleton" in clips[0] else None
+        self.heat = cat("heatmap_list", torch.float32)                     # [F,H,W,15] (pickle's HWC layout, as is)
+        self.frame_base = torch.as_tensor(fb, device=dev)
+        self.clip_idx = torch.as_tensor(clip_idx, device=dev)
+        t_idx = self.frame_base[:, None] + torch.arange(engine.T, device=dev)[None, :]      # [W,T] frame ids
+        self.frame_idx = t_idx
+        # mean bone length per clip from the fp32 cast of the whole clip's local estimate
+        # (BodyPoseOptimizer.__init__, optimizer.py:42-43, 333, 343)
+        parents = torch.as_tensor(KINEMATIC_PARENTS, device=dev)
+        est32 = self.est.to(torch.float32)
+        bone = torch.linalg.vector_norm(est32 - est32[:, parents, :], dim=-1)   # [F,15]
+        self.mean_bone = torch.stack([bone[offs[i]:offs[i + 1]].mean(0) for i in range(len(clips))])
+
+    def gather(self, per_frame):
+        return per_frame[self.frame_idx]                                    # [W,T,...]
+
+
+class SequenceOptimizer:
+    """Two-stage optimisation of whole clips, all windows in one batch."""
+
+    def __init__(self, engine: Engine, vae_weight=0.0, smoothness_weight=0.001, bone_length_weight=0.01,
+                 weight_3d=0.01, reproj_weight=0.01, lr=2, max_iter=25):
+        self.engine = engine
+        self.w_local, self.w_global = stage_weights(vae_weight, smoothness_weight, bone_length_weight, weight_3d,
+                                                    reproj_weight)
+        self.params = lbfgs_params(lr=lr, max_iter=max_iter)
+
+    def solve(self, batch: WindowBatch, eps=None, want_trace=False):
+        """Runs both stages for every window of ``batch``; returns per-window device tensors."""
+        eng = self.engine
+        W = batch.W
+        if eps is None:
+            eps = torch.randn(W, 2, eng.n, device=eng.device, dtype=torch.float32)
+        eps = eng._dev(eps, torch.float32)
+        x_local64 = batch.gather(batch.est)                               # [W,T,15,3] f64
+        cams_w = batch.gather(batch.cams)                                 # [W,T,4,4] f64
+        # local stage                                                     optimizer.py:386
+        loc = eng.solve_stage(0, x_local64.to(torch.float32), batch.heat, batch.frame_base, batch.clip_idx,
+                              batch.mean_bone, eps[:, 0], self.w_local, self.params, want_trace=want_trace)
+        # SLAM: camera-relative frames of the window -> first camera's frame   optimizer.py:394-398
+        rel64, rel32 = eng.relative_global(loc["pose"], cams_w)
+        # global stage                                                    optimizer.py:414
+        glo = eng.solve_stage(1, rel32, None, None, batch.clip_idx, batch.mean_bone, eps[:, 1], self.w_global,
+                              self.params, want_trace=want_trace)
+        return dict(local=loc, glob=glo, rel64=rel64, cams=cams_w, x_local64=x_local64)
+
+    def stitch(self, batch: WindowBatch, sol, final_smooth=True):
+        """Per clip: the six merged sequences of optimizer.py:442-450 (device float64 tensors)."""
+        eng = self.engine
+        cams_w = sol["cams"]
+        est_rel64, _ = eng.relative_global(sol["x_local64"], cams_w, want_f32=False)
+        est_global = eng.to_global(est_rel64, cams_w)                     # optimizer.py:400
+        mid_global = eng.to_global(sol["rel64"], cams_w)                  # optimizer.py:401-402
+        opt_global = eng.to_global(sol["glob"]["pose"], cams_w)           # optimizer.py:421
+        gt_w = batch.gather(batch.gt) if batch.gt is not None else None
+        mid_local = sol["local"]["pose"].to(torch.float64)
+        out = []
+        w0 = 0
+        for nw in batch.n_windows:
+            sl = slice(w0, w0 + nw)
+            w0 += nw
+            if nw == 0:
+                out.append(None)
+                continue
+            r = dict(final_estimated_seq=eng.merge_windows(est_global[sl]),
+                     mid_estimated_seq=eng.merge_windows(mid_global[sl]),
+                     mid_local_pose_seq=eng.merge_windows(mid_local[sl]).to(torch.float32),
+                     final_optimized_seq=eng.merge_windows(opt_global[sl]),
+                     final_estimated_local_seq=eng.merge_windows(sol["x_local64"][sl]),
+                     final_gt_seq=None if gt_w is None else eng.merge_windows(gt_w[sl]))
+            if final_smooth:
+                r["final_optimized_seq"] = eng.gaussian_smooth(r["final_optimized_seq"], 1.0)
+            out.append(r)
+        return out
+
+    def run(self, clips, eps=None, final_smooth=True, want_trace=False):
+        batch = WindowBatch(self.engine, clips)
+        sol = self.solve(batch, eps=eps, want_trace=want_trace)
+        return batch, sol, self.stitch(batch, sol, final_smooth=final_smooth)

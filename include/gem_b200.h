@@ -1,0 +1,172 @@
+/*
+ * gem_b200.h — C ABI of the B200-native GlobalEgoMocap pose-sequence optimiser.
+ *
+ * The reference (jianwang-mpi/GlobalEgoMocap) is pure Python and has no FFI of its
+ * own; its boundary for this path is the Python surface
+ *     BodyPoseOptimizer.optimize_pose_seq_pytorch_LBFGS   (optimizer.py:242-276)
+ *     BodyPoseOptimizer.total_loss                        (optimizer.py:226-240)
+ *     optimizer.main window loop + stitching              (optimizer.py:370-450)
+ * The Python shim `globalegomocap_b200.optimizer` keeps those names/signatures and
+ * binds the entry points below with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative gem_status otherwise;
+ *     gem_last_error() gives a thread-local message.  No C++ exceptions cross the ABI.
+ *   - all `*_d` / pointer arguments are DEVICE pointers owned by the caller unless
+ *     the name ends in `_h` (host).  The library never frees caller memory; scratch
+ *     (activations, L-BFGS vectors/history) is owned by the gem_ctx, sized for
+ *     `max_windows` at creation.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the
+ *     calls do not synchronise unless stated.
+ *   - one host thread per gem_ctx; one gem_ctx per device (multi-GPU = one process
+ *     per GPU).
+ *   - window geometry: T frames x J joints x 3, pose tensors are [W][T][J][3] fp32,
+ *     heatmaps are the pickle's HWC layout [frames][H][Wd][J] fp32 and are gathered
+ *     in place (map of window w, frame t, joint j = frame_base[w]+t, channel j;
+ *     optimizer.py:251-252 permutes to t*15+j).
+ */
+#ifndef GEM_B200_H
+#define GEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gem_ctx gem_ctx;
+
+enum gem_status {
+    GEM_OK = 0,
+    GEM_ERR_INVALID = -1,   /* bad argument */
+    GEM_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+    GEM_ERR_STATE = -3,     /* call order / missing weights */
+    GEM_ERR_CAPACITY = -4   /* more windows than the ctx was created for */
+};
+
+/* per-window status bits written by the energy kernel */
+#define GEM_WIN_NORM_ZERO 1u /* a joint had x = y = 0 in the camera frame: the reference raises
+                                Exception("norm is zero!") (FishEyeCalibrated.py:108,124-127) */
+
+/* weights of total_loss in the reference's order of appearance (optimizer.py:239-240) */
+typedef struct gem_energy_weights {
+    float w3d;     /* weight_3d          * pose_energy_3d      (optimizer.py:210-213) */
+    float smooth;  /* smooth_weight      * smooth_accelerate   (optimizer.py:202-208) */
+    float bone;    /* bone_length_weight * bone_length_energy  (optimizer.py:172-177) */
+    float vae;     /* vae_weight         * vae_energy(pose)    (optimizer.py:215-218,238) */
+    float reproj;  /* reproj_weight      * reprojection_energy_heatmap_fast (optimizer.py:139-149);
+                      exactly 0 skips the term like optimizer.py:232-235 */
+} gem_energy_weights;
+
+/* torch.optim.LBFGS(lr, max_iter, max_eval, tolerance_grad, tolerance_change,
+ * line_search_fn='strong_wolfe') as constructed at optimizer.py:261-262 */
+typedef struct gem_lbfgs_params {
+    double lr;               /* 2 */
+    int32_t max_iter;        /* 25 */
+    int32_t max_eval;        /* max_iter*5/4 = 31 */
+    double tolerance_grad;   /* 1e-7 */
+    double tolerance_change; /* 1e-6 (outer loop; the line search keeps torch's own 1e-9) */
+} gem_lbfgs_params;
+
+/* One generic layer: out[m][n] = act( bias[n] + sum_tap sum_k in[m + tap - taps/2][k] * w[tap][k][n] ),
+ * rows m are (window, frame) tokens, taps that leave the window's T frames read zeros. */
+typedef struct gem_layer {
+    const float* w_d;    /* [taps][k][n] fp32 */
+    const float* bias_d; /* [n] or NULL */
+    int32_t taps, k, n;
+} gem_layer;
+
+/* BatchNorm-folded, tap-arranged weights of one ConvVAE (SeqConvVAE.py:27-92) prepared by the
+ * host shim (globalegomocap_b200/vae_prep.py).  dec[0] is decoder_input fused with decoder.0's
+ * ConvTranspose1d (both linear, no activation between them): latent -> [T][256]. */
+typedef struct gem_vae_weights {
+    gem_layer dec[6];      /* forward: latent->T*256, 256->128, 128->64, 64->64, 64->64, 64->45 */
+    gem_layer dec_bwd[6];  /* bwd-data of dec[5]..dec[0] in execution order (no bias) */
+    gem_layer enc[6];      /* 45->64, 64->64, 64->128, 128->256, 256->512, T*512 -> 2*latent (mu|logvar) */
+} gem_vae_weights;
+
+int gem_version(void);
+const char* gem_last_error(void);
+
+/* ---- context ---------------------------------------------------------------------------- */
+int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, int seq_len, int num_joints,
+                   int heat_h, int heat_w, int max_history);
+int gem_ctx_destroy(gem_ctx* ctx);
+/* polynomialW2C coefficients + principal point (FishEyeCalibrated.py:8-14) */
+int gem_ctx_set_camera(gem_ctx* ctx, const double* poly_h, int n_poly, double cx, double cy);
+/* kinematic_parents (optimizer.py:34) */
+int gem_ctx_set_skeleton(gem_ctx* ctx, const int32_t* parents_h, int num_joints);
+/* which: 0 = local-stage VAE, 1 = global-stage VAE (optimizer.py:334,344); struct is copied */
+int gem_ctx_set_vae(gem_ctx* ctx, int which, const gem_vae_weights* weights_h);
+/* bytes of device scratch owned by the ctx */
+int64_t gem_ctx_scratch_bytes(const gem_ctx* ctx);
+/* 0: hand-written SIMT fp32 GEMM everywhere; 1: tcgen05/TMEM 3xTF32 GEMM for the latent<->T*256
+ * contraction (default when available) */
+int gem_ctx_set_gemm_mode(gem_ctx* ctx, int mode);
+
+/* ---- the fused energy + analytic gradient (total_loss with the decoder bypassed) -------- */
+/* pose_d, pose0_d, grad_d: [W][T][J][3]; frame_base_d: [W] int64 first frame of each window inside
+ * heat_d (may be NULL when weights->reproj == 0); clip_d: [W] int32 row of mean_bone_d [clips][J];
+ * energy_d [W], terms_d [W][5] (E_3d, E_smooth, E_bone, E_vae, E_reproj; may be NULL),
+ * status_d [W] uint32 OR-ed with GEM_WIN_* bits (may be NULL). */
+int gem_energy_grad(gem_ctx* ctx, void* stream, int W, const float* pose_d, const float* pose0_d,
+                    const float* heat_d, const int64_t* frame_base_d, const int32_t* clip_d,
+                    const float* mean_bone_d, const gem_energy_weights* weights_h, float* energy_d,
+                    float* terms_d, float* grad_d, uint32_t* status_d);
+
+/* ---- VAE pieces (ConvVAE.decode_to_bodypose / get_latent_space) -------------------------- */
+/* z_d [W][latent] -> pose_d [W][T][J][3]; keeps the activations for gem_decode_vjp */
+int gem_decode(gem_ctx* ctx, void* stream, int which, int W, const float* z_d, float* pose_d);
+/* dpose_d [W][T][J][3] -> dz_d [W][latent] (bwd-data only; uses the last gem_decode's activations) */
+int gem_decode_vjp(gem_ctx* ctx, void* stream, int which, int W, const float* dpose_d, float* dz_d);
+/* pose_d [W][T][J*3], eps_d [W][latent] -> z0 = mu + eps*exp(0.5*logvar); mu_d/std_d optional */
+int gem_encode(gem_ctx* ctx, void* stream, int which, int W, const float* pose_d, const float* eps_d,
+               float* z0_d, float* mu_d, float* std_d);
+
+/* ---- batched L-BFGS (torch.optim.LBFGS.step semantics, one independent solve per window) - */
+/* start W solves from z0_d [W][n]; afterwards gem_lbfgs_trial() is the point to evaluate */
+int gem_lbfgs_begin(gem_ctx* ctx, void* stream, int W, const float* z0_d, const gem_lbfgs_params* params_h);
+/* device pointer [W][n] of the points whose (loss, gradient) the next gem_lbfgs_advance expects */
+const float* gem_lbfgs_trial(gem_ctx* ctx);
+/* feed loss_d [W] and grad_d [W][n] evaluated at gem_lbfgs_trial(); advances every unfinished
+ * window to its next evaluation point (or to termination) without host synchronisation */
+int gem_lbfgs_advance(gem_ctx* ctx, void* stream, int W, const float* loss_d, const float* grad_d);
+/* current iterate [W][n] (the optimum once finished) */
+const float* gem_lbfgs_x(gem_ctx* ctx);
+/* copies per-window counters to caller device arrays (any may be NULL): n_iter, func_evals int32,
+ * finished int32 (1 when the solve has terminated), final step t (double), loss (double),
+ * trace_d [W][trace_stride] fp32 losses in evaluation order */
+int gem_lbfgs_stats(gem_ctx* ctx, void* stream, int W, int32_t* n_iter_d, int32_t* func_evals_d,
+                    int32_t* finished_d, double* t_d, double* loss_d, float* trace_d, int trace_stride);
+
+/* ---- one full stage: optimize_pose_seq_pytorch_LBFGS for W windows at once --------------- */
+/* pose0_d [W][T][J][3] (the stage's input pose = x0 of E_3d), eps_d [W][latent] reparameterisation
+ * noise, outputs pose_out_d [W][T][J][3]; energy_trace_d [W][max_eval+1] (optional),
+ * n_iter_d / func_evals_d [W] (optional), status_d [W] (optional). */
+int gem_solve_stage(gem_ctx* ctx, void* stream, int which, int W, const float* pose0_d, const float* heat_d,
+                    const int64_t* frame_base_d, const int32_t* clip_d, const float* mean_bone_d,
+                    const float* eps_d, const gem_energy_weights* weights_h, const gem_lbfgs_params* params_h,
+                    float* pose_out_d, float* energy_trace_d, int32_t* n_iter_d, int32_t* func_evals_d,
+                    uint32_t* status_d);
+
+/* ---- SLAM camera transforms and stitching (float64 like the reference's numpy) ----------- */
+/* get_relative_global_pose_with_camera_matrix (utils/utils.py:99-112): out[w][t] = inv(C[w][0]) C[w][t] x.
+ * pose_d fp32 [W][T][J][3] (a stage result) or, when pose_is_f64, float64; cams_d float64 [W][T][4][4];
+ * out_f64_d [W][T][J][3] float64 and/or out_f32_d (the fp32 cast the next stage consumes). */
+int gem_relative_global(gem_ctx* ctx, void* stream, int W, const void* pose_d, int pose_is_f64,
+                        const double* cams_d, double* out_f64_d, float* out_f32_d);
+/* relative_global_pose_to_global_pose (optimizer.py:302-308): out[w][t] = C[w][0] x */
+int gem_to_global(gem_ctx* ctx, void* stream, int W, const void* pose_d, int pose_is_f64, const double* cams_d,
+                  double* out_f64_d);
+/* merge_batches (optimizer.py:425-437) of W consecutive windows of one sequence, overlap frames
+ * averaged: windows_d float64 [W][T][J][3] -> out_d float64 [(T-overlap)*W+overlap][J][3] */
+int gem_merge_windows(gem_ctx* ctx, void* stream, int W, int overlap, const double* windows_d, double* out_d);
+/* scipy.ndimage.gaussian_filter1d(seq, sigma, axis=0, mode='reflect') (optimizer.py:450) on
+ * seq_d float64 [N][row] -> out_d */
+int gem_gaussian_smooth(gem_ctx* ctx, void* stream, int N, int row, double sigma, const double* seq_d,
+                        double* out_d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEM_B200_H */
