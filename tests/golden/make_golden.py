@@ -291,6 +291,56 @@ def gen_traces(h: Harness, max_iters=(1, 2, 3, 5, 25), fname="traces.npz"):
     np.savez_compressed(os.path.join(OUT, fname), **out)
 
 
+def gen_traces_grad(h: Harness):
+    """max_iter=25 runs with the closure's gradient recorded as well, so that an optimiser
+    implementation can be replayed on the reference's exact (loss, gradient) stream."""
+    import torch.optim.lbfgs as tl
+    inj = EpsInjector(h.ref)
+    tracer = LossTracer(h.ref)
+    grads = []
+    orig = tl.LBFGS._gather_flat_grad
+
+    def gather(self_):
+        gflat = orig(self_)
+        grads.append(gflat.detach().clone().numpy())
+        return gflat
+
+    tl.LBFGS._gather_flat_grad = gather
+    est = np.asarray(h.clip["estimated_local_skeleton"])
+    heat_all = np.asarray(h.clip["heatmap_list"])
+    cams = np.asarray(h.clip["camera_pose_list"])
+    rng = np.random.default_rng(2024)
+    eps_all = rng.standard_normal((3, 2, 2048)).astype(np.float32)       # same noise as traces.npz
+    out = {"eps": eps_all}
+    try:
+        for wi, s in ((1, 8), (2, 16)):
+            lopt = h.make_optimizer("local", W_LOCAL, max_iter=25)
+            gopt = h.make_optimizer("global", W_GLOBAL, max_iter=25)
+            inj.push(eps_all[wi, 0])
+            grads.clear()
+            res_l = lopt.optimize_pose_seq_pytorch_LBFGS(est[s:s + 10], heat_all[s:s + 10], est[s:s + 10].copy())
+            rec = tracer.take()
+            assert len(rec) == len(grads)
+            out[f"w{wi}_local_E"] = np.asarray([r[0] for r in rec], dtype=np.float64)
+            out[f"w{wi}_local_z"] = np.stack([r[1] for r in rec]).astype(np.float32)
+            out[f"w{wi}_local_g"] = np.stack(grads).astype(np.float32)
+            rel = h.ref.get_relative_global_pose_with_camera_matrix(res_l, cams[s:s + 10])
+            inj.push(eps_all[wi, 1])
+            grads.clear()
+            gopt.optimize_pose_seq_pytorch_LBFGS(rel, heat_all[s:s + 10], rel.copy())
+            rec = tracer.take()
+            assert len(rec) == len(grads)
+            out[f"w{wi}_global_E"] = np.asarray([r[0] for r in rec], dtype=np.float64)
+            out[f"w{wi}_global_z"] = np.stack([r[1] for r in rec]).astype(np.float32)
+            out[f"w{wi}_global_g"] = np.stack(grads).astype(np.float32)
+            print(f"traces_grad w{wi}: evals L/G = {len(out[f'w{wi}_local_E'])}/{len(rec)}")
+    finally:
+        tl.LBFGS._gather_flat_grad = orig
+        tracer.restore()
+        inj.restore()
+    np.savez_compressed(os.path.join(OUT, "traces_grad.npz"), **out)
+
+
 def gen_main(h: Harness, max_iter=3):
     """End-to-end optimizer.main on the clip with a fixed small iteration count.
     main hard-codes max_iter=25 (optimizer.py:340,350); it is a constructor
@@ -347,7 +397,7 @@ def main():
     clip = syn.make_clip(58, seed=7)
     scratch = tempfile.mkdtemp(prefix="gem_golden_")
     h = Harness(scratch, clip)
-    todo = args.only or ["clip", "fisheye", "energy", "vae", "traces", "main", "traces_g2"]
+    todo = args.only or ["clip", "fisheye", "energy", "vae", "traces", "main", "traces_grad", "traces_g2"]
     if "clip" in todo:
         gen_clip_fixture(clip)
     if "fisheye" in todo:
@@ -360,6 +410,8 @@ def main():
         gen_traces(h)
     if "main" in todo:
         gen_main(h, 3)
+    if "traces_grad" in todo:
+        gen_traces_grad(h)
     if "traces_g2" in todo:
         # weights drawn with twice PyTorch's default bound: larger decoder Jacobian, the energy
         # drops by orders of magnitude and most 25-iteration trajectories are well conditioned

@@ -145,3 +145,25 @@ def test_free_running_matches_reference(golden_dir, clip58, vae_weights, vae_wei
     assert n_strict >= 0.6 * len(long_runs), (n_strict, len(long_runs))
     full = [c for c in cases if c[0][-3] == 25 and c[3]]
     assert len(full) >= 4          # complete 25-iteration solves that track the reference to 0.5 mm
+
+
+def test_replay_of_reference_closure_stream_reproduces_every_trial_point(golden_dir):
+    """Teacher-forced OPTIMISER parity: fed the reference's exact (loss, gradient) stream, the
+    restated L-BFGS must ask for exactly the points the reference evaluated — all ~30 of them,
+    both stages — and stop after the same number of evaluations.  With the closure taken out of
+    the loop the decisions are well conditioned, so this is strict."""
+    g = np.load(os.path.join(golden_dir, "traces_grad.npz"))
+    for key in ("w1_local", "w1_global", "w2_local", "w2_global"):
+        E, Z, G = g[key + "_E"], g[key + "_z"], g[key + "_g"]
+        calls = []
+
+        def closure(z):
+            k = len(calls)
+            assert k < len(E), "optimiser asked for more evaluations than the reference"
+            scale = max(np.abs(Z[k] - Z[0]).max(), 1e-3)
+            assert np.abs(z - Z[k]).max() <= 2e-4 * scale + 1e-6, (key, k, np.abs(z - Z[k]).max(), scale)
+            calls.append(k)
+            return float(E[k]), G[k]
+
+        x, info = lbfgs_minimize(closure, Z[0], lr=2, max_iter=25, tolerance_change=1e-6)
+        assert len(calls) == len(E) == info["func_evals"], (key, len(calls), len(E))
