@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 pose-sequence optimiser (BASELINE.json metric: optimised frames/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = the whole hot path over one batch of synthetic input: encoder -> local-stage batched
+L-BFGS (max_iter 25, <= 32 closure evaluations) -> SLAM transform -> global-stage L-BFGS -> global
+transform -> overlap-average stitching -> Gaussian smoothing, for every window of
+`--sequences` x `--frames` synthetic frames per GPU (default: BASELINE.json configs[2], 5 x 3000
+frames -> 1870 windows -> 14970 output frames per GPU).  Weak scaling: every rank owns one
+contiguous block of each sequence's windows; ranks exchange only boundary windows for stitching.
+
+`value` is measured with the inputs resident in HBM, `e2e` through host (pinned) buffers with
+the H2D/D2H copies inside the timed region.  `--impl reference` times the reference's CPU path
+(oracle/torch_port.py: the reference is pure Python and /root/reference does not exist on the GPU
+box, so the port — same ATen ops, same torch.optim.LBFGS — stands in) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "optimised frames/sec (windows x iters, device-timed)"
+FLOPS_PER_WINDOW_EVAL_ALGORITHMIC = 63.9e6   # decoder fwd + bwd-data as the reference runs it
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sequences", type=int, default=5)
+    ap.add_argument("--frames", type=int, default=3000, help="frames per sequence per GPU")
+    ap.add_argument("--max-iter", type=int, default=25)
+    ap.add_argument("--gemm-mode", type=int, default=-1, help="-1 library default, 0 SIMT fp32, 1 tcgen05 3xTF32")
+    ap.add_argument("--cpu-windows", type=int, default=4, help="windows timed for cpu_baseline (after 1 warm-up)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------- data
+def make_rank_clips(sequences, frames, rank):
+    from globalegomocap_b200 import synthetic as syn
+    return [syn.make_clip(frames, seed=1000 * rank + 17 + s) for s in range(sequences)]
+
+
+def make_weights(clip):
+    from globalegomocap_b200 import synthetic as syn
+    bias = syn.mean_pose_bias(clip)
+    return (syn.make_vae_state_dict(11, perturb_bn=True, pose_bias=bias),
+            syn.make_vae_state_dict(12, perturb_bn=True, pose_bias=bias))
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU every 100 ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------- CPU baseline
+def cpu_baseline(clips, weights, camera, n_windows, max_iter):
+    """The reference's CPU path (oracle/torch_port.py), all host threads, on the first windows of
+    the workload: one warm-up window, then `n_windows` timed (both stages each)."""
+    import torch
+    from oracle import energy_np as en
+    from oracle.pipeline_np import relative_global_pose
+    from oracle.torch_port import TorchPortOptimizer
+    clip = clips[0]
+    est, heat, cams = clip["estimated_local_skeleton"], clip["heatmap_list"], clip["camera_pose_list"]
+    mb = en.mean_bone_length(est)
+    w_local = (0.01 / 10000, 0.001 / 100, 0.01, 0.0, 0.01)
+    w_global = (0.01, 0.001, 0.01, 0.0, 0)
+    loc = TorchPortOptimizer(weights[0], camera, mb, w_local, max_iter=max_iter)
+    glo = TorchPortOptimizer(weights[1], camera, mb, w_global, max_iter=max_iter)
+    gen = torch.Generator().manual_seed(0)
+    times, evals = [], 0
+    for i in range(n_windows + 1):
+        s = 8 * i
+        eps = torch.randn(2, 2048, generator=gen).numpy()
+        t0 = time.perf_counter()
+        res, info_l = loc.solve(est[s:s + 10], heat[s:s + 10], eps[0])
+        rel = relative_global_pose(res, cams[s:s + 10])
+        _, info_g = glo.solve(rel, heat[s:s + 10], eps[1])
+        dt = time.perf_counter() - t0
+        if i > 0:                                  # first window discarded (lazy init / oneDNN warm-up)
+            times.append(dt)
+            evals += info_l["func_evals"] + info_g["func_evals"]
+    total = float(np.sum(times))
+    return {"value": 8.0 * n_windows / total, "unit": "frames/s", "cores": int(torch.get_num_threads()),
+            "kind": "port",
+            "sample": f"{n_windows} windows x 2 stages of the same workload (max_iter={max_iter}, "
+                      f"{evals} closure evaluations, {total:.1f} s) after 1 warm-up window; "
+                      "oracle/torch_port.py = the reference's ATen ops + torch.optim.LBFGS incl. its unused weight grads",
+            "seconds_per_window": total / n_windows}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from globalegomocap_b200 import synthetic as syn
+    torch.set_num_threads(os.cpu_count() or 1)
+    clips = [syn.make_clip(8 * (args.cpu_windows * max(args.steps, 1) + 2) + 10, seed=17)]
+    weights = make_weights(clips[0])
+    cam = syn.load_camera()
+    # warm-up steps are folded into the discarded first window; each step is a bounded sample
+    per_step = []
+    for _ in range(max(args.steps, 1)):
+        per_step.append(cpu_baseline(clips, weights, cam, args.cpu_windows, args.max_iter))
+    value = float(np.mean([p["value"] for p in per_step]))
+    base = per_step[-1]
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * base["seconds_per_window"] * args.cpu_windows,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, None), "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, extra):
+    cfg = {"workload": f"BASELINE configs[2]: {args.sequences} synthetic sequences x {args.frames} frames per GPU, "
+                       "15 joints, 64x64x15 HWC fp32 heatmaps, random-init motion VAEs (local + global), "
+                       f"windows of 10 frames stride 8, L-BFGS max_iter={args.max_iter} both stages",
+           "sequences_per_gpu": args.sequences, "frames_per_sequence_per_gpu": args.frames, "max_iter": args.max_iter,
+           "cache": "inputs (3.7 GB heatmaps, 0.9 GB L-BFGS state per GPU) are larger than L2 (126 MB); no flush needed"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------- ours
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from globalegomocap_b200 import distributed as gdist
+    from globalegomocap_b200 import synthetic as syn
+    from globalegomocap_b200.engine import Engine
+    from globalegomocap_b200.pipeline import SequenceOptimizer, WindowBatch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic workload in pinned host memory -------------------------------------------------
+    clips_np = make_rank_clips(args.sequences, args.frames, rank)
+    weights = make_weights(make_rank_clips(1, 64, 0)[0])           # same weights on every rank
+    cam = syn.load_camera()
+    clips = []
+    for c in clips_np:
+        clips.append({k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in c.items()
+                      if k != "gt_global_skeleton"})
+    h2d_bytes = sum(t.numel() * t.element_size() for c in clips for t in c.values())
+
+    n_win = sum(len(range(0, args.frames - 10 + 1, 8)) for _ in range(args.sequences))
+    eng = Engine(max_windows=n_win, max_history=max(args.max_iter - 1, 1))
+    eng.set_camera(*cam)
+    eng.set_vae(0, weights[0])
+    eng.set_vae(1, weights[1])
+    if args.gemm_mode >= 0:
+        eng.set_gemm_mode(args.gemm_mode)
+    so = SequenceOptimizer(eng, max_iter=args.max_iter)
+    stride, overlap = eng.T - 2, 2
+
+    out_frames_rank = sum(stride * nw + (overlap if rank == world - 1 else 0)
+                          for nw in [len(range(0, args.frames - 10 + 1, 8))] * args.sequences)
+    host_out = torch.empty(out_frames_rank, 15, 3, dtype=torch.float64).pin_memory()
+
+    def stitch_all(batch, sol):
+        """Global transform + overlap merge + Gaussian smoothing of this rank's shard of every sequence."""
+        opt_global = eng.to_global(sol["glob"]["pose"], sol["cams"])
+        nw = batch.n_windows[0]
+        S = len(batch.n_windows)
+        wins = opt_global.view(S, nw, eng.T, eng.J, 3)
+        left, right = gdist.exchange_boundary_windows(wins) if world > 1 else (None, None)
+        outs = []
+        for s in range(S):
+            outs.append(gdist.stitch_shard(wins[s], None if left is None else left[s],
+                                           None if right is None else right[s],
+                                           lambda w, ov: eng.merge_windows(w, ov), lambda q: eng.gaussian_smooth(q, 1.0),
+                                           stride, overlap, final_smooth=True))
+        return torch.cat(outs, dim=0)
+
+    resident = WindowBatch(eng, clips)
+    torch.cuda.synchronize()
+
+    def step_device():
+        sol = so.solve(resident, eps=None)
+        return sol, stitch_all(resident, sol)
+
+    def step_e2e():
+        batch = WindowBatch(eng, clips)                       # H2D of every input from pinned memory
+        sol = so.solve(batch, eps=None)
+        out = stitch_all(batch, sol)
+        host_out.copy_(out, non_blocking=True)                # D2H of the step's result
+        return sol
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        if profile:
+            eng.read_profile()
+            eng.set_profiling(True)
+        launches0 = eng.launch_count()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        last = None
+        for _ in range(steps):
+            last = fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        prof = None
+        if profile:
+            prof = eng.read_profile()
+            eng.set_profiling(False)
+        launches = eng.launch_count() - launches0
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms, prof, launches, last
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, prof, launches, last = timed(step_device, args.steps, profile=True)
+    clocks = sampler.stop()
+    sol = last[0]
+    evals = int(sol["local"]["func_evals"].sum().item() + sol["glob"]["func_evals"].sum().item())
+    n_iter = int(sol["local"]["n_iter"].sum().item() + sol["glob"]["n_iter"].sum().item())
+    total_frames = out_frames_rank
+    if world > 1:
+        t = torch.tensor([total_frames, evals, n_iter, launches], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_frames, evals, n_iter, launches = (int(v) for v in t.tolist())
+    ms_per_step = ms / args.steps
+    value = total_frames / (ms_per_step / 1000.0)
+
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            step_e2e()
+        ms_e, _, _, _ = timed(step_e2e, args.steps)
+        e2e = {"value": total_frames / (ms_e / args.steps / 1000.0), "unit": "frames/s",
+               "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(host_out.numel() * 8),
+               "ms_per_step": ms_e / args.steps}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        W = n_win
+        rounds = 2 * (so.params.max_eval + 1)
+        per_tag = {int(k): {"launches": v[0], "ms_total": v[1], "ms_avg": v[1] / max(v[0], 1)} for k, v in prof.items()}
+        kern_ms = sum(v["ms_total"] for v in per_tag.values())
+        # dominant kernel: the latent <-> T*256 GEMM pair (tags 100 and 205), tensor-bound class
+        gemm_tags = [100, 205]
+        g_ms = sum(per_tag[t]["ms_total"] for t in gemm_tags if t in per_tag)
+        g_n = sum(per_tag[t]["launches"] for t in gemm_tags if t in per_tag)
+        flop_per_launch = 2.0 * W * 2048 * 2560
+        roof = {"bound": "tensor", "kernel": "decoder latent<->T*256 GEMM (tags 100, 205)",
+                "achieved": flop_per_launch / (g_ms / max(g_n, 1) / 1e3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
+                "traffic": None, "peak_source": peak_src + ", bf16 sustained",
+                "share_of_kernel_time": g_ms / max(kern_ms, 1e-9),
+                "note": "executed FLOPs of the fused layer (2*W*2048*2560 per launch); fp32-faithful arithmetic"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        # energy kernel: HBM bound, 7.8 KB (local) / 5.4 KB (global) algorithmic bytes per window
+        e = per_tag.get(1)
+        energy = None
+        if e:
+            bytes_per_launch = W * (7800 + 5400) / 2.0
+            energy = {"bound": "hbm", "achieved": bytes_per_launch / (e["ms_avg"] / 1e3) / 1e9, "peak": hbm_peak,
+                      "unit": "GB/s", "ms_avg": e["ms_avg"], "launches": e["launches"],
+                      "note": "mean of local (7.8 KB/window) and global (5.4 KB/window) launches"}
+            energy["frac"] = energy["achieved"] / hbm_peak
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            cpu = cpu_baseline(clips_np, weights, cam, args.cpu_windows, args.max_iter)
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, {"windows_total": W * world, "closure_evaluations_last_step": evals,
+                                                 "lbfgs_iterations_last_step": n_iter,
+                                                 "rounds_per_step": rounds, "gemm_mode": args.gemm_mode}),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+                "energy_kernel": energy, "kernel_ms_per_step": {str(k): v["ms_total"] / args.steps for k, v in
+                                                                sorted(per_tag.items())},
+                "effective_tflops_reference_flop_count": evals * FLOPS_PER_WINDOW_EVAL_ALGORITHMIC / (ms_per_step / 1e3) / 1e12,
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -45,7 +45,36 @@ struct gem_ctx {
     bool lb_started = false;
     void* tc_workspace = nullptr;
     size_t tc_workspace_bytes = 0;
+    // instrumentation: kernel-launch counter and optional CUDA-event pairs around every launch
+    int64_t launches = 0;
+    bool prof_on = false;
+    struct ProfEntry {
+        int tag;
+        cudaEvent_t a, b;
+    };
+    std::vector<ProfEntry> prof;
+    size_t prof_used = 0;
 };
+
+// Runs one kernel launch `f` under the ctx's instrumentation (tag identifies the kernel class).
+template <typename F>
+static int timed(gem_ctx* c, cudaStream_t s, int tag, F&& f) {
+    c->launches += 1;
+    if (!c->prof_on) return f();
+    if (c->prof_used == c->prof.size()) {
+        gem_ctx::ProfEntry e;
+        e.tag = tag;
+        GEM_CUDA(cudaEventCreate(&e.a));
+        GEM_CUDA(cudaEventCreate(&e.b));
+        c->prof.push_back(e);
+    }
+    gem_ctx::ProfEntry& e = c->prof[c->prof_used++];
+    e.tag = tag;
+    GEM_CUDA(cudaEventRecord(e.a, s));
+    const int rc = f();
+    GEM_CUDA(cudaEventRecord(e.b, s));
+    return rc;
+}
 
 static const int kDecC[6] = {256, 128, 64, 64, 64, 0};   // channels after dec[0..4]; dec[5] -> J*3
 static const int kEncC[5] = {64, 64, 128, 256, 512};
@@ -128,6 +157,7 @@ int gem_ctx_destroy(gem_ctx* c) {
     cudaSetDevice(c->device);
     for (void* p : c->allocs) cudaFree(p);
     if (c->tc_workspace) cudaFree(c->tc_workspace);
+    for (auto& e : c->prof) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
     delete c;
     return GEM_OK;
 }
@@ -142,6 +172,39 @@ int gem_ctx_set_gemm_mode(gem_ctx* c, int mode) {
         return GEM_ERR_STATE;
     }
     c->gemm_mode = mode;
+    return GEM_OK;
+}
+
+int gem_ctx_set_profiling(gem_ctx* c, int enable) {
+    GEM_REQUIRE(c != nullptr, "ctx is NULL");
+    c->prof_on = enable != 0;
+    c->prof_used = 0;
+    return GEM_OK;
+}
+
+int64_t gem_ctx_launch_count(const gem_ctx* c) { return c ? c->launches : 0; }
+
+int gem_ctx_read_profile(gem_ctx* c, int max_tags, int32_t* tags_h, int32_t* counts_h, float* total_ms_h,
+                         int32_t* n_tags_h) {
+    GEM_REQUIRE(c && tags_h && counts_h && total_ms_h && n_tags_h && max_tags > 0, "bad arguments");
+    GEM_CUDA(cudaSetDevice(c->device));
+    GEM_CUDA(cudaDeviceSynchronize());
+    int n = 0;
+    for (size_t i = 0; i < c->prof_used; ++i) {
+        float ms = 0.f;
+        GEM_CUDA(cudaEventElapsedTime(&ms, c->prof[i].a, c->prof[i].b));
+        int k = 0;
+        while (k < n && tags_h[k] != c->prof[i].tag) ++k;
+        if (k == n) {
+            if (n == max_tags) continue;
+            tags_h[n] = c->prof[i].tag, counts_h[n] = 0, total_ms_h[n] = 0.f;
+            ++n;
+        }
+        counts_h[k] += 1;
+        total_ms_h[k] += ms;
+    }
+    *n_tags_h = n;
+    c->prof_used = 0;
     return GEM_OK;
 }
 
@@ -196,27 +259,28 @@ int gem_ctx_set_vae(gem_ctx* c, int which, const gem_vae_weights* w) {
 }  // extern "C"
 
 // ---- layer runner ----------------------------------------------------------------------------
-static int run_layer(gem_ctx* c, cudaStream_t s, const gem_layer& L, const float* A, int lda, int M, float* C, int ldc,
-                     int epi, const float* aux) {
+static int run_layer(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, const float* A, int lda, int M, float* C,
+                     int ldc, int epi, const float* aux) {
     TapGemmArgs g;
     g.A = A, g.B = L.w_d, g.bias = L.bias_d, g.aux = aux, g.C = C;
     g.M = M, g.N = L.n, g.K = L.k, g.taps = L.taps, g.T = c->T;
     g.lda = lda, g.ldb = (L.n + 3) & ~3, g.ldc = ldc, g.ldaux = L.n, g.epi = epi;
-    if (c->gemm_mode == 1 && L.taps == 1)
-        return launch_tap_gemm_tc(s, g, c->tc_workspace, c->tc_workspace_bytes);
-    return launch_tap_gemm_simt(s, g);
+    return timed(c, s, tag, [&]() {
+        if (c->gemm_mode == 1 && L.taps == 1) return launch_tap_gemm_tc(s, g, c->tc_workspace, c->tc_workspace_bytes);
+        return launch_tap_gemm_simt(s, g);
+    });
 }
 
 static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const float* z, float* pose_out) {
     const gem_vae_weights& v = c->vae[which];
     const int T = c->T, M = W * T, P = c->J * 3;
-    GEM_TRY(run_layer(c, s, v.dec[0], z, c->n, W, c->act[0], T * 256, EPI_LRELU, nullptr));
+    GEM_TRY(run_layer(c, s, GEM_TAG_DEC + 0, v.dec[0], z, c->n, W, c->act[0], T * 256, EPI_LRELU, nullptr));
     const float* in = c->act[0];
     for (int i = 1; i <= 4; ++i) {
-        GEM_TRY(run_layer(c, s, v.dec[i], in, v.dec[i].k, M, c->act[i], v.dec[i].n, EPI_LRELU, nullptr));
+        GEM_TRY(run_layer(c, s, GEM_TAG_DEC + i, v.dec[i], in, v.dec[i].k, M, c->act[i], v.dec[i].n, EPI_LRELU, nullptr));
         in = c->act[i];
     }
-    return run_layer(c, s, v.dec[5], in, 64, M, pose_out, P, EPI_NONE, nullptr);
+    return run_layer(c, s, GEM_TAG_DEC + 5, v.dec[5], in, 64, M, pose_out, P, EPI_NONE, nullptr);
 }
 
 static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const float* dpose, float* dz) {
@@ -227,11 +291,12 @@ static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const f
     int lda = P;
     for (int i = 0; i < 5; ++i) {
         const int a = 4 - i;   // activation whose LeakyReLU derivative masks this output
-        GEM_TRY(run_layer(c, s, v.dec_bwd[i], in, lda, M, c->gact[a], v.dec_bwd[i].n, EPI_MASK, c->act[a]));
+        GEM_TRY(run_layer(c, s, GEM_TAG_DEC_BWD + i, v.dec_bwd[i], in, lda, M, c->gact[a], v.dec_bwd[i].n, EPI_MASK,
+                          c->act[a]));
         in = c->gact[a];
         lda = v.dec_bwd[i].n;
     }
-    return run_layer(c, s, v.dec_bwd[5], c->gact[0], T * 256, W, dz, c->n, EPI_NONE, nullptr);
+    return run_layer(c, s, GEM_TAG_DEC_BWD + 5, v.dec_bwd[5], c->gact[0], T * 256, W, dz, c->n, EPI_NONE, nullptr);
 }
 
 static int encode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const float* pose, const float* eps, float* z0,
@@ -241,12 +306,12 @@ static int encode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const float
     const float* in = pose;
     int lda = P;
     for (int i = 0; i < 5; ++i) {
-        GEM_TRY(run_layer(c, s, v.enc[i], in, lda, M, c->eact[i], v.enc[i].n, EPI_LRELU, nullptr));
+        GEM_TRY(run_layer(c, s, GEM_TAG_ENC + i, v.enc[i], in, lda, M, c->eact[i], v.enc[i].n, EPI_LRELU, nullptr));
         in = c->eact[i];
         lda = v.enc[i].n;
     }
-    GEM_TRY(run_layer(c, s, v.enc[5], in, T * 512, W, c->fc, 2 * c->n, EPI_NONE, nullptr));
-    return launch_reparam(s, c->fc, eps, z0, mu, sd, W, c->n);
+    GEM_TRY(run_layer(c, s, GEM_TAG_ENC + 5, v.enc[5], in, T * 512, W, c->fc, 2 * c->n, EPI_NONE, nullptr));
+    return timed(c, s, GEM_TAG_REPARAM, [&]() { return launch_reparam(s, c->fc, eps, z0, mu, sd, W, c->n); });
 }
 
 #define GEM_ENTER(c, W)                                                          \
@@ -269,8 +334,10 @@ int gem_energy_grad(gem_ctx* c, void* stream, int W, const float* pose_d, const 
         set_error("camera not set");
         return GEM_ERR_STATE;
     }
-    return launch_energy_grad((cudaStream_t)stream, W, c->T, c->J, c->H, c->Wd, pose_d, pose0_d, heat_d, frame_base_d,
-                              clip_d, mean_bone_d, *wt, energy_d, terms_d, grad_d, status_d);
+    return timed(c, (cudaStream_t)stream, GEM_TAG_ENERGY, [&]() {
+        return launch_energy_grad((cudaStream_t)stream, W, c->T, c->J, c->H, c->Wd, pose_d, pose0_d, heat_d,
+                                  frame_base_d, clip_d, mean_bone_d, *wt, energy_d, terms_d, grad_d, status_d);
+    });
 }
 
 int gem_decode(gem_ctx* c, void* stream, int which, int W, const float* z_d, float* pose_d) {
@@ -319,7 +386,8 @@ int gem_lbfgs_begin(gem_ctx* c, void* stream, int W, const float* z0_d, const ge
     GEM_REQUIRE(z0_d != nullptr, "z0 is NULL");
     GEM_TRY(lbfgs_configure(c, params_h, nullptr, 0));
     c->lb_started = true;
-    return launch_lbfgs_begin((cudaStream_t)stream, c->lb, z0_d, W);
+    return timed(c, (cudaStream_t)stream, GEM_TAG_LBFGS_BEGIN,
+                 [&]() { return launch_lbfgs_begin((cudaStream_t)stream, c->lb, z0_d, W); });
 }
 
 const float* gem_lbfgs_trial(gem_ctx* c) { return c ? c->lb.ZT : nullptr; }
@@ -332,7 +400,8 @@ int gem_lbfgs_advance(gem_ctx* c, void* stream, int W, const float* loss_d, cons
         set_error("gem_lbfgs_begin has not been called");
         return GEM_ERR_STATE;
     }
-    return launch_lbfgs_advance((cudaStream_t)stream, c->lb, loss_d, grad_d, W);
+    return timed(c, (cudaStream_t)stream, GEM_TAG_LBFGS_ADVANCE,
+                 [&]() { return launch_lbfgs_advance((cudaStream_t)stream, c->lb, loss_d, grad_d, W); });
 }
 
 __global__ void copy_trace_kernel(const float* src, int src_stride, float* dst, int dst_stride, int W, int cols) {
@@ -374,49 +443,59 @@ int gem_solve_stage(gem_ctx* c, void* stream, int which, int W, const float* pos
         GEM_CUDA(cudaMemsetAsync(energy_trace_d, 0xff, (size_t)W * (params_h->max_eval + 1) * sizeof(float), s));   // NaN
     // z0 = mu + eps * std                                   optimizer.py:255-259
     GEM_TRY(encode_impl(c, s, which, W, pose0_d, eps_d, c->z0, nullptr, nullptr));
-    GEM_TRY(launch_lbfgs_begin(s, c->lb, c->z0, W));
+    GEM_TRY(timed(c, s, GEM_TAG_LBFGS_BEGIN, [&]() { return launch_lbfgs_begin(s, c->lb, c->z0, W); }));
     c->lb_started = true;
     // LBFGS.step: at most max_eval + 1 closure evaluations per window (lbfgs.py:478-487, App. B)
     for (int round = 0; round <= params_h->max_eval; ++round) {
         GEM_TRY(decode_impl(c, s, which, W, c->lb.ZT, c->pose));
-        GEM_TRY(launch_energy_grad(s, W, c->T, c->J, c->H, c->Wd, c->pose, pose0_d, heat_d, frame_base_d, clip_d,
-                                   mean_bone_d, *wt, c->f_new, nullptr, c->gpose, status_d));
+        GEM_TRY(timed(c, s, GEM_TAG_ENERGY, [&]() {
+            return launch_energy_grad(s, W, c->T, c->J, c->H, c->Wd, c->pose, pose0_d, heat_d, frame_base_d, clip_d,
+                                      mean_bone_d, *wt, c->f_new, nullptr, c->gpose, status_d);
+        }));
         GEM_TRY(decode_vjp_impl(c, s, which, W, c->gpose, c->g_new));
-        GEM_TRY(launch_lbfgs_advance(s, c->lb, c->f_new, c->g_new, W));
+        GEM_TRY(timed(c, s, GEM_TAG_LBFGS_ADVANCE,
+                      [&]() { return launch_lbfgs_advance(s, c->lb, c->f_new, c->g_new, W); }));
     }
     // final decode of the optimum                           optimizer.py:273-276
     GEM_TRY(decode_impl(c, s, which, W, c->lb.X, pose_out_d));
     c->lb.trace = nullptr;   // the caller's buffer is not retained
     c->lb.trace_stride = 0;
-    return launch_lbfgs_stats(s, c->lb, W, n_iter_d, func_evals_d, nullptr, nullptr, nullptr);
+    return timed(c, s, GEM_TAG_OTHER,
+                 [&]() { return launch_lbfgs_stats(s, c->lb, W, n_iter_d, func_evals_d, nullptr, nullptr, nullptr); });
 }
 
 int gem_relative_global(gem_ctx* c, void* stream, int W, const void* pose_d, int pose_is_f64, const double* cams_d,
                         double* out_f64_d, float* out_f32_d) {
     GEM_ENTER(c, W);
     GEM_REQUIRE(pose_d && cams_d && (out_f64_d || out_f32_d), "NULL argument");
-    return launch_transform((cudaStream_t)stream, W, c->T, c->J, pose_d, pose_is_f64, cams_d, out_f64_d, out_f32_d, 0);
+    return timed(c, (cudaStream_t)stream, GEM_TAG_TRANSFORM, [&]() {
+        return launch_transform((cudaStream_t)stream, W, c->T, c->J, pose_d, pose_is_f64, cams_d, out_f64_d, out_f32_d, 0);
+    });
 }
 
 int gem_to_global(gem_ctx* c, void* stream, int W, const void* pose_d, int pose_is_f64, const double* cams_d,
                   double* out_f64_d) {
     GEM_ENTER(c, W);
     GEM_REQUIRE(pose_d && cams_d && out_f64_d, "NULL argument");
-    return launch_transform((cudaStream_t)stream, W, c->T, c->J, pose_d, pose_is_f64, cams_d, out_f64_d, nullptr, 1);
+    return timed(c, (cudaStream_t)stream, GEM_TAG_TRANSFORM, [&]() {
+        return launch_transform((cudaStream_t)stream, W, c->T, c->J, pose_d, pose_is_f64, cams_d, out_f64_d, nullptr, 1);
+    });
 }
 
 int gem_merge_windows(gem_ctx* c, void* stream, int W, int overlap, const double* windows_d, double* out_d) {
     GEM_REQUIRE(c != nullptr && W >= 0, "bad arguments");
     GEM_REQUIRE(windows_d && out_d, "NULL argument");
     GEM_CUDA(cudaSetDevice(c->device));
-    return launch_merge((cudaStream_t)stream, W, c->T, overlap, c->J * 3, windows_d, out_d);
+    return timed(c, (cudaStream_t)stream, GEM_TAG_STITCH,
+                 [&]() { return launch_merge((cudaStream_t)stream, W, c->T, overlap, c->J * 3, windows_d, out_d); });
 }
 
 int gem_gaussian_smooth(gem_ctx* c, void* stream, int N, int row, double sigma, const double* seq_d, double* out_d) {
     GEM_REQUIRE(c != nullptr && N >= 0 && row > 0, "bad arguments");
     GEM_REQUIRE(seq_d && out_d, "NULL argument");
     GEM_CUDA(cudaSetDevice(c->device));
-    return launch_gauss((cudaStream_t)stream, N, row, sigma, seq_d, out_d);
+    return timed(c, (cudaStream_t)stream, GEM_TAG_STITCH,
+                 [&]() { return launch_gauss((cudaStream_t)stream, N, row, sigma, seq_d, out_d); });
 }
 
 }  // extern "C"

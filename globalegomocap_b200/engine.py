@@ -71,6 +71,20 @@ class Engine:
     def scratch_bytes(self):
         return int(self.lib.gem_ctx_scratch_bytes(self._ctx))
 
+    def launch_count(self) -> int:
+        return int(self.lib.gem_ctx_launch_count(self._ctx))
+
+    def set_profiling(self, enable: bool):
+        check(self.lib.gem_ctx_set_profiling(self._ctx, int(bool(enable))))
+
+    def read_profile(self):
+        """{tag: (launches, total_ms)} of the event pairs recorded since the last read (synchronises)."""
+        n_max = 64
+        tags, counts = (C.c_int32 * n_max)(), (C.c_int32 * n_max)()
+        ms, n = (C.c_float * n_max)(), C.c_int32(0)
+        check(self.lib.gem_ctx_read_profile(self._ctx, n_max, tags, counts, ms, C.byref(n)))
+        return {int(tags[i]): (int(counts[i]), float(ms[i])) for i in range(n.value)}
+
     def set_gemm_mode(self, mode: int):
         check(self.lib.gem_ctx_set_gemm_mode(self._ctx, int(mode)))
 

@@ -47,10 +47,18 @@ class WindowBatch:
         clip_idx = np.concatenate([np.full(len(s), i, dtype=np.int32) for i, s in enumerate(self.starts)]
                                   or [np.zeros(0, np.int32)])
 
+        total = int(offs[-1])
+
         def cat(key, dtype):
-            arrs = [torch.as_tensor(np.asarray(c[key])) for c in clips]
-            t = torch.cat(arrs, dim=0) if len(arrs) > 1 else arrs[0]
-            return t.to(device=dev, dtype=dtype, non_blocking=True)
+            # one device buffer for all clips; each clip is copied straight into its slice
+            # (asynchronously when the source is a pinned torch tensor)
+            first = clips[0][key]
+            first = first if isinstance(first, torch.Tensor) else torch.as_tensor(np.asarray(first))
+            buf = torch.empty((total,) + tuple(first.shape[1:]), dtype=dtype, device=dev)
+            for i, c in enumerate(clips):
+                src = c[key] if isinstance(c[key], torch.Tensor) else torch.as_tensor(np.asarray(c[key]))
+                buf[offs[i]:offs[i + 1]].copy_(src, non_blocking=True)
+            return buf
 
         self.est = cat("estimated_local_skeleton", torch.float64)          # [F,15,3]
         self.cams = cat("camera_pose_list", torch.float64)                 # [F,4,4]

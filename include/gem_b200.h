@@ -104,6 +104,27 @@ int64_t gem_ctx_scratch_bytes(const gem_ctx* ctx);
  * contraction (default when available) */
 int gem_ctx_set_gemm_mode(gem_ctx* ctx, int mode);
 
+/* ---- instrumentation ---------------------------------------------------------------------- */
+/* kernel classes reported by gem_ctx_read_profile */
+#define GEM_TAG_DEC 100           /* +i: decoder forward layer i (0 = latent -> T*256 GEMM) */
+#define GEM_TAG_DEC_BWD 200       /* +i: decoder bwd-data layer i (5 = T*256 -> latent GEMM) */
+#define GEM_TAG_ENC 300           /* +i: encoder layer i (5 = T*512 -> 2*latent GEMM) */
+#define GEM_TAG_ENERGY 1
+#define GEM_TAG_LBFGS_BEGIN 2
+#define GEM_TAG_LBFGS_ADVANCE 3
+#define GEM_TAG_REPARAM 4
+#define GEM_TAG_TRANSFORM 5
+#define GEM_TAG_STITCH 6
+#define GEM_TAG_OTHER 7
+/* number of CUDA kernels this ctx has launched since creation */
+int64_t gem_ctx_launch_count(const gem_ctx* ctx);
+/* when enabled, every kernel launch is bracketed by a CUDA event pair on its stream */
+int gem_ctx_set_profiling(gem_ctx* ctx, int enable);
+/* synchronises the device, aggregates the recorded event pairs per tag into the host arrays
+ * (count and total milliseconds), writes the number of distinct tags and clears the record */
+int gem_ctx_read_profile(gem_ctx* ctx, int max_tags, int32_t* tags_h, int32_t* counts_h, float* total_ms_h,
+                         int32_t* n_tags_h);
+
 /* ---- the fused energy + analytic gradient (total_loss with the decoder bypassed) -------- */
 /* pose_d, pose0_d, grad_d: [W][T][J][3]; frame_base_d: [W] int64 first frame of each window inside
  * heat_d (may be NULL when weights->reproj == 0); clip_d: [W] int32 row of mean_bone_d [clips][J];
