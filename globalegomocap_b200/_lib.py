@@ -51,6 +51,7 @@ _SIGNATURES = {
     "gem_ctx_read_profile": (C.c_int, [_P, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float),
                                         C.POINTER(C.c_int32)]),
     "gem_energy_grad": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, C.POINTER(EnergyWeights), _P, _P, _P, _P]),
+    "gem_gemm": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P, _P, _I, _P, _I, _I]),
     "gem_decode": (C.c_int, [_P, _P, _I, _I, _P, _P]),
     "gem_decode_vjp": (C.c_int, [_P, _P, _I, _I, _P, _P]),
     "gem_encode": (C.c_int, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),

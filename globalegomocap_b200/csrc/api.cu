@@ -1,6 +1,7 @@
 // C ABI of libgem_b200.so (declared in include/gem_b200.h): context, scratch ownership and the
 // per-stage pipeline that strings the kernels together without host synchronisation.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -138,7 +139,9 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
         gem_ctx_destroy(c);
         return rc;
     }
-    c->gemm_mode = tc_gemm_available() ? 1 : 0;
+    // default: tcgen05 3xTF32 for the plain GEMMs; GEM_GEMM_MODE=0 (or gem_ctx_set_gemm_mode) selects fp32 CUDA cores
+    c->gemm_mode = 1;
+    if (const char* env = getenv("GEM_GEMM_MODE")) c->gemm_mode = (env[0] == '0') ? 0 : 1;
     // default skeleton: the reference's 15-joint kinematic tree (optimizer.py:34)
     if (num_joints == 15) {
         static const int32_t parents[15] = {0, 0, 1, 2, 0, 4, 5, 1, 7, 8, 9, 4, 11, 12, 13};
@@ -156,7 +159,7 @@ int gem_ctx_destroy(gem_ctx* c) {
     if (!c) return GEM_OK;
     cudaSetDevice(c->device);
     for (void* p : c->allocs) cudaFree(p);
-    if (c->tc_workspace) cudaFree(c->tc_workspace);
+    tc_gemm_release(c);
     for (auto& e : c->prof) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
     delete c;
     return GEM_OK;
@@ -253,6 +256,13 @@ int gem_ctx_set_vae(gem_ctx* c, int which, const gem_vae_weights* w) {
     }
     c->vae[which] = *w;
     c->have_vae[which] = true;
+    // K-major TF32 hi/lo copies of the three plain-GEMM weight matrices for the tcgen05 path
+    GEM_CUDA(cudaSetDevice(c->device));
+    const gem_layer* big[3] = {&w->dec[0], &w->dec_bwd[5], &w->enc[5]};
+    for (const gem_layer* L : big)
+        if (L->k % 32 == 0 && L->n % 128 == 0)
+            GEM_TRY(tc_gemm_prepare_weight(c, 0, L->w_d, (L->n + 3) & ~3, L->k, L->n));
+    GEM_CUDA(cudaStreamSynchronize(0));
     return GEM_OK;
 }
 
@@ -266,7 +276,8 @@ static int run_layer(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, co
     g.M = M, g.N = L.n, g.K = L.k, g.taps = L.taps, g.T = c->T;
     g.lda = lda, g.ldb = (L.n + 3) & ~3, g.ldc = ldc, g.ldaux = L.n, g.epi = epi;
     return timed(c, s, tag, [&]() {
-        if (c->gemm_mode == 1 && L.taps == 1) return launch_tap_gemm_tc(s, g, c->tc_workspace, c->tc_workspace_bytes);
+        if (c->gemm_mode == 1 && L.taps == 1 && M >= 64 && L.k % 32 == 0 && L.n % 128 == 0)
+            return launch_tap_gemm_tc(s, g, c, 0);
         return launch_tap_gemm_simt(s, g);
     });
 }
@@ -338,6 +349,22 @@ int gem_energy_grad(gem_ctx* c, void* stream, int W, const float* pose_d, const 
         return launch_energy_grad((cudaStream_t)stream, W, c->T, c->J, c->H, c->Wd, pose_d, pose0_d, heat_d,
                                   frame_base_d, clip_d, mean_bone_d, *wt, energy_d, terms_d, grad_d, status_d);
     });
+}
+
+int gem_gemm(gem_ctx* c, void* stream, int M, int N, int K, const float* a_d, int lda, const float* b_d,
+             const float* bias_d, int leaky_relu, float* c_d, int ldc, int use_tensor_cores) {
+    GEM_REQUIRE(c && a_d && b_d && c_d && M >= 0 && N > 0 && K > 0, "bad arguments");
+    GEM_REQUIRE(N % 4 == 0, "N must be a multiple of 4");
+    GEM_CUDA(cudaSetDevice(c->device));
+    gem_layer L;
+    L.w_d = b_d, L.bias_d = bias_d, L.taps = 1, L.k = K, L.n = N;
+    const int saved = c->gemm_mode;
+    if (use_tensor_cores) GEM_TRY(tc_gemm_prepare_weight(c, (cudaStream_t)stream, b_d, N, K, N));
+    c->gemm_mode = use_tensor_cores ? 1 : 0;
+    const int rc = run_layer(c, (cudaStream_t)stream, GEM_TAG_OTHER, L, a_d, lda, M, c_d, ldc,
+                             leaky_relu ? EPI_LRELU : EPI_NONE, nullptr);
+    c->gemm_mode = saved;
+    return rc;
 }
 
 int gem_decode(gem_ctx* c, void* stream, int which, int W, const float* z_d, float* pose_d) {

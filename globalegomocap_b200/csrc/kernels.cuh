@@ -22,7 +22,9 @@ struct TapGemmArgs {
     int epi;
 };
 int launch_tap_gemm_simt(cudaStream_t stream, const TapGemmArgs& g);
-int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* workspace, size_t workspace_bytes);
+int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, size_t reserved);
+int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N);
+void tc_gemm_release(void* owner);
 bool tc_gemm_available();
 
 struct LbfgsWin;

@@ -145,6 +145,17 @@ class Engine:
                                        self._p(E), self._p(terms), self._p(grad), self._p(status)))
         return E, terms, grad, status
 
+    def gemm(self, a, b, bias=None, leaky_relu=False, tensor_cores=False):
+        """c = act(bias + a @ b) on the library's GEMM kernels (test hook)."""
+        a, b = self._dev(a, torch.float32), self._dev(b, torch.float32)
+        bias = None if bias is None else self._dev(bias, torch.float32)
+        M, K = a.shape
+        N = b.shape[1]
+        c = torch.empty(M, N, dtype=torch.float32, device=self.device)
+        check(self.lib.gem_gemm(self._ctx, self.stream, M, N, K, self._p(a), K, self._p(b), self._p(bias),
+                                int(leaky_relu), self._p(c), N, int(tensor_cores)))
+        return c
+
     # ------------------------------------------------------------------ VAE pieces
     def decode(self, which, z):
         z = self._dev(z, torch.float32)

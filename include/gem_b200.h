@@ -135,6 +135,12 @@ int gem_energy_grad(gem_ctx* ctx, void* stream, int W, const float* pose_d, cons
                     const float* mean_bone_d, const gem_energy_weights* weights_h, float* energy_d,
                     float* terms_d, float* grad_d, uint32_t* status_d);
 
+/* ---- the GEMM both VAE contractions run on (exported for tests) ---------------------------- */
+/* c[M][N] = act( bias[N] + a[M][K] b[K][N] ), row-major fp32, N % 4 == 0.  use_tensor_cores = 1 takes the
+ * tcgen05 3xTF32 kernel (needs K % 32 == 0, N % 128 == 0, M >= 64), 0 the CUDA-core fp32 kernel. */
+int gem_gemm(gem_ctx* ctx, void* stream, int M, int N, int K, const float* a_d, int lda, const float* b_d,
+             const float* bias_d, int leaky_relu, float* c_d, int ldc, int use_tensor_cores);
+
 /* ---- VAE pieces (ConvVAE.decode_to_bodypose / get_latent_space) -------------------------- */
 /* z_d [W][latent] -> pose_d [W][T][J][3]; keeps the activations for gem_decode_vjp */
 int gem_decode(gem_ctx* ctx, void* stream, int which, int W, const float* z_d, float* pose_d);

@@ -1,0 +1,88 @@
+"""tcgen05/TMEM/TMA 3xTF32 GEMM path against the fp32 CUDA-core path and the reference goldens.
+Needs a B200: `pytest -m gpu`."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.fixture(scope="module")
+def engine(vae_weights, camera):
+    from globalegomocap_b200.engine import Engine
+    eng = Engine(max_windows=700)
+    eng.set_camera(*camera)
+    eng.set_vae(0, vae_weights[0])
+    eng.set_vae(1, vae_weights[1])
+    yield eng
+    eng.close()
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 128, 32), (128, 128, 64), (64, 128, 96), (64, 128, 128), (64, 128, 2560),
+                                   (64, 2048, 2560), (300, 2560, 2048), (641, 256, 5120)])
+def test_gemm_kernels_against_float64(engine, M, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(K, N, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    ref = a.double() @ b.double() + bias.double()
+    ref_act = torch.where(ref > 0, ref, ref * 0.01)
+    for tc in (False, True):
+        c = engine.gemm(a, b, bias, leaky_relu=False, tensor_cores=tc).cpu()
+        c_act = engine.gemm(a, b, bias, leaky_relu=True, tensor_cores=tc).cpu()
+        r, r_act = _rel(c, ref), _rel(c_act, ref_act)
+        print((M, N, K), "tensor cores" if tc else "cuda cores", "relative max error vs float64:", r, r_act)
+        assert r < 1e-5 and r_act < 1e-5, (M, N, K, tc, r, r_act)
+
+
+@pytest.mark.parametrize("W", [64, 128, 300, 641])
+def test_tc_gemm_matches_fp32_path(engine, W):
+    """Full tiles, a ragged last M tile, several waves: decoder fwd, bwd-data and encoder."""
+    g = torch.Generator(device="cpu").manual_seed(W)
+    z = torch.randn(W, 2048, generator=g)
+    up = torch.randn(W, 10, 15, 3, generator=g)
+    pose_in = torch.randn(W, 10, 45, generator=g) * 0.3
+    eps = torch.randn(W, 2048, generator=g)
+    out = {}
+    engine.set_gemm_mode(0)
+    engine.decode(0, z)          # activations (LeakyReLU masks) of this decode are used by BOTH vjp calls:
+    for mode in (0, 1):          # a mask that flips between two 1e-6-different forwards would dominate dz
+        engine.set_gemm_mode(mode)
+        dz = engine.decode_vjp(0, up)
+        pose = engine.decode(0, z)
+        z0, mu, std = engine.encode(1, pose_in, eps)
+        torch.cuda.synchronize()
+        out[mode] = (pose.clone(), dz.clone(), z0.clone(), mu.clone(), std.clone())
+        engine.set_gemm_mode(0)
+        engine.decode(0, z)
+    engine.set_gemm_mode(0)
+    names = ("pose", "dz", "z0", "mu", "std")
+    for name, a, b in zip(names, out[1], out[0]):
+        r = _rel(a, b)
+        print(W, name, "tcgen05 vs fp32 CUDA-core relative max error:", r)
+        assert r < (3e-5 if name == "mu" else 1e-5), (W, name, r)   # mu: K = 5120 and cancellation in the sum
+
+
+def test_tc_gemm_matches_reference_goldens(engine, golden_dir):
+    """M < 64 falls back to the CUDA-core kernel by design; replicate the golden rows to fill a tile."""
+    g = np.load(os.path.join(golden_dir, "vae.npz"))
+    reps = 43
+    z = np.tile(g["z"], (reps, 1))
+    up = np.tile(g["upstream"], (reps, 1, 1, 1))
+    engine.set_gemm_mode(1)
+    pose = engine.decode(0, z).cpu().numpy()
+    dz = engine.decode_vjp(0, up).cpu().numpy()
+    z0, mu, std = engine.encode(0, np.tile(g["enc_in"], (reps, 1, 1)), np.zeros((3 * reps, 2048), np.float32))
+    engine.set_gemm_mode(0)
+    for r in range(0, reps, 14):
+        sl = slice(3 * r, 3 * r + 3)
+        assert np.abs(pose[sl] - g["pose"]).max() / np.abs(g["pose"]).max() < 2e-5
+        assert np.abs(dz[sl] - g["dz"]).max() / np.abs(g["dz"]).max() < 2e-4
+        assert np.abs(mu.cpu().numpy()[sl] - g["mu"]).max() / np.abs(g["mu"]).max() < 2e-5
