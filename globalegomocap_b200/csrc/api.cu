@@ -125,7 +125,7 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     A(&c->fc, W * 2 * n), A(&c->z0, W * n), A(&c->f_new, W), A(&c->g_new, W * n);
     LbfgsBuffers& b = c->lb;
     memset(&b, 0, sizeof(b));
-    A(&b.X, W * n), A(&b.D, W * n), A(&b.G, W * n), A(&b.PG, W * n), A(&b.GP, W * n), A(&b.BG0, W * n),
+    A(&b.X, W * n), A(&b.D, W * n), A(&b.G, W * n), A(&b.GP, W * n), A(&b.BG0, W * n),
         A(&b.BG1, W * n), A(&b.ZT, W * n);
     A(&b.Y, W * max_history * n), A(&b.S, W * max_history * n), A(&b.RO, W * max_history);
     if (rc == GEM_OK) {

@@ -30,7 +30,7 @@ bool tc_gemm_available();
 struct LbfgsWin;
 struct LbfgsBuffers {
     LbfgsWin* st;
-    float *X, *D, *G, *PG, *GP, *BG0, *BG1, *ZT;   // [W][n]
+    float *X, *D, *G, *GP, *BG0, *BG1, *ZT;   // [W][n]  (prev_flat_grad is G itself, see lbfgs.cu)
     float *Y, *S;                                   // [W][m][n]
     float* RO;                                      // [W][m]
     float* trace;                                   // [W][trace_stride] or NULL

@@ -8,9 +8,10 @@
 // the next point it needs evaluated and writes that point; finished windows are parked.
 //
 // One CTA per window; the n-vector work (dots, axpys, two-loop recursion over the (y, s) history in
-// HBM) is spread over the CTA, the scalar decision logic runs on thread 0.  torch mixes Python
-// floats (double) with fp32 0-d tensors; `Num` reproduces that typing so that step lengths round
-// the way the reference's do.  Compiled with --fmad=false.
+// HBM, streamed through a shared-memory ring by the TMA engine) is spread over the CTA, the scalar
+// decision logic runs on thread 0.  torch mixes Python floats (double) with fp32 0-d tensors; `Num`
+// reproduces that typing so that step lengths round the way the reference's do.  Compiled with
+// --fmad=false.
 #include "kernels.cuh"
 
 namespace gem {
@@ -61,7 +62,7 @@ enum { PH_INIT = 0, PH_BRACKET = 1, PH_ZOOM = 2, PH_DONE = 3 };
 struct LbfgsWin {
     int phase, n_iter, evals, hist_len;
     int ls_iter, max_ls, ls_evals, ls_first;
-    int ls_done, insuf, low_pos, high_pos, nbracket, pad0;
+    int ls_done, insuf, low_pos, high_pos, nbracket, gp_is_g;   // gp_is_g: the bracket's g_prev is still G
     double loss, prev_loss;
     float h_diag, gtd, d_norm, pad1;
     Num t, t_prev, br[2];
@@ -70,28 +71,58 @@ struct LbfgsWin {
 };
 
 constexpr int kLbThreads = 256;
-constexpr int kMaxPerThread = 8;   // n <= 2048 keeps a vector in registers
+constexpr int kWarps = kLbThreads / 32;
+constexpr int kChunks = 2;          // float4 chunks per thread: n <= 2048 keeps a vector in 8 registers
+constexpr int kPer = 4 * kChunks;
+constexpr int kRing = 4;            // rows (n floats each) of the (y, s) history in flight per CTA
+constexpr int kMaxHist = 64;
 
-// block-wide sum / max with a fixed reduction tree (deterministic run to run)
-__device__ __forceinline__ float block_sum(float v, float* red) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float r = 0.f;
+// ---- per-thread slices: chunk c = tid + i*kLbThreads covers elements [4c, 4c+4) ---------------
+__device__ __forceinline__ void ld8(float (&r)[kPer], const float* __restrict__ p, int tid, int n4) {
 #pragma unroll
-    for (int i = 0; i < kLbThreads / 32; ++i) r += red[i];
-    return r;
+    for (int i = 0; i < kChunks; ++i) {
+        const int c = tid + i * kLbThreads;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < n4) v = *reinterpret_cast<const float4*>(p + 4 * c);
+        r[4 * i + 0] = v.x, r[4 * i + 1] = v.y, r[4 * i + 2] = v.z, r[4 * i + 3] = v.w;
+    }
 }
-__device__ __forceinline__ float block_max(float v, float* red) {
-    v = warp_max(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float r = red[0];
+__device__ __forceinline__ void st8(float* __restrict__ p, const float (&r)[kPer], int tid, int n4) {
 #pragma unroll
-    for (int i = 1; i < kLbThreads / 32; ++i) r = fmaxf(r, red[i]);
-    return r;
+    for (int i = 0; i < kChunks; ++i) {
+        const int c = tid + i * kLbThreads;
+        if (c < n4) *reinterpret_cast<float4*>(p + 4 * c) = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+    }
+}
+__device__ __forceinline__ float dot8(const float (&a)[kPer], const float (&b)[kPer]) {
+    float p = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) p += a[i] * b[i];
+    return p;
+}
+
+// Up to three block-wide reductions with ONE barrier (partials are double-buffered by `par`); bit j of
+// MAXMASK makes value j a max instead of a sum.  Fixed tree: deterministic run to run.
+struct RedBuf {
+    float v[2][3][kWarps];
+};
+template <int NV, int MAXMASK>
+__device__ __forceinline__ void block_reduce(float (&x)[NV], RedBuf& red, int& par) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        x[j] = ((MAXMASK >> j) & 1) ? warp_max(x[j]) : warp_sum(x[j]);
+        if (lane == 0) red.v[par][j][warp] = x[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        float r = red.v[par][j][0];
+#pragma unroll
+        for (int i = 1; i < kWarps; ++i) r = ((MAXMASK >> j) & 1) ? fmaxf(r, red.v[par][j][i]) : r + red.v[par][j][i];
+        x[j] = r;
+    }
+    par ^= 1;
 }
 
 // _cubic_interpolate (lbfgs.py:12-37); f's are Python floats, g's fp32 tensors
@@ -144,73 +175,93 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_begin_kernel(LbfgsBuffers b,
     }
 }
 
-// Per-thread strided ownership of vector elements: element e = threadIdx.x + i*kLbThreads.
-#define FOR_OWN(i, e) for (int i = 0, e = threadIdx.x; i < kMaxPerThread && e < b.n; ++i, e += kLbThreads)
+// One CTA per window.  Vector work is spread over the CTA (8 elements per thread, float4 accesses),
+// the scalar decisions run on thread 0.  The two-loop recursion streams the window's (y, s) history
+// from HBM through a kRing-row shared-memory ring filled by the TMA engine (cp.async.bulk + mbarrier),
+// so the dependent chain dot -> reduce -> axpy never waits on a cold global load.
+//
+// torch keeps g, prev_flat_grad and the bracket's g_prev as separate clones; here
+//   * prev_flat_grad is G itself: y = g_new - G is formed before G is overwritten;
+//   * g_prev aliases G until the bracket phase interpolates (LbfgsWin::gp_is_g);
+//   * the bracket gradients are only stored while the line search is still running.
+__global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffers b, const float* __restrict__ loss_in,
+                                                                     const float* __restrict__ grad_in, int W) {
+    extern __shared__ __align__(16) float ring[];     // [kRing][n]
+    __shared__ RedBuf red;
+    __shared__ LbfgsWin s;                             // thread 0 mutates; others only read the snapshot below
+    __shared__ int sh_action, sh_code, sh_copy_gp, sh_gsrc, sh_gp_is_g, sh_stop, sh_done2;
+    __shared__ float sh_tf, sh_tf2;
+    __shared__ float al_s[kMaxHist], ro_s[kMaxHist];
+    __shared__ __align__(8) uint64_t full_bar[kRing];
 
-__global__ void __launch_bounds__(kLbThreads) lbfgs_advance_kernel(LbfgsBuffers b, const float* __restrict__ loss_in,
-                                                                  const float* __restrict__ grad_in, int W) {
-    __shared__ float red[kLbThreads / 32];
-    __shared__ LbfgsWin s;          // thread 0 mutates, everyone reads after barriers
-    __shared__ int action;          // what the vector phase has to do next
-    __shared__ float bcast[4];
-
+    const int tid = threadIdx.x, n = b.n, n4 = b.n >> 2;
     const int w = blockIdx.x;
-    const size_t off = (size_t)w * b.n;
-    float *X = b.X + off, *D = b.D + off, *G = b.G + off, *PG = b.PG + off, *GP = b.GP + off, *BG0 = b.BG0 + off,
-          *BG1 = b.BG1 + off, *ZT = b.ZT + off;
-    float* BG[2] = {BG0, BG1};
+    const size_t off = (size_t)w * n;
+    float *X = b.X + off, *D = b.D + off, *G = b.G + off, *GP = b.GP + off, *BG0 = b.BG0 + off, *BG1 = b.BG1 + off,
+          *ZT = b.ZT + off;
+    int par = 0;
 
-    if (threadIdx.x == 0) s = b.st[w];
+    if (tid == 0) {
+        s = b.st[w];
+#pragma unroll
+        for (int i = 0; i < kRing; ++i) mbar_init(&full_bar[i], 1);
+        fence_barrier_init();
+    }
     __syncthreads();
-    if (s.phase == PH_DONE) return;
+    const int phase0 = s.phase, hist0 = s.hist_len, n_iter0 = s.n_iter;
+    const float h_diag0 = s.h_diag;
+    if (phase0 == PH_DONE) return;
 
     const double f_new = (double)loss_in[w];
-    float gn[kMaxPerThread];
-    FOR_OWN(i, e) gn[i] = grad_in[off + e];
-    if (threadIdx.x == 0 && b.trace) {
-        const int idx = s.evals + ((s.phase == PH_INIT) ? 0 : s.ls_evals);
+    float gn[kPer];
+    ld8(gn, grad_in + off, tid, n4);
+    if (tid == 0 && b.trace) {
+        const int idx = s.evals + ((phase0 == PH_INIT) ? 0 : s.ls_evals);
         if (idx < b.trace_stride) b.trace[(size_t)w * b.trace_stride + idx] = (float)f_new;
     }
 
-    enum { ACT_NEW_ITER = 1, ACT_EVAL = 2, ACT_LS_FINISH = 3, ACT_STOP = 4 };
-    bool new_iter = false;
+    enum { ACT_EVAL = 2, ACT_LS_FINISH = 3 };
+    float yv[kPer], sv[kPer];          // newest curvature pair (valid when !first_iter)
+    bool first_iter;
 
-    if (s.phase == PH_INIT) {
+    if (phase0 == PH_INIT) {
         // lbfgs.py:361-373: first evaluation
-        float gmax = 0.f;
-        FOR_OWN(i, e) {
-            G[e] = gn[i];
-            gmax = fmaxf(gmax, fabsf(gn[i]));
-        }
-        gmax = block_max(gmax, red);
-        if (threadIdx.x == 0) {
+        st8(G, gn, tid, n4);
+        float r1[1] = {0.f};
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) r1[0] = fmaxf(r1[0], fabsf(gn[i]));
+        block_reduce<1, 1>(r1, red, par);
+        if (tid == 0) {
             s.loss = f_new;
             s.evals = 1;
             s.n_iter = 0;
-            if ((double)gmax <= (double)(float)b.tol_grad) s.phase = PH_DONE;
+            sh_stop = 0;
+            if ((double)r1[0] <= (double)(float)b.tol_grad) {
+                s.phase = PH_DONE;
+                sh_stop = 1;
+                b.st[w] = s;
+            }
         }
         __syncthreads();
-        if (s.phase == PH_DONE) {
-            if (threadIdx.x == 0) b.st[w] = s;
-            return;
-        }
-        new_iter = true;
+        if (sh_stop) return;
+        first_iter = true;
     } else {
         // ---- an evaluation requested by the line search has arrived ----------------------------
-        float part = 0.f;
-        FOR_OWN(i, e) part += gn[i] * D[e];
-        const float gtd_new = block_sum(part, red);
-        // The scalar logic may need several vector copies; it is run as a small loop of
-        // (decide on thread 0) -> (vector action by all threads).
-        int copy_gp_from_new = 0;     // GP = g_new.clone()
-        if (threadIdx.x == 0) {
+        float d[kPer];
+        ld8(d, D, tid, n4);
+        float r1[1] = {dot8(gn, d)};
+        block_reduce<1, 0>(r1, red, par);
+        const float gtd_new = r1[0];
+        if (tid == 0) {
             const double c1 = 1e-4, c2 = 0.9;
             const Num gtd = t32(s.gtd);
-            int act = 0;
+            int act = 0, code = 0, copy_gp = 0;
+            // what each bracket-gradient slot holds after this call: 0 g_new, 1 BG0, 2 BG1 (as stored), 3 GP, 4 G
+            int slot_src[2] = {1, 2};
             s.ls_evals += 1;
-            bool to_zoom_entry = false;
-            int set_br = 0;   // 1: bracket=[t_prev,t] with g=[GP,g_new]; 2: bracket=[t] g=[g_new]; 3: [0,t] g=[G,g_new]
             if (s.phase == PH_BRACKET) {
+                bool to_zoom_entry = false;
+                int set_br = 0;   // 1: bracket=[t_prev,t] g=[g_prev,g_new]; 2: bracket=[t] g=[g_new]; 3: [0,t] g=[g,g_new]
                 if (!s.ls_first) s.ls_iter += 1;
                 s.ls_first = 0;
                 if (s.ls_iter < s.max_ls) {
@@ -236,7 +287,7 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_advance_kernel(LbfgsBuffers 
                         s.t_prev = tmp;
                         s.f_prev = f_new;
                         s.gtd_prev = gtd_new;
-                        copy_gp_from_new = 1;
+                        copy_gp = 1;                 // g_prev = g_new.clone()
                         act = ACT_EVAL;
                     }
                 } else {
@@ -249,14 +300,17 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_advance_kernel(LbfgsBuffers 
                         s.br_f[0] = s.f_prev, s.br_f[1] = f_new;
                         s.br_gtd[0] = s.gtd_prev, s.br_gtd[1] = gtd_new;
                         s.nbracket = 2;
+                        slot_src[0] = s.gp_is_g ? 4 : 3, slot_src[1] = 0;
                     } else if (set_br == 2) {
                         s.br[0] = s.t;
                         s.br_f[0] = f_new;
                         s.nbracket = 1;
+                        slot_src[0] = 0;
                     } else {
                         s.br[0] = py(0.0), s.br[1] = s.t;
                         s.br_f[0] = s.loss, s.br_f[1] = f_new;
                         s.nbracket = 2;
+                        slot_src[0] = 4, slot_src[1] = 0;
                     }
                     s.insuf = 0;
                     const double flast = s.br_f[s.nbracket - 1];
@@ -264,7 +318,7 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_advance_kernel(LbfgsBuffers 
                     else s.low_pos = 1, s.high_pos = 0;
                     s.phase = PH_ZOOM;
                 }
-                bcast[0] = (float)set_br;
+                code = set_br;
             } else {   // PH_ZOOM: an evaluation inside the zoom loop (lbfgs.py:152-199)
                 s.ls_iter += 1;
                 const Num rhs = nadd(py(s.loss), nmul(nmul(py(c1), s.t), gtd));
@@ -272,11 +326,12 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_advance_kernel(LbfgsBuffers 
                     s.br[s.high_pos] = s.t;
                     s.br_f[s.high_pos] = f_new;
                     s.br_gtd[s.high_pos] = gtd_new;
-                    bcast[0] = (float)(10 + s.high_pos);      // BG[high] = g_new
+                    code = 10 + s.high_pos;                   // BG[high] = g_new
+                    slot_src[s.high_pos] = 0;
                     if (s.br_f[0] <= s.br_f[1]) s.low_pos = 0, s.high_pos = 1;
                     else s.low_pos = 1, s.high_pos = 0;
                 } else {
-                    int code = 20 + s.low_pos;                // BG[low] = g_new
+                    code = 20 + s.low_pos;                    // BG[low] = g_new
                     if (nle(t32(fabsf(gtd_new)), nmul(py(-c2), gtd))) {
                         s.ls_done = 1;
                     } else if (nge(nmul(t32(gtd_new), nsub(s.br[s.high_pos], s.br[s.low_pos])), py(0.0))) {
@@ -284,11 +339,12 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_advance_kernel(LbfgsBuffers 
                         s.br_f[s.high_pos] = s.br_f[s.low_pos];
                         s.br_gtd[s.high_pos] = s.br_gtd[s.low_pos];
                         code = 30 + s.low_pos;                // BG[high] = BG[low]; BG[low] = g_new
+                        slot_src[s.high_pos] = slot_src[s.low_pos];
                     }
+                    slot_src[s.low_pos] = 0;
                     s.br[s.low_pos] = s.t;
                     s.br_f[s.low_pos] = f_new;
                     s.br_gtd[s.low_pos] = gtd_new;
-                    bcast[0] = (float)code;
                 }
             }
             // ---- zoom loop head (lbfgs.py:109-150): either ask for another evaluation or finish
@@ -319,197 +375,257 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_advance_kernel(LbfgsBuffers 
                 }
                 act = fin ? ACT_LS_FINISH : ACT_EVAL;
             }
-            action = act;
-            bcast[1] = (float)copy_gp_from_new;
+            sh_action = act, sh_code = code, sh_copy_gp = copy_gp, sh_gp_is_g = s.gp_is_g;
+            sh_gsrc = slot_src[s.low_pos];
+            sh_tf = (act == ACT_EVAL) ? (float)s.t.v : (float)s.br[s.low_pos].v;
+            if (copy_gp) s.gp_is_g = 0;
+            if (act == ACT_EVAL) b.st[w] = s;     // (a finishing call stores the state after its stop test)
         }
         __syncthreads();
-        // ---- vector side effects of the decision ---------------------------------------------
-        {
-            const int code = (int)bcast[0];
-            if (s.phase == PH_BRACKET || (s.phase == PH_ZOOM && code >= 1 && code <= 3)) {
-                if (bcast[1] != 0.f) FOR_OWN(i, e) GP[e] = gn[i];
-                if (code == 1) {            // bracket_g = [g_prev, g_new.clone()]
-                    FOR_OWN(i, e) { BG0[e] = GP[e]; BG1[e] = gn[i]; }
-                } else if (code == 2) {     // bracket_g = [g_new]
-                    FOR_OWN(i, e) BG0[e] = gn[i];
-                } else if (code == 3) {     // bracket_g = [g, g_new]
-                    FOR_OWN(i, e) { BG0[e] = G[e]; BG1[e] = gn[i]; }
-                }
-            } else if (code >= 10 && code < 20) {
-                float* dst = BG[code - 10];
-                FOR_OWN(i, e) dst[e] = gn[i];
-            } else if (code >= 20 && code < 30) {
-                float* dst = BG[code - 20];
-                FOR_OWN(i, e) dst[e] = gn[i];
+        const int code = sh_code;
+        const float tf = sh_tf;
+        if (sh_action == ACT_EVAL) {
+            // ---- vector side effects of the decision: the bracket's gradient clones ----------------
+            if (sh_copy_gp) st8(GP, gn, tid, n4);
+            if (code == 1) {                 // bracket_g = [g_prev, g_new.clone()]
+                float t8[kPer];
+                ld8(t8, sh_gp_is_g ? G : GP, tid, n4);
+                st8(BG0, t8, tid, n4), st8(BG1, gn, tid, n4);
+            } else if (code == 2) {          // bracket_g = [g_new]
+                st8(BG0, gn, tid, n4);
+            } else if (code == 3) {          // bracket_g = [g, g_new]
+                float t8[kPer];
+                ld8(t8, G, tid, n4);
+                st8(BG0, t8, tid, n4), st8(BG1, gn, tid, n4);
+            } else if (code >= 10 && code < 30) {
+                st8((code % 10) ? BG1 : BG0, gn, tid, n4);
             } else if (code >= 30) {
-                float* lo = BG[code - 30];
-                float* hi = BG[1 - (code - 30)];
-                FOR_OWN(i, e) { hi[e] = lo[e]; lo[e] = gn[i]; }
+                float* lo = (code - 30) ? BG1 : BG0;
+                float* hi = (code - 30) ? BG0 : BG1;
+                float t8[kPer];
+                ld8(t8, lo, tid, n4);
+                st8(hi, t8, tid, n4), st8(lo, gn, tid, n4);
             }
-        }
-        if (action == ACT_EVAL) {
-            const float tf = (float)s.t.v;
-            FOR_OWN(i, e) ZT[e] = X[e] + tf * D[e];          // _add_grad(t, d) from x_init
-            if (threadIdx.x == 0) b.st[w] = s;
+            float x[kPer];
+            ld8(x, X, tid, n4);
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) x[i] = x[i] + tf * d[i];      // _add_grad(t, d) from x_init
+            st8(ZT, x, tid, n4);
             return;
         }
-        // ---- line search finished (lbfgs.py:201-209, 488-527) ------------------------------
-        __syncthreads();
-        const float* gsel = BG[s.low_pos];
-        const float tf = (float)s.br[s.low_pos].v;
-        float gmax = 0.f, stepmax = 0.f;
-        FOR_OWN(i, e) {
-            const float gv = gsel[e];
-            G[e] = gv;
-            gmax = fmaxf(gmax, fabsf(gv));
-            const float step = tf * D[e];
-            X[e] = X[e] + step;
-            stepmax = fmaxf(stepmax, fabsf(step));
+        // ---- line search finished (lbfgs.py:201-209, 488-527): accept the low bracket point -----
+        float g[kPer], x[kPer];
+        {
+            const int src = sh_gsrc;
+            if (src == 0) {
+#pragma unroll
+                for (int i = 0; i < kPer; ++i) g[i] = gn[i];
+            } else {
+                ld8(g, src == 1 ? BG0 : src == 2 ? BG1 : src == 3 ? GP : G, tid, n4);
+            }
         }
-        gmax = block_max(gmax, red);
-        stepmax = block_max(stepmax, red);
-        if (threadIdx.x == 0) {
+        ld8(yv, G, tid, n4);           // prev_flat_grad
+        ld8(x, X, tid, n4);
+        float r2[2] = {0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            yv[i] = g[i] - yv[i];                                   // y = flat_grad - prev_flat_grad
+            sv[i] = tf * d[i];                                      // s = d * t
+            x[i] = x[i] + sv[i];
+            r2[0] = fmaxf(r2[0], fabsf(g[i]));
+            r2[1] = fmaxf(r2[1], fabsf(sv[i]));
+        }
+        st8(G, g, tid, n4);
+        st8(X, x, tid, n4);
+        block_reduce<2, 3>(r2, red, par);
+        if (tid == 0) {
             s.t = s.br[s.low_pos];
             s.loss = s.br_f[s.low_pos];
             s.evals += s.ls_evals;
             bool stop = false;
             if (s.n_iter == b.max_iter) stop = true;
             else if (s.evals >= b.max_eval) stop = true;
-            else if ((double)gmax <= (double)(float)b.tol_grad) stop = true;
-            else if ((double)stepmax <= (double)(float)b.tol_change) stop = true;
+            else if ((double)r2[0] <= (double)(float)b.tol_grad) stop = true;
+            else if ((double)r2[1] <= (double)(float)b.tol_change) stop = true;
             else if (fabs(s.loss - s.prev_loss) < b.tol_change) stop = true;
-            if (stop) s.phase = PH_DONE;
+            sh_stop = stop;
+            if (stop) {
+                s.phase = PH_DONE;
+                b.st[w] = s;
+            }
         }
         __syncthreads();
-        if (s.phase == PH_DONE) {
-            FOR_OWN(i, e) ZT[e] = X[e];
-            if (threadIdx.x == 0) b.st[w] = s;
+        if (sh_stop) {
+            st8(ZT, x, tid, n4);
             return;
         }
-        new_iter = true;
+        first_iter = false;
     }
 
-    if (new_iter) {
-        // ---- next outer iteration: direction (lbfgs.py:388-442), step, first trial point ------
-        __syncthreads();
-        if (threadIdx.x == 0) s.n_iter += 1;
-        __syncthreads();
-        float dreg[kMaxPerThread];
-        if (s.n_iter == 1) {
-            FOR_OWN(i, e) dreg[i] = -G[e];
+    // ---- next outer iteration: direction (lbfgs.py:388-442), step length, first trial point --------
+    float q[kPer];
+    int k = hist0;
+    float hd = h_diag0;
+    if (first_iter) {
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) q[i] = -gn[i];
+    } else {
+        float* Yw = b.Y + (size_t)w * b.m * n;
+        float* Sw = b.S + (size_t)w * b.m * n;
+        float* ROw = b.RO + (size_t)w * b.m;
+        const uint32_t row_bytes = (uint32_t)n * 4u;
+        // the rows the recursion will stream do not depend on whether this iteration's pair is kept:
+        // start filling the ring before the y.s / y.y reductions
+        const int kr = k;                       // stored pairs to stream: h = kr-1 .. 0, then 0 .. kr-1
+        const int total = 4 * kr;
+        int issued = 0;                         // thread 0
+        auto row_src = [&](int r) -> const float* {
+            if (r < 2 * kr) return ((r & 1) ? Yw : Sw) + (size_t)(kr - 1 - (r >> 1)) * n;
+            const int rr = r - 2 * kr;
+            return ((rr & 1) ? Sw : Yw) + (size_t)(rr >> 1) * n;
+        };
+        auto issue_upto = [&](int limit) {
+            limit = limit < total ? limit : total;
+            while (issued < limit) {
+                const int slot = issued % kRing;
+                mbar_arrive_expect_tx(&full_bar[slot], row_bytes);
+                bulk_g2s(ring + (size_t)slot * n, row_src(issued), row_bytes, &full_bar[slot]);
+                ++issued;
+            }
+        };
+        if (tid == 0) issue_upto(kRing);
+        if (tid < k) ro_s[tid] = ROw[tid];
+        float r2[2] = {dot8(yv, sv), dot8(yv, yv)};
+        block_reduce<2, 0>(r2, red, par);
+        const float ys = r2[0], yy = r2[1];
+        // ys > 1e-10: keep the pair.  max_iter - 1 <= m (checked by the host), so the history never overflows.
+        const bool pushed = (double)ys > (double)1e-10f;
+        float ro_new = 0.f;
+        if (pushed) {
+            st8(Yw + (size_t)k * n, yv, tid, n4);
+            st8(Sw + (size_t)k * n, sv, tid, n4);
+            ro_new = __frcp_rn(ys);                   // 1. / ys  (reciprocal)
+            hd = __fdiv_rn(ys, yy);                   // H_diag = ys / y.dot(y)
+            if (tid == 0) ROw[k] = ro_new;
+            k += 1;
+        }
+        // two-loop recursion; G already holds flat_grad
+        ld8(q, G, tid, n4);
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) q[i] = -q[i];
+        int r = 0;                                    // rows consumed from the ring
+        float row[kPer];
+        auto next_row = [&]() {
+            const int slot = r % kRing;
+            mbar_wait(&full_bar[slot], (uint32_t)((r / kRing) & 1));
+            ld8(row, ring + (size_t)slot * n, tid, n4);
+            ++r;
+        };
+        if (pushed) {
+            float r1[1] = {dot8(sv, q)};
+            block_reduce<1, 0>(r1, red, par);
+            const float a = r1[0] * ro_new;
+            if (tid == 0) al_s[k - 1] = a;
+            const float na = -a;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) q[i] = q[i] + yv[i] * na;
+        }
+        for (int h = kr - 1; h >= 0; --h) {
+            next_row();                               // s_h
+            float r1[1] = {dot8(row, q)};
+            block_reduce<1, 0>(r1, red, par);
+            if (tid == 0) issue_upto(r + kRing);      // every row < r has been consumed by the whole CTA
+            const float a = r1[0] * ro_s[h];
+            if (tid == 0) al_s[h] = a;
+            const float na = -a;
+            next_row();                               // y_h
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) q[i] = q[i] + row[i] * na;
+        }
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) q[i] = q[i] * hd;
+        for (int h = 0; h < kr; ++h) {
+            next_row();                               // y_h
+            float r1[1] = {dot8(row, q)};
+            block_reduce<1, 0>(r1, red, par);
+            if (tid == 0) issue_upto(r + kRing);
+            const float c = al_s[h] - r1[0] * ro_s[h];
+            next_row();                               // s_h
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) q[i] = q[i] + row[i] * c;
+        }
+        if (pushed) {
+            float r1[1] = {dot8(yv, q)};
+            block_reduce<1, 0>(r1, red, par);
+            const float c = al_s[k - 1] - r1[0] * ro_new;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) q[i] = q[i] + sv[i] * c;
+        }
+    }
+    // d = q; prev_flat_grad = flat_grad (G itself); gtd = g.d; t
+    st8(D, q, tid, n4);
+    float r3[3] = {0.f, 0.f, 0.f};
+    {
+        float g[kPer];
+        if (first_iter) {
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) g[i] = gn[i];
         } else {
-            const float tprev = (float)s.t.v;
-            float* Yw = b.Y + (size_t)w * b.m * b.n;
-            float* Sw = b.S + (size_t)w * b.m * b.n;
-            float* ROw = b.RO + (size_t)w * b.m;
-            float yv[kMaxPerThread], sv[kMaxPerThread];
-            float p_ys = 0.f, p_yy = 0.f;
-            FOR_OWN(i, e) {
-                yv[i] = G[e] - PG[e];
-                sv[i] = D[e] * tprev;
-                p_ys += yv[i] * sv[i];
-                p_yy += yv[i] * yv[i];
-            }
-            const float ys = block_sum(p_ys, red);
-            const float yy = block_sum(p_yy, red);
-            int k = s.hist_len;
-            if ((double)ys > (double)1e-10f) {
-                if (k == b.m) {
-                    // history full (never reached with max_iter <= m+1): drop the oldest pair
-                    for (int h = 1; h < k; ++h) {
-                        FOR_OWN(i, e) {
-                            Yw[(size_t)(h - 1) * b.n + e] = Yw[(size_t)h * b.n + e];
-                            Sw[(size_t)(h - 1) * b.n + e] = Sw[(size_t)h * b.n + e];
-                        }
-                        if (threadIdx.x == 0) ROw[h - 1] = ROw[h];
-                    }
-                    k -= 1;
-                }
-                FOR_OWN(i, e) {
-                    Yw[(size_t)k * b.n + e] = yv[i];
-                    Sw[(size_t)k * b.n + e] = sv[i];
-                }
-                if (threadIdx.x == 0) {
-                    ROw[k] = __frcp_rn(ys);               // 1. / ys  (reciprocal)
-                    s.h_diag = __fdiv_rn(ys, yy);
-                }
-                k += 1;
-                __syncthreads();
-                if (threadIdx.x == 0) s.hist_len = k;
-            }
-            __syncthreads();
-            // two-loop recursion
-            float q[kMaxPerThread];
-            float al[64];
-            FOR_OWN(i, e) q[i] = -G[e];
-            for (int h = k - 1; h >= 0; --h) {
-                float part = 0.f;
-                FOR_OWN(i, e) part += Sw[(size_t)h * b.n + e] * q[i];
-                const float a = block_sum(part, red) * ROw[h];
-                if (h < 64) al[h] = a;
-                const float na = -a;
-                FOR_OWN(i, e) q[i] = q[i] + Yw[(size_t)h * b.n + e] * na;
-            }
-            const float hd = s.h_diag;
-            FOR_OWN(i, e) q[i] = q[i] * hd;
-            for (int h = 0; h < k; ++h) {
-                float part = 0.f;
-                FOR_OWN(i, e) part += Yw[(size_t)h * b.n + e] * q[i];
-                const float be = block_sum(part, red) * ROw[h];
-                const float c = al[h] - be;
-                FOR_OWN(i, e) q[i] = q[i] + Sw[(size_t)h * b.n + e] * c;
-            }
-            FOR_OWN(i, e) dreg[i] = q[i];
+            ld8(g, G, tid, n4);
         }
-        // prev_flat_grad = flat_grad; prev_loss = loss; t; gtd = g.d
-        float p_gtd = 0.f, p_l1 = 0.f, p_dmax = 0.f;
-        FOR_OWN(i, e) {
-            const float gv = G[e];
-            D[e] = dreg[i];
-            PG[e] = gv;
-            GP[e] = gv;                                       // g_prev = g (clone) for the bracket phase
-            p_gtd += gv * dreg[i];
-            p_l1 += fabsf(gv);
-            p_dmax = fmaxf(p_dmax, fabsf(dreg[i]));
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            r3[0] += g[i] * q[i];
+            r3[1] += fabsf(g[i]);
+            r3[2] = fmaxf(r3[2], fabsf(q[i]));
         }
-        const float gtd = block_sum(p_gtd, red);
-        const float l1 = block_sum(p_l1, red);
-        const float dmax = block_max(p_dmax, red);
-        if (threadIdx.x == 0) {
-            s.prev_loss = s.loss;
-            Num t;
-            if (s.n_iter == 1) {
-                // t = min(1., 1. / flat_grad.abs().sum()) * lr
-                const Num inv = t32(__frcp_rn(l1));
-                t = nmul(nminp(py(1.0), inv), py(b.lr));
-            } else {
-                t = py(b.lr);
-            }
-            s.t = t;
-            s.gtd = gtd;
-            if ((double)gtd > (double)(float)(-b.tol_change)) {
-                s.phase = PH_DONE;                            // directional derivative below tolerance
-            } else {
-                s.d_norm = dmax;
-                s.t_prev = py(0.0);
-                s.f_prev = s.loss;
-                s.gtd_prev = gtd;
-                s.ls_iter = 0;
-                s.ls_evals = 0;
-                s.ls_first = 1;
-                s.ls_done = 0;
-                s.max_ls = b.max_eval - s.evals;
-                s.phase = PH_BRACKET;
-            }
-        }
-        __syncthreads();
-        if (s.phase == PH_DONE) {
-            FOR_OWN(i, e) ZT[e] = X[e];
+    }
+    block_reduce<3, 4>(r3, red, par);
+    if (tid == 0) {
+        const float gtd = r3[0], l1 = r3[1], dmax = r3[2];
+        s.n_iter = n_iter0 + 1;
+        s.hist_len = k;
+        s.h_diag = hd;
+        s.gp_is_g = 1;
+        s.prev_loss = s.loss;
+        Num t;
+        if (first_iter) {
+            // t = min(1., 1. / flat_grad.abs().sum()) * lr
+            const Num inv = t32(__frcp_rn(l1));
+            t = nmul(nminp(py(1.0), inv), py(b.lr));
         } else {
-            const float tf = (float)s.t.v;
-            FOR_OWN(i, e) ZT[e] = X[e] + tf * dreg[i];
+            t = py(b.lr);
         }
-        if (threadIdx.x == 0) b.st[w] = s;
+        s.t = t;
+        s.gtd = gtd;
+        if ((double)gtd > (double)(float)(-b.tol_change)) {
+            s.phase = PH_DONE;                            // directional derivative below tolerance
+        } else {
+            s.d_norm = dmax;
+            s.t_prev = py(0.0);
+            s.f_prev = s.loss;
+            s.gtd_prev = gtd;
+            s.ls_iter = 0;
+            s.ls_evals = 0;
+            s.ls_first = 1;
+            s.ls_done = 0;
+            s.max_ls = b.max_eval - s.evals;
+            s.phase = PH_BRACKET;
+        }
+        sh_done2 = s.phase == PH_DONE;
+        sh_tf2 = (float)t.v;
+        b.st[w] = s;
+    }
+    __syncthreads();
+    {
+        float x[kPer];
+        ld8(x, X, tid, n4);
+        if (!sh_done2) {
+            const float tf = sh_tf2;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) x[i] = x[i] + tf * q[i];
+        }
+        st8(ZT, x, tid, n4);
     }
 }
 
@@ -529,15 +645,16 @@ size_t lbfgs_state_bytes() { return sizeof(LbfgsWin); }
 
 int launch_lbfgs_begin(cudaStream_t stream, const LbfgsBuffers& b, const float* z0, int W) {
     if (W <= 0) return GEM_OK;
-    GEM_REQUIRE(b.n <= kLbThreads * kMaxPerThread, "latent_dim must be <= 2048");
-    GEM_REQUIRE(b.m <= 64, "max_history must be <= 64");
+    GEM_REQUIRE(b.n % 4 == 0 && b.n <= kLbThreads * kPer, "latent_dim must be a multiple of 4, <= 2048");
+    GEM_REQUIRE(b.m <= kMaxHist, "max_history must be <= 64");
     lbfgs_begin_kernel<<<W, kLbThreads, 0, stream>>>(b, z0, W);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }
 int launch_lbfgs_advance(cudaStream_t stream, const LbfgsBuffers& b, const float* loss, const float* grad, int W) {
     if (W <= 0) return GEM_OK;
-    lbfgs_advance_kernel<<<W, kLbThreads, 0, stream>>>(b, loss, grad, W);
+    const size_t smem = (size_t)kRing * b.n * sizeof(float);
+    lbfgs_advance_kernel<<<W, kLbThreads, smem, stream>>>(b, loss, grad, W);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }
