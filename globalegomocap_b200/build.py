@@ -27,6 +27,7 @@ SOURCES = {
     "pose_ops.cu": ["--fmad=false"],
     "gemm_simt.cu": [],
     "gemm_tc.cu": [],
+    "gemm_tap_tc.cu": [],
 }
 
 

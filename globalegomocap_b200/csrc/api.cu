@@ -37,6 +37,12 @@ struct gem_ctx {
     // decoder activations (token-major [W*T][C]) and their gradients
     float *act[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *pose = nullptr;
     float *gact[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *gpose = nullptr;
+    // the same activations as TF32 hi / lo pairs: what the tensor-core layers read and write (gemm_mode 1)
+    float *act_hi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *act_lo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float *gact_hi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *gact_lo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    float *gp_hi = nullptr, *gp_lo = nullptr;   // d pose, [W*T][kPosePad]
+    bool act_split = false;                      // the last decode left its activations in act_hi/act_lo
+    bool tap_tc[2] = {false, false};             // the VAE's conv layers are prepared for the tcgen05 tap kernel
     // encoder activations, fc output
     float *eact[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *fc = nullptr, *z0 = nullptr;
     // closure outputs
@@ -78,6 +84,7 @@ static int timed(gem_ctx* c, cudaStream_t s, int tag, F&& f) {
 }
 
 static const int kDecC[6] = {256, 128, 64, 64, 64, 0};   // channels after dec[0..4]; dec[5] -> J*3
+static int pose_pad(const gem_ctx* c) { return (c->J * 3 + 3) & ~3; }   // row pitch of the split d pose (TMA: 16-byte pitch)
 static const int kEncC[5] = {64, 64, 128, 256, 512};
 
 template <typename T>
@@ -120,6 +127,16 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     int rc = GEM_OK;
     auto A = [&](float** p, size_t cnt) { if (rc == GEM_OK) rc = ctx_alloc(c, p, cnt); };
     for (int i = 0; i < 5; ++i) A(&c->act[i], tok * kDecC[i]), A(&c->gact[i], tok * kDecC[i]);
+    for (int i = 0; i < 5; ++i) {
+        A(&c->act_hi[i], tok * kDecC[i]), A(&c->act_lo[i], tok * kDecC[i]);
+        A(&c->gact_hi[i], tok * kDecC[i]), A(&c->gact_lo[i], tok * kDecC[i]);
+    }
+    {
+        const size_t cnt = tok * (size_t)((num_joints * 3 + 3) & ~3);
+        A(&c->gp_hi, cnt), A(&c->gp_lo, cnt);
+        if (rc == GEM_OK && cudaMemset(c->gp_hi, 0, cnt * sizeof(float)) != cudaSuccess) rc = GEM_ERR_CUDA;
+        if (rc == GEM_OK && cudaMemset(c->gp_lo, 0, cnt * sizeof(float)) != cudaSuccess) rc = GEM_ERR_CUDA;
+    }
     A(&c->pose, Weven * seq_len * num_joints * 3), A(&c->gpose, Weven * seq_len * num_joints * 3);
     for (int i = 0; i < 5; ++i) A(&c->eact[i], tok * kEncC[i]);
     A(&c->fc, W * 2 * n), A(&c->z0, W * n), A(&c->f_new, W), A(&c->g_new, W * n);
@@ -160,6 +177,7 @@ int gem_ctx_destroy(gem_ctx* c) {
     cudaSetDevice(c->device);
     for (void* p : c->allocs) cudaFree(p);
     tc_gemm_release(c);
+    tc_tap_release(c);
     for (auto& e : c->prof) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
     delete c;
     return GEM_OK;
@@ -262,6 +280,19 @@ int gem_ctx_set_vae(gem_ctx* c, int which, const gem_vae_weights* w) {
     for (const gem_layer* L : big)
         if (L->k % 32 == 0 && L->n % 128 == 0)
             GEM_TRY(tc_gemm_prepare_weight(c, 0, L->w_d, (L->n + 3) & ~3, L->k, L->n));
+    // K-major, tap-concatenated hi/lo slabs of the decoder's k=3 convolutions and their bwd-data
+    bool tap_ok = c->T <= 32;
+    for (int i = 1; i <= 5 && tap_ok; ++i) tap_ok = tc_tap_supported(w->dec[i].k, w->dec[i].n, c->T);
+    for (int i = 0; i <= 4 && tap_ok; ++i) tap_ok = tc_tap_supported(w->dec_bwd[i].k, w->dec_bwd[i].n, c->T);
+    tap_ok = tap_ok && c->vae[which].dec[0].k % 32 == 0 && c->vae[which].dec[0].n % 128 == 0;
+    if (tap_ok) {
+        for (int i = 1; i <= 5; ++i)
+            GEM_TRY(tc_tap_prepare_weight(c, 0, w->dec[i].w_d, (w->dec[i].n + 3) & ~3, w->dec[i].k, w->dec[i].n));
+        for (int i = 0; i <= 4; ++i)
+            GEM_TRY(tc_tap_prepare_weight(c, 0, w->dec_bwd[i].w_d, (w->dec_bwd[i].n + 3) & ~3, w->dec_bwd[i].k,
+                                          w->dec_bwd[i].n));
+    }
+    c->tap_tc[which] = tap_ok;
     GEM_CUDA(cudaStreamSynchronize(0));
     return GEM_OK;
 }
@@ -270,40 +301,84 @@ int gem_ctx_set_vae(gem_ctx* c, int which, const gem_vae_weights* w) {
 
 // ---- layer runner ----------------------------------------------------------------------------
 static int run_layer(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, const float* A, int lda, int M, float* C,
-                     int ldc, int epi, const float* aux) {
+                     int ldc, int epi, const float* aux, const float* A_hi = nullptr, const float* A_lo = nullptr,
+                     float* C_lo = nullptr) {
     TapGemmArgs g;
     g.A = A, g.B = L.w_d, g.bias = L.bias_d, g.aux = aux, g.C = C;
+    g.A_hi = A_hi, g.A_lo = A_lo, g.C_lo = C_lo;
     g.M = M, g.N = L.n, g.K = L.k, g.taps = L.taps, g.T = c->T;
     g.lda = lda, g.ldb = (L.n + 3) & ~3, g.ldc = ldc, g.ldaux = L.n, g.epi = epi;
     return timed(c, s, tag, [&]() {
-        if (c->gemm_mode == 1 && L.taps == 1 && M >= 64 && L.k % 32 == 0 && L.n % 128 == 0)
+        if (c->gemm_mode == 1 && L.taps == 1 && (M >= 64 || A_hi || C_lo) && L.k % 32 == 0 && L.n % 128 == 0)
             return launch_tap_gemm_tc(s, g, c, 0);
         return launch_tap_gemm_simt(s, g);
     });
 }
 
+// one k=3 convolution on the tcgen05 tap kernel; activations are TF32 hi / lo pairs
+static int run_tap_tc(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, const float* A_hi, const float* A_lo, int lda,
+                      int W, float* out_hi, float* out_lo, int ldo, int epi, const float* aux) {
+    TapTcLaunch t;
+    t.B = L.w_d, t.A_hi = A_hi, t.A_lo = A_lo, t.lda = lda, t.Kreal = lda;
+    t.bias = L.bias_d, t.aux = aux, t.ldaux = L.n, t.out_hi = out_hi, t.out_lo = out_lo, t.ldo = ldo;
+    t.W = W, t.T = c->T, t.epi = epi;
+    return timed(c, s, tag, [&]() { return launch_tap_tc(s, c, t); });
+}
+
+static bool use_tc_chain(const gem_ctx* c, int which, int W) { return c->gemm_mode == 1 && c->tap_tc[which] && W >= 1; }
+
 static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const float* z, float* pose_out) {
     const gem_vae_weights& v = c->vae[which];
     const int T = c->T, M = W * T, P = c->J * 3;
+    if (use_tc_chain(c, which, W)) {
+        // latent -> [T][256] on the tcgen05 GEMM, its epilogue writes the activation already split
+        GEM_TRY(run_layer(c, s, GEM_TAG_DEC + 0, v.dec[0], z, c->n, W, c->act_hi[0], T * 256, EPI_LRELU, nullptr, nullptr,
+                          nullptr, c->act_lo[0]));
+        for (int i = 1; i <= 4; ++i)
+            GEM_TRY(run_tap_tc(c, s, GEM_TAG_DEC + i, v.dec[i], c->act_hi[i - 1], c->act_lo[i - 1], v.dec[i].k, W,
+                               c->act_hi[i], c->act_lo[i], v.dec[i].n, EPI_LRELU, nullptr));
+        c->act_split = true;
+        return run_tap_tc(c, s, GEM_TAG_DEC + 5, v.dec[5], c->act_hi[4], c->act_lo[4], 64, W, pose_out, nullptr, P, EPI_NONE,
+                          nullptr);
+    }
     GEM_TRY(run_layer(c, s, GEM_TAG_DEC + 0, v.dec[0], z, c->n, W, c->act[0], T * 256, EPI_LRELU, nullptr));
     const float* in = c->act[0];
     for (int i = 1; i <= 4; ++i) {
         GEM_TRY(run_layer(c, s, GEM_TAG_DEC + i, v.dec[i], in, v.dec[i].k, M, c->act[i], v.dec[i].n, EPI_LRELU, nullptr));
         in = c->act[i];
     }
+    c->act_split = false;
     return run_layer(c, s, GEM_TAG_DEC + 5, v.dec[5], in, 64, M, pose_out, P, EPI_NONE, nullptr);
 }
 
 static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const float* dpose, float* dz) {
     const gem_vae_weights& v = c->vae[which];
     const int T = c->T, M = W * T, P = c->J * 3;
+    // the LeakyReLU derivative only needs the sign of the saved activation, which its TF32 hi part keeps
+    float* const* saved = c->act_split ? c->act_hi : c->act;
     // dec_bwd[i] is the bwd-data of dec[5-i]; its output is d(pre-activation of dec[4-i])
+    if (use_tc_chain(c, which, W)) {
+        const int pp = pose_pad(c);
+        GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 0,
+                      [&]() { return launch_split_pad(s, dpose, P, (size_t)M, pp, c->gp_hi, c->gp_lo); }));
+        const float *in_hi = c->gp_hi, *in_lo = c->gp_lo;
+        int lda = pp;
+        for (int i = 0; i < 5; ++i) {
+            const int a = 4 - i;
+            GEM_TRY(run_tap_tc(c, s, GEM_TAG_DEC_BWD + i, v.dec_bwd[i], in_hi, in_lo, lda, W, c->gact_hi[a], c->gact_lo[a],
+                               v.dec_bwd[i].n, EPI_MASK, saved[a]));
+            in_hi = c->gact_hi[a], in_lo = c->gact_lo[a];
+            lda = v.dec_bwd[i].n;
+        }
+        return run_layer(c, s, GEM_TAG_DEC_BWD + 5, v.dec_bwd[5], nullptr, T * 256, W, dz, c->n, EPI_NONE, nullptr,
+                         c->gact_hi[0], c->gact_lo[0]);
+    }
     const float* in = dpose;
     int lda = P;
     for (int i = 0; i < 5; ++i) {
         const int a = 4 - i;   // activation whose LeakyReLU derivative masks this output
         GEM_TRY(run_layer(c, s, GEM_TAG_DEC_BWD + i, v.dec_bwd[i], in, lda, M, c->gact[a], v.dec_bwd[i].n, EPI_MASK,
-                          c->act[a]));
+                          saved[a]));
         in = c->gact[a];
         lda = v.dec_bwd[i].n;
     }

@@ -1,0 +1,371 @@
+// tcgen05 / TMEM / TMA kernel for the VAE's k=3 convolutions (Conv1d / ConvTranspose1d, stride 1,
+// pad 1, SeqConvVAE.py:27-92) and their bwd-data, in fp32-faithful 3xTF32 arithmetic.
+//
+//   out[m][n] = epi( bias[n] + sum_{tap<3} sum_k A[m + tap - 1][k] * B[tap][k][n] ),   m = (window, frame) token,
+//   taps that leave the window's T frames read zeros.
+//
+// Instead of shifting the activation rows per tap (which a swizzled shared-memory operand cannot do), the
+// three taps sit side by side in the accumulator:  P[m][tap*N + n] = sum_k A[m][k] * B[tap][k][n]  is ONE
+// GEMM with 3N output columns, and the convolution is finished in the epilogue:
+//   out[m] = P_0[m-1] + P_1[m] + P_2[m+1]   (rows of the same window only).
+// An M tile is 128 TMEM lanes = 4 warps' lane quarters; each quarter holds floor(32/T) whole windows
+// (T = 10: 3 windows, 30 rows, 2 idle), so the +-1 row shift is a warp shuffle and never crosses a warp.
+// The activation tile is fetched by 3-D TMA boxes {32 channels, T frames, 3 windows} from the token-major
+// [W][T][C] tensor; windows beyond W are zero-filled by the TMA unit.
+//
+// 3xTF32: x = hi + lo (hi = top 19 bits, exact TF32; lo = x - hi); hi*hi + hi*lo + lo*hi accumulate in one
+// fp32 TMEM accumulator (K <= 256 here: few enough accumulation steps that the tensor core's truncating
+// adds stay at the 1e-6 level, see gemm_tc.cu).  Activations travel between layers already split: the
+// epilogue of the producing kernel writes hi and lo, so no separate split pass touches HBM.
+//
+// CTA anatomy (192 threads, one stage of shared memory; two CTAs share an SM and overlap each other's
+// load / MMA / epilogue phases): warp 0 = TMA producer, warp 1 = TMEM allocation + single-thread
+// tcgen05.mma issue (M128, N = 3*NCTA, K8, kind::tf32), warps 2-5 = epilogue (tcgen05.ld, shuffle shift-add,
+// bias / LeakyReLU / LeakyReLU-derivative mask, hi/lo split, row-segment stores).
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <unordered_map>
+
+#include "tc_common.cuh"
+
+namespace gem {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kRows = 128;                 // UMMA M
+constexpr int BK = 32;                     // fp32 per 128-byte swizzle row
+constexpr int kATile = kRows * BK * 4;     // 16 KB
+constexpr int kQuarterBytes = 32 * BK * 4; // 4 KB: one warp's 32 rows
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 256;
+
+template <int NCTA>
+struct Cfg {
+    static constexpr int NP = 3 * NCTA;                       // accumulator columns: the taps side by side
+    static constexpr int kBTile = NP * BK * 4;
+    static constexpr int kStage = 2 * kATile + 2 * kBTile;    // A_hi, A_lo, B_hi, B_lo
+    static constexpr size_t kSmem = (size_t)kStage + 1024 /*align slack*/ + 128 /*barriers*/;
+    static_assert(NP % 16 == 0 && NP <= 256, "UMMA N");
+    static_assert(kBTile % 1024 == 0, "B tile must keep the swizzle atom alignment");
+};
+
+struct TapTcArgs {
+    const float* bias;   // [N] or NULL
+    const float* aux;    // [tokens][ldaux]: sign of the saved activation (EPI_MASK)
+    float* out_hi;       // [tokens][ldo]: TF32 hi part, or the plain result when out_lo is NULL
+    float* out_lo;
+    int W, T, wpq;       // windows, frames per window, windows per 32-lane quarter
+    int N, ldo, ldaux, epi, num_kb;
+};
+
+template <int NCTA>
+__global__ void __launch_bounds__(kThreads)
+tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, TapTcArgs g) {
+    using C = Cfg<NCTA>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA_hi = smem;
+    uint8_t* sA_lo = smem + kATile;
+    uint8_t* sB_hi = smem + 2 * kATile;
+    uint8_t* sB_lo = sB_hi + C::kBTile;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStage);
+    uint64_t* empty_bar = full_bar + 1;
+    uint64_t* tmem_full_bar = full_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 3);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int win0 = blockIdx.x * 4 * g.wpq;      // first window of this M tile
+    const int y = blockIdx.y;                      // output-channel slab of NCTA channels
+    const int rows_q = g.wpq * g.T;                // rows in use per quarter
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a_hi), prefetch_tmap(&map_a_lo), prefetch_tmap(&map_b_hi), prefetch_tmap(&map_b_lo);
+        mbar_init(full_bar, 1), mbar_init(empty_bar, 1), mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    // the idle rows of each quarter are never written by TMA: clear them once so the MMA reads zeros
+    {
+        const int idle = 32 - rows_q;                          // rows per quarter
+        const int total = 2 * 4 * idle * 8;                    // float4 slots in both A tiles
+        for (int i = threadIdx.x; i < total; i += kThreads) {
+            const int tile = i / (4 * idle * 8), r = i % (4 * idle * 8);
+            const int q = r / (idle * 8), rr = (r % (idle * 8)) / 8, c16 = r % 8;
+            uint8_t* p = (tile ? sA_lo : sA_hi) + q * kQuarterBytes + (rows_q + rr) * 128 + c16 * 16;
+            *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint32_t box_bytes = (uint32_t)rows_q * BK * 4;
+            for (int kb = 0; kb < g.num_kb; ++kb) {
+                mbar_wait(empty_bar, (uint32_t)((kb & 1) ^ 1));
+                mbar_arrive_expect_tx(full_bar, 8 * box_bytes + 2 * C::kBTile);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    tma_load_3d(sA_hi + q * kQuarterBytes, &map_a_hi, kb * BK, 0, win0 + q * g.wpq, full_bar);
+                    tma_load_3d(sA_lo + q * kQuarterBytes, &map_a_lo, kb * BK, 0, win0 + q * g.wpq, full_bar);
+                }
+                tma_load_2d(sB_hi, &map_b_hi, kb * BK, y * C::NP, full_bar);
+                tma_load_2d(sB_lo, &map_b_lo, kb * BK, y * C::NP, full_bar);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc_tf32(kRows, C::NP);
+            const uint64_t a_hi = make_smem_desc(smem_u32(sA_hi)), a_lo = make_smem_desc(smem_u32(sA_lo));
+            const uint64_t b_hi = make_smem_desc(smem_u32(sB_hi)), b_lo = make_smem_desc(smem_u32(sB_lo));
+            for (int kb = 0; kb < g.num_kb; ++kb) {
+                mbar_wait(full_bar, (uint32_t)(kb & 1));
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);     // 32 bytes per K=8 step inside the 128-B row
+                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb > 0) || (k != 0));   // small terms first
+                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
+                }
+                umma_commit(empty_bar);              // the stage may be refilled once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int wl = lane / g.T, t = lane - wl * g.T;         // window inside the quarter, frame
+        const int win = win0 + q * g.wpq + wl;
+        const bool row_ok = lane < rows_q && win < g.W;
+        const bool has_prev = t > 0, has_next = t < g.T - 1;
+        const size_t token = (size_t)win * g.T + t;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < NCTA / 16; ++c) {
+            uint32_t p0[16], p1[16], p2[16];
+            tmem_ld_32x32b_x16(trow + (uint32_t)(0 * NCTA + c * 16), p0);
+            tmem_ld_32x32b_x16(trow + (uint32_t)(1 * NCTA + c * 16), p1);
+            tmem_ld_32x32b_x16(trow + (uint32_t)(2 * NCTA + c * 16), p2);
+            tmem_ld_wait();
+            const int nb = y * NCTA + c * 16;
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(p0[j]), 1);     // P_0 of the previous frame
+                const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(p2[j]), 1);   // P_2 of the next frame
+                float v = __uint_as_float(p1[j]);
+                v += has_prev ? up : 0.f;
+                v += has_next ? dn : 0.f;
+                o[j] = v;
+            }
+            if (row_ok) {
+                if (g.bias) {
+    #pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (nb + j < g.N) o[j] += __ldg(g.bias + nb + j);
+                }
+                if (g.epi == EPI_LRELU) {
+    #pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * 0.01f;
+                } else if (g.epi == EPI_MASK) {
+                    const float* ax = g.aux + token * g.ldaux + nb;
+    #pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 s4 = *reinterpret_cast<const float4*>(ax + j);
+                        o[j + 0] = s4.x > 0.f ? o[j + 0] : o[j + 0] * 0.01f;
+                        o[j + 1] = s4.y > 0.f ? o[j + 1] : o[j + 1] * 0.01f;
+                        o[j + 2] = s4.z > 0.f ? o[j + 2] : o[j + 2] * 0.01f;
+                        o[j + 3] = s4.w > 0.f ? o[j + 3] : o[j + 3] * 0.01f;
+                    }
+                }
+                if (g.out_lo) {
+                    float* dh = g.out_hi + token * g.ldo + nb;
+                    float* dl = g.out_lo + token * g.ldo + nb;
+    #pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 h, l;
+                        split_tf32(o[j + 0], h.x, l.x), split_tf32(o[j + 1], h.y, l.y);
+                        split_tf32(o[j + 2], h.z, l.z), split_tf32(o[j + 3], h.w, l.w);
+                        *reinterpret_cast<float4*>(dh + j) = h;
+                        *reinterpret_cast<float4*>(dl + j) = l;
+                    }
+                } else {
+                    float* dp = g.out_hi + token * g.ldo + nb;
+    #pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (nb + j < g.N) dp[j] = o[j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// weights [3][K][ldb] (tap, in, out) -> K-major slabs [gridy][3][NCTA][Kp], split into TF32 hi / lo
+__global__ void tap_weight_prep_kernel(const float* __restrict__ B, int ldb, int K, int N, int Kp, int ncta, int gridy,
+                                       float* __restrict__ hi, float* __restrict__ lo) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)gridy * 3 * ncta * Kp;
+    if (i >= total) return;
+    const int k = (int)(i % Kp);
+    const size_t row = i / Kp;
+    const int np = (int)(row % ncta), tap = (int)((row / ncta) % 3), yy = (int)(row / (3 * (size_t)ncta));
+    const int n = yy * ncta + np;
+    float x = 0.f;
+    if (k < K && n < N) x = B[((size_t)tap * K + k) * ldb + n];
+    float h, l;
+    split_tf32(x, h, l);
+    hi[i] = h, lo[i] = l;
+}
+
+// [tokens][C] -> zero-padded [tokens][ldo] hi / lo (the bwd-data entry: d pose with 45 -> 48 columns)
+__global__ void split_pad_kernel(const float* __restrict__ src, int C, size_t tokens, int ldo, float* __restrict__ hi,
+                                 float* __restrict__ lo) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= tokens * (size_t)ldo) return;
+    const size_t m = i / ldo;
+    const int c = (int)(i - m * ldo);
+    float h = 0.f, l = 0.f;
+    if (c < C) split_tf32(src[m * C + c], h, l);
+    hi[i] = h, lo[i] = l;
+}
+
+struct TapWeight {
+    float *hi = nullptr, *lo = nullptr;
+    int K = 0, Kp = 0, N = 0, ncta = 0, gridy = 0;
+    CUtensorMap map_hi, map_lo;
+};
+struct AMaps {
+    CUtensorMap hi, lo;
+};
+struct TapState {
+    std::unordered_map<const float*, TapWeight> weights;                       // keyed by the layer's weight pointer
+    std::map<std::tuple<const float*, const float*, int, int, int, int>, AMaps> amaps;   // (hi, lo, lda, K, W, T)
+    bool attr_set = false;
+};
+std::mutex g_mu;
+std::unordered_map<void*, TapState*> g_states;
+
+TapState* state_of(void* owner) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_states.find(owner);
+    if (it == g_states.end()) it = g_states.emplace(owner, new TapState()).first;
+    return it->second;
+}
+
+}  // namespace
+
+bool tc_tap_supported(int K, int N, int T) {
+    return T >= 1 && T <= 32 && K >= 1 && K <= 1024 && N >= 1 && (N <= 48 || N % 64 == 0);
+}
+
+int tc_tap_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N) {
+    GEM_REQUIRE(tc_tap_supported(K, N, 1), "layer shape not supported by the tcgen05 tap kernel");
+    TapState* st = state_of(owner);
+    auto old = st->weights.find(B);
+    if (old != st->weights.end()) {
+        GEM_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(old->second.hi), cudaFree(old->second.lo);
+        st->weights.erase(old);
+    }
+    TapWeight w;
+    w.K = K, w.N = N, w.Kp = (K + BK - 1) / BK * BK;
+    w.ncta = N <= 48 ? 48 : 64;
+    w.gridy = N <= 48 ? 1 : N / 64;
+    const size_t total = (size_t)w.gridy * 3 * w.ncta * w.Kp;
+    GEM_CUDA(cudaMalloc(&w.hi, total * sizeof(float)));
+    GEM_CUDA(cudaMalloc(&w.lo, total * sizeof(float)));
+    tap_weight_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(B, ldb, K, N, w.Kp, w.ncta, w.gridy, w.hi,
+                                                                              w.lo);
+    GEM_CHECK_LAUNCH();
+    const uint64_t dims[2] = {(uint64_t)w.Kp, (uint64_t)w.gridy * 3 * w.ncta};
+    const uint64_t strides[1] = {(uint64_t)w.Kp * sizeof(float)};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(3 * w.ncta)};
+    int rc = make_map_f32(&w.map_hi, w.hi, 2, dims, strides, box);
+    if (rc == GEM_OK) rc = make_map_f32(&w.map_lo, w.lo, 2, dims, strides, box);
+    if (rc != GEM_OK) return rc;
+    st->weights.emplace(B, w);
+    return GEM_OK;
+}
+
+int launch_split_pad(cudaStream_t stream, const float* src, int C, size_t tokens, int ldo, float* hi, float* lo) {
+    const size_t total = tokens * (size_t)ldo;
+    if (total == 0) return GEM_OK;
+    split_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(src, C, tokens, ldo, hi, lo);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+int launch_tap_tc(cudaStream_t stream, void* owner, const TapTcLaunch& L) {
+    if (L.W <= 0) return GEM_OK;
+    TapState* st = state_of(owner);
+    auto wit = st->weights.find(L.B);
+    if (wit == st->weights.end()) {
+        set_error("tcgen05 tap path: weights were not prepared (tc_tap_prepare_weight)");
+        return GEM_ERR_STATE;
+    }
+    const TapWeight& w = wit->second;
+    GEM_REQUIRE(L.T >= 1 && L.T <= 32, "seq_len must be <= 32 on the tcgen05 tap path");
+    GEM_REQUIRE(L.lda % 4 == 0 && L.Kreal <= L.lda && L.Kreal <= w.Kp && L.Kreal >= w.K, "bad activation layout");
+    GEM_REQUIRE(L.out_lo == nullptr || (L.ldo % 4 == 0 && w.N % 16 == 0), "split output needs N % 16 == 0");
+    GEM_REQUIRE(L.epi != EPI_MASK || (L.aux && L.ldaux % 4 == 0 && w.N % 16 == 0), "mask epilogue needs an aligned aux");
+    if (!st->attr_set) {
+        GEM_CUDA(cudaFuncSetAttribute(tc_tap_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64>::kSmem));
+        GEM_CUDA(cudaFuncSetAttribute(tc_tap_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<48>::kSmem));
+        st->attr_set = true;
+    }
+    const int wpq = 32 / L.T;
+    const auto key = std::make_tuple(L.A_hi, L.A_lo, L.lda, L.Kreal, L.W, L.T);
+    auto mit = st->amaps.find(key);
+    if (mit == st->amaps.end()) {
+        if (st->amaps.size() > 256) st->amaps.clear();
+        AMaps m;
+        const uint64_t dims[3] = {(uint64_t)L.Kreal, (uint64_t)L.T, (uint64_t)L.W};
+        const uint64_t strides[2] = {(uint64_t)L.lda * sizeof(float), (uint64_t)L.T * L.lda * sizeof(float)};
+        const uint32_t box[3] = {(uint32_t)BK, (uint32_t)L.T, (uint32_t)wpq};
+        int rc = make_map_f32(&m.hi, L.A_hi, 3, dims, strides, box);
+        if (rc == GEM_OK) rc = make_map_f32(&m.lo, L.A_lo, 3, dims, strides, box);
+        if (rc != GEM_OK) return rc;
+        mit = st->amaps.emplace(key, m).first;
+    }
+    TapTcArgs a;
+    a.bias = L.bias, a.aux = L.aux, a.out_hi = L.out_hi, a.out_lo = L.out_lo;
+    a.W = L.W, a.T = L.T, a.wpq = wpq, a.N = w.N, a.ldo = L.ldo, a.ldaux = L.ldaux, a.epi = L.epi;
+    a.num_kb = w.Kp / BK;
+    dim3 grid((L.W + 4 * wpq - 1) / (4 * wpq), w.gridy);
+    if (w.ncta == 64)
+        tc_tap_kernel<64><<<grid, kThreads, Cfg<64>::kSmem, stream>>>(mit->second.hi, mit->second.lo, w.map_hi, w.map_lo, a);
+    else
+        tc_tap_kernel<48><<<grid, kThreads, Cfg<48>::kSmem, stream>>>(mit->second.hi, mit->second.lo, w.map_hi, w.map_lo, a);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+void tc_tap_release(void* owner) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_states.find(owner);
+    if (it == g_states.end()) return;
+    TapState* st = it->second;
+    for (auto& kv : st->weights) cudaFree(kv.second.hi), cudaFree(kv.second.lo);
+    delete st;
+    g_states.erase(it);
+}
+
+}  // namespace gem

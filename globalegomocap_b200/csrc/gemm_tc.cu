@@ -24,14 +24,14 @@
 //            LeakyReLU, 128-byte row segments straight to global memory
 // Weights are transposed to K-major [N][K] and split once per checkpoint; activations are split by a
 // small elementwise kernel before each GEMM.
-#include <cuda.h>
-
 #include <mutex>
 #include <unordered_map>
 
-#include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace gem {
+
+using namespace tc;
 
 namespace {
 
@@ -44,65 +44,12 @@ constexpr int kTmemCols = kAcc * BN;              // 512 = all of TMEM
 constexpr int kThreads = 192;
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, fp32 accumulate, issued by ONE thread
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// all previously issued MMAs of this thread arrive on `bar` when they complete
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row groups of
-// 128-byte rows, 1024 bytes apart (SBO); version 1 (Blackwell); layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-           (2ull << 61);
-}
-// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kInstrDesc = instr_desc_tf32(BM, BN);
 
 struct TcArgs {
     const float* bias;
-    float* C;
+    float* C;        // result, or its TF32 hi part when C_lo is set
+    float* C_lo;     // optional: the epilogue writes the result already split for the next tensor-core layer
     int M, N, K, ldc, epi;
 };
 
@@ -204,6 +151,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         if (g.epi == EPI_LRELU) x = x > 0.f ? x : x * 0.01f;
                         po[e] = x;
                     }
+                    if (g.C_lo) {
+                        float4 l;
+                        split_tf32(o.x, o.x, l.x), split_tf32(o.y, o.y, l.y), split_tf32(o.z, o.z, l.z), split_tf32(o.w, o.w, l.w);
+                        *reinterpret_cast<float4*>(g.C_lo + (size_t)m * g.ldc + nb + j) = l;
+                    }
                     *reinterpret_cast<float4*>(dst + j) = o;
                 }
             }
@@ -256,42 +208,12 @@ __global__ void transpose_split_kernel(const float* __restrict__ B, int ldb, int
 }
 
 // ---------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, []() {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    });
-    return fn;
-}
-
 // rows x K fp32 row-major (pitch K), box = 128 rows x 32 floats, 128-byte swizzle, OOB rows read zero
-int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t K) {
-    EncodeTiledFn enc = get_encode_fn();
-    if (!enc) {
-        set_error("cuTensorMapEncodeTiled not available from the driver");
-        return GEM_ERR_CUDA;
-    }
-    cuuint64_t dims[2] = {K, rows};
-    cuuint64_t strides[1] = {K * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
-        return GEM_ERR_CUDA;
-    }
-    return GEM_OK;
+int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t K, uint64_t pitch = 0) {
+    const uint64_t dims[2] = {K, rows};
+    const uint64_t strides[1] = {(pitch ? pitch : K) * sizeof(float)};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
+    return make_map_f32(map, base, 2, dims, strides, box);
 }
 
 struct WeightSplit {
@@ -309,6 +231,44 @@ std::mutex g_mu;
 std::unordered_map<void*, TcState*> g_states;                // one per workspace owner (ctx)
 
 }  // namespace
+
+namespace tc {
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int make_map_f32(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return GEM_ERR_CUDA;
+    }
+    cuuint64_t d[5], st[4];
+    cuuint32_t bx[5], estr[5];
+    for (int i = 0; i < rank; ++i) d[i] = dims[i], bx[i] = box[i], estr[i] = 1;
+    for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), d, st, bx, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return GEM_ERR_CUDA;
+    }
+    return GEM_OK;
+}
+
+}  // namespace tc
 
 bool tc_gemm_available() { return true; }
 
@@ -336,26 +296,29 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
         set_error("tcgen05 path: weight matrix was not prepared (tc_gemm_prepare_weight)");
         return GEM_ERR_STATE;
     }
-    // activations: split into the ctx-owned scratch
-    const size_t need = (size_t)g.M * g.K;
-    if (need > st->a_capacity) {
-        GEM_CUDA(cudaStreamSynchronize(stream));
-        if (st->a_hi) cudaFree(st->a_hi), cudaFree(st->a_lo);
-        GEM_CUDA(cudaMalloc(&st->a_hi, need * sizeof(float)));
-        GEM_CUDA(cudaMalloc(&st->a_lo, need * sizeof(float)));
-        st->a_capacity = need;
-    }
-    {
+    // activations: already split by the producing kernel, or split here into the ctx-owned scratch
+    const float *a_hi = g.A_hi, *a_lo = g.A_lo;
+    uint64_t pitch = (uint64_t)g.lda;
+    if (!a_hi) {
+        const size_t need = (size_t)g.M * g.K;
+        if (need > st->a_capacity) {
+            GEM_CUDA(cudaStreamSynchronize(stream));
+            if (st->a_hi) cudaFree(st->a_hi), cudaFree(st->a_lo);
+            GEM_CUDA(cudaMalloc(&st->a_hi, need * sizeof(float)));
+            GEM_CUDA(cudaMalloc(&st->a_lo, need * sizeof(float)));
+            st->a_capacity = need;
+        }
         const size_t n4 = (size_t)g.M * (g.K / 4);
         split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(g.A, g.lda, g.M, g.K, st->a_hi, st->a_lo);
         GEM_CHECK_LAUNCH();
+        a_hi = st->a_hi, a_lo = st->a_lo, pitch = (uint64_t)g.K;
     }
     CUtensorMap map_a_hi, map_a_lo;
-    int rc = make_map(&map_a_hi, st->a_hi, (uint64_t)g.M, (uint64_t)g.K);
-    if (rc == GEM_OK) rc = make_map(&map_a_lo, st->a_lo, (uint64_t)g.M, (uint64_t)g.K);
+    int rc = make_map(&map_a_hi, a_hi, (uint64_t)g.M, (uint64_t)g.K, pitch);
+    if (rc == GEM_OK) rc = make_map(&map_a_lo, a_lo, (uint64_t)g.M, (uint64_t)g.K, pitch);
     if (rc != GEM_OK) return rc;
     TcArgs a;
-    a.bias = g.bias, a.C = g.C, a.M = g.M, a.N = g.N, a.K = g.K, a.ldc = g.ldc, a.epi = g.epi;
+    a.bias = g.bias, a.C = g.C, a.C_lo = g.C_lo, a.M = g.M, a.N = g.N, a.K = g.K, a.ldc = g.ldc, a.epi = g.epi;
     dim3 grid((g.M + BM - 1) / BM, g.N / BN);
     tc_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_a_hi, map_a_lo, wit->second.map_hi, wit->second.map_lo, a);
     GEM_CHECK_LAUNCH();

@@ -13,6 +13,9 @@ int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, 
 enum { EPI_NONE = 0, EPI_LRELU = 1, EPI_MASK = 2 };
 struct TapGemmArgs {
     const float* A;      // [M][lda]
+    const float* A_hi = nullptr;   // tensor-core path only: A already split into TF32 hi / lo parts ([M][lda] each)
+    const float* A_lo = nullptr;
+    float* C_lo = nullptr;         // tensor-core path only: write the result split (hi to C, lo to C_lo)
     const float* B;      // [taps][K][ldb]
     const float* bias;   // [N] or NULL
     const float* aux;    // [M][ldaux] saved activation for EPI_MASK
@@ -26,6 +29,24 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
 int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N);
 void tc_gemm_release(void* owner);
 bool tc_gemm_available();
+
+// tcgen05 kernel for the k=3 convolutions (gemm_tap_tc.cu); activations travel as TF32 hi / lo pairs
+struct TapTcLaunch {
+    const float* B;                 // the layer's weight pointer (key of tc_tap_prepare_weight)
+    const float *A_hi, *A_lo;       // [W*T][lda]
+    int lda, Kreal;                 // row pitch and valid columns (the rest of a 32-wide K block reads zero)
+    const float* bias;              // [N] or NULL
+    const float* aux;               // EPI_MASK: [W*T][ldaux], only the sign is used
+    int ldaux;
+    float *out_hi, *out_lo;         // [W*T][ldo]; out_lo == NULL writes the plain result to out_hi
+    int ldo;
+    int W, T, epi;
+};
+bool tc_tap_supported(int K, int N, int T);
+int tc_tap_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N);
+int launch_tap_tc(cudaStream_t stream, void* owner, const TapTcLaunch& L);
+int launch_split_pad(cudaStream_t stream, const float* src, int C, size_t tokens, int ldo, float* hi, float* lo);
+void tc_tap_release(void* owner);
 
 struct LbfgsWin;
 struct LbfgsBuffers {

@@ -67,7 +67,9 @@ def test_tc_gemm_matches_fp32_path(engine, W):
     for name, a, b in zip(names, out[1], out[0]):
         r = _rel(a, b)
         print(W, name, "tcgen05 vs fp32 CUDA-core relative max error:", r)
-        assert r < (3e-5 if name == "mu" else 1e-5), (W, name, r)   # mu: K = 5120 and cancellation in the sum
+        # mu: K = 5120 and cancellation in the sum; dz: six tensor-core layers in a row, each adding the
+        # tensor core's truncating fp32 accumulation (~1e-6 per layer, gemm_tc.cu)
+        assert r < {"mu": 3e-5, "dz": 2e-5}.get(name, 1e-5), (W, name, r)
 
 
 def test_tc_gemm_matches_reference_goldens(engine, golden_dir):
@@ -86,3 +88,21 @@ def test_tc_gemm_matches_reference_goldens(engine, golden_dir):
         assert np.abs(pose[sl] - g["pose"]).max() / np.abs(g["pose"]).max() < 2e-5
         assert np.abs(dz[sl] - g["dz"]).max() / np.abs(g["dz"]).max() < 2e-4
         assert np.abs(mu.cpu().numpy()[sl] - g["mu"]).max() / np.abs(g["mu"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("W", [1, 2, 11, 12, 13, 37, 149])
+def test_tc_tap_chain_ragged_window_counts(engine, W):
+    """The tcgen05 tap kernel packs 3 windows per 32-lane TMEM quarter (12 per CTA): window counts that
+    leave quarters / tiles partly empty, and a single window, must match the CUDA-core layers."""
+    g = torch.Generator(device="cpu").manual_seed(1000 + W)
+    z = torch.randn(W, 2048, generator=g)
+    up = torch.randn(W, 10, 15, 3, generator=g)
+    engine.set_gemm_mode(1)
+    pose_tc = engine.decode(0, z).clone()          # leaves the (split) activations both vjp calls mask with
+    dz_tc = engine.decode_vjp(0, up).clone()
+    engine.set_gemm_mode(0)
+    dz_simt = engine.decode_vjp(0, up).clone()
+    pose_simt = engine.decode(0, z).clone()
+    torch.cuda.synchronize()
+    assert _rel(pose_tc, pose_simt) < 1e-5, (W, _rel(pose_tc, pose_simt))
+    assert _rel(dz_tc, dz_simt) < 2e-5, (W, _rel(dz_tc, dz_simt))   # six tensor-core layers in a row
