@@ -46,6 +46,7 @@ _SIGNATURES = {
     "gem_ctx_set_vae": (C.c_int, [_P, _I, C.POINTER(VaeWeights)]),
     "gem_ctx_scratch_bytes": (C.c_int64, [_P]),
     "gem_ctx_set_gemm_mode": (C.c_int, [_P, _I]),
+    "gem_ctx_set_chunks": (C.c_int, [_P, _I]),
     "gem_ctx_launch_count": (C.c_int64, [_P]),
     "gem_ctx_set_profiling": (C.c_int, [_P, _I]),
     "gem_ctx_read_profile": (C.c_int, [_P, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float),

@@ -40,6 +40,7 @@ struct gem_ctx {
     // the same activations as TF32 hi / lo pairs: what the tensor-core layers read and write (gemm_mode 1)
     float *act_hi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *act_lo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float *gact_hi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *gact_lo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t* act_sign[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // packed signs of act[i]: the bwd-data masks
     float *gp_hi = nullptr, *gp_lo = nullptr;   // d pose, [W*T][kPosePad]
     bool act_split = false;                      // the last decode left its activations in act_hi/act_lo
     bool tap_tc[2] = {false, false};             // the VAE's conv layers are prepared for the tcgen05 tap kernel
@@ -50,6 +51,11 @@ struct gem_ctx {
     LbfgsBuffers lb;
     gem_lbfgs_params lb_params;
     bool lb_started = false;
+    // chunked execution of a stage (gem_ctx_set_chunks): internal streams and fork/join events
+    int n_chunks = 1;
+    std::vector<cudaStream_t> streams;
+    std::vector<cudaEvent_t> join_ev;
+    cudaEvent_t fork_ev = nullptr;
     void* tc_workspace = nullptr;
     size_t tc_workspace_bytes = 0;
     // instrumentation: kernel-launch counter and optional CUDA-event pairs around every launch
@@ -86,6 +92,19 @@ static int timed(gem_ctx* c, cudaStream_t s, int tag, F&& f) {
 static const int kDecC[6] = {256, 128, 64, 64, 64, 0};   // channels after dec[0..4]; dec[5] -> J*3
 static int pose_pad(const gem_ctx* c) { return (c->J * 3 + 3) & ~3; }   // row pitch of the split d pose (TMA: 16-byte pitch)
 static const int kEncC[5] = {64, 64, 128, 256, 512};
+
+static int ensure_streams(gem_ctx* c, int n) {
+    if (n <= 1) return GEM_OK;
+    if (!c->fork_ev) GEM_CUDA(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+    while ((int)c->streams.size() < n) {
+        cudaStream_t st;
+        cudaEvent_t ev;
+        GEM_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        GEM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        c->streams.push_back(st), c->join_ev.push_back(ev);
+    }
+    return GEM_OK;
+}
 
 template <typename T>
 static int ctx_alloc(gem_ctx* c, T** p, size_t count) {
@@ -130,6 +149,7 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     for (int i = 0; i < 5; ++i) {
         A(&c->act_hi[i], tok * kDecC[i]), A(&c->act_lo[i], tok * kDecC[i]);
         A(&c->gact_hi[i], tok * kDecC[i]), A(&c->gact_lo[i], tok * kDecC[i]);
+        if (rc == GEM_OK) rc = ctx_alloc(c, &c->act_sign[i], tok * kDecC[i] / 32);
     }
     {
         const size_t cnt = tok * (size_t)((num_joints * 3 + 3) & ~3);
@@ -143,7 +163,7 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     LbfgsBuffers& b = c->lb;
     memset(&b, 0, sizeof(b));
     A(&b.X, W * n), A(&b.D, W * n), A(&b.G, W * n), A(&b.GP, W * n), A(&b.BG0, W * n),
-        A(&b.BG1, W * n), A(&b.ZT, W * n);
+        A(&b.BG1, W * n), A(&b.ZT, W * n), A(&b.ZT_hi, W * n), A(&b.ZT_lo, W * n);
     A(&b.Y, W * max_history * n), A(&b.S, W * max_history * n), A(&b.RO, W * max_history);
     if (rc == GEM_OK) {
         void* st = nullptr;
@@ -159,6 +179,9 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     // default: tcgen05 3xTF32 for the plain GEMMs; GEM_GEMM_MODE=0 (or gem_ctx_set_gemm_mode) selects fp32 CUDA cores
     c->gemm_mode = 1;
     if (const char* env = getenv("GEM_GEMM_MODE")) c->gemm_mode = (env[0] == '0') ? 0 : 1;
+    c->n_chunks = 4;
+    if (const char* env = getenv("GEM_CHUNKS")) c->n_chunks = atoi(env) >= 1 ? atoi(env) : 1;
+    if (c->n_chunks > 16) c->n_chunks = 16;
     // default skeleton: the reference's 15-joint kinematic tree (optimizer.py:34)
     if (num_joints == 15) {
         static const int32_t parents[15] = {0, 0, 1, 2, 0, 4, 5, 1, 7, 8, 9, 4, 11, 12, 13};
@@ -176,6 +199,9 @@ int gem_ctx_destroy(gem_ctx* c) {
     if (!c) return GEM_OK;
     cudaSetDevice(c->device);
     for (void* p : c->allocs) cudaFree(p);
+    for (cudaStream_t st : c->streams) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : c->join_ev) cudaEventDestroy(ev);
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     tc_gemm_release(c);
     tc_tap_release(c);
     for (auto& e : c->prof) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
@@ -193,6 +219,18 @@ int gem_ctx_set_gemm_mode(gem_ctx* c, int mode) {
         return GEM_ERR_STATE;
     }
     c->gemm_mode = mode;
+    return GEM_OK;
+}
+
+/* debug hook (not in the public header): per-CTA phase timestamps of the tcgen05 tap kernel */
+int gem_debug_tap_timestamps(long long* buf_d) {
+    gem::g_tap_dbg = buf_d;
+    return GEM_OK;
+}
+
+int gem_ctx_set_chunks(gem_ctx* c, int n_chunks) {
+    GEM_REQUIRE(c != nullptr && n_chunks >= 1 && n_chunks <= 16, "n_chunks must be in [1, 16]");
+    c->n_chunks = n_chunks;
     return GEM_OK;
 }
 
@@ -302,10 +340,10 @@ int gem_ctx_set_vae(gem_ctx* c, int which, const gem_vae_weights* w) {
 // ---- layer runner ----------------------------------------------------------------------------
 static int run_layer(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, const float* A, int lda, int M, float* C,
                      int ldc, int epi, const float* aux, const float* A_hi = nullptr, const float* A_lo = nullptr,
-                     float* C_lo = nullptr) {
+                     float* C_lo = nullptr, uint32_t* C_sign = nullptr) {
     TapGemmArgs g;
     g.A = A, g.B = L.w_d, g.bias = L.bias_d, g.aux = aux, g.C = C;
-    g.A_hi = A_hi, g.A_lo = A_lo, g.C_lo = C_lo;
+    g.A_hi = A_hi, g.A_lo = A_lo, g.C_lo = C_lo, g.C_sign = C_sign;
     g.M = M, g.N = L.n, g.K = L.k, g.taps = L.taps, g.T = c->T;
     g.lda = lda, g.ldb = (L.n + 3) & ~3, g.ldc = ldc, g.ldaux = L.n, g.epi = epi;
     return timed(c, s, tag, [&]() {
@@ -317,8 +355,10 @@ static int run_layer(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, co
 
 // one k=3 convolution on the tcgen05 tap kernel; activations are TF32 hi / lo pairs
 static int run_tap_tc(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, const float* A_hi, const float* A_lo, int lda,
-                      int W, float* out_hi, float* out_lo, int ldo, int epi, const float* aux) {
+                      int W, float* out_hi, float* out_lo, int ldo, int epi, const float* aux,
+                      const uint32_t* aux_bits = nullptr, uint32_t* sign_out = nullptr) {
     TapTcLaunch t;
+    t.aux_bits = aux_bits, t.sign_out = sign_out;
     t.B = L.w_d, t.A_hi = A_hi, t.A_lo = A_lo, t.lda = lda, t.Kreal = lda;
     t.bias = L.bias_d, t.aux = aux, t.ldaux = L.n, t.out_hi = out_hi, t.out_lo = out_lo, t.ldo = ldo;
     t.W = W, t.T = c->T, t.epi = epi;
@@ -327,62 +367,98 @@ static int run_tap_tc(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, c
 
 static bool use_tc_chain(const gem_ctx* c, int which, int W) { return c->gemm_mode == 1 && c->tap_tc[which] && W >= 1; }
 
-static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const float* z, float* pose_out) {
+// Scratch of the windows [w0, w0 + W): every per-window buffer of the ctx shifted by w0.  Chunks of one
+// stage run concurrently on different streams, each on its own slice.
+struct Slice {
+    int w0;
+    size_t tok0;                                  // first token
+    float *act[5], *gact[5], *act_hi[5], *act_lo[5], *gact_hi[5], *gact_lo[5];
+    uint32_t* act_sign[5];
+    float *pose, *gpose, *gp_hi, *gp_lo, *f_new, *g_new;
+    LbfgsBuffers lb;
+};
+static Slice slice_of(gem_ctx* c, int w0) {
+    Slice v;
+    v.w0 = w0, v.tok0 = (size_t)w0 * c->T;
+    for (int i = 0; i < 5; ++i) {
+        const size_t o = v.tok0 * kDecC[i];
+        v.act[i] = c->act[i] + o, v.gact[i] = c->gact[i] + o;
+        v.act_hi[i] = c->act_hi[i] + o, v.act_lo[i] = c->act_lo[i] + o;
+        v.gact_hi[i] = c->gact_hi[i] + o, v.gact_lo[i] = c->gact_lo[i] + o;
+        v.act_sign[i] = c->act_sign[i] + o / 32;
+    }
+    const size_t P = (size_t)c->J * 3, n = c->n, m = c->m;
+    v.pose = c->pose + v.tok0 * P, v.gpose = c->gpose + v.tok0 * P;
+    v.gp_hi = c->gp_hi + v.tok0 * pose_pad(c), v.gp_lo = c->gp_lo + v.tok0 * pose_pad(c);
+    v.f_new = c->f_new + w0, v.g_new = c->g_new + (size_t)w0 * n;
+    v.lb = c->lb;
+    LbfgsBuffers& b = v.lb;
+    const size_t on = (size_t)w0 * n;
+    b.X += on, b.D += on, b.G += on, b.GP += on, b.BG0 += on, b.BG1 += on, b.ZT += on, b.ZT_hi += on, b.ZT_lo += on;
+    b.Y += on * m, b.S += on * m, b.RO += (size_t)w0 * m;
+    b.st = reinterpret_cast<LbfgsWin*>(reinterpret_cast<char*>(b.st) + (size_t)w0 * lbfgs_state_bytes());
+    if (b.trace) b.trace += (size_t)w0 * b.trace_stride;
+    return v;
+}
+
+// z: plain latent [W][n]; or, when z_hi/z_lo are given, the same already split into TF32 parts
+static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice& v_, const float* z, float* pose_out,
+                       const float* z_hi = nullptr, const float* z_lo = nullptr) {
     const gem_vae_weights& v = c->vae[which];
     const int T = c->T, M = W * T, P = c->J * 3;
     if (use_tc_chain(c, which, W)) {
         // latent -> [T][256] on the tcgen05 GEMM, its epilogue writes the activation already split
-        GEM_TRY(run_layer(c, s, GEM_TAG_DEC + 0, v.dec[0], z, c->n, W, c->act_hi[0], T * 256, EPI_LRELU, nullptr, nullptr,
-                          nullptr, c->act_lo[0]));
+        GEM_TRY(run_layer(c, s, GEM_TAG_DEC + 0, v.dec[0], z, c->n, W, v_.act_hi[0], T * 256, EPI_LRELU, nullptr, z_hi,
+                          z_lo, v_.act_lo[0], v_.act_sign[0]));
         for (int i = 1; i <= 4; ++i)
-            GEM_TRY(run_tap_tc(c, s, GEM_TAG_DEC + i, v.dec[i], c->act_hi[i - 1], c->act_lo[i - 1], v.dec[i].k, W,
-                               c->act_hi[i], c->act_lo[i], v.dec[i].n, EPI_LRELU, nullptr));
+            GEM_TRY(run_tap_tc(c, s, GEM_TAG_DEC + i, v.dec[i], v_.act_hi[i - 1], v_.act_lo[i - 1], v.dec[i].k, W,
+                               v_.act_hi[i], v_.act_lo[i], v.dec[i].n, EPI_LRELU, nullptr, nullptr, v_.act_sign[i]));
         c->act_split = true;
-        return run_tap_tc(c, s, GEM_TAG_DEC + 5, v.dec[5], c->act_hi[4], c->act_lo[4], 64, W, pose_out, nullptr, P, EPI_NONE,
+        return run_tap_tc(c, s, GEM_TAG_DEC + 5, v.dec[5], v_.act_hi[4], v_.act_lo[4], 64, W, pose_out, nullptr, P, EPI_NONE,
                           nullptr);
     }
-    GEM_TRY(run_layer(c, s, GEM_TAG_DEC + 0, v.dec[0], z, c->n, W, c->act[0], T * 256, EPI_LRELU, nullptr));
-    const float* in = c->act[0];
+    GEM_TRY(run_layer(c, s, GEM_TAG_DEC + 0, v.dec[0], z, c->n, W, v_.act[0], T * 256, EPI_LRELU, nullptr));
+    const float* in = v_.act[0];
     for (int i = 1; i <= 4; ++i) {
-        GEM_TRY(run_layer(c, s, GEM_TAG_DEC + i, v.dec[i], in, v.dec[i].k, M, c->act[i], v.dec[i].n, EPI_LRELU, nullptr));
-        in = c->act[i];
+        GEM_TRY(run_layer(c, s, GEM_TAG_DEC + i, v.dec[i], in, v.dec[i].k, M, v_.act[i], v.dec[i].n, EPI_LRELU, nullptr));
+        in = v_.act[i];
     }
     c->act_split = false;
     return run_layer(c, s, GEM_TAG_DEC + 5, v.dec[5], in, 64, M, pose_out, P, EPI_NONE, nullptr);
 }
 
-static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const float* dpose, float* dz) {
+static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice& v_, const float* dpose, float* dz) {
     const gem_vae_weights& v = c->vae[which];
     const int T = c->T, M = W * T, P = c->J * 3;
     // the LeakyReLU derivative only needs the sign of the saved activation, which its TF32 hi part keeps
-    float* const* saved = c->act_split ? c->act_hi : c->act;
+    float* const* saved = c->act_split ? v_.act_hi : v_.act;
     // dec_bwd[i] is the bwd-data of dec[5-i]; its output is d(pre-activation of dec[4-i])
     if (use_tc_chain(c, which, W)) {
         const int pp = pose_pad(c);
         GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 0,
-                      [&]() { return launch_split_pad(s, dpose, P, (size_t)M, pp, c->gp_hi, c->gp_lo); }));
-        const float *in_hi = c->gp_hi, *in_lo = c->gp_lo;
+                      [&]() { return launch_split_pad(s, dpose, P, (size_t)M, pp, v_.gp_hi, v_.gp_lo); }));
+        const float *in_hi = v_.gp_hi, *in_lo = v_.gp_lo;
         int lda = pp;
         for (int i = 0; i < 5; ++i) {
             const int a = 4 - i;
-            GEM_TRY(run_tap_tc(c, s, GEM_TAG_DEC_BWD + i, v.dec_bwd[i], in_hi, in_lo, lda, W, c->gact_hi[a], c->gact_lo[a],
-                               v.dec_bwd[i].n, EPI_MASK, saved[a]));
-            in_hi = c->gact_hi[a], in_lo = c->gact_lo[a];
+            GEM_TRY(run_tap_tc(c, s, GEM_TAG_DEC_BWD + i, v.dec_bwd[i], in_hi, in_lo, lda, W, v_.gact_hi[a], v_.gact_lo[a],
+                               v.dec_bwd[i].n, EPI_MASK, saved[a], c->act_split ? v_.act_sign[a] : nullptr));
+            in_hi = v_.gact_hi[a], in_lo = v_.gact_lo[a];
             lda = v.dec_bwd[i].n;
         }
         return run_layer(c, s, GEM_TAG_DEC_BWD + 5, v.dec_bwd[5], nullptr, T * 256, W, dz, c->n, EPI_NONE, nullptr,
-                         c->gact_hi[0], c->gact_lo[0]);
+                         v_.gact_hi[0], v_.gact_lo[0]);
     }
     const float* in = dpose;
     int lda = P;
     for (int i = 0; i < 5; ++i) {
         const int a = 4 - i;   // activation whose LeakyReLU derivative masks this output
-        GEM_TRY(run_layer(c, s, GEM_TAG_DEC_BWD + i, v.dec_bwd[i], in, lda, M, c->gact[a], v.dec_bwd[i].n, EPI_MASK,
+        GEM_TRY(run_layer(c, s, GEM_TAG_DEC_BWD + i, v.dec_bwd[i], in, lda, M, v_.gact[a], v.dec_bwd[i].n, EPI_MASK,
                           saved[a]));
-        in = c->gact[a];
+        in = v_.gact[a];
         lda = v.dec_bwd[i].n;
     }
-    return run_layer(c, s, GEM_TAG_DEC_BWD + 5, v.dec_bwd[5], c->gact[0], T * 256, W, dz, c->n, EPI_NONE, nullptr);
+    return run_layer(c, s, GEM_TAG_DEC_BWD + 5, v.dec_bwd[5], v_.gact[0], T * 256, W, dz, c->n, EPI_NONE, nullptr);
 }
 
 static int encode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const float* pose, const float* eps, float* z0,
@@ -449,7 +525,7 @@ int gem_decode(gem_ctx* c, void* stream, int which, int W, const float* z_d, flo
         set_error("VAE weights not set");
         return GEM_ERR_STATE;
     }
-    return decode_impl(c, (cudaStream_t)stream, which, W, z_d, pose_d);
+    return decode_impl(c, (cudaStream_t)stream, which, W, slice_of(c, 0), z_d, pose_d);
 }
 
 int gem_decode_vjp(gem_ctx* c, void* stream, int which, int W, const float* dpose_d, float* dz_d) {
@@ -459,7 +535,7 @@ int gem_decode_vjp(gem_ctx* c, void* stream, int which, int W, const float* dpos
         set_error("VAE weights not set");
         return GEM_ERR_STATE;
     }
-    return decode_vjp_impl(c, (cudaStream_t)stream, which, W, dpose_d, dz_d);
+    return decode_vjp_impl(c, (cudaStream_t)stream, which, W, slice_of(c, 0), dpose_d, dz_d);
 }
 
 int gem_encode(gem_ctx* c, void* stream, int which, int W, const float* pose_d, const float* eps_d, float* z0_d,
@@ -545,25 +621,73 @@ int gem_solve_stage(gem_ctx* c, void* stream, int which, int W, const float* pos
         GEM_CUDA(cudaMemsetAsync(energy_trace_d, 0xff, (size_t)W * (params_h->max_eval + 1) * sizeof(float), s));   // NaN
     // z0 = mu + eps * std                                   optimizer.py:255-259
     GEM_TRY(encode_impl(c, s, which, W, pose0_d, eps_d, c->z0, nullptr, nullptr));
-    GEM_TRY(timed(c, s, GEM_TAG_LBFGS_BEGIN, [&]() { return launch_lbfgs_begin(s, c->lb, c->z0, W); }));
+
+    // The windows are independent: split them into chunks that run the same kernel sequence on separate
+    // streams, so that one chunk's launch gaps, tails and HBM-bound L-BFGS updates overlap another chunk's
+    // tensor-core layers.  Chunk boundaries are multiples of 12 windows (the tap kernel's M tile).
+    int nchunks = c->prof_on ? 1 : c->n_chunks;
+    const int kAlign = 12, kMinChunk = 96;
+    if (nchunks > W / kMinChunk) nchunks = W / kMinChunk;
+    if (nchunks < 1) nchunks = 1;
+    GEM_TRY(ensure_streams(c, nchunks));
+    std::vector<int> w0(nchunks + 1, W);
+    w0[0] = 0;
+    for (int k = 1; k < nchunks; ++k) w0[k] = (int)((int64_t)W * k / nchunks) / kAlign * kAlign;
+    std::vector<cudaStream_t> cs(nchunks, s);
+    if (nchunks > 1) {
+        GEM_CUDA(cudaEventRecord(c->fork_ev, s));
+        for (int k = 0; k < nchunks; ++k) {
+            cs[k] = c->streams[k];
+            GEM_CUDA(cudaStreamWaitEvent(cs[k], c->fork_ev, 0));
+        }
+    }
+    const size_t P = (size_t)c->T * c->J * 3;
+    std::vector<Slice> sl;
+    for (int k = 0; k < nchunks; ++k) sl.push_back(slice_of(c, w0[k]));
+    for (int k = 0; k < nchunks; ++k) {
+        const int Wk = w0[k + 1] - w0[k];
+        GEM_TRY(timed(c, cs[k], GEM_TAG_LBFGS_BEGIN,
+                      [&]() { return launch_lbfgs_begin(cs[k], sl[k].lb, c->z0 + (size_t)w0[k] * c->n, Wk); }));
+    }
     c->lb_started = true;
     // LBFGS.step: at most max_eval + 1 closure evaluations per window (lbfgs.py:478-487, App. B)
+    const bool tc = use_tc_chain(c, which, W);
     for (int round = 0; round <= params_h->max_eval; ++round) {
-        GEM_TRY(decode_impl(c, s, which, W, c->lb.ZT, c->pose));
-        GEM_TRY(timed(c, s, GEM_TAG_ENERGY, [&]() {
-            return launch_energy_grad(s, W, c->T, c->J, c->H, c->Wd, c->pose, pose0_d, heat_d, frame_base_d, clip_d,
-                                      mean_bone_d, *wt, c->f_new, nullptr, c->gpose, status_d);
-        }));
-        GEM_TRY(decode_vjp_impl(c, s, which, W, c->gpose, c->g_new));
-        GEM_TRY(timed(c, s, GEM_TAG_LBFGS_ADVANCE,
-                      [&]() { return launch_lbfgs_advance(s, c->lb, c->f_new, c->g_new, W); }));
+        for (int k = 0; k < nchunks; ++k) {
+            const int Wk = w0[k + 1] - w0[k];
+            const Slice& v = sl[k];
+            cudaStream_t q = cs[k];
+            GEM_TRY(decode_impl(c, q, which, Wk, v, v.lb.ZT, v.pose, tc ? v.lb.ZT_hi : nullptr, tc ? v.lb.ZT_lo : nullptr));
+            GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
+                return launch_energy_grad(q, Wk, c->T, c->J, c->H, c->Wd, v.pose, pose0_d + w0[k] * P, heat_d,
+                                          frame_base_d ? frame_base_d + w0[k] : nullptr, clip_d + w0[k], mean_bone_d, *wt,
+                                          v.f_new, nullptr, v.gpose, status_d ? status_d + w0[k] : nullptr);
+            }));
+            GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, v.gpose, v.g_new));
+            GEM_TRY(timed(c, q, GEM_TAG_LBFGS_ADVANCE,
+                          [&]() { return launch_lbfgs_advance(q, v.lb, v.f_new, v.g_new, Wk); }));
+        }
     }
-    // final decode of the optimum                           optimizer.py:273-276
-    GEM_TRY(decode_impl(c, s, which, W, c->lb.X, pose_out_d));
+    // final decode of the optimum (every window is parked with its trial point = x)      optimizer.py:273-276
+    for (int k = 0; k < nchunks; ++k) {
+        const int Wk = w0[k + 1] - w0[k];
+        const Slice& v = sl[k];
+        GEM_TRY(decode_impl(c, cs[k], which, Wk, v, v.lb.X, pose_out_d + w0[k] * P, tc ? v.lb.ZT_hi : nullptr,
+                            tc ? v.lb.ZT_lo : nullptr));
+        GEM_TRY(timed(c, cs[k], GEM_TAG_OTHER, [&]() {
+            return launch_lbfgs_stats(cs[k], v.lb, Wk, n_iter_d ? n_iter_d + w0[k] : nullptr,
+                                      func_evals_d ? func_evals_d + w0[k] : nullptr, nullptr, nullptr, nullptr);
+        }));
+    }
+    if (nchunks > 1) {
+        for (int k = 0; k < nchunks; ++k) {
+            GEM_CUDA(cudaEventRecord(c->join_ev[k], cs[k]));
+            GEM_CUDA(cudaStreamWaitEvent(s, c->join_ev[k], 0));
+        }
+    }
     c->lb.trace = nullptr;   // the caller's buffer is not retained
     c->lb.trace_stride = 0;
-    return timed(c, s, GEM_TAG_OTHER,
-                 [&]() { return launch_lbfgs_stats(s, c->lb, W, n_iter_d, func_evals_d, nullptr, nullptr, nullptr); });
+    return GEM_OK;
 }
 
 int gem_relative_global(gem_ctx* c, void* stream, int W, const void* pose_d, int pose_is_f64, const double* cams_d,

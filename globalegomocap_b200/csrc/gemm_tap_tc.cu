@@ -54,17 +54,25 @@ struct Cfg {
 
 struct TapTcArgs {
     const float* bias;   // [N] or NULL
-    const float* aux;    // [tokens][ldaux]: sign of the saved activation (EPI_MASK)
+    const float* aux;    // [tokens][ldaux]: sign of the saved activation (EPI_MASK) ...
+    const uint32_t* aux_bits;   // ... or, preferred, its packed sign bits [tokens][N/32]
+    uint32_t* sign_out;  // optional: packed sign bits of this layer's output [tokens][N/32]
     float* out_hi;       // [tokens][ldo]: TF32 hi part, or the plain result when out_lo is NULL
     float* out_lo;
     int W, T, wpq;       // windows, frames per window, windows per 32-lane quarter
     int N, ldo, ldaux, epi, num_kb;
+    long long* dbg;      // optional per-CTA phase timestamps (SM clock), 16 slots per CTA; NULL in production
 };
+#define TAP_DBG(slot)                                                                                      \
+    do {                                                                                                   \
+        if (g.dbg) g.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64();          \
+    } while (0)
 
 template <int NCTA>
 __global__ void __launch_bounds__(kThreads)
 tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, TapTcArgs g) {
+              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+              const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo, TapTcArgs g) {
     using C = Cfg<NCTA>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -78,6 +86,7 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) TAP_DBG(0);
     const int win0 = blockIdx.x * 4 * g.wpq;      // first window of this M tile
     const int y = blockIdx.y;                      // output-channel slab of NCTA channels
     const int rows_q = g.wpq * g.T;                // rows in use per quarter
@@ -104,6 +113,7 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TAP_DBG(1);
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -130,6 +140,7 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             for (int kb = 0; kb < g.num_kb; ++kb) {
                 mbar_wait(full_bar, (uint32_t)(kb & 1));
                 tc_fence_after();
+                if (kb < 2) TAP_DBG(2 + kb);
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {
                     const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);     // 32 bytes per K=8 step inside the 128-B row
@@ -143,23 +154,34 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         }
     } else {
         // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+        // All MMAs have completed when tmem_full_bar fires, so the operand stage is free: the result tile
+        // is staged there (split outputs in the 128-byte-swizzled layout a 3-D TMA store expects, which is
+        // also the next layer's operand layout) and leaves by TMA / coalesced rows.  Per-thread row-segment
+        // stores would cost 32 L1 wavefronts per instruction.
         const int q = warp & 3;
         const int wl = lane / g.T, t = lane - wl * g.T;         // window inside the quarter, frame
-        const int win = win0 + q * g.wpq + wl;
+        const int winq = win0 + q * g.wpq;                      // first window of this quarter
+        const int win = winq + wl;
         const bool row_ok = lane < rows_q && win < g.W;
         const bool has_prev = t > 0, has_next = t < g.T - 1;
         const size_t token = (size_t)win * g.T + t;
+        const int words = g.N >> 5;                             // sign words per token
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) TAP_DBG(4);
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        uint32_t sbits = 0, mbits = 0;
 #pragma unroll 1
         for (int c = 0; c < NCTA / 16; ++c) {
             uint32_t p0[16], p1[16], p2[16];
             tmem_ld_32x32b_x16(trow + (uint32_t)(0 * NCTA + c * 16), p0);
             tmem_ld_32x32b_x16(trow + (uint32_t)(1 * NCTA + c * 16), p1);
             tmem_ld_32x32b_x16(trow + (uint32_t)(2 * NCTA + c * 16), p2);
-            tmem_ld_wait();
             const int nb = y * NCTA + c * 16;
+            const int sh = (c & 1) * 16;
+            if (g.epi == EPI_MASK && g.aux_bits && sh == 0 && row_ok) mbits = __ldg(g.aux_bits + token * words + (nb >> 5));
+            tmem_ld_wait();
+            if (threadIdx.x == 64 && c < 4) TAP_DBG(8 + c);
             float o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -170,18 +192,21 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 v += has_next ? dn : 0.f;
                 o[j] = v;
             }
-            if (row_ok) {
-                if (g.bias) {
-    #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (nb + j < g.N) o[j] += __ldg(g.bias + nb + j);
-                }
-                if (g.epi == EPI_LRELU) {
-    #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * 0.01f;
-                } else if (g.epi == EPI_MASK) {
+            if (g.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (nb + j < g.N) o[j] += __ldg(g.bias + nb + j);
+            }
+            if (g.epi == EPI_LRELU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * 0.01f;
+            } else if (g.epi == EPI_MASK) {
+                if (g.aux_bits) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = ((mbits >> (sh + j)) & 1u) ? o[j] : o[j] * 0.01f;
+                } else if (row_ok) {
                     const float* ax = g.aux + token * g.ldaux + nb;
-    #pragma unroll
+#pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const float4 s4 = *reinterpret_cast<const float4*>(ax + j);
                         o[j + 0] = s4.x > 0.f ? o[j + 0] : o[j + 0] * 0.01f;
@@ -190,32 +215,66 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                         o[j + 3] = s4.w > 0.f ? o[j + 3] : o[j + 3] * 0.01f;
                     }
                 }
-                if (g.out_lo) {
-                    float* dh = g.out_hi + token * g.ldo + nb;
-                    float* dl = g.out_lo + token * g.ldo + nb;
-    #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float4 h, l;
-                        split_tf32(o[j + 0], h.x, l.x), split_tf32(o[j + 1], h.y, l.y);
-                        split_tf32(o[j + 2], h.z, l.z), split_tf32(o[j + 3], h.w, l.w);
-                        *reinterpret_cast<float4*>(dh + j) = h;
-                        *reinterpret_cast<float4*>(dl + j) = l;
-                    }
-                } else {
-                    float* dp = g.out_hi + token * g.ldo + nb;
-    #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (nb + j < g.N) dp[j] = o[j];
+            }
+            if (g.sign_out) {                     // LeakyReLU keeps the sign: one bit per channel for the bwd-data mask
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sbits |= (o[j] > 0.f ? 1u : 0u) << (sh + j);
+                if (sh == 16) {
+                    if (row_ok) g.sign_out[token * words + (nb >> 5)] = sbits;
+                    sbits = 0;
                 }
             }
+            if (g.out_lo) {
+                uint8_t* th = smem + ((c >> 1) * 2 + 0) * kATile + q * kQuarterBytes + lane * 128;
+                uint8_t* tl = th + kATile;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 h, l;
+                    split_tf32(o[j + 0], h.x, l.x), split_tf32(o[j + 1], h.y, l.y);
+                    split_tf32(o[j + 2], h.z, l.z), split_tf32(o[j + 3], h.w, l.w);
+                    const int off = ((((c & 1) * 4 + (j >> 2)) ^ (lane & 7)) << 4);     // SWIZZLE_128B
+                    *reinterpret_cast<float4*>(th + off) = h;
+                    *reinterpret_cast<float4*>(tl + off) = l;
+                }
+            } else {
+                float* sp = reinterpret_cast<float*>(smem + q * 2 * kQuarterBytes) + lane * g.N + c * 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (nb + j < g.N) sp[j] = o[j];
+            }
+        }
+        if (threadIdx.x == 64) TAP_DBG(7);
+        if (g.out_lo) {
+            fence_proxy_async_smem();             // generic-proxy writes -> visible to the TMA store
+            __syncwarp();
+            if (lane == 0 && winq < g.W) {
+#pragma unroll
+                for (int b = 0; b < NCTA / 32; ++b) {
+                    tma_store_3d(&map_o_hi, smem + (b * 2 + 0) * kATile + q * kQuarterBytes, y * NCTA + b * 32, 0, winq);
+                    tma_store_3d(&map_o_lo, smem + (b * 2 + 1) * kATile + q * kQuarterBytes, y * NCTA + b * 32, 0, winq);
+                }
+                bulk_commit();
+                bulk_wait_read0();                // the staging memory must outlive the engine's reads, not its writes
+            }
+        } else {
+            // plain output (the pose): the quarter's windows are consecutive, dense rows in global memory
+            __syncwarp();
+            int nwin = g.W - winq;
+            nwin = nwin < 0 ? 0 : (nwin > g.wpq ? g.wpq : nwin);
+            const int count = nwin * g.T * g.N;
+            const float* sp = reinterpret_cast<const float*>(smem + q * 2 * kQuarterBytes);
+            float* dp = g.out_hi + (size_t)winq * g.T * g.N;
+            for (int i = lane; i < count; i += 32) dp[i] = sp[i];
         }
     }
+    if (threadIdx.x == 64) TAP_DBG(5);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
+    if (threadIdx.x == 0) TAP_DBG(6);
 }
 
 // weights [3][K][ldb] (tap, in, out) -> K-major slabs [gridy][3][NCTA][Kp], split into TF32 hi / lo
@@ -313,6 +372,8 @@ int launch_split_pad(cudaStream_t stream, const float* src, int C, size_t tokens
     return GEM_OK;
 }
 
+long long* g_tap_dbg = nullptr;   // set by gem_debug_tap_timestamps (tests / profiling only)
+
 int launch_tap_tc(cudaStream_t stream, void* owner, const TapTcLaunch& L) {
     if (L.W <= 0) return GEM_OK;
     TapState* st = state_of(owner);
@@ -324,36 +385,51 @@ int launch_tap_tc(cudaStream_t stream, void* owner, const TapTcLaunch& L) {
     const TapWeight& w = wit->second;
     GEM_REQUIRE(L.T >= 1 && L.T <= 32, "seq_len must be <= 32 on the tcgen05 tap path");
     GEM_REQUIRE(L.lda % 4 == 0 && L.Kreal <= L.lda && L.Kreal <= w.Kp && L.Kreal >= w.K, "bad activation layout");
-    GEM_REQUIRE(L.out_lo == nullptr || (L.ldo % 4 == 0 && w.N % 16 == 0), "split output needs N % 16 == 0");
-    GEM_REQUIRE(L.epi != EPI_MASK || (L.aux && L.ldaux % 4 == 0 && w.N % 16 == 0), "mask epilogue needs an aligned aux");
+    GEM_REQUIRE(L.out_lo == nullptr || (L.ldo % 4 == 0 && w.ncta == 64), "split output needs N % 64 == 0");
+    GEM_REQUIRE(L.epi != EPI_MASK || L.aux_bits || (L.aux && L.ldaux % 4 == 0 && w.N % 16 == 0),
+                "mask epilogue needs sign bits or an aligned aux");
+    GEM_REQUIRE((!L.aux_bits && !L.sign_out) || w.N % 32 == 0, "sign bits need N % 32 == 0");
+    GEM_REQUIRE(L.out_lo != nullptr || (L.ldo == w.N && w.N <= 48), "plain output must be dense and N <= 48");
     if (!st->attr_set) {
         GEM_CUDA(cudaFuncSetAttribute(tc_tap_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64>::kSmem));
         GEM_CUDA(cudaFuncSetAttribute(tc_tap_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<48>::kSmem));
         st->attr_set = true;
     }
     const int wpq = 32 / L.T;
-    const auto key = std::make_tuple(L.A_hi, L.A_lo, L.lda, L.Kreal, L.W, L.T);
-    auto mit = st->amaps.find(key);
-    if (mit == st->amaps.end()) {
-        if (st->amaps.size() > 256) st->amaps.clear();
-        AMaps m;
-        const uint64_t dims[3] = {(uint64_t)L.Kreal, (uint64_t)L.T, (uint64_t)L.W};
-        const uint64_t strides[2] = {(uint64_t)L.lda * sizeof(float), (uint64_t)L.T * L.lda * sizeof(float)};
-        const uint32_t box[3] = {(uint32_t)BK, (uint32_t)L.T, (uint32_t)wpq};
-        int rc = make_map_f32(&m.hi, L.A_hi, 3, dims, strides, box);
-        if (rc == GEM_OK) rc = make_map_f32(&m.lo, L.A_lo, 3, dims, strides, box);
+    auto maps_for = [&](const float* hi, const float* lo, int ld, int cols, AMaps** out) -> int {
+        const auto key = std::make_tuple(hi, lo, ld, cols, L.W, L.T);
+        auto mit = st->amaps.find(key);
+        if (mit == st->amaps.end()) {
+            AMaps m;
+            const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)L.T, (uint64_t)L.W};
+            const uint64_t strides[2] = {(uint64_t)ld * sizeof(float), (uint64_t)L.T * ld * sizeof(float)};
+            const uint32_t box[3] = {(uint32_t)BK, (uint32_t)L.T, (uint32_t)wpq};
+            int rc = make_map_f32(&m.hi, hi, 3, dims, strides, box);
+            if (rc == GEM_OK) rc = make_map_f32(&m.lo, lo, 3, dims, strides, box);
+            if (rc != GEM_OK) return rc;
+            mit = st->amaps.emplace(key, m).first;
+        }
+        *out = &mit->second;
+        return GEM_OK;
+    };
+    if (st->amaps.size() > 512) st->amaps.clear();
+    AMaps *am = nullptr, *om = nullptr;
+    {
+        int rc = maps_for(L.A_hi, L.A_lo, L.lda, L.Kreal, &am);
+        if (rc == GEM_OK) rc = L.out_lo ? maps_for(L.out_hi, L.out_lo, L.ldo, w.N, &om) : GEM_OK;
         if (rc != GEM_OK) return rc;
-        mit = st->amaps.emplace(key, m).first;
+        if (!om) om = am;      // unused by the kernel when the output is plain
     }
     TapTcArgs a;
-    a.bias = L.bias, a.aux = L.aux, a.out_hi = L.out_hi, a.out_lo = L.out_lo;
+    a.bias = L.bias, a.aux = L.aux, a.aux_bits = L.aux_bits, a.sign_out = L.sign_out, a.out_hi = L.out_hi, a.out_lo = L.out_lo;
     a.W = L.W, a.T = L.T, a.wpq = wpq, a.N = w.N, a.ldo = L.ldo, a.ldaux = L.ldaux, a.epi = L.epi;
     a.num_kb = w.Kp / BK;
+    a.dbg = g_tap_dbg;
     dim3 grid((L.W + 4 * wpq - 1) / (4 * wpq), w.gridy);
     if (w.ncta == 64)
-        tc_tap_kernel<64><<<grid, kThreads, Cfg<64>::kSmem, stream>>>(mit->second.hi, mit->second.lo, w.map_hi, w.map_lo, a);
+        tc_tap_kernel<64><<<grid, kThreads, Cfg<64>::kSmem, stream>>>(am->hi, am->lo, w.map_hi, w.map_lo, om->hi, om->lo, a);
     else
-        tc_tap_kernel<48><<<grid, kThreads, Cfg<48>::kSmem, stream>>>(mit->second.hi, mit->second.lo, w.map_hi, w.map_lo, a);
+        tc_tap_kernel<48><<<grid, kThreads, Cfg<48>::kSmem, stream>>>(am->hi, am->lo, w.map_hi, w.map_lo, om->hi, om->lo, a);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }

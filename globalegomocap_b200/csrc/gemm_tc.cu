@@ -50,6 +50,7 @@ struct TcArgs {
     const float* bias;
     float* C;        // result, or its TF32 hi part when C_lo is set
     float* C_lo;     // optional: the epilogue writes the result already split for the next tensor-core layer
+    uint32_t* sign;  // optional: packed sign bits of the result, [M][N/32]
     int M, N, K, ldc, epi;
 };
 
@@ -139,6 +140,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
             if (m < g.M) {
                 const int nb = n0 + c * 32;
+                uint32_t sbits = 0;
                 float* dst = g.C + (size_t)m * g.ldc + nb;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -150,6 +152,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         if (g.bias) x += __ldg(g.bias + nb + j + e);
                         if (g.epi == EPI_LRELU) x = x > 0.f ? x : x * 0.01f;
                         po[e] = x;
+                        sbits |= (x > 0.f ? 1u : 0u) << (j + e);
                     }
                     if (g.C_lo) {
                         float4 l;
@@ -158,6 +161,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     }
                     *reinterpret_cast<float4*>(dst + j) = o;
                 }
+                if (g.sign) g.sign[(size_t)m * (g.N >> 5) + (nb >> 5)] = sbits;
             }
         }
     }
@@ -318,7 +322,7 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
     if (rc == GEM_OK) rc = make_map(&map_a_lo, a_lo, (uint64_t)g.M, (uint64_t)g.K, pitch);
     if (rc != GEM_OK) return rc;
     TcArgs a;
-    a.bias = g.bias, a.C = g.C, a.C_lo = g.C_lo, a.M = g.M, a.N = g.N, a.K = g.K, a.ldc = g.ldc, a.epi = g.epi;
+    a.bias = g.bias, a.C = g.C, a.C_lo = g.C_lo, a.sign = g.C_sign, a.M = g.M, a.N = g.N, a.K = g.K, a.ldc = g.ldc, a.epi = g.epi;
     dim3 grid((g.M + BM - 1) / BM, g.N / BN);
     tc_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_a_hi, map_a_lo, wit->second.map_hi, wit->second.map_lo, a);
     GEM_CHECK_LAUNCH();

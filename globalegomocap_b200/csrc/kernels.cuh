@@ -16,6 +16,7 @@ struct TapGemmArgs {
     const float* A_hi = nullptr;   // tensor-core path only: A already split into TF32 hi / lo parts ([M][lda] each)
     const float* A_lo = nullptr;
     float* C_lo = nullptr;         // tensor-core path only: write the result split (hi to C, lo to C_lo)
+    uint32_t* C_sign = nullptr;    // tensor-core path only: packed sign bits of the result [M][N/32]
     const float* B;      // [taps][K][ldb]
     const float* bias;   // [N] or NULL
     const float* aux;    // [M][ldaux] saved activation for EPI_MASK
@@ -36,8 +37,10 @@ struct TapTcLaunch {
     const float *A_hi, *A_lo;       // [W*T][lda]
     int lda, Kreal;                 // row pitch and valid columns (the rest of a 32-wide K block reads zero)
     const float* bias;              // [N] or NULL
-    const float* aux;               // EPI_MASK: [W*T][ldaux], only the sign is used
+    const float* aux;               // EPI_MASK: [W*T][ldaux], only the sign is used ...
     int ldaux;
+    const uint32_t* aux_bits = nullptr;   // ... or its packed sign bits [W*T][N/32] (preferred)
+    uint32_t* sign_out = nullptr;         // optional: packed sign bits of the output [W*T][N/32]
     float *out_hi, *out_lo;         // [W*T][ldo]; out_lo == NULL writes the plain result to out_hi
     int ldo;
     int W, T, epi;
@@ -47,11 +50,13 @@ int tc_tap_prepare_weight(void* owner, cudaStream_t stream, const float* B, int 
 int launch_tap_tc(cudaStream_t stream, void* owner, const TapTcLaunch& L);
 int launch_split_pad(cudaStream_t stream, const float* src, int C, size_t tokens, int ldo, float* hi, float* lo);
 void tc_tap_release(void* owner);
+extern long long* g_tap_dbg;   // debug: per-CTA phase timestamps of the tap kernel (NULL in production)
 
 struct LbfgsWin;
 struct LbfgsBuffers {
     LbfgsWin* st;
     float *X, *D, *G, *GP, *BG0, *BG1, *ZT;   // [W][n]  (prev_flat_grad is G itself, see lbfgs.cu)
+    float *ZT_hi, *ZT_lo;                           // optional [W][n]: the trial point as TF32 hi / lo parts
     float *Y, *S;                                   // [W][m][n]
     float* RO;                                      // [W][m]
     float* trace;                                   // [W][trace_stride] or NULL

@@ -94,6 +94,21 @@ __device__ __forceinline__ void st8(float* __restrict__ p, const float (&r)[kPer
         if (c < n4) *reinterpret_cast<float4*>(p + 4 * c) = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
     }
 }
+// trial point: plain (host-driven closures read it) and, when requested, split into TF32 hi / lo parts so the
+// decoder's first tensor-core GEMM can consume it without a separate split pass
+__device__ __forceinline__ void st_trial(const LbfgsBuffers& b, size_t off, const float (&r)[kPer], int tid, int n4) {
+    st8(b.ZT + off, r, tid, n4);
+    if (b.ZT_hi) {
+        float h[kPer], l[kPer];
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            h[i] = __uint_as_float(__float_as_uint(r[i]) & 0xFFFFE000u);
+            l[i] = r[i] - h[i];
+        }
+        st8(b.ZT_hi + off, h, tid, n4);
+        st8(b.ZT_lo + off, l, tid, n4);
+    }
+}
 __device__ __forceinline__ float dot8(const float (&a)[kPer], const float (&b)[kPer]) {
     float p = 0.f;
 #pragma unroll
@@ -165,6 +180,11 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_begin_kernel(LbfgsBuffers b,
         const float v = z0[off + i];
         b.X[off + i] = v;
         b.ZT[off + i] = v;
+        if (b.ZT_hi) {
+            const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            b.ZT_hi[off + i] = h;
+            b.ZT_lo[off + i] = v - h;
+        }
     }
     if (threadIdx.x == 0) {
         LbfgsWin s;
@@ -199,6 +219,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
     const size_t off = (size_t)w * n;
     float *X = b.X + off, *D = b.D + off, *G = b.G + off, *GP = b.GP + off, *BG0 = b.BG0 + off, *BG1 = b.BG1 + off,
           *ZT = b.ZT + off;
+    (void)ZT;
     int par = 0;
 
     if (tid == 0) {
@@ -410,7 +431,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
             ld8(x, X, tid, n4);
 #pragma unroll
             for (int i = 0; i < kPer; ++i) x[i] = x[i] + tf * d[i];      // _add_grad(t, d) from x_init
-            st8(ZT, x, tid, n4);
+            st_trial(b, off, x, tid, n4);
             return;
         }
         // ---- line search finished (lbfgs.py:201-209, 488-527): accept the low bracket point -----
@@ -456,7 +477,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
         }
         __syncthreads();
         if (sh_stop) {
-            st8(ZT, x, tid, n4);
+            st_trial(b, off, x, tid, n4);
             return;
         }
         first_iter = false;
@@ -625,7 +646,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
 #pragma unroll
             for (int i = 0; i < kPer; ++i) x[i] = x[i] + tf * q[i];
         }
-        st8(ZT, x, tid, n4);
+        st_trial(b, off, x, tid, n4);
     }
 }
 

@@ -88,6 +88,10 @@ class Engine:
     def set_gemm_mode(self, mode: int):
         check(self.lib.gem_ctx_set_gemm_mode(self._ctx, int(mode)))
 
+    def set_chunks(self, n_chunks: int):
+        """Number of window slices a stage runs concurrently on internal streams (results are unaffected)."""
+        check(self.lib.gem_ctx_set_chunks(self._ctx, int(n_chunks)))
+
     def _dev(self, t, dtype):
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(np.asarray(t))

@@ -104,6 +104,13 @@ int64_t gem_ctx_scratch_bytes(const gem_ctx* ctx);
  * contraction (default when available) */
 int gem_ctx_set_gemm_mode(gem_ctx* ctx, int mode);
 
+/* A stage's windows are independent: gem_solve_stage splits them into n_chunks slices (boundaries at
+ * multiples of 12 windows, at least 96 windows each) that run the same kernel sequence on internal streams,
+ * forked from and joined to the caller's stream, so one slice's launch gaps and HBM-bound L-BFGS updates
+ * overlap another's tensor-core layers.  Default 4 (env GEM_CHUNKS); 1 = everything on the caller's stream.
+ * Results do not depend on the setting.  Profiling (gem_ctx_set_profiling) forces 1. */
+int gem_ctx_set_chunks(gem_ctx* ctx, int n_chunks);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* kernel classes reported by gem_ctx_read_profile */
 #define GEM_TAG_DEC 100           /* +i: decoder forward layer i (0 = latent -> T*256 GEMM) */
