@@ -253,11 +253,27 @@ def main():
         sol = so.solve(resident, eps=None)
         return sol, stitch_all(resident, sol)
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    e2e_marks = {}
+
     def step_e2e():
-        batch = WindowBatch(eng, clips)                       # H2D of every input from pinned memory
+        # H2D of every input from pinned memory, piece by piece on a copy stream; the library starts on the first
+        # pieces while the later ones are still in flight
+        t0 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        batch = WindowBatch(eng, clips, copy_stream=copy_stream)
+        t_up = torch.cuda.Event(enable_timing=True)
+        t_up.record(copy_stream)
         sol = so.solve(batch, eps=None)
+        t_solve = torch.cuda.Event(enable_timing=True)
+        t_solve.record()
         out = stitch_all(batch, sol)
         host_out.copy_(out, non_blocking=True)                # D2H of the step's result
+        t_end = torch.cuda.Event(enable_timing=True)
+        t_end.record()
+        eng.set_slices(None)
+        e2e_marks["ev"] = (t0, t_up, t_solve, t_end)
         return sol
 
     def barrier():
@@ -320,6 +336,9 @@ def main():
         e2e = {"value": total_frames / (ms_e / args.steps / 1000.0), "unit": "frames/s",
                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(host_out.numel() * 8),
                "ms_per_step": ms_e / args.steps}
+        t0, t_up, t_solve, t_end = e2e_marks["ev"]
+        e2e["last_step_ms"] = {"upload_done": t0.elapsed_time(t_up), "solve_done": t0.elapsed_time(t_solve),
+                               "result_on_host": t0.elapsed_time(t_end)}
 
     if rank == 0:
         peaks = {}

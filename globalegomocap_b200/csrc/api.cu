@@ -46,6 +46,7 @@ struct gem_ctx {
     bool tap_tc[2] = {false, false};             // the VAE's conv layers are prepared for the tcgen05 tap kernel
     // encoder activations, fc output
     float *eact[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *fc = nullptr, *z0 = nullptr;
+    float *e4_hi = nullptr, *e4_lo = nullptr;    // last encoder conv activation split for the tcgen05 fc GEMM
     // closure outputs
     float *f_new = nullptr, *g_new = nullptr;
     LbfgsBuffers lb;
@@ -56,6 +57,28 @@ struct gem_ctx {
     std::vector<cudaStream_t> streams;
     std::vector<cudaEvent_t> join_ev;
     cudaEvent_t fork_ev = nullptr;
+    // graph-stable copies of a stage's per-window inputs / outputs (so that a captured round can be replayed
+    // by later calls whatever buffers the caller passes)
+    float *pose0_own = nullptr, *mb_own = nullptr, *trace_own = nullptr;
+    int64_t* fb_own = nullptr;
+    int32_t* clip_own = nullptr;
+    uint32_t* status_own = nullptr;
+    int trace_cap = 0;                           // columns of trace_own
+    bool use_graphs = true;
+    struct RoundGraph {
+        int which, w0, Wk, gemm_mode, has_heat, trace_stride, launches;
+        const void* heat;
+        gem_energy_weights wt;
+        gem_lbfgs_params p;
+        cudaGraphExec_t exec;
+    };
+    std::vector<RoundGraph> graphs;
+    std::vector<int> user_slices;                // first window of each slice (gem_ctx_set_slices); empty = automatic
+    struct Ready {
+        int first_window;
+        cudaEvent_t ev;
+    };
+    std::vector<Ready> ready;                    // one-shot: inputs of windows >= first_window are complete after ev
     void* tc_workspace = nullptr;
     size_t tc_workspace_bytes = 0;
     // instrumentation: kernel-launch counter and optional CUDA-event pairs around every launch
@@ -94,7 +117,7 @@ static int pose_pad(const gem_ctx* c) { return (c->J * 3 + 3) & ~3; }   // row p
 static const int kEncC[5] = {64, 64, 128, 256, 512};
 
 static int ensure_streams(gem_ctx* c, int n) {
-    if (n <= 1) return GEM_OK;
+    if (n <= 0) return GEM_OK;
     if (!c->fork_ev) GEM_CUDA(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
     while ((int)c->streams.size() < n) {
         cudaStream_t st;
@@ -159,7 +182,14 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     }
     A(&c->pose, Weven * seq_len * num_joints * 3), A(&c->gpose, Weven * seq_len * num_joints * 3);
     for (int i = 0; i < 5; ++i) A(&c->eact[i], tok * kEncC[i]);
+    A(&c->e4_hi, tok * kEncC[4]), A(&c->e4_lo, tok * kEncC[4]);
     A(&c->fc, W * 2 * n), A(&c->z0, W * n), A(&c->f_new, W), A(&c->g_new, W * n);
+    A(&c->pose0_own, Weven * seq_len * num_joints * 3), A(&c->mb_own, W * num_joints);
+    c->trace_cap = max_history + 8;              // max_eval + 1 <= (max_history + 1) * 5 / 4 + 1
+    A(&c->trace_own, W * (size_t)c->trace_cap);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->fb_own, W);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->clip_own, W);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->status_own, W);
     LbfgsBuffers& b = c->lb;
     memset(&b, 0, sizeof(b));
     A(&b.X, W * n), A(&b.D, W * n), A(&b.G, W * n), A(&b.GP, W * n), A(&b.BG0, W * n),
@@ -182,6 +212,7 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     c->n_chunks = 4;
     if (const char* env = getenv("GEM_CHUNKS")) c->n_chunks = atoi(env) >= 1 ? atoi(env) : 1;
     if (c->n_chunks > 16) c->n_chunks = 16;
+    if (const char* env = getenv("GEM_GRAPHS")) c->use_graphs = env[0] != '0';
     // default skeleton: the reference's 15-joint kinematic tree (optimizer.py:34)
     if (num_joints == 15) {
         static const int32_t parents[15] = {0, 0, 1, 2, 0, 4, 5, 1, 7, 8, 9, 4, 11, 12, 13};
@@ -199,6 +230,7 @@ int gem_ctx_destroy(gem_ctx* c) {
     if (!c) return GEM_OK;
     cudaSetDevice(c->device);
     for (void* p : c->allocs) cudaFree(p);
+    for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
     for (cudaStream_t st : c->streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : c->join_ev) cudaEventDestroy(ev);
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
@@ -375,6 +407,11 @@ struct Slice {
     float *act[5], *gact[5], *act_hi[5], *act_lo[5], *gact_hi[5], *gact_lo[5];
     uint32_t* act_sign[5];
     float *pose, *gpose, *gp_hi, *gp_lo, *f_new, *g_new;
+    float *eact[5], *e4_hi, *e4_lo, *fc, *z0;    // encoder activations, fc output, initial latent
+    float *pose0_own, *mb_own, *trace_own;       // staged inputs / outputs of this slice
+    int64_t* fb_own;
+    int32_t* clip_own;
+    uint32_t* status_own;
     LbfgsBuffers lb;
 };
 static Slice slice_of(gem_ctx* c, int w0) {
@@ -391,6 +428,12 @@ static Slice slice_of(gem_ctx* c, int w0) {
     v.pose = c->pose + v.tok0 * P, v.gpose = c->gpose + v.tok0 * P;
     v.gp_hi = c->gp_hi + v.tok0 * pose_pad(c), v.gp_lo = c->gp_lo + v.tok0 * pose_pad(c);
     v.f_new = c->f_new + w0, v.g_new = c->g_new + (size_t)w0 * n;
+    for (int i = 0; i < 5; ++i) v.eact[i] = c->eact[i] + v.tok0 * kEncC[i];
+    v.e4_hi = c->e4_hi + v.tok0 * kEncC[4], v.e4_lo = c->e4_lo + v.tok0 * kEncC[4];
+    v.fc = c->fc + (size_t)w0 * 2 * n, v.z0 = c->z0 + (size_t)w0 * n;
+    v.pose0_own = c->pose0_own + v.tok0 * P, v.mb_own = c->mb_own;     // (mean bones are indexed by absolute window)
+    v.trace_own = c->trace_own + (size_t)w0 * c->trace_cap;
+    v.fb_own = c->fb_own + w0, v.clip_own = c->clip_own + w0, v.status_own = c->status_own + w0;
     v.lb = c->lb;
     LbfgsBuffers& b = v.lb;
     const size_t on = (size_t)w0 * n;
@@ -461,19 +504,49 @@ static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const S
     return run_layer(c, s, GEM_TAG_DEC_BWD + 5, v.dec_bwd[5], v_.gact[0], T * 256, W, dz, c->n, EPI_NONE, nullptr);
 }
 
-static int encode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const float* pose, const float* eps, float* z0,
-                       float* mu, float* sd) {
+static int encode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice& v_, const float* pose, const float* eps,
+                       float* z0, float* mu, float* sd, size_t eps_stride = 0) {
     const gem_vae_weights& v = c->vae[which];
     const int T = c->T, M = W * T, P = c->J * 3;
     const float* in = pose;
     int lda = P;
     for (int i = 0; i < 5; ++i) {
-        GEM_TRY(run_layer(c, s, GEM_TAG_ENC + i, v.enc[i], in, lda, M, c->eact[i], v.enc[i].n, EPI_LRELU, nullptr));
-        in = c->eact[i];
+        GEM_TRY(run_layer(c, s, GEM_TAG_ENC + i, v.enc[i], in, lda, M, v_.eact[i], v.enc[i].n, EPI_LRELU, nullptr));
+        in = v_.eact[i];
         lda = v.enc[i].n;
     }
-    GEM_TRY(run_layer(c, s, GEM_TAG_ENC + 5, v.enc[5], in, T * 512, W, c->fc, 2 * c->n, EPI_NONE, nullptr));
-    return timed(c, s, GEM_TAG_REPARAM, [&]() { return launch_reparam(s, c->fc, eps, z0, mu, sd, W, c->n); });
+    const gem_layer& fcL = v.enc[5];
+    if (c->gemm_mode == 1 && fcL.k % 32 == 0 && fcL.n % 128 == 0) {
+        // split into the slice's own buffers (the GEMM's internal split scratch is shared by the whole ctx)
+        GEM_TRY(timed(c, s, GEM_TAG_ENC + 5,
+                      [&]() { return launch_split_tf32(s, in, T * 512, W, T * 512, v_.e4_hi, v_.e4_lo); }));
+        GEM_TRY(run_layer(c, s, GEM_TAG_ENC + 5, fcL, nullptr, T * 512, W, v_.fc, 2 * c->n, EPI_NONE, nullptr, v_.e4_hi,
+                          v_.e4_lo));
+    } else {
+        GEM_TRY(run_layer(c, s, GEM_TAG_ENC + 5, fcL, in, T * 512, W, v_.fc, 2 * c->n, EPI_NONE, nullptr));
+    }
+    return timed(c, s, GEM_TAG_REPARAM, [&]() {
+        return launch_reparam(s, v_.fc, eps, eps_stride ? eps_stride : (size_t)c->n, z0, mu, sd, W, c->n);
+    });
+}
+
+// copies a stage's per-window inputs into ctx-owned buffers: anchor pose, first heat-map frame, the window's
+// mean bone lengths (gathered through its clip index, so the staged clip index is the window itself)
+__global__ void stage_inputs_kernel(int w_abs0, int TJ3, int J, const float* __restrict__ pose0, const int64_t* __restrict__ fb,
+                                    const int32_t* __restrict__ clip, const float* __restrict__ mean_bone,
+                                    float* __restrict__ pose0_own, int64_t* __restrict__ fb_own,
+                                    int32_t* __restrict__ clip_own, float* __restrict__ mb_own,
+                                    uint32_t* __restrict__ status_own) {
+    // all pointers are the slice's (window blockIdx.x of the slice); mb_own is the ctx-wide table indexed by the
+    // absolute window w_abs0 + blockIdx.x, which is what the staged clip index points at
+    const int w = blockIdx.x;
+    for (int i = threadIdx.x; i < TJ3; i += blockDim.x) pose0_own[(size_t)w * TJ3 + i] = pose0[(size_t)w * TJ3 + i];
+    if (threadIdx.x < J) mb_own[(size_t)(w_abs0 + w) * J + threadIdx.x] = mean_bone[(size_t)clip[w] * J + threadIdx.x];
+    if (threadIdx.x == 0) {
+        fb_own[w] = fb ? fb[w] : 0;
+        clip_own[w] = w_abs0 + w;
+        status_own[w] = 0;
+    }
 }
 
 #define GEM_ENTER(c, W)                                                          \
@@ -546,7 +619,7 @@ int gem_encode(gem_ctx* c, void* stream, int which, int W, const float* pose_d, 
         set_error("VAE weights not set");
         return GEM_ERR_STATE;
     }
-    return encode_impl(c, (cudaStream_t)stream, which, W, pose_d, eps_d, z0_d, mu_d, std_d);
+    return encode_impl(c, (cudaStream_t)stream, which, W, slice_of(c, 0), pose_d, eps_d, z0_d, mu_d, std_d);
 }
 
 static int lbfgs_configure(gem_ctx* c, const gem_lbfgs_params* p, float* trace, int trace_stride) {
@@ -602,6 +675,212 @@ int gem_lbfgs_stats(gem_ctx* c, void* stream, int W, int32_t* n_iter_d, int32_t*
     return launch_lbfgs_stats((cudaStream_t)stream, c->lb, W, n_iter_d, func_evals_d, finished_d, t_d, loss_d);
 }
 
+}  // extern "C"
+
+// Everything one stage does for the windows [w0, w0 + Wk) of a call, enqueued on stream q (the slice's own):
+// input staging, encoder, L-BFGS begin, max_eval + 1 closure rounds (round 0 launched directly, the rest a
+// replayed CUDA graph), final decode and counters.  All pointers are the call's (un-sliced) arguments.
+struct StageCall {
+    int which;
+    const float* pose0;         // [W][T][J][3]
+    const float* heat;
+    const int64_t* frame_base;  // [W] or NULL
+    const int32_t* clip;        // [W]
+    const float* mean_bone;
+    const float* eps;           // [W][eps_stride]
+    size_t eps_stride;
+    gem_energy_weights wt;
+    gem_lbfgs_params p;
+    float* pose_out;            // [W][T][J][3]
+    float* trace;               // [W][max_eval + 1] or NULL
+    int32_t *n_iter, *func_evals;
+    uint32_t* status;
+};
+
+static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, int w0, int Wk, bool graphs) {
+    if (Wk <= 0) return GEM_OK;
+    const int which = a.which;
+    const int TJ3 = c->T * c->J * 3;
+    const size_t P = (size_t)TJ3;
+    const int trace_cols = a.p.max_eval + 1;
+    Slice v = slice_of(c, w0);
+    // L-BFGS view of this slice with the stage's parameters
+    LbfgsBuffers& lb = v.lb;
+    lb.lr = a.p.lr, lb.tol_grad = a.p.tolerance_grad, lb.tol_change = a.p.tolerance_change;
+    lb.max_iter = a.p.max_iter, lb.max_eval = a.p.max_eval;
+    lb.trace = a.trace ? v.trace_own : nullptr;
+    lb.trace_stride = a.trace ? c->trace_cap : 0;
+    if (a.trace) GEM_CUDA(cudaMemsetAsync(v.trace_own, 0xff, (size_t)Wk * c->trace_cap * sizeof(float), q));   // NaN
+    stage_inputs_kernel<<<Wk, 128, 0, q>>>(w0, TJ3, c->J, a.pose0 + w0 * P, a.frame_base ? a.frame_base + w0 : nullptr,
+                                           a.clip + w0, a.mean_bone, v.pose0_own, v.fb_own, v.clip_own, v.mb_own,
+                                           v.status_own);
+    GEM_CHECK_LAUNCH();
+    c->launches += 1;
+    // z0 = mu + eps * std                                   optimizer.py:255-259
+    GEM_TRY(encode_impl(c, q, which, Wk, v, a.pose0 + w0 * P, a.eps + (size_t)w0 * a.eps_stride, v.z0, nullptr, nullptr,
+                        a.eps_stride));
+    GEM_TRY(timed(c, q, GEM_TAG_LBFGS_BEGIN, [&]() { return launch_lbfgs_begin(q, lb, v.z0, Wk); }));
+    const bool tc = use_tc_chain(c, which, Wk);
+    // one closure round: decode -> fused energy/gradient -> decoder bwd-data -> L-BFGS advance
+    auto enqueue_round = [&]() -> int {
+        GEM_TRY(decode_impl(c, q, which, Wk, v, lb.ZT, v.pose, tc ? lb.ZT_hi : nullptr, tc ? lb.ZT_lo : nullptr));
+        GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
+            return launch_energy_grad(q, Wk, c->T, c->J, c->H, c->Wd, v.pose, v.pose0_own, a.heat, v.fb_own, v.clip_own,
+                                      v.mb_own, a.wt, v.f_new, nullptr, v.gpose, v.status_own);
+        }));
+        GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, v.gpose, v.g_new));
+        return timed(c, q, GEM_TAG_LBFGS_ADVANCE, [&]() { return launch_lbfgs_advance(q, lb, v.f_new, v.g_new, Wk); });
+    };
+    // LBFGS.step: at most max_eval + 1 closure evaluations per window (lbfgs.py:478-487, App. B)
+    GEM_TRY(enqueue_round());                        // round 0: direct (also performs every lazy initialisation)
+    cudaGraphExec_t exec = nullptr;
+    int round_launches = 0;
+    if (graphs && a.p.max_eval >= 2) {
+        for (auto& g : c->graphs) {
+            if (g.which == which && g.w0 == w0 && g.Wk == Wk && g.gemm_mode == c->gemm_mode && g.heat == a.heat &&
+                g.has_heat == (a.wt.reproj != 0.f) && g.trace_stride == lb.trace_stride &&
+                memcmp(&g.wt, &a.wt, sizeof(a.wt)) == 0 && g.p.lr == a.p.lr && g.p.max_iter == a.p.max_iter &&
+                g.p.max_eval == a.p.max_eval && g.p.tolerance_grad == a.p.tolerance_grad &&
+                g.p.tolerance_change == a.p.tolerance_change) {
+                exec = g.exec, round_launches = g.launches;
+                break;
+            }
+        }
+        if (!exec) {
+            cudaGraph_t graph = nullptr;
+            GEM_CUDA(cudaStreamBeginCapture(q, cudaStreamCaptureModeRelaxed));
+            const int64_t launches_before = c->launches;
+            const int rc_round = enqueue_round();
+            round_launches = (int)(c->launches - launches_before);
+            c->launches = launches_before;               // captured, not executed
+            cudaError_t e = cudaStreamEndCapture(q, &graph);
+            if (rc_round != GEM_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc_round;
+            }
+            GEM_CUDA(e);
+            gem_ctx::RoundGraph g;
+            g.which = which, g.w0 = w0, g.Wk = Wk, g.gemm_mode = c->gemm_mode, g.heat = a.heat;
+            g.has_heat = a.wt.reproj != 0.f, g.trace_stride = lb.trace_stride, g.wt = a.wt, g.p = a.p;
+            g.launches = round_launches;
+            e = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            GEM_CUDA(e);
+            if (c->graphs.size() >= 64) {
+                cudaGraphExecDestroy(c->graphs.front().exec);
+                c->graphs.erase(c->graphs.begin());
+            }
+            c->graphs.push_back(g);
+            exec = g.exec;
+        }
+    }
+    for (int round = 1; round <= a.p.max_eval; ++round) {
+        if (exec) {
+            GEM_CUDA(cudaGraphLaunch(exec, q));
+            c->launches += round_launches;
+        } else {
+            GEM_TRY(enqueue_round());
+        }
+    }
+    // final decode of the optimum (every window is parked with its trial point = x)      optimizer.py:273-276
+    GEM_TRY(decode_impl(c, q, which, Wk, v, lb.X, a.pose_out + w0 * P, tc ? lb.ZT_hi : nullptr, tc ? lb.ZT_lo : nullptr));
+    GEM_TRY(timed(c, q, GEM_TAG_OTHER, [&]() {
+        return launch_lbfgs_stats(q, lb, Wk, a.n_iter ? a.n_iter + w0 : nullptr, a.func_evals ? a.func_evals + w0 : nullptr,
+                                  nullptr, nullptr, nullptr);
+    }));
+    if (a.status)
+        GEM_CUDA(cudaMemcpyAsync(a.status + w0, v.status_own, (size_t)Wk * sizeof(uint32_t), cudaMemcpyDeviceToDevice, q));
+    if (a.trace)
+        GEM_CUDA(cudaMemcpy2DAsync(a.trace + (size_t)w0 * trace_cols, trace_cols * sizeof(float), v.trace_own,
+                                   c->trace_cap * sizeof(float), trace_cols * sizeof(float), Wk, cudaMemcpyDeviceToDevice, q));
+    return GEM_OK;
+}
+
+// Slice boundaries of a call over W windows: the caller's (gem_ctx_set_slices) when they fit, else n_chunks
+// equal parts at multiples of 12 windows (the tap kernel's M tile), at least 96 windows each.
+static std::vector<int> slice_bounds(const gem_ctx* c, int W) {
+    std::vector<int> w0;
+    if (!c->prof_on && !c->user_slices.empty() && c->user_slices.back() < W) {
+        w0 = c->user_slices;
+        w0.push_back(W);
+        return w0;
+    }
+    int n = c->prof_on ? 1 : c->n_chunks;
+    const int kAlign = 12, kMinChunk = 96;
+    if (n > W / kMinChunk) n = W / kMinChunk;
+    if (n < 1) n = 1;
+    w0.assign(n + 1, W);
+    w0[0] = 0;
+    for (int k = 1; k < n; ++k) w0[k] = (int)((int64_t)W * k / n) / kAlign * kAlign;
+    return w0;
+}
+
+struct Fork {
+    std::vector<cudaStream_t> cs;
+    bool forked = false;
+};
+// slice k runs on its own stream, after everything already on the caller's stream `s` and after the ready
+// events that cover its windows (gem_ctx_set_ready_events; consumed by this call)
+static int fork_slices(gem_ctx* c, cudaStream_t s, const std::vector<int>& w0, bool graphs, Fork* f) {
+    const int n = (int)w0.size() - 1;
+    f->forked = n > 1 || graphs || !c->ready.empty();      // (the caller's stream may be the legacy one: not capturable)
+    f->cs.assign(n, s);
+    if (!f->forked) return GEM_OK;
+    GEM_TRY(ensure_streams(c, n));
+    GEM_CUDA(cudaEventRecord(c->fork_ev, s));
+    for (int k = 0; k < n; ++k) {
+        f->cs[k] = c->streams[k];
+        GEM_CUDA(cudaStreamWaitEvent(f->cs[k], c->fork_ev, 0));
+        for (auto& r : c->ready)           // events are in window order: wait for all that cover windows below the slice end
+            if (r.first_window < w0[k + 1]) GEM_CUDA(cudaStreamWaitEvent(f->cs[k], r.ev, 0));
+    }
+    c->ready.clear();
+    return GEM_OK;
+}
+static int join_slices(gem_ctx* c, cudaStream_t s, const Fork& f) {
+    if (!f.forked) return GEM_OK;
+    for (size_t k = 0; k < f.cs.size(); ++k) {
+        GEM_CUDA(cudaEventRecord(c->join_ev[k], f.cs[k]));
+        GEM_CUDA(cudaStreamWaitEvent(s, c->join_ev[k], 0));
+    }
+    return GEM_OK;
+}
+
+static int check_stage_args(gem_ctx* c, int which, const gem_energy_weights* wt, const gem_lbfgs_params* p, bool want_trace) {
+    GEM_REQUIRE(p && p->max_iter >= 1 && p->max_eval >= 1 && p->lr > 0, "bad L-BFGS parameters");
+    GEM_REQUIRE(p->max_iter - 1 <= c->m, "max_iter - 1 exceeds the ctx's max_history");
+    if (!c->have_vae[which] || (wt->reproj != 0.f && !c->have_camera)) {
+        set_error("VAE weights / camera not set");
+        return GEM_ERR_STATE;
+    }
+    if (want_trace && p->max_eval + 1 > c->trace_cap) {
+        set_error("max_eval exceeds the trace capacity of the ctx (raise max_history)");
+        return GEM_ERR_CAPACITY;
+    }
+    return GEM_OK;
+}
+
+extern "C" {
+
+int gem_ctx_set_slices(gem_ctx* c, int n, const int32_t* first_window_h) {
+    GEM_REQUIRE(c != nullptr && n >= 0 && n <= 64 && (n == 0 || first_window_h), "bad arguments");
+    std::vector<int> v;
+    for (int i = 0; i < n; ++i) {
+        GEM_REQUIRE(first_window_h[i] % 2 == 0 && (i == 0 ? first_window_h[i] == 0 : first_window_h[i] > first_window_h[i - 1]),
+                    "slice starts must be even, strictly increasing and begin at 0");
+        v.push_back(first_window_h[i]);
+    }
+    c->user_slices = v;
+    return GEM_OK;
+}
+
+int gem_ctx_set_ready_events(gem_ctx* c, int n, const int32_t* first_window_h, void* const* events_h) {
+    GEM_REQUIRE(c != nullptr && n >= 0 && (n == 0 || (first_window_h && events_h)), "bad arguments");
+    c->ready.clear();
+    for (int i = 0; i < n; ++i) c->ready.push_back({first_window_h[i], (cudaEvent_t)events_h[i]});
+    return GEM_OK;
+}
+
 int gem_solve_stage(gem_ctx* c, void* stream, int which, int W, const float* pose0_d, const float* heat_d,
                     const int64_t* frame_base_d, const int32_t* clip_d, const float* mean_bone_d, const float* eps_d,
                     const gem_energy_weights* wt, const gem_lbfgs_params* params_h, float* pose_out_d,
@@ -609,85 +888,65 @@ int gem_solve_stage(gem_ctx* c, void* stream, int which, int W, const float* pos
     GEM_ENTER(c, W);
     GEM_REQUIRE((which == 0 || which == 1) && pose0_d && clip_d && mean_bone_d && eps_d && wt && params_h && pose_out_d,
                 "bad arguments");
-    if (!c->have_vae[which] || (wt->reproj != 0.f && !c->have_camera)) {
-        set_error("VAE weights / camera not set");
-        return GEM_ERR_STATE;
-    }
+    GEM_REQUIRE(wt->reproj == 0.f || (heat_d && frame_base_d), "heatmaps required when reproj != 0");
+    GEM_TRY(check_stage_args(c, which, wt, params_h, energy_trace_d != nullptr));
     cudaStream_t s = (cudaStream_t)stream;
     if (W == 0) return GEM_OK;
-    GEM_TRY(lbfgs_configure(c, params_h, energy_trace_d, energy_trace_d ? params_h->max_eval + 1 : 0));
-    if (status_d) GEM_CUDA(cudaMemsetAsync(status_d, 0, (size_t)W * sizeof(uint32_t), s));
-    if (energy_trace_d)
-        GEM_CUDA(cudaMemsetAsync(energy_trace_d, 0xff, (size_t)W * (params_h->max_eval + 1) * sizeof(float), s));   // NaN
-    // z0 = mu + eps * std                                   optimizer.py:255-259
-    GEM_TRY(encode_impl(c, s, which, W, pose0_d, eps_d, c->z0, nullptr, nullptr));
+    GEM_TRY(lbfgs_configure(c, params_h, nullptr, 0));
+    StageCall a;
+    a.which = which, a.pose0 = pose0_d, a.heat = heat_d, a.frame_base = frame_base_d, a.clip = clip_d;
+    a.mean_bone = mean_bone_d, a.eps = eps_d, a.eps_stride = (size_t)c->n, a.wt = *wt, a.p = *params_h;
+    a.pose_out = pose_out_d, a.trace = energy_trace_d, a.n_iter = n_iter_d, a.func_evals = func_evals_d, a.status = status_d;
+    const bool graphs = c->use_graphs && !c->prof_on;
+    const std::vector<int> w0 = slice_bounds(c, W);
+    Fork f;
+    GEM_TRY(fork_slices(c, s, w0, graphs, &f));
+    for (size_t k = 0; k + 1 < w0.size(); ++k) GEM_TRY(enqueue_stage_slice(c, f.cs[k], a, w0[k], w0[k + 1] - w0[k], graphs));
+    c->lb_started = true;
+    return join_slices(c, s, f);
+}
 
-    // The windows are independent: split them into chunks that run the same kernel sequence on separate
-    // streams, so that one chunk's launch gaps, tails and HBM-bound L-BFGS updates overlap another chunk's
-    // tensor-core layers.  Chunk boundaries are multiples of 12 windows (the tap kernel's M tile).
-    int nchunks = c->prof_on ? 1 : c->n_chunks;
-    const int kAlign = 12, kMinChunk = 96;
-    if (nchunks > W / kMinChunk) nchunks = W / kMinChunk;
-    if (nchunks < 1) nchunks = 1;
-    GEM_TRY(ensure_streams(c, nchunks));
-    std::vector<int> w0(nchunks + 1, W);
-    w0[0] = 0;
-    for (int k = 1; k < nchunks; ++k) w0[k] = (int)((int64_t)W * k / nchunks) / kAlign * kAlign;
-    std::vector<cudaStream_t> cs(nchunks, s);
-    if (nchunks > 1) {
-        GEM_CUDA(cudaEventRecord(c->fork_ev, s));
-        for (int k = 0; k < nchunks; ++k) {
-            cs[k] = c->streams[k];
-            GEM_CUDA(cudaStreamWaitEvent(cs[k], c->fork_ev, 0));
-        }
-    }
+int gem_solve_windows(gem_ctx* c, void* stream, int W, const float* pose0_d, const float* heat_d,
+                      const int64_t* frame_base_d, const int32_t* clip_d, const float* mean_bone_d, const double* cams_d,
+                      const float* eps_d, const gem_energy_weights* wt_local, const gem_energy_weights* wt_global,
+                      const gem_lbfgs_params* params_h, float* local_pose_d, double* rel_f64_d, float* rel_f32_d,
+                      float* global_pose_d, int32_t* n_iter_d, int32_t* func_evals_d, uint32_t* status_d) {
+    GEM_ENTER(c, W);
+    GEM_REQUIRE(pose0_d && clip_d && mean_bone_d && cams_d && eps_d && wt_local && wt_global && params_h && local_pose_d &&
+                    rel_f32_d && global_pose_d,
+                "bad arguments");
+    GEM_REQUIRE(wt_local->reproj == 0.f || (heat_d && frame_base_d), "heatmaps required when reproj != 0");
+    GEM_REQUIRE(wt_global->reproj == 0.f, "the global stage has no reprojection term (optimizer.py:344-358)");
+    GEM_TRY(check_stage_args(c, 0, wt_local, params_h, false));
+    GEM_TRY(check_stage_args(c, 1, wt_global, params_h, false));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (W == 0) return GEM_OK;
+    GEM_TRY(lbfgs_configure(c, params_h, nullptr, 0));
+    StageCall a, b;
+    a.which = 0, a.pose0 = pose0_d, a.heat = heat_d, a.frame_base = frame_base_d, a.clip = clip_d;
+    a.mean_bone = mean_bone_d, a.eps = eps_d, a.eps_stride = 2 * (size_t)c->n, a.wt = *wt_local, a.p = *params_h;
+    a.pose_out = local_pose_d, a.trace = nullptr, a.n_iter = n_iter_d, a.func_evals = func_evals_d, a.status = status_d;
+    b = a;
+    b.which = 1, b.pose0 = rel_f32_d, b.heat = nullptr, b.frame_base = nullptr, b.eps = eps_d + c->n, b.wt = *wt_global;
+    b.pose_out = global_pose_d, b.status = nullptr;
+    b.n_iter = n_iter_d ? n_iter_d + W : nullptr, b.func_evals = func_evals_d ? func_evals_d + W : nullptr;
+    const bool graphs = c->use_graphs && !c->prof_on;
+    const std::vector<int> w0 = slice_bounds(c, W);
+    Fork f;
+    GEM_TRY(fork_slices(c, s, w0, graphs, &f));
     const size_t P = (size_t)c->T * c->J * 3;
-    std::vector<Slice> sl;
-    for (int k = 0; k < nchunks; ++k) sl.push_back(slice_of(c, w0[k]));
-    for (int k = 0; k < nchunks; ++k) {
+    for (size_t k = 0; k + 1 < w0.size(); ++k) {
         const int Wk = w0[k + 1] - w0[k];
-        GEM_TRY(timed(c, cs[k], GEM_TAG_LBFGS_BEGIN,
-                      [&]() { return launch_lbfgs_begin(cs[k], sl[k].lb, c->z0 + (size_t)w0[k] * c->n, Wk); }));
+        cudaStream_t q = f.cs[k];
+        GEM_TRY(enqueue_stage_slice(c, q, a, w0[k], Wk, graphs));                      // local stage     optimizer.py:386
+        GEM_TRY(timed(c, q, GEM_TAG_TRANSFORM, [&]() {                                  // SLAM transform  optimizer.py:394-398
+            return launch_transform(q, Wk, c->T, c->J, local_pose_d + w0[k] * P, 0, cams_d + (size_t)w0[k] * c->T * 16,
+                                    rel_f64_d ? rel_f64_d + w0[k] * P : nullptr, rel_f32_d + w0[k] * P, 0);
+        }));
+        GEM_TRY(enqueue_stage_slice(c, q, b, w0[k], Wk, graphs));                      // global stage    optimizer.py:414
     }
     c->lb_started = true;
-    // LBFGS.step: at most max_eval + 1 closure evaluations per window (lbfgs.py:478-487, App. B)
-    const bool tc = use_tc_chain(c, which, W);
-    for (int round = 0; round <= params_h->max_eval; ++round) {
-        for (int k = 0; k < nchunks; ++k) {
-            const int Wk = w0[k + 1] - w0[k];
-            const Slice& v = sl[k];
-            cudaStream_t q = cs[k];
-            GEM_TRY(decode_impl(c, q, which, Wk, v, v.lb.ZT, v.pose, tc ? v.lb.ZT_hi : nullptr, tc ? v.lb.ZT_lo : nullptr));
-            GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
-                return launch_energy_grad(q, Wk, c->T, c->J, c->H, c->Wd, v.pose, pose0_d + w0[k] * P, heat_d,
-                                          frame_base_d ? frame_base_d + w0[k] : nullptr, clip_d + w0[k], mean_bone_d, *wt,
-                                          v.f_new, nullptr, v.gpose, status_d ? status_d + w0[k] : nullptr);
-            }));
-            GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, v.gpose, v.g_new));
-            GEM_TRY(timed(c, q, GEM_TAG_LBFGS_ADVANCE,
-                          [&]() { return launch_lbfgs_advance(q, v.lb, v.f_new, v.g_new, Wk); }));
-        }
-    }
-    // final decode of the optimum (every window is parked with its trial point = x)      optimizer.py:273-276
-    for (int k = 0; k < nchunks; ++k) {
-        const int Wk = w0[k + 1] - w0[k];
-        const Slice& v = sl[k];
-        GEM_TRY(decode_impl(c, cs[k], which, Wk, v, v.lb.X, pose_out_d + w0[k] * P, tc ? v.lb.ZT_hi : nullptr,
-                            tc ? v.lb.ZT_lo : nullptr));
-        GEM_TRY(timed(c, cs[k], GEM_TAG_OTHER, [&]() {
-            return launch_lbfgs_stats(cs[k], v.lb, Wk, n_iter_d ? n_iter_d + w0[k] : nullptr,
-                                      func_evals_d ? func_evals_d + w0[k] : nullptr, nullptr, nullptr, nullptr);
-        }));
-    }
-    if (nchunks > 1) {
-        for (int k = 0; k < nchunks; ++k) {
-            GEM_CUDA(cudaEventRecord(c->join_ev[k], cs[k]));
-            GEM_CUDA(cudaStreamWaitEvent(s, c->join_ev[k], 0));
-        }
-    }
-    c->lb.trace = nullptr;   // the caller's buffer is not retained
-    c->lb.trace_stride = 0;
-    return GEM_OK;
+    return join_slices(c, s, f);
 }
 
 int gem_relative_global(gem_ctx* c, void* stream, int W, const void* pose_d, int pose_is_f64, const double* cams_d,

@@ -329,6 +329,16 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
     return GEM_OK;
 }
 
+// x -> (hi, lo) TF32 parts for M rows of K floats (K % 4 == 0; output pitch K)
+int launch_split_tf32(cudaStream_t stream, const float* A, int lda, int M, int K, float* hi, float* lo) {
+    if (M <= 0) return GEM_OK;
+    GEM_REQUIRE(K % 4 == 0 && lda % 4 == 0, "K and lda must be multiples of 4");
+    const size_t n4 = (size_t)M * (K / 4);
+    split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(A, lda, M, K, hi, lo);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
 // Transposes B [K][ldb] to K-major [N][K] and splits it into TF32 hi / lo parts; replaces any earlier
 // registration of the same pointer (the caller may have refilled the buffer).
 int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N) {

@@ -28,6 +28,7 @@ struct TapGemmArgs {
 int launch_tap_gemm_simt(cudaStream_t stream, const TapGemmArgs& g);
 int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, size_t reserved);
 int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N);
+int launch_split_tf32(cudaStream_t stream, const float* A, int lda, int M, int K, float* hi, float* lo);
 void tc_gemm_release(void* owner);
 bool tc_gemm_available();
 
@@ -70,7 +71,8 @@ int launch_lbfgs_advance(cudaStream_t stream, const LbfgsBuffers& b, const float
 int launch_lbfgs_stats(cudaStream_t stream, const LbfgsBuffers& b, int W, int32_t* n_iter, int32_t* evals,
                        int32_t* finished, double* t, double* loss);
 
-int launch_reparam(cudaStream_t stream, const float* fc, const float* eps, float* z0, float* mu, float* sd, int W, int n);
+int launch_reparam(cudaStream_t stream, const float* fc, const float* eps, size_t eps_stride, float* z0, float* mu,
+                   float* sd, int W, int n);
 int launch_transform(cudaStream_t stream, int W, int T, int J, const void* pose, int pose_is_f64, const double* cams,
                      double* out64, float* out32, int mode);
 int launch_merge(cudaStream_t stream, int W, int T, int overlap, int row, const double* win, double* out);

@@ -5,24 +5,25 @@
 namespace gem {
 
 // z0 = eps * exp(0.5 * logvar) + mu        (SeqConvVAE.py:159-169, 184-189); fc = [W][2n] (mu | logvar)
-__global__ void reparam_kernel(const float* __restrict__ fc, const float* __restrict__ eps, float* __restrict__ z0,
-                               float* __restrict__ mu_out, float* __restrict__ std_out, int W, int n) {
+__global__ void reparam_kernel(const float* __restrict__ fc, const float* __restrict__ eps, size_t eps_stride,
+                               float* __restrict__ z0, float* __restrict__ mu_out, float* __restrict__ std_out, int W,
+                               int n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)W * n) return;
     const size_t w = i / n, c = i - w * n;
     const float mu = fc[w * 2 * n + c];
     const float lv = fc[w * 2 * n + n + c];
     const float sd = expf(0.5f * lv);
-    z0[i] = eps[i] * sd + mu;
+    z0[i] = eps[w * eps_stride + c] * sd + mu;
     if (mu_out) mu_out[i] = mu;
     if (std_out) std_out[i] = sd;
 }
 
-int launch_reparam(cudaStream_t stream, const float* fc, const float* eps, float* z0, float* mu, float* sd, int W,
-                   int n) {
+int launch_reparam(cudaStream_t stream, const float* fc, const float* eps, size_t eps_stride, float* z0, float* mu,
+                   float* sd, int W, int n) {
     if (W <= 0) return GEM_OK;
     const size_t total = (size_t)W * n;
-    reparam_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fc, eps, z0, mu, sd, W, n);
+    reparam_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fc, eps, eps_stride, z0, mu, sd, W, n);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }

@@ -92,6 +92,21 @@ class Engine:
         """Number of window slices a stage runs concurrently on internal streams (results are unaffected)."""
         check(self.lib.gem_ctx_set_chunks(self._ctx, int(n_chunks)))
 
+    def set_slices(self, first_windows):
+        """Explicit slice boundaries (first window of each slice, even, starting at 0); None/[] = automatic."""
+        fw = list(first_windows or [])
+        arr = (C.c_int32 * max(len(fw), 1))(*fw)
+        check(self.lib.gem_ctx_set_slices(self._ctx, len(fw), arr))
+
+    def set_ready_events(self, first_windows, events):
+        """One-shot for the next solve: ``events[i]`` (torch.cuda.Event) completes when the inputs of the windows
+        from ``first_windows[i]`` up to the next entry are resident."""
+        n = len(events)
+        fw = (C.c_int32 * max(n, 1))(*[int(v) for v in first_windows])
+        ev = (C.c_void_p * max(n, 1))(*[C.c_void_p(e.cuda_event) for e in events])
+        self._keep_events = list(events)
+        check(self.lib.gem_ctx_set_ready_events(self._ctx, n, fw, ev))
+
     def _dev(self, t, dtype):
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(np.asarray(t))
@@ -237,6 +252,33 @@ class Engine:
                                        C.byref(weights), C.byref(params), self._p(pose_out), self._p(trace),
                                        self._p(n_iter), self._p(evals), self._p(status)))
         return dict(pose=pose_out, trace=trace, n_iter=n_iter, func_evals=evals, status=status)
+
+    def solve_windows(self, pose0, heat, frame_base, clip, mean_bone, cams, eps, w_local: EnergyWeights,
+                      w_global: EnergyWeights, params: LbfgsParams):
+        """Local stage -> SLAM transform -> global stage for W windows, slice by slice (gem_solve_windows)."""
+        pose0, eps = self._dev(pose0, torch.float32), self._dev(eps, torch.float32)
+        W = pose0.shape[0]
+        self._check_w(W)
+        heat = None if heat is None else self._dev(heat, torch.float32)
+        frame_base = None if frame_base is None else self._dev(frame_base, torch.int64)
+        clip = self._dev(clip, torch.int32)
+        mean_bone = self._dev(mean_bone, torch.float32).reshape(-1, self.J)
+        cams = self._dev(cams, torch.float64)
+        shape = (W, self.T, self.J, 3)
+        local = torch.empty(shape, dtype=torch.float32, device=self.device)
+        glob = torch.empty(shape, dtype=torch.float32, device=self.device)
+        rel32 = torch.empty(shape, dtype=torch.float32, device=self.device)
+        rel64 = torch.empty(shape, dtype=torch.float64, device=self.device)
+        n_iter = torch.empty(2, W, dtype=torch.int32, device=self.device)
+        evals = torch.empty_like(n_iter)
+        status = torch.empty(W, dtype=torch.int32, device=self.device)
+        check(self.lib.gem_solve_windows(self._ctx, self.stream, W, self._p(pose0), self._p(heat), self._p(frame_base),
+                                         self._p(clip), self._p(mean_bone), self._p(cams), self._p(eps),
+                                         C.byref(w_local), C.byref(w_global), C.byref(params), self._p(local),
+                                         self._p(rel64), self._p(rel32), self._p(glob), self._p(n_iter), self._p(evals),
+                                         self._p(status)))
+        return dict(local=dict(pose=local, n_iter=n_iter[0], func_evals=evals[0], status=status, trace=None),
+                    glob=dict(pose=glob, n_iter=n_iter[1], func_evals=evals[1], trace=None), rel64=rel64, rel32=rel32)
 
     # ------------------------------------------------------------------ SLAM transforms and stitching
     def relative_global(self, pose, cams, want_f32=True):

@@ -32,9 +32,14 @@ def stage_weights(vae_weight, smoothness_weight, bone_length_weight, weight_3d, 
 
 
 class WindowBatch:
-    """Device-resident inputs of all windows of a list of clips."""
+    """Device-resident inputs of all windows of a list of clips.
 
-    def __init__(self, engine: Engine, clips, pinned=False):
+    With ``copy_stream`` the host-to-device copies run on that stream, clip after clip, and every clip's
+    heat maps get a completion event: ``SequenceOptimizer.solve`` hands the events to the library, which
+    starts optimising the first clips while the later ones are still crossing PCIe (the clips become the
+    library's slices)."""
+
+    def __init__(self, engine: Engine, clips, copy_stream=None, min_piece_windows=96):
         dev = engine.device
         self.n_frames = [len(c["estimated_local_skeleton"]) for c in clips]
         self.starts = [window_starts(n, engine.T, OVERLAP) for n in self.n_frames]
@@ -46,34 +51,94 @@ class WindowBatch:
         self.W = int(fb.shape[0])
         clip_idx = np.concatenate([np.full(len(s), i, dtype=np.int32) for i, s in enumerate(self.starts)]
                                   or [np.zeros(0, np.int32)])
+        self.window_offsets = np.concatenate([[0], np.cumsum(self.n_windows)]).astype(np.int64)
+        self.ready_events, self.ready_first_windows = [], []
+
+        # small host-built index tensors first: a pageable H2D copy issued after the big heat-map copies would
+        # queue behind them on the copy engine
+        self.frame_base = torch.as_tensor(fb, device=dev)
+        self.clip_idx = torch.as_tensor(clip_idx, device=dev)
+        parents = torch.as_tensor(KINEMATIC_PARENTS, device=dev)
+        t_idx = self.frame_base[:, None] + torch.arange(engine.T, device=dev)[None, :]      # [W,T] frame ids
+        self.frame_idx = t_idx
 
         total = int(offs[-1])
 
-        def cat(key, dtype):
-            # one device buffer for all clips; each clip is copied straight into its slice
-            # (asynchronously when the source is a pinned torch tensor)
-            first = clips[0][key]
-            first = first if isinstance(first, torch.Tensor) else torch.as_tensor(np.asarray(first))
-            buf = torch.empty((total,) + tuple(first.shape[1:]), dtype=dtype, device=dev)
-            for i, c in enumerate(clips):
-                src = c[key] if isinstance(c[key], torch.Tensor) else torch.as_tensor(np.asarray(c[key]))
-                buf[offs[i]:offs[i + 1]].copy_(src, non_blocking=True)
-            return buf
+        def src_of(c, key):
+            return c[key] if isinstance(c[key], torch.Tensor) else torch.as_tensor(np.asarray(c[key]))
 
-        self.est = cat("estimated_local_skeleton", torch.float64)          # [F,15,3]
-        self.cams = cat("camera_pose_list", torch.float64)                 # [F,4,4]
-        self.gt = cat("gt_global_skeleton", torch.float64) if "gt_global_skeleton" in clips[0] else None
-        self.heat = cat("heatmap_list", torch.float32)                     # [F,H,W,15] (pickle's HWC layout, as is)
-        self.frame_base = torch.as_tensor(fb, device=dev)
-        self.clip_idx = torch.as_tensor(clip_idx, device=dev)
-        t_idx = self.frame_base[:, None] + torch.arange(engine.T, device=dev)[None, :]      # [W,T] frame ids
-        self.frame_idx = t_idx
+        def alloc(key, dtype):
+            first = src_of(clips[0], key)
+            return torch.empty((total,) + tuple(first.shape[1:]), dtype=dtype, device=dev)
+
+        def fill(buf, key, clip_range):
+            # each clip is copied straight into its slice (asynchronously when the source is a pinned tensor)
+            for i in clip_range:
+                buf[offs[i]:offs[i + 1]].copy_(src_of(clips[i], key), non_blocking=True)
+
+        has_gt = "gt_global_skeleton" in clips[0]
+        self.est = alloc("estimated_local_skeleton", torch.float64)        # [F,15,3]
+        self.cams = alloc("camera_pose_list", torch.float64)               # [F,4,4]
+        self.gt = alloc("gt_global_skeleton", torch.float64) if has_gt else None
+        self.heat = alloc("heatmap_list", torch.float32)                   # [F,H,W,15] (pickle's HWC layout, as is)
+        every = range(len(clips))
+        if copy_stream is None:
+            fill(self.est, "estimated_local_skeleton", every), fill(self.cams, "camera_pose_list", every)
+            if has_gt:
+                fill(self.gt, "gt_global_skeleton", every)
+            fill(self.heat, "heatmap_list", every)
+        else:
+            main = torch.cuda.current_stream(dev)
+            copy_stream.wait_stream(main)                # the buffers may be recycled blocks still in use on `main`
+            with torch.cuda.stream(copy_stream):
+                # the small per-frame arrays of every clip first: the host-side bookkeeping below needs them all
+                fill(self.est, "estimated_local_skeleton", every), fill(self.cams, "camera_pose_list", every)
+                if has_gt:
+                    fill(self.gt, "gt_global_skeleton", every)
+                small = torch.cuda.Event()
+                small.record(copy_stream)
+                # heat maps in pieces of whole windows (a clip is cut while its pieces keep >= min_piece_windows
+                # windows and an even window count): piece = windows [a, b) -> frames up to 8(b-1)+T, the next
+                # piece starts where this one ended
+                stride = engine.T - OVERLAP
+                for i in every:
+                    nw = self.n_windows[i]
+                    if nw == 0:
+                        continue
+                    n_pieces = max(1, min(4, nw // max(min_piece_windows, 1)))
+                    cuts = [(nw * k // n_pieces) // 2 * 2 for k in range(n_pieces)] + [nw]
+                    src = src_of(clips[i], "heatmap_list")
+                    f_prev = 0
+                    for k in range(n_pieces):
+                        a, b = cuts[k], cuts[k + 1]
+                        f_end = self.n_frames[i] if k == n_pieces - 1 else stride * (b - 1) + engine.T
+                        self.heat[offs[i] + f_prev:offs[i] + f_end].copy_(src[f_prev:f_end], non_blocking=True)
+                        f_prev = f_end
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                        self.ready_events.append(ev)
+                        self.ready_first_windows.append(int(self.window_offsets[i]) + a)
+            main.wait_event(small)
+            for t in (self.est, self.cams, self.gt, self.heat):
+                if t is not None:
+                    t.record_stream(copy_stream)
         # mean bone length per clip from the fp32 cast of the whole clip's local estimate
         # (BodyPoseOptimizer.__init__, optimizer.py:42-43, 333, 343)
-        parents = torch.as_tensor(KINEMATIC_PARENTS, device=dev)
         est32 = self.est.to(torch.float32)
         bone = torch.linalg.vector_norm(est32 - est32[:, parents, :], dim=-1)   # [F,15]
         self.mean_bone = torch.stack([bone[offs[i]:offs[i + 1]].mean(0) for i in range(len(clips))])
+
+    def clip_slices(self, min_windows=96):
+        """Slice starts for the library: the upload pieces when the batch was uploaded on a copy stream, else
+        the clips; None (automatic slicing) when a start is odd or a slice would be too small."""
+        if self.ready_first_windows:
+            starts = list(self.ready_first_windows)
+        else:
+            starts = [int(self.window_offsets[i]) for i, n in enumerate(self.n_windows) if n > 0]
+        sizes = np.diff(starts + [self.W])
+        if len(starts) < 2 or len(starts) > 64 or any(s % 2 for s in starts) or sizes.min() < min_windows:
+            return None
+        return starts
 
     def gather(self, per_frame):
         return per_frame[self.frame_idx]                                    # [W,T,...]
@@ -88,6 +153,7 @@ class SequenceOptimizer:
         self.w_local, self.w_global = stage_weights(vae_weight, smoothness_weight, bone_length_weight, weight_3d,
                                                     reproj_weight)
         self.params = lbfgs_params(lr=lr, max_iter=max_iter)
+        self.slice_by_clip = False      # resident inputs: let the library cut equal slices
 
     def solve(self, batch: WindowBatch, eps=None, want_trace=False):
         """Runs both stages for every window of ``batch``; returns per-window device tensors."""
@@ -98,6 +164,23 @@ class SequenceOptimizer:
         eps = eng._dev(eps, torch.float32)
         x_local64 = batch.gather(batch.est)                               # [W,T,15,3] f64
         cams_w = batch.gather(batch.cams)                                 # [W,T,4,4] f64
+        if not want_trace:
+            if batch.ready_events:
+                # inputs still in flight: one library slice per clip, each starting when its clip has landed
+                slices = batch.clip_slices()
+                eng.set_slices(slices)
+                if slices is not None:
+                    eng.set_ready_events(batch.ready_first_windows, batch.ready_events)
+                else:                                   # cannot slice by clip: wait for everything
+                    torch.cuda.current_stream(eng.device).wait_event(batch.ready_events[-1])
+            elif self.slice_by_clip:
+                eng.set_slices(batch.clip_slices())
+            # the whole per-window path in one call: local stage -> SLAM transform -> global stage, slice by
+            # slice on the library's internal streams                     optimizer.py:386-419
+            sol = eng.solve_windows(x_local64.to(torch.float32), batch.heat, batch.frame_base, batch.clip_idx,
+                                    batch.mean_bone, cams_w, eps, self.w_local, self.w_global, self.params)
+            sol.update(cams=cams_w, x_local64=x_local64)
+            return sol
         # local stage                                                     optimizer.py:386
         loc = eng.solve_stage(0, x_local64.to(torch.float32), batch.heat, batch.frame_base, batch.clip_idx,
                               batch.mean_bone, eps[:, 0], self.w_local, self.params, want_trace=want_trace)

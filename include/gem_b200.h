@@ -108,8 +108,19 @@ int gem_ctx_set_gemm_mode(gem_ctx* ctx, int mode);
  * multiples of 12 windows, at least 96 windows each) that run the same kernel sequence on internal streams,
  * forked from and joined to the caller's stream, so one slice's launch gaps and HBM-bound L-BFGS updates
  * overlap another's tensor-core layers.  Default 4 (env GEM_CHUNKS); 1 = everything on the caller's stream.
- * Results do not depend on the setting.  Profiling (gem_ctx_set_profiling) forces 1. */
+ * Results do not depend on the setting.  Profiling (gem_ctx_set_profiling) forces 1.
+ * Closure rounds 1.. of a stage replay a CUDA graph of round 0's launches (captured once per slice and
+ * configuration, cached in the ctx; env GEM_GRAPHS=0 disables). */
 int gem_ctx_set_chunks(gem_ctx* ctx, int n_chunks);
+/* Explicit slice boundaries instead of n_chunks equal parts: first_window_h[0] = 0 < first_window_h[1] < ...
+ * (all even).  Used by calls whose W exceeds the last entry; n = 0 returns to automatic slicing.  A caller
+ * that uploads its clips one after the other makes the slices the clips. */
+int gem_ctx_set_slices(gem_ctx* ctx, int n, const int32_t* first_window_h);
+/* One-shot, consumed by the next gem_solve_stage / gem_solve_windows: cudaEvent_t events_h[i] completes when
+ * the inputs (heatmaps, poses, cameras) of all windows in [first_window_h[i], first_window_h[i+1]) are in
+ * device memory.  A slice starts once every event covering windows below its end has completed, so the
+ * optimisation of the first clips overlaps the host-to-device copy of the later ones. */
+int gem_ctx_set_ready_events(gem_ctx* ctx, int n, const int32_t* first_window_h, void* const* events_h);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* kernel classes reported by gem_ctx_read_profile */
@@ -182,6 +193,19 @@ int gem_solve_stage(gem_ctx* ctx, void* stream, int which, int W, const float* p
                     const float* eps_d, const gem_energy_weights* weights_h, const gem_lbfgs_params* params_h,
                     float* pose_out_d, float* energy_trace_d, int32_t* n_iter_d, int32_t* func_evals_d,
                     uint32_t* status_d);
+
+/* ---- the whole per-window path: local stage -> SLAM transform -> global stage (optimizer.py:386-419) ----
+ * Per slice of windows, on the slice's stream: gem_solve_stage(which = 0) with weights_local_h, then
+ * gem_relative_global of its result with cams_d [W][T][4][4] float64, then gem_solve_stage(which = 1) with
+ * weights_global_h (reproj must be 0) anchored at the transformed pose.  eps_d is [W][2][latent] (local, global).
+ * Outputs: local_pose_d, global_pose_d [W][T][J][3] fp32; rel_f32_d (required) / rel_f64_d (optional) the
+ * transformed local result; n_iter_d, func_evals_d [2][W] (optional); status_d [W] (optional, local stage). */
+int gem_solve_windows(gem_ctx* ctx, void* stream, int W, const float* pose0_d, const float* heat_d,
+                      const int64_t* frame_base_d, const int32_t* clip_d, const float* mean_bone_d,
+                      const double* cams_d, const float* eps_d, const gem_energy_weights* weights_local_h,
+                      const gem_energy_weights* weights_global_h, const gem_lbfgs_params* params_h,
+                      float* local_pose_d, double* rel_f64_d, float* rel_f32_d, float* global_pose_d,
+                      int32_t* n_iter_d, int32_t* func_evals_d, uint32_t* status_d);
 
 /* ---- SLAM camera transforms and stitching (float64 like the reference's numpy) ----------- */
 /* get_relative_global_pose_with_camera_matrix (utils/utils.py:99-112): out[w][t] = inv(C[w][0]) C[w][t] x.
