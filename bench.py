@@ -27,6 +27,9 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)

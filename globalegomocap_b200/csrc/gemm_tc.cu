@@ -24,6 +24,8 @@
 //            LeakyReLU, 128-byte row segments straight to global memory
 // Weights are transposed to K-major [N][K] and split once per checkpoint; activations are split by a
 // small elementwise kernel before each GEMM.
+#include <stdlib.h>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -35,31 +37,45 @@ using namespace tc;
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32;        // BK fp32 = 128 bytes = one swizzle row
+constexpr int BM = 128, BK = 32;                  // BK fp32 = 128 bytes = one swizzle row
 constexpr int kStages = 3;
-constexpr int kTileBytes = BM * BK * 4;           // 16 KB
-constexpr int kStageBytes = 4 * kTileBytes;       // A_hi, A_lo, B_hi, B_lo
-constexpr int kAcc = 4;                           // independent fp32 accumulators (see below)
-constexpr int kTmemCols = kAcc * BN;              // 512 = all of TMEM
+constexpr int kATileBytes = BM * BK * 4;          // 16 KB
 constexpr int kThreads = 192;
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kTmemCols = 512;                    // all of TMEM: up to four BN-column accumulators
 
-constexpr uint32_t kInstrDesc = instr_desc_tf32(BM, BN);
+// The N tile is a template parameter chosen per launch (launch_tap_gemm_tc): with ~15 M tiles the tile count
+// of a 128-wide N tile lands just above a multiple of the 148 SMs (300 tiles = 2.03 waves for the latent ->
+// T*256 layer); 160 / 112 / 144 columns bring it under the wave boundary.
+template <int BN>
+struct GemmCfg {
+    static constexpr int kBTileBytes = BN * BK * 4;
+    static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;      // A_hi, A_lo, B_hi, B_lo
+    static constexpr int kAcc = (kTmemCols / BN) < 4 ? (kTmemCols / BN) : 4;   // independent fp32 accumulators
+    static constexpr int kPitch = BN + 4;                                      // staging row pitch (floats)
+    static constexpr int kStageOut = 32 * kPitch * 4;                          // one warp's staged 32 x BN block
+    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(BN % 16 == 0 && BN <= 256, "UMMA N");
+    static_assert(kBTileBytes % 1024 == 0, "B tile must keep the swizzle atom alignment");
+    static_assert(8 * kStageOut <= kStages * kStageBytes, "epilogue staging must fit in the pipeline's memory");
+};
 
 struct TcArgs {
     const float* bias;
     float* C;        // result, or its TF32 hi part when C_lo is set
     float* C_lo;     // optional: the epilogue writes the result already split for the next tensor-core layer
-    uint32_t* sign;  // optional: packed sign bits of the result, [M][N/32]
+    uint32_t* sign;  // optional: packed sign bits of the result, [M][N/32] (needs BN % 32 == 0)
     int M, N, K, ldc, epi;
 };
 
+template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, TcArgs g) {
+    using C = GemmCfg<BN>;
+    constexpr int kAcc = C::kAcc;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * C::kStageBytes);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full_bar = empty_bar + kStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -87,82 +103,112 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const int s = kb % kStages;
                 const uint32_t parity = ((kb / kStages) & 1) ^ 1;
                 mbar_wait(&empty_bar[s], parity);
-                uint8_t* st = smem + s * kStageBytes;
-                mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-                tma_load_2d(st + 0 * kTileBytes, &map_a_hi, kb * BK, m0, &full_bar[s]);
-                tma_load_2d(st + 1 * kTileBytes, &map_a_lo, kb * BK, m0, &full_bar[s]);
-                tma_load_2d(st + 2 * kTileBytes, &map_b_hi, kb * BK, n0, &full_bar[s]);
-                tma_load_2d(st + 3 * kTileBytes, &map_b_lo, kb * BK, n0, &full_bar[s]);
+                uint8_t* st = smem + s * C::kStageBytes;
+                mbar_arrive_expect_tx(&full_bar[s], C::kStageBytes);
+                tma_load_2d(st, &map_a_hi, kb * BK, m0, &full_bar[s]);
+                tma_load_2d(st + kATileBytes, &map_a_lo, kb * BK, m0, &full_bar[s]);
+                tma_load_2d(st + 2 * kATileBytes, &map_b_hi, kb * BK, n0, &full_bar[s]);
+                tma_load_2d(st + 2 * kATileBytes + C::kBTileBytes, &map_b_lo, kb * BK, n0, &full_bar[s]);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc_tf32(BM, BN);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kStages;
                 mbar_wait(&full_bar[s], (kb / kStages) & 1);
                 tc_fence_after();
-                const uint32_t base = smem_u32(smem + s * kStageBytes);
-                const uint64_t a_hi = make_smem_desc(base + 0 * kTileBytes), a_lo = make_smem_desc(base + 1 * kTileBytes);
-                const uint64_t b_hi = make_smem_desc(base + 2 * kTileBytes), b_lo = make_smem_desc(base + 3 * kTileBytes);
+                const uint32_t base = smem_u32(smem + s * C::kStageBytes);
+                const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + kATileBytes);
+                const uint64_t b_hi = make_smem_desc(base + 2 * kATileBytes);
+                const uint64_t b_lo = make_smem_desc(base + 2 * kATileBytes + C::kBTileBytes);
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {
                     const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);     // 32 bytes per K=8 step inside the 128-B row
                     // small terms first, then the dominant one
                     const uint32_t acc = tmem_base + (uint32_t)((kb % kAcc) * BN);
-                    umma_tf32(acc, a_lo + adv, b_hi + adv, kInstrDesc, (kb >= kAcc) || (k != 0));
-                    umma_tf32(acc, a_hi + adv, b_lo + adv, kInstrDesc, 1);
-                    umma_tf32(acc, a_hi + adv, b_hi + adv, kInstrDesc, 1);
+                    umma_tf32(acc, a_lo + adv, b_hi + adv, idesc, (kb >= kAcc) || (k != 0));
+                    umma_tf32(acc, a_hi + adv, b_lo + adv, idesc, 1);
+                    umma_tf32(acc, a_hi + adv, b_hi + adv, idesc, 1);
                 }
                 umma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs have read it
             }
-            umma_commit(tmem_full_bar);              // accumulator complete
+            umma_commit(tmem_full_bar);              // accumulators complete
         }
     } else {
         // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
+        // The accumulators' sum, bias and activation are formed one row per thread, staged in the (now idle)
+        // pipeline memory and written out by the whole warp along the rows: 128-byte segments per instruction
+        // instead of 32 row segments of 16 bytes.
         const int q = warp & 3;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int m = m0 + q * 32 + lane;
+        float* stage_hi = reinterpret_cast<float*>(smem + (size_t)(q * 2 + 0) * C::kStageOut);
+        float* stage_lo = reinterpret_cast<float*>(smem + (size_t)(q * 2 + 1) * C::kStageOut);
+        const int nacc = num_kb < kAcc ? num_kb : kAcc;
+        uint32_t sbits = 0;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
-            tmem_ld_32x32b_x32(taddr, v);
+        for (int c = 0; c < BN / 16; ++c) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16);
+            tmem_ld_32x32b_x16(taddr, v);
             tmem_ld_wait();
-            const int nacc = num_kb < kAcc ? num_kb : kAcc;
             for (int a = 1; a < nacc; ++a) {
-                uint32_t t[32];
-                tmem_ld_32x32b_x32(taddr + (uint32_t)(a * BN), t);
+                uint32_t t[16];
+                tmem_ld_32x32b_x16(taddr + (uint32_t)(a * BN), t);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t[j]));
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t[j]));
             }
-            if (m < g.M) {
-                const int nb = n0 + c * 32;
-                uint32_t sbits = 0;
-                float* dst = g.C + (size_t)m * g.ldc + nb;
+            const int nb = n0 + c * 16;
+            float o[16];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    float* po = reinterpret_cast<float*>(&o);
+            for (int j = 0; j < 16; ++j) {
+                float x = __uint_as_float(v[j]);
+                if (g.bias && nb + j < g.N) x += __ldg(g.bias + nb + j);
+                if (g.epi == EPI_LRELU) x = x > 0.f ? x : x * 0.01f;
+                o[j] = x;
+            }
+            if (g.sign) {
+                const int sh = (c & 1) * 16;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float x = __uint_as_float(v[j + e]);
-                        if (g.bias) x += __ldg(g.bias + nb + j + e);
-                        if (g.epi == EPI_LRELU) x = x > 0.f ? x : x * 0.01f;
-                        po[e] = x;
-                        sbits |= (x > 0.f ? 1u : 0u) << (j + e);
-                    }
-                    if (g.C_lo) {
-                        float4 l;
-                        split_tf32(o.x, o.x, l.x), split_tf32(o.y, o.y, l.y), split_tf32(o.z, o.z, l.z), split_tf32(o.w, o.w, l.w);
-                        *reinterpret_cast<float4*>(g.C_lo + (size_t)m * g.ldc + nb + j) = l;
-                    }
-                    *reinterpret_cast<float4*>(dst + j) = o;
+                for (int j = 0; j < 16; ++j) sbits |= (o[j] > 0.f ? 1u : 0u) << (sh + j);
+                if (sh == 16 || c == BN / 16 - 1) {
+                    if (m < g.M && nb < g.N) g.sign[(size_t)m * (g.N >> 5) + (nb >> 5)] = sbits;
+                    sbits = 0;
                 }
-                if (g.sign) g.sign[(size_t)m * (g.N >> 5) + (nb >> 5)] = sbits;
             }
+            float* sh_row = stage_hi + lane * C::kPitch + c * 16;
+            if (g.C_lo) {
+                float* sl_row = stage_lo + lane * C::kPitch + c * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 h, l;
+                    split_tf32(o[j + 0], h.x, l.x), split_tf32(o[j + 1], h.y, l.y);
+                    split_tf32(o[j + 2], h.z, l.z), split_tf32(o[j + 3], h.w, l.w);
+                    *reinterpret_cast<float4*>(sh_row + j) = h;
+                    *reinterpret_cast<float4*>(sl_row + j) = l;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(sh_row + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            }
+        }
+        __syncwarp();
+        // coalesced write-out of this warp's 32 x BN block (N, ldc multiples of 4)
+        constexpr int kV4 = BN / 4;
+        const int rows = min(32, g.M - (m0 + q * 32));
+        const int ncols4 = min(kV4, (g.N - n0) / 4);
+        for (int i = lane; i < rows * kV4; i += 32) {
+            const int r = i / kV4, c4 = i - r * kV4;
+            if (c4 >= ncols4) continue;
+            const size_t off = (size_t)(m0 + q * 32 + r) * g.ldc + n0 + c4 * 4;
+            *reinterpret_cast<float4*>(g.C + off) = *reinterpret_cast<const float4*>(stage_hi + r * C::kPitch + c4 * 4);
+            if (g.C_lo)
+                *reinterpret_cast<float4*>(g.C_lo + off) = *reinterpret_cast<const float4*>(stage_lo + r * C::kPitch + c4 * 4);
         }
     }
     tc_fence_before();
@@ -213,23 +259,24 @@ __global__ void transpose_split_kernel(const float* __restrict__ B, int ldb, int
 
 // ---------------------------------------------------------------- host side
 // rows x K fp32 row-major (pitch K), box = 128 rows x 32 floats, 128-byte swizzle, OOB rows read zero
-int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t K, uint64_t pitch = 0) {
+int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t K, uint64_t pitch = 0, int box_rows = BM) {
     const uint64_t dims[2] = {K, rows};
     const uint64_t strides[1] = {(pitch ? pitch : K) * sizeof(float)};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)box_rows};
     return make_map_f32(map, base, 2, dims, strides, box);
 }
 
+constexpr int kNumBN = 4;
+constexpr int kBNs[kNumBN] = {112, 128, 144, 160};
 struct WeightSplit {
     float *hi = nullptr, *lo = nullptr;
     int K = 0, N = 0;
-    CUtensorMap map_hi, map_lo;
+    CUtensorMap map_hi[kNumBN], map_lo[kNumBN];       // one box height per N-tile width
 };
 struct TcState {
     std::unordered_map<const float*, WeightSplit> weights;   // keyed by the caller's weight pointer
     float *a_hi = nullptr, *a_lo = nullptr;
     size_t a_capacity = 0;                                    // floats in each of a_hi / a_lo
-    bool attr_set = false;
 };
 std::mutex g_mu;
 std::unordered_map<void*, TcState*> g_states;                // one per workspace owner (ctx)
@@ -277,10 +324,26 @@ int make_map_f32(CUtensorMap* map, const float* base, int rank, const uint64_t* 
 bool tc_gemm_available() { return true; }
 
 // `owner` identifies the ctx; scratch grows on demand and lives until tc_gemm_release(owner).
+template <int BN>
+static int launch_bn(cudaStream_t stream, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const WeightSplit& w, int idx,
+                     const TcArgs& a) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GEM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)GemmCfg<BN>::kSmemBytes));
+        attr_set = true;
+    }
+    dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN);
+    tc_gemm_kernel<BN><<<grid, kThreads, GemmCfg<BN>::kSmemBytes, stream>>>(a_hi, a_lo, w.map_hi[idx], w.map_lo[idx], a);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+// `owner` identifies the ctx; scratch grows on demand and lives until tc_gemm_release(owner).
 int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, size_t) {
     if (g.M <= 0) return GEM_OK;
     GEM_REQUIRE(g.taps == 1, "tcgen05 path handles plain GEMMs only");
-    GEM_REQUIRE(g.K % BK == 0 && g.N % BN == 0, "K must be a multiple of 32 and N of 128 for the tcgen05 path");
+    GEM_REQUIRE(g.K % BK == 0 && g.N % 128 == 0, "K must be a multiple of 32 and N of 128 for the tcgen05 path");
     GEM_REQUIRE(g.lda % 4 == 0 && g.ldc % 4 == 0, "lda/ldc must be multiples of 4");
     GEM_REQUIRE(g.epi == EPI_NONE || g.epi == EPI_LRELU, "unsupported epilogue on the tcgen05 path");
     TcState* st;
@@ -289,10 +352,6 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
         auto it = g_states.find(owner);
         if (it == g_states.end()) it = g_states.emplace(owner, new TcState()).first;
         st = it->second;
-    }
-    if (!st->attr_set) {
-        GEM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        st->attr_set = true;
     }
     // weights: K-major hi/lo copies registered by tc_gemm_prepare_weight
     auto wit = st->weights.find(g.B);
@@ -323,10 +382,30 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
     if (rc != GEM_OK) return rc;
     TcArgs a;
     a.bias = g.bias, a.C = g.C, a.C_lo = g.C_lo, a.sign = g.C_sign, a.M = g.M, a.N = g.N, a.K = g.K, a.ldc = g.ldc, a.epi = g.epi;
-    dim3 grid((g.M + BM - 1) / BM, g.N / BN);
-    tc_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_a_hi, map_a_lo, wit->second.map_hi, wit->second.map_lo, a);
-    GEM_CHECK_LAUNCH();
-    return GEM_OK;
+    // N-tile width.  Up to one wave of 128-wide tiles: keep 128 (kernels of concurrent slices share the SMs, the
+    // least padded tiling wins).  Beyond: the fewest waves x columns over the 148 SMs (sign words need
+    // 32-column alignment).
+    const int mt = (g.M + BM - 1) / BM;
+    int best = 1;
+    if ((long)mt * (g.N / 128) > kNumSMs) {
+        long best_cost = -1;
+        for (int i = 0; i < kNumBN; ++i) {
+            if (g.C_sign && kBNs[i] % 32 != 0) continue;
+            const long tiles = (long)mt * ((g.N + kBNs[i] - 1) / kBNs[i]);
+            const long cost = ((tiles + kNumSMs - 1) / kNumSMs) * kBNs[i];
+            if (best_cost < 0 || cost < best_cost || (cost == best_cost && kBNs[i] == 128)) best = i, best_cost = cost;
+        }
+    }
+    if (const char* env = getenv("GEM_GEMM_BN")) {
+        for (int i = 0; i < kNumBN; ++i)
+            if (atoi(env) == kBNs[i] && !(g.C_sign && kBNs[i] % 32 != 0)) best = i;
+    }
+    switch (kBNs[best]) {
+        case 112: return launch_bn<112>(stream, map_a_hi, map_a_lo, wit->second, best, a);
+        case 144: return launch_bn<144>(stream, map_a_hi, map_a_lo, wit->second, best, a);
+        case 160: return launch_bn<160>(stream, map_a_hi, map_a_lo, wit->second, best, a);
+        default: return launch_bn<128>(stream, map_a_hi, map_a_lo, wit->second, best, a);
+    }
 }
 
 // x -> (hi, lo) TF32 parts for M rows of K floats (K % 4 == 0; output pitch K)
@@ -342,7 +421,7 @@ int launch_split_tf32(cudaStream_t stream, const float* A, int lda, int M, int K
 // Transposes B [K][ldb] to K-major [N][K] and splits it into TF32 hi / lo parts; replaces any earlier
 // registration of the same pointer (the caller may have refilled the buffer).
 int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N) {
-    GEM_REQUIRE(K % BK == 0 && N % BN == 0, "K must be a multiple of 32 and N of 128 for the tcgen05 path");
+    GEM_REQUIRE(K % BK == 0 && N % 128 == 0, "K must be a multiple of 32 and N of 128 for the tcgen05 path");
     TcState* st;
     {
         std::lock_guard<std::mutex> lk(g_mu);
@@ -363,9 +442,11 @@ int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int
     dim3 grid((K + 31) / 32, (N + 31) / 32), block(32, 8);
     transpose_split_kernel<<<grid, block, 0, stream>>>(B, ldb, K, N, ws.hi, ws.lo);
     GEM_CHECK_LAUNCH();
-    int rc = make_map(&ws.map_hi, ws.hi, (uint64_t)N, (uint64_t)K);
-    if (rc == GEM_OK) rc = make_map(&ws.map_lo, ws.lo, (uint64_t)N, (uint64_t)K);
-    if (rc != GEM_OK) return rc;
+    for (int i = 0; i < kNumBN; ++i) {
+        int rc = make_map(&ws.map_hi[i], ws.hi, (uint64_t)N, (uint64_t)K, 0, kBNs[i]);
+        if (rc == GEM_OK) rc = make_map(&ws.map_lo[i], ws.lo, (uint64_t)N, (uint64_t)K, 0, kBNs[i]);
+        if (rc != GEM_OK) return rc;
+    }
     st->weights.emplace(B, ws);
     return GEM_OK;
 }
