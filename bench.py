@@ -36,6 +36,24 @@ if REPO not in sys.path:
 
 METRIC = "optimised frames/sec (windows x iters, device-timed)"
 FLOPS_PER_WINDOW_EVAL_ALGORITHMIC = 63.9e6   # decoder fwd + bwd-data as the reference runs it
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at W = 1870 from one `ncu --set full` capture of this
+# command (profiles/r01_ncu_full_tc_chain_summary.csv)
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 101.0e6             # mean of the latent->T*256 (104 MB) and T*256->latent (98 MB) layers
+NCU_LBFGS_DRAM_BYTES_PER_LAUNCH = 472.0e6
+NCU_ENERGY_DRAM_BYTES_PER_LAUNCH_LOCAL = 103.8e6
+
+
+def lbfgs_rows(sol):
+    """8 KB vector rows moved by the L-BFGS kernel over one step, from the executed counters: a window that ran I
+    iterations with E evaluations started iterations 1..I (10 vectors + 4(k-1) history rows when k pairs are
+    stored, k = 0..I-1... capped by the history) and had E - I line-search evaluations of 5 vectors."""
+    total = 0.0
+    for stage in ("local", "glob"):
+        it = sol[stage]["n_iter"].to("cpu").double()
+        ev = sol[stage]["func_evals"].to("cpu").double()
+        hist = (it - 1).clamp(min=0)                       # pairs stored when the last iteration started
+        total += float((10.0 * it + 4.0 * (hist * (hist - 1) / 2.0).clamp(min=0) + 5.0 * (ev - it).clamp(min=0)).sum())
+    return total
 
 
 def parse_args():
@@ -361,21 +379,48 @@ def main():
         g_ms = sum(per_tag[t]["ms_total"] for t in gemm_tags if t in per_tag)
         g_n = sum(per_tag[t]["launches"] for t in gemm_tags if t in per_tag)
         flop_per_launch = 2.0 * W * 2048 * 2560
-        roof = {"bound": "tensor", "kernel": "decoder latent<->T*256 GEMM (tags 100, 205)",
-                "achieved": flop_per_launch / (g_ms / max(g_n, 1) / 1e3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
-                "traffic": None, "peak_source": peak_src + ", bf16 sustained",
+        g_tf = flop_per_launch / (g_ms / max(g_n, 1) / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "tc_gemm_kernel: decoder latent<->T*256 GEMM (tags 100, 205)",
+                "achieved": g_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": g_tf / tf_peak,
+                # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the two layers
+                # (profiles/r01_ncu_full_tc_chain_summary.csv; algorithmic operand bytes are 36 MB + 42 MB weights)
+                "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH if W == 1870 else None,
+                "peak_source": peak_src + ", bf16 sustained",
                 "share_of_kernel_time": g_ms / max(kern_ms, 1e-9),
-                "note": "executed FLOPs of the fused layer (2*W*2048*2560 per launch); fp32-faithful arithmetic"}
-        roof["frac"] = roof["achieved"] / roof["peak"]
-        # energy kernel: HBM bound, 7.8 KB (local) / 5.4 KB (global) algorithmic bytes per window
+                "algorithmic_flop_per_launch": flop_per_launch,
+                "executed_tf32_tflops": 3.0 * g_tf,
+                "frac_of_tf32_pipe": 3.0 * g_tf / (tf_peak / 2.0),
+                "note": "achieved = algorithmic FLOPs of the layer (2*W*2048*2560) / mean launch duration; the kernel "
+                        "executes 3 TF32 MMAs per product (fp32-faithful 3xTF32), and TF32 runs at half the bf16 rate "
+                        "the peak was measured in, so frac is capped at 1/6; frac_of_tf32_pipe = executed TF32 "
+                        "FLOP/s / (bf16 peak / 2)"}
+        # the other rooflines: L-BFGS update (HBM) and the fused energy/gradient kernel (nominally HBM)
+        others = []
+        e = per_tag.get(3)
+        if e:
+            rows_total = lbfgs_rows(sol)          # 8 KB rows the executed iterations / evaluations move
+            bytes_per_launch = rows_total * 2048 * 4.0 / max(e["launches"], 1)
+            gbs = bytes_per_launch / (e["ms_avg"] / 1e3) / 1e9
+            others.append({"bound": "hbm", "kernel": "lbfgs_advance_kernel (tag 3)", "achieved": gbs, "peak": hbm_peak,
+                           "unit": "GB/s", "frac": gbs / hbm_peak, "ms_avg": e["ms_avg"], "launches": e["launches"],
+                           "traffic": NCU_LBFGS_DRAM_BYTES_PER_LAUNCH if W == 1870 else None,
+                           "note": "algorithmic bytes from the executed iteration counts: 10 vectors + 4(k-1) history "
+                                   "rows of 8 KB per window that starts iteration k+1, 5 vectors per line-search "
+                                   "evaluation; mean over the step's launches"})
+        # energy kernel: 7.8 KB (local) / 5.4 KB (global) algorithmic bytes per window
         e = per_tag.get(1)
         energy = None
         if e:
             bytes_per_launch = W * (7800 + 5400) / 2.0
-            energy = {"bound": "hbm", "achieved": bytes_per_launch / (e["ms_avg"] / 1e3) / 1e9, "peak": hbm_peak,
+            energy = {"bound": "hbm", "kernel": "energy_grad_kernel (tag 1)",
+                      "achieved": bytes_per_launch / (e["ms_avg"] / 1e3) / 1e9, "peak": hbm_peak,
                       "unit": "GB/s", "ms_avg": e["ms_avg"], "launches": e["launches"],
-                      "note": "mean of local (7.8 KB/window) and global (5.4 KB/window) launches"}
+                      "traffic": NCU_ENERGY_DRAM_BYTES_PER_LAUNCH_LOCAL if W == 1870 else None,
+                      "note": "mean of local (7.8 KB/window) and global (5.4 KB/window) launches; traffic = ncu DRAM "
+                              "bytes of a local-stage launch (32-byte sectors per 4-byte texel of the HWC maps); the "
+                              "kernel is issue-bound, see DESIGN.md section 5"}
             energy["frac"] = energy["achieved"] / hbm_peak
+            others.append(energy)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
@@ -387,7 +432,7 @@ def main():
                                                  "lbfgs_iterations_last_step": n_iter,
                                                  "rounds_per_step": rounds, "gemm_mode": args.gemm_mode}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
-                "energy_kernel": energy, "kernel_ms_per_step": {str(k): v["ms_total"] for k, v in sorted(per_tag.items())},
+                "other_rooflines": others, "energy_kernel": energy, "kernel_ms_per_step": {str(k): v["ms_total"] for k, v in sorted(per_tag.items())},
                 "kernel_pass": {"ms_per_step_single_stream_with_events": ms_prof,
                                 "note": "kernel_ms_per_step, roofline and energy_kernel come from one extra step run "
                                         "on a single stream with a CUDA-event pair around every launch"},
