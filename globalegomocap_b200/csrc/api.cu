@@ -320,6 +320,13 @@ int gem_ctx_set_skeleton(gem_ctx* c, const int32_t* parents_h, int num_joints) {
         sk.parent[j] = parents_h[j];
     }
     sk.num_joints = num_joints;
+    int nc = 0;
+    for (int j = 0; j < num_joints; ++j) {
+        sk.child_start[j] = nc;
+        for (int cj = 0; cj < num_joints; ++cj)
+            if (cj != j && parents_h[cj] == j) sk.child_list[nc++] = cj;
+    }
+    for (int j = num_joints; j <= kMaxJoints; ++j) sk.child_start[j] = nc;
     GEM_CUDA(cudaSetDevice(c->device));
     GEM_TRY(upload_skeleton(sk));
     c->have_skeleton = true;
@@ -470,7 +477,9 @@ static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice
     return run_layer(c, s, GEM_TAG_DEC + 5, v.dec[5], in, 64, M, pose_out, P, EPI_NONE, nullptr);
 }
 
-static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice& v_, const float* dpose, float* dz) {
+// dpose_is_split: the slice's gp_hi / gp_lo already hold dpose (written by the energy kernel)
+static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice& v_, const float* dpose, float* dz,
+                           bool dpose_is_split = false) {
     const gem_vae_weights& v = c->vae[which];
     const int T = c->T, M = W * T, P = c->J * 3;
     // the LeakyReLU derivative only needs the sign of the saved activation, which its TF32 hi part keeps
@@ -478,8 +487,9 @@ static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const S
     // dec_bwd[i] is the bwd-data of dec[5-i]; its output is d(pre-activation of dec[4-i])
     if (use_tc_chain(c, which, W)) {
         const int pp = pose_pad(c);
-        GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 0,
-                      [&]() { return launch_split_pad(s, dpose, P, (size_t)M, pp, v_.gp_hi, v_.gp_lo); }));
+        if (!dpose_is_split)
+            GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 0,
+                          [&]() { return launch_split_pad(s, dpose, P, (size_t)M, pp, v_.gp_hi, v_.gp_lo); }));
         const float *in_hi = v_.gp_hi, *in_lo = v_.gp_lo;
         int lda = pp;
         for (int i = 0; i < 5; ++i) {
@@ -726,9 +736,10 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
         GEM_TRY(decode_impl(c, q, which, Wk, v, lb.ZT, v.pose, tc ? lb.ZT_hi : nullptr, tc ? lb.ZT_lo : nullptr));
         GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
             return launch_energy_grad(q, Wk, c->T, c->J, c->H, c->Wd, v.pose, v.pose0_own, a.heat, v.fb_own, v.clip_own,
-                                      v.mb_own, a.wt, v.f_new, nullptr, v.gpose, v.status_own);
+                                      v.mb_own, a.wt, v.f_new, nullptr, v.gpose, v.status_own, tc ? v.gp_hi : nullptr,
+                                      v.gp_lo, pose_pad(c));
         }));
-        GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, v.gpose, v.g_new));
+        GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, v.gpose, v.g_new, tc));
         return timed(c, q, GEM_TAG_LBFGS_ADVANCE, [&]() { return launch_lbfgs_advance(q, lb, v.f_new, v.g_new, Wk); });
     };
     // LBFGS.step: at most max_eval + 1 closure evaluations per window (lbfgs.py:478-487, App. B)

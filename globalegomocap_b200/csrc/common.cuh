@@ -41,6 +41,8 @@ struct CameraConst {
 struct SkeletonConst {
     int parent[kMaxJoints];
     int num_joints;
+    int child_start[kMaxJoints + 1];   // CSR of each joint's children (joints whose parent it is, itself excluded)
+    int child_list[kMaxJoints];
 };
 
 // ---- warp / block reductions -------------------------------------------------------------

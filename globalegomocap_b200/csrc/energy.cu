@@ -32,6 +32,7 @@ int upload_skeleton(const SkeletonConst& sk) {
 constexpr int kSlot = 160;             // threads per window (>= T*J, multiple of 32)
 constexpr int kWinPerCta = 2;
 constexpr int kThreads = kSlot * kWinPerCta;
+constexpr int kSplitMax = 512;         // floats per window of the split gradient tile: T * pp <= 512
 
 struct EnergyArgs {
     const float* pose;
@@ -47,6 +48,10 @@ struct EnergyArgs {
     int W, T, J, H, Wd;
     float w3d, ws, wb, wv, wr;
     int use_bulk;
+    // optional: dE/dpose also as TF32 hi / lo parts in the token-major, zero-padded [W*T][pp] layout the
+    // tensor-core bwd-data layers read (saves a separate split pass)
+    float *gp_hi, *gp_lo;
+    int pp;
 };
 
 __device__ __forceinline__ float texel(const float* __restrict__ heat, int64_t frame, int y, int x, int j, int H,
@@ -61,6 +66,8 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
     __shared__ __align__(16) float s_g[kWinPerCta * kSlot * 3];
     __shared__ float s_red[kThreads / 32][5];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(16) float s_gh[kWinPerCta * kSplitMax];
+    __shared__ __align__(16) float s_gl[kWinPerCta * kSplitMax];
 
     const int tid = threadIdx.x;
     const int TJ = a.T * a.J;
@@ -149,8 +156,8 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
                 const float c = a.wb * (2.f * diff) / len;
                 gx += c * bx, gy += c * by, gz += c * bz;
             }
-            for (int cj = 0; cj < a.J; ++cj) {      // this joint as the parent of cj
-                if (cj == j || c_skel.parent[cj] != j) continue;
+            for (int ci = c_skel.child_start[j]; ci < c_skel.child_start[j + 1]; ++ci) {   // this joint as a parent
+                const int cj = c_skel.child_list[ci];
                 const float cx = X[(t * a.J + cj) * 3 + 0] - x, cy = X[(t * a.J + cj) * 3 + 1] - y,
                             cz = X[(t * a.J + cj) * 3 + 2] - z;
                 const float cl = sqrtf(cx * cx + cy * cy + cz * cz);
@@ -198,16 +205,20 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
                     const float ds_diy = -nw * wx0 - ne * wx1 + sw * wx0 + se * wx1;
                     const float du = ds_dix * ((float)(a.Wd - 1) * 0.5f / 512.f);   // dS/du
                     const float dv = ds_diy * ((float)(a.H - 1) * 0.5f / 512.f);    // dS/dv
-                    // fisheye Jacobian
-                    const float r2 = r * r, q = r2 + z * z, r3 = r2 * r;
-                    const float dth_dx = z * x / (r * q), dth_dy = z * y / (r * q), dth_dz = -r / q;
-                    const float xr = x / r, yr = y / r;
-                    const float du_dx = rho / r - x * x * rho / r3 + xr * drho * dth_dx;
-                    const float du_dy = -x * y * rho / r3 + xr * drho * dth_dy;
-                    const float du_dz = xr * drho * dth_dz;
-                    const float dv_dx = -x * y * rho / r3 + yr * drho * dth_dx;
-                    const float dv_dy = rho / r - y * y * rho / r3 + yr * drho * dth_dy;
-                    const float dv_dz = yr * drho * dth_dz;
+                    // fisheye Jacobian.  Only the energy's forward chain has to round like ATen's
+                    // ops; the gradient is held to 1e-4, so one reciprocal replaces the dozen IEEE divisions.
+                    const float r2 = r * r, q = r2 + z * z;
+                    const float inv_q = __frcp_rn(q), inv_rq = inv * inv_q;
+                    const float dth_dx = z * x * inv_rq, dth_dy = z * y * inv_rq, dth_dz = -r * inv_q;
+                    const float xr = x * inv, yr = y * inv;
+                    const float rho_r = rho * inv, rho_r3 = rho_r * inv * inv;
+                    const float xd = xr * drho, yd = yr * drho;
+                    const float du_dx = rho_r - x * x * rho_r3 + xd * dth_dx;
+                    const float du_dy = -x * y * rho_r3 + xd * dth_dy;
+                    const float du_dz = xd * dth_dz;
+                    const float dv_dx = -x * y * rho_r3 + yd * dth_dx;
+                    const float dv_dy = rho_r - y * y * rho_r3 + yd * dth_dy;
+                    const float dv_dz = yd * dth_dz;
                     gx -= a.wr * (du * du_dx + dv * dv_dx);
                     gy -= a.wr * (du * du_dy + dv * dv_dy);
                     gz -= a.wr * (du * du_dz + dv * dv_dz);
@@ -218,6 +229,18 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
     if (wl < kWinPerCta && k < TJ) {
         float* G = s_g + wl * n;
         G[k * 3 + 0] = gx, G[k * 3 + 1] = gy, G[k * 3 + 2] = gz;
+        if (a.gp_hi) {
+            const int t = k / a.J, j = k - t * a.J;
+            const int o = wl * a.T * a.pp + t * a.pp + j * 3;
+            const float g3[3] = {gx, gy, gz};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float h = __uint_as_float(__float_as_uint(g3[c]) & 0xFFFFE000u);
+                s_gh[o + c] = h, s_gl[o + c] = g3[c] - h;
+            }
+            if (j == 0)
+                for (int c = a.J * 3; c < a.pp; ++c) s_gh[wl * a.T * a.pp + t * a.pp + c] = 0.f, s_gl[wl * a.T * a.pp + t * a.pp + c] = 0.f;
+        }
     }
 
     // ---- per-window energy reduction: shuffle inside each warp, then kSlot/32 partials --------
@@ -245,21 +268,31 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
         if (a.wr != 0.f) E += a.wr * t5[4];
         a.energy[ww] = E;
     }
+    const int ns = a.T * a.pp;                     // floats per window of the split tile
     if (bulk) {
         if (tid == 0) {
             bulk_s2g(a.grad + (size_t)w0 * n, s_g, (uint32_t)(kWinPerCta * n * sizeof(float)));
+            if (a.gp_hi) {
+                bulk_s2g(a.gp_hi + (size_t)w0 * ns, s_gh, (uint32_t)(kWinPerCta * ns * sizeof(float)));
+                bulk_s2g(a.gp_lo + (size_t)w0 * ns, s_gl, (uint32_t)(kWinPerCta * ns * sizeof(float)));
+            }
             bulk_commit();
             bulk_wait_read0();
         }
     } else {
         for (int i = tid; i < nwin * n; i += kThreads) a.grad[(size_t)w0 * n + i] = s_g[i];
+        if (a.gp_hi)
+            for (int i = tid; i < nwin * ns; i += kThreads) {
+                a.gp_hi[(size_t)w0 * ns + i] = s_gh[i];
+                a.gp_lo[(size_t)w0 * ns + i] = s_gl[i];
+            }
     }
 }
 
 int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, const float* pose,
                        const float* pose0, const float* heat, const int64_t* frame_base, const int32_t* clip,
                        const float* mean_bone, const gem_energy_weights& wt, float* energy, float* terms,
-                       float* grad, uint32_t* status) {
+                       float* grad, uint32_t* status, float* gp_hi, float* gp_lo, int pp) {
     if (W <= 0) return GEM_OK;
     GEM_REQUIRE(T * J <= kSlot, "T*J must be <= 160");
     GEM_REQUIRE(T >= 3, "seq_len must be >= 3");
@@ -267,11 +300,14 @@ int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, 
     EnergyArgs a;
     a.pose = pose, a.pose0 = pose0, a.heat = heat, a.frame_base = frame_base, a.clip = clip, a.mean_bone = mean_bone;
     a.energy = energy, a.terms = terms, a.grad = grad, a.status = status;
+    a.gp_hi = gp_hi, a.gp_lo = gp_hi ? gp_lo : nullptr, a.pp = gp_hi ? pp : 0;
+    GEM_REQUIRE(!gp_hi || (gp_lo && pp >= J * 3 && T * pp <= kSplitMax && (T * pp) % 4 == 0), "bad split gradient layout");
     a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd;
     a.w3d = wt.w3d, a.ws = wt.smooth, a.wb = wt.bone, a.wv = wt.vae, a.wr = wt.reproj;
     const size_t pair_bytes = (size_t)kWinPerCta * T * J * 3 * sizeof(float);
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    a.use_bulk = (pair_bytes % 16 == 0) && al16(pose) && al16(pose0) && al16(grad);
+    a.use_bulk = (pair_bytes % 16 == 0) && al16(pose) && al16(pose0) && al16(grad) &&
+                 (!gp_hi || (al16(gp_hi) && al16(gp_lo)));
     const int grid = (W + kWinPerCta - 1) / kWinPerCta;
     energy_grad_kernel<<<grid, kThreads, 0, stream>>>(a);
     GEM_CHECK_LAUNCH();

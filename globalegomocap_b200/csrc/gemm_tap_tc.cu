@@ -18,10 +18,11 @@
 // adds stay at the 1e-6 level, see gemm_tc.cu).  Activations travel between layers already split: the
 // epilogue of the producing kernel writes hi and lo, so no separate split pass touches HBM.
 //
-// CTA anatomy (192 threads, one stage of shared memory; two CTAs share an SM and overlap each other's
+// CTA anatomy (320 threads, one stage of shared memory; two CTAs share an SM and overlap each other's
 // load / MMA / epilogue phases): warp 0 = TMA producer, warp 1 = TMEM allocation + single-thread
-// tcgen05.mma issue (M128, N = 3*NCTA, K8, kind::tf32), warps 2-5 = epilogue (tcgen05.ld, shuffle shift-add,
-// bias / LeakyReLU / LeakyReLU-derivative mask, hi/lo split, row-segment stores).
+// tcgen05.mma issue (M128, N = 3*NCTA, K8, kind::tf32), warps 2-9 = epilogue, two per TMEM lane quarter
+// (tcgen05.ld, shuffle shift-add, bias / LeakyReLU / LeakyReLU-derivative mask, hi/lo split, staging in the
+// idle operand memory, 3-D TMA store).
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -39,7 +40,7 @@ constexpr int kRows = 128;                 // UMMA M
 constexpr int BK = 32;                     // fp32 per 128-byte swizzle row
 constexpr int kATile = kRows * BK * 4;     // 16 KB
 constexpr int kQuarterBytes = 32 * BK * 4; // 4 KB: one warp's 32 rows
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;              // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kTmemCols = 256;
 
 template <int NCTA>
@@ -87,6 +88,11 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) TAP_DBG(0);
+    if (threadIdx.x == 0 && g.dbg) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 14] = (long long)gt;
+    }
     const int win0 = blockIdx.x * 4 * g.wpq;      // first window of this M tile
     const int y = blockIdx.y;                      // output-channel slab of NCTA channels
     const int rows_q = g.wpq * g.T;                // rows in use per quarter
@@ -159,6 +165,9 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         // also the next layer's operand layout) and leaves by TMA / coalesced rows.  Per-thread row-segment
         // stores would cost 32 L1 wavefronts per instruction.
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;                       // the quarter's two warps split the column chunks
+        constexpr int kChunks = NCTA / 16;
+        const int c_begin = half ? (kChunks + 1) / 2 : 0, c_end = half ? kChunks : (kChunks + 1) / 2;
         const int wl = lane / g.T, t = lane - wl * g.T;         // window inside the quarter, frame
         const int winq = win0 + q * g.wpq;                      // first window of this quarter
         const int win = winq + wl;
@@ -172,7 +181,7 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         uint32_t sbits = 0, mbits = 0;
 #pragma unroll 1
-        for (int c = 0; c < NCTA / 16; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
             uint32_t p0[16], p1[16], p2[16];
             tmem_ld_32x32b_x16(trow + (uint32_t)(0 * NCTA + c * 16), p0);
             tmem_ld_32x32b_x16(trow + (uint32_t)(1 * NCTA + c * 16), p1);
@@ -248,8 +257,7 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             fence_proxy_async_smem();             // generic-proxy writes -> visible to the TMA store
             __syncwarp();
             if (lane == 0 && winq < g.W) {
-#pragma unroll
-                for (int b = 0; b < NCTA / 32; ++b) {
+                for (int b = c_begin >> 1; b < (c_end + 1) >> 1; ++b) {       // this warp's 32-channel blocks
                     tma_store_3d(&map_o_hi, smem + (b * 2 + 0) * kATile + q * kQuarterBytes, y * NCTA + b * 32, 0, winq);
                     tma_store_3d(&map_o_lo, smem + (b * 2 + 1) * kATile + q * kQuarterBytes, y * NCTA + b * 32, 0, winq);
                 }
@@ -257,14 +265,15 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 bulk_wait_read0();                // the staging memory must outlive the engine's reads, not its writes
             }
         } else {
-            // plain output (the pose): the quarter's windows are consecutive, dense rows in global memory
-            __syncwarp();
+            // plain output (the pose): the quarter's windows are consecutive, dense rows in global memory;
+            // the quarter's two warps meet on a named barrier and share the copy
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
             int nwin = g.W - winq;
             nwin = nwin < 0 ? 0 : (nwin > g.wpq ? g.wpq : nwin);
             const int count = nwin * g.T * g.N;
             const float* sp = reinterpret_cast<const float*>(smem + q * 2 * kQuarterBytes);
             float* dp = g.out_hi + (size_t)winq * g.T * g.N;
-            for (int i = lane; i < count; i += 32) dp[i] = sp[i];
+            for (int i = half * 32 + lane; i < count; i += 64) dp[i] = sp[i];
         }
     }
     if (threadIdx.x == 64) TAP_DBG(5);
@@ -275,6 +284,11 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         tmem_dealloc(tmem_base, kTmemCols);
     }
     if (threadIdx.x == 0) TAP_DBG(6);
+    if (threadIdx.x == 0 && g.dbg) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + 15] = (long long)gt;
+    }
 }
 
 // weights [3][K][ldb] (tap, in, out) -> K-major slabs [gridy][3][NCTA][Kp], split into TF32 hi / lo

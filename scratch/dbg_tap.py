@@ -25,7 +25,8 @@ for cta in (0, 155):
     print(cta, [(n, int(t[cta, i] - t[cta, 0])) for i, n in enumerate(names)], "start offset", int(t[cta, 0] - base))
 d = t[:, 1:12] - t[:, :1]
 print("median cycles since CTA start:", dict(zip(names[1:], np.median(d, 0).astype(int))))
-print("spread of CTA starts (cycles):", int(t[:, 0].max() - base), " last end - first start:", int(t[:, 6].max() - base))
+print("globaltimer: CTA start spread %d ns, kernel span %d ns, median CTA life %d ns" % (t[:, 14].max() - t[:, 14].min(), t[:, 15].max() - t[:, 14].min(), np.median(t[:, 15] - t[:, 14])))
+order = np.argsort(t[:, 14]); print("start offsets (ns) of CTAs sorted:", (t[order, 14] - t[:, 14].min())[[0, 1, 50, 100, 140, 147, 148, 150, 155]])
 
 # same for a split-output layer: run the vjp (its last tap layer, dec_bwd[4], has grid (156, 4))
 up = torch.randn(W, 10, 15, 3, device="cuda")
