@@ -230,10 +230,16 @@ def main():
     clips_np = make_rank_clips(args.sequences, args.frames, rank)
     weights = make_weights(make_rank_clips(1, 64, 0)[0])           # same weights on every rank
     cam = syn.load_camera()
+    # pinned host copies of every clip; the heat maps of all clips sit back to back in ONE pinned buffer (each
+    # clip's tensor is a view of it), which is also what the zero-copy path reads in place
+    heat_all = torch.empty((args.sequences * args.frames, 64, 64, 15), dtype=torch.float32).pin_memory()
     clips = []
-    for c in clips_np:
-        clips.append({k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in c.items()
-                      if k != "gt_global_skeleton"})
+    for i, c in enumerate(clips_np):
+        d = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in c.items()
+             if k not in ("gt_global_skeleton", "heatmap_list")}
+        d["heatmap_list"] = heat_all[i * args.frames:(i + 1) * args.frames]
+        d["heatmap_list"].copy_(torch.from_numpy(np.ascontiguousarray(c["heatmap_list"])))
+        clips.append(d)
     h2d_bytes = sum(t.numel() * t.element_size() for c in clips for t in c.values())
 
     n_win = sum(len(range(0, args.frames - 10 + 1, 8)) for _ in range(args.sequences))
@@ -295,6 +301,14 @@ def main():
         t_end.record()
         eng.set_slices(None)
         e2e_marks["ev"] = (t0, t_up, t_solve, t_end)
+        return sol
+
+    def step_e2e_zero_copy():
+        # the heat maps stay in pinned host memory; the energy kernel fetches the texels it samples over PCIe
+        batch = WindowBatch(eng, clips, host_heat=heat_all)
+        sol = so.solve(batch, eps=None)
+        out = stitch_all(batch, sol)
+        host_out.copy_(out, non_blocking=True)
         return sol
 
     def barrier():
@@ -360,6 +374,24 @@ def main():
         t0, t_up, t_solve, t_end = e2e_marks["ev"]
         e2e["last_step_ms"] = {"upload_done": t0.elapsed_time(t_up), "solve_done": t0.elapsed_time(t_solve),
                                "result_on_host": t0.elapsed_time(t_end)}
+        e2e["mode"] = "explicit piecewise upload of every input overlapped with the solve"
+        # the same through zero-copy heat maps: nothing but the small per-frame arrays is copied up front, the energy
+        # kernel reads the maps from pinned host memory through its texel cache
+        for _ in range(2):
+            step_e2e_zero_copy()
+        ms_z, _, _, _ = timed(step_e2e_zero_copy, args.steps)
+        eng.texel_cache_stats(True)
+        step_e2e_zero_copy()
+        lookups, rebuilds = eng.texel_cache_stats(False)
+        small = sum(t.numel() * t.element_size() for c in clips for k, t in c.items() if k != "heatmap_list")
+        zc = {"value": total_frames / (ms_z / args.steps / 1000.0), "unit": "frames/s", "ms_per_step": ms_z / args.steps,
+              "h2d_bytes_per_step": int(small + rebuilds * 16 * 32), "d2h_bytes_per_step": int(host_out.numel() * 8),
+              "texel_cache": {"lookups": lookups, "rebuilds": rebuilds},
+              "mode": "zero-copy heat maps: pinned host memory read over PCIe by the energy kernel through a per-joint "
+                      "texel cache; h2d bytes = small arrays + 16 texels x one 32-byte sector per cache rebuild"}
+        if zc["value"] > e2e["value"]:
+            e2e, zc = zc, e2e
+        e2e["other_mode"] = zc
 
     if rank == 0:
         peaks = {}

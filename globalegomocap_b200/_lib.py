@@ -51,6 +51,8 @@ _SIGNATURES = {
     "gem_ctx_set_ready_events": (C.c_int, [_P, _I, C.POINTER(C.c_int32), C.POINTER(C.c_void_p)]),
     "gem_solve_windows": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, C.POINTER(EnergyWeights),
                                     C.POINTER(EnergyWeights), C.POINTER(LbfgsParams), _P, _P, _P, _P, _P, _P, _P]),
+    "gem_ctx_set_texel_cache": (C.c_int, [_P, _I]),
+    "gem_ctx_texel_cache_stats": (C.c_int, [_P, _I, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gem_ctx_launch_count": (C.c_int64, [_P]),
     "gem_ctx_set_profiling": (C.c_int, [_P, _I]),
     "gem_ctx_read_profile": (C.c_int, [_P, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float),

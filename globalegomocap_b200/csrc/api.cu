@@ -63,6 +63,12 @@ struct gem_ctx {
     int64_t* fb_own = nullptr;
     int32_t* clip_own = nullptr;
     uint32_t* status_own = nullptr;
+    // energy kernel's texel cache (heat maps read from pinned host memory): [W][T*J][16] + origins, and counters
+    float* patch = nullptr;
+    short2* patch_origin = nullptr;
+    unsigned long long* patch_stats = nullptr;   // {lookups, rebuilds}, counted while patch_stats_on
+    bool patch_stats_on = false;
+    int texel_cache = -1;                        // -1 auto (on when the maps are host memory), 0 off, 1 on
     int trace_cap = 0;                           // columns of trace_own
     bool use_graphs = true;
     struct RoundGraph {
@@ -190,6 +196,10 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     if (rc == GEM_OK) rc = ctx_alloc(c, &c->fb_own, W);
     if (rc == GEM_OK) rc = ctx_alloc(c, &c->clip_own, W);
     if (rc == GEM_OK) rc = ctx_alloc(c, &c->status_own, W);
+    A(&c->patch, Weven * seq_len * num_joints * 16);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->patch_origin, Weven * seq_len * num_joints);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->patch_stats, 2);
+    if (rc == GEM_OK && cudaMemset(c->patch_stats, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) rc = GEM_ERR_CUDA;
     LbfgsBuffers& b = c->lb;
     memset(&b, 0, sizeof(b));
     A(&b.X, W * n), A(&b.D, W * n), A(&b.G, W * n), A(&b.GP, W * n), A(&b.BG0, W * n),
@@ -213,6 +223,7 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     if (const char* env = getenv("GEM_CHUNKS")) c->n_chunks = atoi(env) >= 1 ? atoi(env) : 1;
     if (c->n_chunks > 16) c->n_chunks = 16;
     if (const char* env = getenv("GEM_GRAPHS")) c->use_graphs = env[0] != '0';
+    if (const char* env = getenv("GEM_TEXEL_CACHE")) c->texel_cache = atoi(env);
     // default skeleton: the reference's 15-joint kinematic tree (optimizer.py:34)
     if (num_joints == 15) {
         static const int32_t parents[15] = {0, 0, 1, 2, 0, 4, 5, 1, 7, 8, 9, 4, 11, 12, 13};
@@ -263,6 +274,25 @@ int gem_debug_tap_timestamps(long long* buf_d) {
 int gem_ctx_set_chunks(gem_ctx* c, int n_chunks) {
     GEM_REQUIRE(c != nullptr && n_chunks >= 1 && n_chunks <= 16, "n_chunks must be in [1, 16]");
     c->n_chunks = n_chunks;
+    return GEM_OK;
+}
+
+int gem_ctx_set_texel_cache(gem_ctx* c, int mode) {
+    GEM_REQUIRE(c != nullptr && mode >= -1 && mode <= 1, "mode must be -1 (auto), 0 or 1");
+    c->texel_cache = mode;
+    return GEM_OK;
+}
+
+int gem_ctx_texel_cache_stats(gem_ctx* c, int enable, uint64_t* lookups_h, uint64_t* rebuilds_h) {
+    GEM_REQUIRE(c != nullptr, "ctx is NULL");
+    GEM_CUDA(cudaSetDevice(c->device));
+    GEM_CUDA(cudaDeviceSynchronize());
+    unsigned long long v[2] = {0, 0};
+    GEM_CUDA(cudaMemcpy(v, c->patch_stats, sizeof(v), cudaMemcpyDeviceToHost));
+    if (lookups_h) *lookups_h = v[0];
+    if (rebuilds_h) *rebuilds_h = v[1];
+    GEM_CUDA(cudaMemset(c->patch_stats, 0, sizeof(v)));
+    c->patch_stats_on = enable != 0;
     return GEM_OK;
 }
 
@@ -419,6 +449,8 @@ struct Slice {
     int64_t* fb_own;
     int32_t* clip_own;
     uint32_t* status_own;
+    float* patch;
+    short2* patch_origin;
     LbfgsBuffers lb;
 };
 static Slice slice_of(gem_ctx* c, int w0) {
@@ -441,6 +473,7 @@ static Slice slice_of(gem_ctx* c, int w0) {
     v.pose0_own = c->pose0_own + v.tok0 * P, v.mb_own = c->mb_own;     // (mean bones are indexed by absolute window)
     v.trace_own = c->trace_own + (size_t)w0 * c->trace_cap;
     v.fb_own = c->fb_own + w0, v.clip_own = c->clip_own + w0, v.status_own = c->status_own + w0;
+    v.patch = c->patch + v.tok0 * c->J * 16, v.patch_origin = c->patch_origin + v.tok0 * c->J;
     v.lb = c->lb;
     LbfgsBuffers& b = v.lb;
     const size_t on = (size_t)w0 * n;
@@ -546,12 +579,14 @@ __global__ void stage_inputs_kernel(int w_abs0, int TJ3, int J, const float* __r
                                     const int32_t* __restrict__ clip, const float* __restrict__ mean_bone,
                                     float* __restrict__ pose0_own, int64_t* __restrict__ fb_own,
                                     int32_t* __restrict__ clip_own, float* __restrict__ mb_own,
-                                    uint32_t* __restrict__ status_own) {
+                                    uint32_t* __restrict__ status_own, short2* __restrict__ patch_origin, int TJ) {
     // all pointers are the slice's (window blockIdx.x of the slice); mb_own is the ctx-wide table indexed by the
     // absolute window w_abs0 + blockIdx.x, which is what the staged clip index points at
     const int w = blockIdx.x;
     for (int i = threadIdx.x; i < TJ3; i += blockDim.x) pose0_own[(size_t)w * TJ3 + i] = pose0[(size_t)w * TJ3 + i];
     if (threadIdx.x < J) mb_own[(size_t)(w_abs0 + w) * J + threadIdx.x] = mean_bone[(size_t)clip[w] * J + threadIdx.x];
+    // a new stage reads new maps: every joint's cached texel patch is stale
+    for (int i = threadIdx.x; i < TJ; i += blockDim.x) patch_origin[(size_t)w * TJ + i] = make_short2(-30000, -30000);
     if (threadIdx.x == 0) {
         fb_own[w] = fb ? fb[w] : 0;
         clip_own[w] = w_abs0 + w;
@@ -705,7 +740,20 @@ struct StageCall {
     float* trace;               // [W][max_eval + 1] or NULL
     int32_t *n_iter, *func_evals;
     uint32_t* status;
+    bool texel_cache;           // read the maps through the per-joint texel cache
 };
+
+// The texel cache pays when the maps are read over PCIe from (pinned / registered) host memory
+static bool want_texel_cache(const gem_ctx* c, const void* heat, float reproj) {
+    if (!heat || reproj == 0.f || c->texel_cache == 0) return false;
+    if (c->texel_cache == 1) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, heat) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
 
 static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, int w0, int Wk, bool graphs) {
     if (Wk <= 0) return GEM_OK;
@@ -723,7 +771,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     if (a.trace) GEM_CUDA(cudaMemsetAsync(v.trace_own, 0xff, (size_t)Wk * c->trace_cap * sizeof(float), q));   // NaN
     stage_inputs_kernel<<<Wk, 128, 0, q>>>(w0, TJ3, c->J, a.pose0 + w0 * P, a.frame_base ? a.frame_base + w0 : nullptr,
                                            a.clip + w0, a.mean_bone, v.pose0_own, v.fb_own, v.clip_own, v.mb_own,
-                                           v.status_own);
+                                           v.status_own, v.patch_origin, c->T * c->J);
     GEM_CHECK_LAUNCH();
     c->launches += 1;
     // z0 = mu + eps * std                                   optimizer.py:255-259
@@ -737,7 +785,8 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
         GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
             return launch_energy_grad(q, Wk, c->T, c->J, c->H, c->Wd, v.pose, v.pose0_own, a.heat, v.fb_own, v.clip_own,
                                       v.mb_own, a.wt, v.f_new, nullptr, v.gpose, v.status_own, tc ? v.gp_hi : nullptr,
-                                      v.gp_lo, pose_pad(c));
+                                      v.gp_lo, pose_pad(c), a.texel_cache ? v.patch : nullptr, v.patch_origin,
+                                      c->patch_stats_on ? c->patch_stats : nullptr);
         }));
         GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, v.gpose, v.g_new, tc));
         return timed(c, q, GEM_TAG_LBFGS_ADVANCE, [&]() { return launch_lbfgs_advance(q, lb, v.f_new, v.g_new, Wk); });
@@ -749,7 +798,8 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     if (graphs && a.p.max_eval >= 2) {
         for (auto& g : c->graphs) {
             if (g.which == which && g.w0 == w0 && g.Wk == Wk && g.gemm_mode == c->gemm_mode && g.heat == a.heat &&
-                g.has_heat == (a.wt.reproj != 0.f) && g.trace_stride == lb.trace_stride &&
+                g.has_heat == ((a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on) &&
+                g.trace_stride == lb.trace_stride &&
                 memcmp(&g.wt, &a.wt, sizeof(a.wt)) == 0 && g.p.lr == a.p.lr && g.p.max_iter == a.p.max_iter &&
                 g.p.max_eval == a.p.max_eval && g.p.tolerance_grad == a.p.tolerance_grad &&
                 g.p.tolerance_change == a.p.tolerance_change) {
@@ -772,7 +822,8 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             GEM_CUDA(e);
             gem_ctx::RoundGraph g;
             g.which = which, g.w0 = w0, g.Wk = Wk, g.gemm_mode = c->gemm_mode, g.heat = a.heat;
-            g.has_heat = a.wt.reproj != 0.f, g.trace_stride = lb.trace_stride, g.wt = a.wt, g.p = a.p;
+            g.has_heat = (a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on;
+            g.trace_stride = lb.trace_stride, g.wt = a.wt, g.p = a.p;
             g.launches = round_launches;
             e = cudaGraphInstantiate(&g.exec, graph, 0);
             cudaGraphDestroy(graph);
@@ -908,6 +959,7 @@ int gem_solve_stage(gem_ctx* c, void* stream, int which, int W, const float* pos
     a.which = which, a.pose0 = pose0_d, a.heat = heat_d, a.frame_base = frame_base_d, a.clip = clip_d;
     a.mean_bone = mean_bone_d, a.eps = eps_d, a.eps_stride = (size_t)c->n, a.wt = *wt, a.p = *params_h;
     a.pose_out = pose_out_d, a.trace = energy_trace_d, a.n_iter = n_iter_d, a.func_evals = func_evals_d, a.status = status_d;
+    a.texel_cache = want_texel_cache(c, heat_d, wt->reproj);
     const bool graphs = c->use_graphs && !c->prof_on;
     const std::vector<int> w0 = slice_bounds(c, W);
     Fork f;
@@ -937,7 +989,9 @@ int gem_solve_windows(gem_ctx* c, void* stream, int W, const float* pose0_d, con
     a.which = 0, a.pose0 = pose0_d, a.heat = heat_d, a.frame_base = frame_base_d, a.clip = clip_d;
     a.mean_bone = mean_bone_d, a.eps = eps_d, a.eps_stride = 2 * (size_t)c->n, a.wt = *wt_local, a.p = *params_h;
     a.pose_out = local_pose_d, a.trace = nullptr, a.n_iter = n_iter_d, a.func_evals = func_evals_d, a.status = status_d;
+    a.texel_cache = want_texel_cache(c, heat_d, wt_local->reproj);
     b = a;
+    b.texel_cache = false;
     b.which = 1, b.pose0 = rel_f32_d, b.heat = nullptr, b.frame_base = nullptr, b.eps = eps_d + c->n, b.wt = *wt_global;
     b.pose_out = global_pose_d, b.status = nullptr;
     b.n_iter = n_iter_d ? n_iter_d + W : nullptr, b.func_evals = func_evals_d ? func_evals_d + W : nullptr;

@@ -52,6 +52,15 @@ struct EnergyArgs {
     // tensor-core bwd-data layers read (saves a separate split pass)
     float *gp_hi, *gp_lo;
     int pp;
+    // optional texel cache (used when the heat maps stay in pinned HOST memory and are read over PCIe): per joint
+    // a 4x4 neighbourhood of its map, 64 contiguous bytes in HBM, and the map coordinate of its corner.  The same
+    // few texels are read by every evaluation of a stage (joints move by a fraction of a texel per step), so only
+    // the ~6 % of the maps the optimiser ever looks at cross the bus.  A joint that leaves its patch rebuilds it
+    // around the new cell (which is also how the first evaluation fills it); values are copies of the map's, so
+    // the energy is bit-identical with and without the cache.
+    float* patch;              // [W][T*J][16]
+    short2* patch_origin;      // [W][T*J]
+    unsigned long long* patch_stats;   // optional {lookups, rebuilds}
 };
 
 __device__ __forceinline__ float texel(const float* __restrict__ heat, int64_t frame, int y, int x, int j, int H,
@@ -196,10 +205,41 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
                     const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix;
                     const float wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
                     const int64_t frame = a.frame_base[w] + t;
-                    const float nw = texel(a.heat, frame, y0, x0, j, a.H, a.Wd, a.J);
-                    const float ne = texel(a.heat, frame, y0, x0 + 1, j, a.H, a.Wd, a.J);
-                    const float sw = texel(a.heat, frame, y0 + 1, x0, j, a.H, a.Wd, a.J);
-                    const float se = texel(a.heat, frame, y0 + 1, x0 + 1, j, a.H, a.Wd, a.J);
+                    float nw, ne, sw, se;
+                    if (a.patch) {
+                        const size_t pk = (size_t)w * TJ + k;
+                        float* pe = a.patch + pk * 16;
+                        short2 o = a.patch_origin[pk];
+                        const int dx = x0 - o.x, dy = y0 - o.y;
+                        const bool miss = dx < 0 || dx > 2 || dy < 0 || dy > 2;
+                        if (a.patch_stats) {
+                            atomicAdd(a.patch_stats, 1ull);
+                            if (miss) atomicAdd(a.patch_stats + 1, 1ull);
+                        }
+                        if (miss) {                               // (re)build around the current cell
+                            o.x = (short)(x0 - 1), o.y = (short)(y0 - 1);
+                            float4 rows[4];
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {         // 16 independent loads in flight
+                                rows[r].x = texel(a.heat, frame, o.y + r, o.x + 0, j, a.H, a.Wd, a.J);
+                                rows[r].y = texel(a.heat, frame, o.y + r, o.x + 1, j, a.H, a.Wd, a.J);
+                                rows[r].z = texel(a.heat, frame, o.y + r, o.x + 2, j, a.H, a.Wd, a.J);
+                                rows[r].w = texel(a.heat, frame, o.y + r, o.x + 3, j, a.H, a.Wd, a.J);
+                            }
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) *reinterpret_cast<float4*>(pe + r * 4) = rows[r];
+                            a.patch_origin[pk] = o;
+                            nw = rows[1].y, ne = rows[1].z, sw = rows[2].y, se = rows[2].z;
+                        } else {
+                            const float* p0 = pe + dy * 4 + dx;
+                            nw = p0[0], ne = p0[1], sw = p0[4], se = p0[5];
+                        }
+                    } else {
+                        nw = texel(a.heat, frame, y0, x0, j, a.H, a.Wd, a.J);
+                        ne = texel(a.heat, frame, y0, x0 + 1, j, a.H, a.Wd, a.J);
+                        sw = texel(a.heat, frame, y0 + 1, x0, j, a.H, a.Wd, a.J);
+                        se = texel(a.heat, frame, y0 + 1, x0 + 1, j, a.H, a.Wd, a.J);
+                    }
                     erp = -(nw * (wx0 * wy0) + ne * (wx1 * wy0) + sw * (wx0 * wy1) + se * (wx1 * wy1));
                     const float ds_dix = -nw * wy0 + ne * wy0 - sw * wy1 + se * wy1;
                     const float ds_diy = -nw * wx0 - ne * wx1 + sw * wx0 + se * wx1;
@@ -292,7 +332,8 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
 int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, const float* pose,
                        const float* pose0, const float* heat, const int64_t* frame_base, const int32_t* clip,
                        const float* mean_bone, const gem_energy_weights& wt, float* energy, float* terms,
-                       float* grad, uint32_t* status, float* gp_hi, float* gp_lo, int pp) {
+                       float* grad, uint32_t* status, float* gp_hi, float* gp_lo, int pp, float* patch,
+                       short2* patch_origin, unsigned long long* patch_stats) {
     if (W <= 0) return GEM_OK;
     GEM_REQUIRE(T * J <= kSlot, "T*J must be <= 160");
     GEM_REQUIRE(T >= 3, "seq_len must be >= 3");
@@ -301,6 +342,7 @@ int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, 
     a.pose = pose, a.pose0 = pose0, a.heat = heat, a.frame_base = frame_base, a.clip = clip, a.mean_bone = mean_bone;
     a.energy = energy, a.terms = terms, a.grad = grad, a.status = status;
     a.gp_hi = gp_hi, a.gp_lo = gp_hi ? gp_lo : nullptr, a.pp = gp_hi ? pp : 0;
+    a.patch = patch, a.patch_origin = patch ? patch_origin : nullptr, a.patch_stats = patch ? patch_stats : nullptr;
     GEM_REQUIRE(!gp_hi || (gp_lo && pp >= J * 3 && T * pp <= kSplitMax && (T * pp) % 4 == 0), "bad split gradient layout");
     a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd;
     a.w3d = wt.w3d, a.ws = wt.smooth, a.wb = wt.bone, a.wv = wt.vae, a.wr = wt.reproj;

@@ -9,7 +9,8 @@ int upload_skeleton(const SkeletonConst& sk);
 int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, const float* pose, const float* pose0,
                        const float* heat, const int64_t* frame_base, const int32_t* clip, const float* mean_bone,
                        const gem_energy_weights& wt, float* energy, float* terms, float* grad, uint32_t* status,
-                       float* gp_hi = nullptr, float* gp_lo = nullptr, int pp = 0);
+                       float* gp_hi = nullptr, float* gp_lo = nullptr, int pp = 0, float* patch = nullptr,
+                       short2* patch_origin = nullptr, unsigned long long* patch_stats = nullptr);
 
 enum { EPI_NONE = 0, EPI_LRELU = 1, EPI_MASK = 2 };
 struct TapGemmArgs {

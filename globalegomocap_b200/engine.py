@@ -107,6 +107,26 @@ class Engine:
         self._keep_events = list(events)
         check(self.lib.gem_ctx_set_ready_events(self._ctx, n, fw, ev))
 
+    def set_texel_cache(self, mode: int):
+        """-1 auto (on when the heat maps are pinned host memory), 0 off, 1 on; results are unaffected."""
+        check(self.lib.gem_ctx_set_texel_cache(self._ctx, int(mode)))
+
+    def texel_cache_stats(self, enable: bool):
+        """(lookups, rebuilds) counted since the previous call; switches the counting on or off."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(self.lib.gem_ctx_texel_cache_stats(self._ctx, int(bool(enable)), C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def _heat(self, heat):
+        """Heat maps for the solver: a CUDA tensor, or — left where it is — a pinned host tensor that the energy
+        kernel reads over PCIe through its texel cache (include/gem_b200.h: gem_ctx_set_texel_cache)."""
+        if heat is None:
+            return None
+        if (isinstance(heat, torch.Tensor) and not heat.is_cuda and heat.dtype == torch.float32 and
+                heat.is_contiguous() and heat.is_pinned()):
+            return heat
+        return self._dev(heat, torch.float32)
+
     def _dev(self, t, dtype):
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(np.asarray(t))
@@ -236,7 +256,7 @@ class Engine:
         pose0, eps = self._dev(pose0, torch.float32), self._dev(eps, torch.float32)
         W = pose0.shape[0]
         self._check_w(W)
-        heat = None if heat is None else self._dev(heat, torch.float32)
+        heat = self._heat(heat)
         frame_base = None if frame_base is None else self._dev(frame_base, torch.int64)
         clip = self._dev(clip, torch.int32)
         mean_bone = self._dev(mean_bone, torch.float32).reshape(-1, self.J)
@@ -259,7 +279,7 @@ class Engine:
         pose0, eps = self._dev(pose0, torch.float32), self._dev(eps, torch.float32)
         W = pose0.shape[0]
         self._check_w(W)
-        heat = None if heat is None else self._dev(heat, torch.float32)
+        heat = self._heat(heat)
         frame_base = None if frame_base is None else self._dev(frame_base, torch.int64)
         clip = self._dev(clip, torch.int32)
         mean_bone = self._dev(mean_bone, torch.float32).reshape(-1, self.J)

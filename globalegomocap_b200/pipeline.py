@@ -37,9 +37,13 @@ class WindowBatch:
     With ``copy_stream`` the host-to-device copies run on that stream, clip after clip, and every clip's
     heat maps get a completion event: ``SequenceOptimizer.solve`` hands the events to the library, which
     starts optimising the first clips while the later ones are still crossing PCIe (the clips become the
-    library's slices)."""
+    library's slices).
 
-    def __init__(self, engine: Engine, clips, copy_stream=None, min_piece_windows=96):
+    With ``host_heat`` (ONE pinned float32 tensor [total frames, H, W, J] holding the clips' heat maps back to
+    back) the maps are not copied at all: the energy kernel reads them over PCIe through its texel cache, so
+    only the texels the optimiser samples ever cross the bus."""
+
+    def __init__(self, engine: Engine, clips, copy_stream=None, min_piece_windows=96, host_heat=None):
         dev = engine.device
         self.n_frames = [len(c["estimated_local_skeleton"]) for c in clips]
         self.starts = [window_starts(n, engine.T, OVERLAP) for n in self.n_frames]
@@ -80,9 +84,21 @@ class WindowBatch:
         self.est = alloc("estimated_local_skeleton", torch.float64)        # [F,15,3]
         self.cams = alloc("camera_pose_list", torch.float64)               # [F,4,4]
         self.gt = alloc("gt_global_skeleton", torch.float64) if has_gt else None
-        self.heat = alloc("heatmap_list", torch.float32)                   # [F,H,W,15] (pickle's HWC layout, as is)
         every = range(len(clips))
-        if copy_stream is None:
+        if host_heat is not None:
+            if not (host_heat.is_pinned() and host_heat.dtype == torch.float32 and host_heat.is_contiguous() and
+                    host_heat.shape[0] == total):
+                raise ValueError("host_heat must be one contiguous pinned float32 tensor covering every frame")
+            self.heat = host_heat                                          # stays in host memory
+            fill(self.est, "estimated_local_skeleton", every), fill(self.cams, "camera_pose_list", every)
+            if has_gt:
+                fill(self.gt, "gt_global_skeleton", every)
+            copy_stream = None
+        else:
+            self.heat = alloc("heatmap_list", torch.float32)               # [F,H,W,15] (pickle's HWC layout, as is)
+        if host_heat is not None:
+            pass
+        elif copy_stream is None:
             fill(self.est, "estimated_local_skeleton", every), fill(self.cams, "camera_pose_list", every)
             if has_gt:
                 fill(self.gt, "gt_global_skeleton", every)

@@ -122,6 +122,15 @@ int gem_ctx_set_slices(gem_ctx* ctx, int n, const int32_t* first_window_h);
  * optimisation of the first clips overlaps the host-to-device copy of the later ones. */
 int gem_ctx_set_ready_events(gem_ctx* ctx, int n, const int32_t* first_window_h, void* const* events_h);
 
+/* heat_d may be pinned (or registered) HOST memory: the energy kernel then reads the maps over PCIe through a
+ * per-joint 4x4 texel cache in HBM (64 bytes per joint, rebuilt when the joint leaves it), so only the few per
+ * cent of the maps the optimiser ever samples cross the bus and no up-front copy is needed.  Values are copies:
+ * results are bit-identical.  mode -1 (default): cache on exactly when heat_d is host memory; 0 off; 1 on. */
+int gem_ctx_set_texel_cache(gem_ctx* ctx, int mode);
+/* synchronises; returns the cache's lookups and rebuilds (16 texels each) counted since the previous call while
+ * counting was enabled, then clears them and sets counting on/off */
+int gem_ctx_texel_cache_stats(gem_ctx* ctx, int enable, uint64_t* lookups_h, uint64_t* rebuilds_h);
+
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* kernel classes reported by gem_ctx_read_profile */
 #define GEM_TAG_DEC 100           /* +i: decoder forward layer i (0 = latent -> T*256 GEMM) */

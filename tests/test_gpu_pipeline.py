@@ -113,7 +113,8 @@ def test_many_clips_batch_equals_one_by_one(workdir, clip58, vae_weights, camera
 def test_slices_streams_graphs_and_pipelined_upload_do_not_change_results(vae_weights, camera):
     """The fused local -> transform -> global call gives bit-identical results whether the windows run as one
     slice or several concurrent ones, with or without CUDA-graph replay, through separate stage calls, and
-    with the clips uploaded on a copy stream while the first slices already run."""
+    with the clips uploaded on a copy stream while the first slices already run, or with the heat maps left in
+    pinned host memory and read through the energy kernel's texel cache."""
     from globalegomocap_b200.engine import Engine
     from globalegomocap_b200.pipeline import SequenceOptimizer, WindowBatch
     clips = [syn.make_clip(800, seed=40 + i) for i in range(3)]            # 99 windows each: one slice per clip
@@ -138,12 +139,22 @@ def test_slices_streams_graphs_and_pipelined_upload_do_not_change_results(vae_we
     multi = run(WindowBatch(eng, clips))
     piped = run(WindowBatch(eng, pinned, copy_stream=torch.cuda.Stream()))
     eng.set_slices(None)
+    # heat maps left in pinned host memory, read over PCIe through the energy kernel's texel cache
+    host_heat = torch.cat([c["heatmap_list"] for c in pinned]).pin_memory()
+    eng.texel_cache_stats(True)
+    zero_copy = run(WindowBatch(eng, pinned, host_heat=host_heat))
+    lookups, rebuilds = eng.texel_cache_stats(False)
+    assert lookups > 0 and 0 < rebuilds < lookups / 2, (lookups, rebuilds)
+    eng.set_texel_cache(1)                       # the cache on device-resident maps
+    cached = run(WindowBatch(eng, clips))
+    eng.set_texel_cache(-1)
     eng.set_chunks(1)
     batch = WindowBatch(eng, clips)                                         # separate stage calls (trace path)
     sol = so.solve(batch, eps=eps, want_trace=True)
     torch.cuda.synchronize()
     staged = (sol["local"]["pose"], sol["glob"]["pose"], sol["glob"]["func_evals"])
-    for name, other in (("3 slices", multi), ("pipelined upload", piped), ("separate stages", staged)):
+    for name, other in (("3 slices", multi), ("pipelined upload", piped), ("separate stages", staged),
+                        ("zero-copy heat maps", zero_copy), ("texel cache", cached)):
         for a, b in zip(ref, other):
             assert torch.equal(a, b), name
     eng.close()
