@@ -37,10 +37,10 @@ if REPO not in sys.path:
 METRIC = "optimised frames/sec (windows x iters, device-timed)"
 FLOPS_PER_WINDOW_EVAL_ALGORITHMIC = 63.9e6   # decoder fwd + bwd-data as the reference runs it
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at W = 1870 from one `ncu --set full` capture of this
-# command (profiles/r01_ncu_full_tc_chain_summary.csv)
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 101.0e6             # mean of the latent->T*256 (104 MB) and T*256->latent (98 MB) layers
-NCU_LBFGS_DRAM_BYTES_PER_LAUNCH = 472.0e6
-NCU_ENERGY_DRAM_BYTES_PER_LAUNCH_LOCAL = 103.8e6
+# command (profiles/r01_ncu_full_final_summary.csv)
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 108.7e6             # mean of the latent->T*256 (109.2 MB) and T*256->latent (108.3 MB) layers
+NCU_LBFGS_DRAM_BYTES_PER_LAUNCH = 586.6e6            # a mid-stage round (the history grows with the iteration count)
+NCU_ENERGY_DRAM_BYTES_PER_LAUNCH_LOCAL = 105.8e6
 
 
 def lbfgs_rows(sol):
@@ -415,7 +415,7 @@ def main():
         roof = {"bound": "tensor", "kernel": "tc_gemm_kernel: decoder latent<->T*256 GEMM (tags 100, 205)",
                 "achieved": g_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": g_tf / tf_peak,
                 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the two layers
-                # (profiles/r01_ncu_full_tc_chain_summary.csv; algorithmic operand bytes are 36 MB + 42 MB weights)
+                # (profiles/r01_ncu_full_final_summary.csv; algorithmic operand bytes are 36 MB + 42 MB weights)
                 "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH if W == 1870 else None,
                 "peak_source": peak_src + ", bf16 sustained",
                 "share_of_kernel_time": g_ms / max(kern_ms, 1e-9),
