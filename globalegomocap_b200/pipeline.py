@@ -31,6 +31,26 @@ def stage_weights(vae_weight, smoothness_weight, bone_length_weight, weight_3d, 
     return local, glob
 
 
+def upload_pieces(n_windows, n_frames, seq_len=SEQ_LEN, overlap=OVERLAP, min_piece_windows=96, max_pieces=4):
+    """Cuts one clip into upload pieces of whole windows: [(first window, end window, first frame, end frame)].
+    A clip is cut while its pieces keep >= min_piece_windows windows (at most max_pieces); piece starts are even
+    window indices (the energy kernel pairs windows).  Piece = windows [a, b) -> frames up to stride*(b-1)+seq_len;
+    the next piece starts where this one ended, the last one takes the clip's trailing frames: the frame ranges
+    are disjoint and cover the clip."""
+    if n_windows <= 0:
+        return []
+    stride = seq_len - overlap
+    n_pieces = max(1, min(max_pieces, n_windows // max(min_piece_windows, 1)))
+    cuts = [(n_windows * k // n_pieces) // 2 * 2 for k in range(n_pieces)] + [n_windows]
+    out, f_prev = [], 0
+    for k in range(n_pieces):
+        a, b = cuts[k], cuts[k + 1]
+        f_end = n_frames if k == n_pieces - 1 else stride * (b - 1) + seq_len
+        out.append((a, b, f_prev, f_end))
+        f_prev = f_end
+    return out
+
+
 class WindowBatch:
     """Device-resident inputs of all windows of a list of clips.
 
@@ -113,23 +133,14 @@ class WindowBatch:
                     fill(self.gt, "gt_global_skeleton", every)
                 small = torch.cuda.Event()
                 small.record(copy_stream)
-                # heat maps in pieces of whole windows (a clip is cut while its pieces keep >= min_piece_windows
-                # windows and an even window count): piece = windows [a, b) -> frames up to 8(b-1)+T, the next
-                # piece starts where this one ended
-                stride = engine.T - OVERLAP
+                # heat maps in pieces of whole windows, every piece with its completion event
                 for i in every:
-                    nw = self.n_windows[i]
-                    if nw == 0:
+                    if self.n_windows[i] == 0:
                         continue
-                    n_pieces = max(1, min(4, nw // max(min_piece_windows, 1)))
-                    cuts = [(nw * k // n_pieces) // 2 * 2 for k in range(n_pieces)] + [nw]
                     src = src_of(clips[i], "heatmap_list")
-                    f_prev = 0
-                    for k in range(n_pieces):
-                        a, b = cuts[k], cuts[k + 1]
-                        f_end = self.n_frames[i] if k == n_pieces - 1 else stride * (b - 1) + engine.T
-                        self.heat[offs[i] + f_prev:offs[i] + f_end].copy_(src[f_prev:f_end], non_blocking=True)
-                        f_prev = f_end
+                    for a, _, f0, f1 in upload_pieces(self.n_windows[i], self.n_frames[i], engine.T, OVERLAP,
+                                                      min_piece_windows):
+                        self.heat[offs[i] + f0:offs[i] + f1].copy_(src[f0:f1], non_blocking=True)
                         ev = torch.cuda.Event()
                         ev.record(copy_stream)
                         self.ready_events.append(ev)
