@@ -42,6 +42,9 @@ struct gem_ctx {
     float *gact_hi[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *gact_lo[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t* act_sign[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // packed signs of act[i]: the bwd-data masks
     float *gp_hi = nullptr, *gp_lo = nullptr;   // d pose, [W*T][kPosePad]
+    // gemm_mode 2: d act0 as row-scaled fp16 hi / lo for the T*256 -> latent GEMM, and the rows' exponents
+    uint16_t *g0_h16 = nullptr, *g0_l16 = nullptr;
+    int32_t* row_exp = nullptr;
     bool act_split = false;                      // the last decode left its activations in act_hi/act_lo
     bool tap_tc[2] = {false, false};             // the VAE's conv layers are prepared for the tcgen05 tap kernel
     // encoder activations, fc output
@@ -180,6 +183,9 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
         A(&c->gact_hi[i], tok * kDecC[i]), A(&c->gact_lo[i], tok * kDecC[i]);
         if (rc == GEM_OK) rc = ctx_alloc(c, &c->act_sign[i], tok * kDecC[i] / 32);
     }
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->g0_h16, tok * kDecC[0]);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->g0_l16, tok * kDecC[0]);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->row_exp, W);
     {
         const size_t cnt = tok * (size_t)((num_joints * 3 + 3) & ~3);
         A(&c->gp_hi, cnt), A(&c->gp_lo, cnt);
@@ -216,9 +222,10 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
         gem_ctx_destroy(c);
         return rc;
     }
-    // default: tcgen05 3xTF32 for the plain GEMMs; GEM_GEMM_MODE=0 (or gem_ctx_set_gemm_mode) selects fp32 CUDA cores
-    c->gemm_mode = 1;
-    if (const char* env = getenv("GEM_GEMM_MODE")) c->gemm_mode = (env[0] == '0') ? 0 : 1;
+    // default: tcgen05 everywhere, the plain GEMMs in the fp16 scheme (2); GEM_GEMM_MODE / gem_ctx_set_gemm_mode select
+    // 1 (3xTF32 GEMMs) or 0 (fp32 CUDA cores)
+    c->gemm_mode = 2;
+    if (const char* env = getenv("GEM_GEMM_MODE")) c->gemm_mode = (env[0] == '0') ? 0 : (env[0] == '2' ? 2 : 1);
     c->n_chunks = 4;
     if (const char* env = getenv("GEM_CHUNKS")) c->n_chunks = atoi(env) >= 1 ? atoi(env) : 1;
     if (c->n_chunks > 16) c->n_chunks = 16;
@@ -256,8 +263,8 @@ int64_t gem_ctx_scratch_bytes(const gem_ctx* c) { return c ? c->scratch_bytes : 
 
 int gem_ctx_set_gemm_mode(gem_ctx* c, int mode) {
     GEM_REQUIRE(c != nullptr, "ctx is NULL");
-    GEM_REQUIRE(mode == 0 || mode == 1, "mode must be 0 or 1");
-    if (mode == 1 && !tc_gemm_available()) {
+    GEM_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+    if (mode >= 1 && !tc_gemm_available()) {
         set_error("tcgen05 GEMM path not available in this build");
         return GEM_ERR_STATE;
     }
@@ -386,7 +393,10 @@ int gem_ctx_set_vae(gem_ctx* c, int which, const gem_vae_weights* w) {
     const gem_layer* big[3] = {&w->dec[0], &w->dec_bwd[5], &w->enc[5]};
     for (const gem_layer* L : big)
         if (L->k % 32 == 0 && L->n % 128 == 0)
-            GEM_TRY(tc_gemm_prepare_weight(c, 0, L->w_d, (L->n + 3) & ~3, L->k, L->n));
+        {
+            GEM_TRY(tc_gemm_prepare_weight(c, 0, L->w_d, (L->n + 3) & ~3, L->k, L->n, 1));
+            if (L->k % 64 == 0) GEM_TRY(tc_gemm_prepare_weight(c, 0, L->w_d, (L->n + 3) & ~3, L->k, L->n, 2));
+        }
     // K-major, tap-concatenated hi/lo slabs of the decoder's k=3 convolutions and their bwd-data
     bool tap_ok = c->T <= 32;
     for (int i = 1; i <= 5 && tap_ok; ++i) tap_ok = tc_tap_supported(w->dec[i].k, w->dec[i].n, c->T);
@@ -408,16 +418,17 @@ int gem_ctx_set_vae(gem_ctx* c, int which, const gem_vae_weights* w) {
 
 // ---- layer runner ----------------------------------------------------------------------------
 static int run_layer(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, const float* A, int lda, int M, float* C,
-                     int ldc, int epi, const float* aux, const float* A_hi = nullptr, const float* A_lo = nullptr,
-                     float* C_lo = nullptr, uint32_t* C_sign = nullptr) {
+                     int ldc, int epi, const float* aux, const void* A_hi = nullptr, const void* A_lo = nullptr,
+                     float* C_lo = nullptr, uint32_t* C_sign = nullptr, const int32_t* row_exp = nullptr) {
     TapGemmArgs g;
     g.A = A, g.B = L.w_d, g.bias = L.bias_d, g.aux = aux, g.C = C;
-    g.A_hi = A_hi, g.A_lo = A_lo, g.C_lo = C_lo, g.C_sign = C_sign;
+    g.A_hi = A_hi, g.A_lo = A_lo, g.C_lo = C_lo, g.C_sign = C_sign, g.row_exp = row_exp;
     g.M = M, g.N = L.n, g.K = L.k, g.taps = L.taps, g.T = c->T;
     g.lda = lda, g.ldb = (L.n + 3) & ~3, g.ldc = ldc, g.ldaux = L.n, g.epi = epi;
     return timed(c, s, tag, [&]() {
-        if (c->gemm_mode == 1 && L.taps == 1 && (M >= 64 || A_hi || C_lo) && L.k % 32 == 0 && L.n % 128 == 0)
-            return launch_tap_gemm_tc(s, g, c, 0);
+        if (c->gemm_mode >= 1 && L.taps == 1 && (M >= 64 || A_hi || C_lo) && L.k % (c->gemm_mode == 2 ? 64 : 32) == 0 &&
+            L.n % 128 == 0)
+            return launch_tap_gemm_tc(s, g, c, (size_t)c->gemm_mode);
         return launch_tap_gemm_simt(s, g);
     });
 }
@@ -434,7 +445,7 @@ static int run_tap_tc(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, c
     return timed(c, s, tag, [&]() { return launch_tap_tc(s, c, t); });
 }
 
-static bool use_tc_chain(const gem_ctx* c, int which, int W) { return c->gemm_mode == 1 && c->tap_tc[which] && W >= 1; }
+static bool use_tc_chain(const gem_ctx* c, int which, int W) { return c->gemm_mode >= 1 && c->tap_tc[which] && W >= 1; }
 
 // Scratch of the windows [w0, w0 + W): every per-window buffer of the ctx shifted by w0.  Chunks of one
 // stage run concurrently on different streams, each on its own slice.
@@ -444,6 +455,8 @@ struct Slice {
     float *act[5], *gact[5], *act_hi[5], *act_lo[5], *gact_hi[5], *gact_lo[5];
     uint32_t* act_sign[5];
     float *pose, *gpose, *gp_hi, *gp_lo, *f_new, *g_new;
+    uint16_t *g0_h16, *g0_l16;
+    int32_t* row_exp;
     float *eact[5], *e4_hi, *e4_lo, *fc, *z0;    // encoder activations, fc output, initial latent
     float *pose0_own, *mb_own, *trace_own;       // staged inputs / outputs of this slice
     int64_t* fb_own;
@@ -467,6 +480,7 @@ static Slice slice_of(gem_ctx* c, int w0) {
     v.pose = c->pose + v.tok0 * P, v.gpose = c->gpose + v.tok0 * P;
     v.gp_hi = c->gp_hi + v.tok0 * pose_pad(c), v.gp_lo = c->gp_lo + v.tok0 * pose_pad(c);
     v.f_new = c->f_new + w0, v.g_new = c->g_new + (size_t)w0 * n;
+    v.g0_h16 = c->g0_h16 + v.tok0 * kDecC[0], v.g0_l16 = c->g0_l16 + v.tok0 * kDecC[0], v.row_exp = c->row_exp + w0;
     for (int i = 0; i < 5; ++i) v.eact[i] = c->eact[i] + v.tok0 * kEncC[i];
     v.e4_hi = c->e4_hi + v.tok0 * kEncC[4], v.e4_lo = c->e4_lo + v.tok0 * kEncC[4];
     v.fc = c->fc + (size_t)w0 * 2 * n, v.z0 = c->z0 + (size_t)w0 * n;
@@ -486,7 +500,7 @@ static Slice slice_of(gem_ctx* c, int w0) {
 
 // z: plain latent [W][n]; or, when z_hi/z_lo are given, the same already split into TF32 parts
 static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice& v_, const float* z, float* pose_out,
-                       const float* z_hi = nullptr, const float* z_lo = nullptr) {
+                       const void* z_hi = nullptr, const void* z_lo = nullptr) {
     const gem_vae_weights& v = c->vae[which];
     const int T = c->T, M = W * T, P = c->J * 3;
     if (use_tc_chain(c, which, W)) {
@@ -532,6 +546,14 @@ static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const S
             in_hi = v_.gact_hi[a], in_lo = v_.gact_lo[a];
             lda = v.dec_bwd[i].n;
         }
+        if (c->gemm_mode == 2) {
+            // fp16 scheme: gradient rows are rescaled to ~2^10 before the split (they shrink to 1e-7 near convergence)
+            GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 6, [&]() {
+                return launch_rowscale_split_f16(s, v_.gact_hi[0], v_.gact_lo[0], W, T * 256, v_.g0_h16, v_.g0_l16, v_.row_exp);
+            }));
+            return run_layer(c, s, GEM_TAG_DEC_BWD + 5, v.dec_bwd[5], nullptr, T * 256, W, dz, c->n, EPI_NONE, nullptr,
+                             v_.g0_h16, v_.g0_l16, nullptr, nullptr, v_.row_exp);
+        }
         return run_layer(c, s, GEM_TAG_DEC_BWD + 5, v.dec_bwd[5], nullptr, T * 256, W, dz, c->n, EPI_NONE, nullptr,
                          v_.gact_hi[0], v_.gact_lo[0]);
     }
@@ -559,7 +581,13 @@ static int encode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice
         lda = v.enc[i].n;
     }
     const gem_layer& fcL = v.enc[5];
-    if (c->gemm_mode == 1 && fcL.k % 32 == 0 && fcL.n % 128 == 0) {
+    if (c->gemm_mode == 2 && fcL.k % 64 == 0 && fcL.n % 128 == 0) {
+        GEM_TRY(timed(c, s, GEM_TAG_ENC + 5, [&]() {
+            return launch_split_f16(s, in, T * 512, W, T * 512, nullptr, (uint16_t*)v_.e4_hi, (uint16_t*)v_.e4_lo);
+        }));
+        GEM_TRY(run_layer(c, s, GEM_TAG_ENC + 5, fcL, nullptr, T * 512, W, v_.fc, 2 * c->n, EPI_NONE, nullptr, v_.e4_hi,
+                          v_.e4_lo));
+    } else if (c->gemm_mode == 1 && fcL.k % 32 == 0 && fcL.n % 128 == 0) {
         // split into the slice's own buffers (the GEMM's internal split scratch is shared by the whole ctx)
         GEM_TRY(timed(c, s, GEM_TAG_ENC + 5,
                       [&]() { return launch_split_tf32(s, in, T * 512, W, T * 512, v_.e4_hi, v_.e4_lo); }));
@@ -628,8 +656,8 @@ int gem_gemm(gem_ctx* c, void* stream, int M, int N, int K, const float* a_d, in
     gem_layer L;
     L.w_d = b_d, L.bias_d = bias_d, L.taps = 1, L.k = K, L.n = N;
     const int saved = c->gemm_mode;
-    if (use_tensor_cores) GEM_TRY(tc_gemm_prepare_weight(c, (cudaStream_t)stream, b_d, N, K, N));
-    c->gemm_mode = use_tensor_cores ? 1 : 0;
+    if (use_tensor_cores) GEM_TRY(tc_gemm_prepare_weight(c, (cudaStream_t)stream, b_d, N, K, N, use_tensor_cores == 2 ? 2 : 1));
+    c->gemm_mode = use_tensor_cores == 2 ? 2 : (use_tensor_cores ? 1 : 0);
     const int rc = run_layer(c, (cudaStream_t)stream, GEM_TAG_OTHER, L, a_d, lda, M, c_d, ldc,
                              leaky_relu ? EPI_LRELU : EPI_NONE, nullptr);
     c->gemm_mode = saved;
@@ -766,6 +794,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     LbfgsBuffers& lb = v.lb;
     lb.lr = a.p.lr, lb.tol_grad = a.p.tolerance_grad, lb.tol_change = a.p.tolerance_change;
     lb.max_iter = a.p.max_iter, lb.max_eval = a.p.max_eval;
+    lb.zt_f16 = c->gemm_mode == 2;
     lb.trace = a.trace ? v.trace_own : nullptr;
     lb.trace_stride = a.trace ? c->trace_cap : 0;
     if (a.trace) GEM_CUDA(cudaMemsetAsync(v.trace_own, 0xff, (size_t)Wk * c->trace_cap * sizeof(float), q));   // NaN

@@ -23,7 +23,14 @@
 //   warps 2-5 epilogue: tcgen05.ld the accumulator (32 lanes x 32 columns per instruction), bias /
 //            LeakyReLU, 128-byte row segments straight to global memory
 // Weights are transposed to K-major [N][K] and split once per checkpoint; activations are split by a
-// small elementwise kernel before each GEMM.
+// small elementwise kernel before each GEMM, or arrive already split from the producing kernel.
+//
+// Second scheme, same kernel (template parameter F16), twice the tensor rate and half the operand bytes:
+// x ~ hi + 2^-11 lo with hi = fp16(x), lo = fp16((x - hi) 2^11) (tc_common.cuh: split_f16), the products issued
+// as tcgen05.mma.kind::f16 (K = 16):  hi*hi into the main accumulators,  hi*lo + lo*hi into a separate "cross"
+// accumulator that the epilogue scales by 2^-11.  22 significant bits for |x| in [2^-14, 65504], an absolute
+// 2^-35 below; callers whose rows can be tiny (gradients) pre-scale them by a power of two and pass the
+// exponents (TapGemmArgs::row_exp) so that the epilogue undoes it exactly.
 #include <stdlib.h>
 
 #include <mutex>
@@ -37,9 +44,9 @@ using namespace tc;
 
 namespace {
 
-constexpr int BM = 128, BK = 32;                  // BK fp32 = 128 bytes = one swizzle row
+constexpr int BM = 128;
 constexpr int kStages = 3;
-constexpr int kATileBytes = BM * BK * 4;          // 16 KB
+constexpr int kATileBytes = BM * 128;             // 16 KB: 128 rows of one 128-byte swizzle row (32 fp32 or 64 fp16)
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;                    // all of TMEM: up to four BN-column accumulators
 
@@ -48,9 +55,11 @@ constexpr int kTmemCols = 512;                    // all of TMEM: up to four BN-
 // T*256 layer); 160 / 112 / 144 columns bring it under the wave boundary.
 template <int BN>
 struct GemmCfg {
-    static constexpr int kBTileBytes = BN * BK * 4;
+    static constexpr int kBTileBytes = BN * 128;
     static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;      // A_hi, A_lo, B_hi, B_lo
     static constexpr int kAcc = (kTmemCols / BN) < 4 ? (kTmemCols / BN) : 4;   // independent fp32 accumulators
+    static constexpr int kMain16 = (kAcc - 1) < 2 ? (kAcc - 1) : 2;            // fp16 scheme: main accumulators ...
+    static constexpr int kCross16 = kMain16;                                   // ... and the index of the cross one
     static constexpr int kPitch = BN + 4;                                      // staging row pitch (floats)
     static constexpr int kStageOut = 32 * kPitch * 4;                          // one warp's staged 32 x BN block
     static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -64,10 +73,11 @@ struct TcArgs {
     float* C;        // result, or its TF32 hi part when C_lo is set
     float* C_lo;     // optional: the epilogue writes the result already split for the next tensor-core layer
     uint32_t* sign;  // optional: packed sign bits of the result, [M][N/32] (needs BN % 32 == 0)
+    const int32_t* row_exp;   // optional: row m of A was scaled by 2^row_exp[m]; the result row is scaled back
     int M, N, K, ldc, epi;
 };
 
-template <int BN>
+template <int BN, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, TcArgs g) {
@@ -82,6 +92,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    constexpr int BK = F16 ? 64 : 32;             // elements per 128-byte row
     const int num_kb = g.K / BK;
 
     if (warp == 0 && lane == 0) {
@@ -114,7 +125,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc_tf32(BM, BN);
+            constexpr uint32_t idesc = F16 ? instr_desc_f16(BM, BN) : instr_desc_tf32(BM, BN);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kStages;
                 mbar_wait(&full_bar[s], (kb / kStages) & 1);
@@ -124,13 +135,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const uint64_t b_hi = make_smem_desc(base + 2 * kATileBytes);
                 const uint64_t b_lo = make_smem_desc(base + 2 * kATileBytes + C::kBTileBytes);
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
-                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);     // 32 bytes per K=8 step inside the 128-B row
-                    // small terms first, then the dominant one
-                    const uint32_t acc = tmem_base + (uint32_t)((kb % kAcc) * BN);
-                    umma_tf32(acc, a_lo + adv, b_hi + adv, idesc, (kb >= kAcc) || (k != 0));
-                    umma_tf32(acc, a_hi + adv, b_lo + adv, idesc, 1);
-                    umma_tf32(acc, a_hi + adv, b_hi + adv, idesc, 1);
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 32) >> 4);        // 32 bytes per MMA K step inside the 128-B row
+                    if (F16) {
+                        const uint32_t cross = tmem_base + (uint32_t)(C::kCross16 * BN);
+                        const uint32_t acc = tmem_base + (uint32_t)((kb % C::kMain16) * BN);
+                        umma_f16(cross, a_lo + adv, b_hi + adv, idesc, (kb != 0) || (k != 0));
+                        umma_f16(cross, a_hi + adv, b_lo + adv, idesc, 1);
+                        umma_f16(acc, a_hi + adv, b_hi + adv, idesc, (kb >= C::kMain16) || (k != 0));
+                    } else {
+                        // small terms first, then the dominant one
+                        const uint32_t acc = tmem_base + (uint32_t)((kb % kAcc) * BN);
+                        umma_tf32(acc, a_lo + adv, b_hi + adv, idesc, (kb >= kAcc) || (k != 0));
+                        umma_tf32(acc, a_hi + adv, b_lo + adv, idesc, 1);
+                        umma_tf32(acc, a_hi + adv, b_hi + adv, idesc, 1);
+                    }
                 }
                 umma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs have read it
             }
@@ -147,7 +166,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int m = m0 + q * 32 + lane;
         float* stage_hi = reinterpret_cast<float*>(smem + (size_t)(q * 2 + 0) * C::kStageOut);
         float* stage_lo = reinterpret_cast<float*>(smem + (size_t)(q * 2 + 1) * C::kStageOut);
-        const int nacc = num_kb < kAcc ? num_kb : kAcc;
+        const int nmain = F16 ? C::kMain16 : kAcc;
+        const int nacc = num_kb < nmain ? num_kb : nmain;
+        float row_scale = 1.f;
+        if (g.row_exp && m < g.M) row_scale = exp2f(-(float)g.row_exp[m]);      // exact: a power of two
         uint32_t sbits = 0;
 #pragma unroll 1
         for (int c = 0; c < BN / 16; ++c) {
@@ -162,11 +184,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t[j]));
             }
+            if (F16) {                    // + 2^-11 (hi*lo + lo*hi)
+                uint32_t t[16];
+                tmem_ld_32x32b_x16(taddr + (uint32_t)(C::kCross16 * BN), t);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t[j]) * (1.f / kF16LoScale));
+            }
             const int nb = n0 + c * 16;
             float o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                float x = __uint_as_float(v[j]);
+                float x = __uint_as_float(v[j]) * row_scale;
                 if (g.bias && nb + j < g.N) x += __ldg(g.bias + nb + j);
                 if (g.epi == EPI_LRELU) x = x > 0.f ? x : x * 0.01f;
                 o[j] = x;
@@ -257,26 +287,122 @@ __global__ void transpose_split_kernel(const float* __restrict__ B, int ldb, int
     }
 }
 
+// the fp16 scheme's split (tc_common.cuh: split_f16), optionally of rows pre-scaled by 2^row_exp[m]
+__global__ void split_f16_kernel(const float* __restrict__ A, int lda, int M, int K, const int32_t* __restrict__ row_exp,
+                                 uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one float4 per thread
+    const int kv = K / 4;
+    if (i >= (size_t)M * kv) return;
+    const int m = (int)(i / kv), k = (int)(i - (size_t)m * kv) * 4;
+    float4 x = *reinterpret_cast<const float4*>(A + (size_t)m * lda + k);
+    if (row_exp) {
+        const float sc = exp2f((float)row_exp[m]);
+        x.x *= sc, x.y *= sc, x.z *= sc, x.w *= sc;
+    }
+    uint16_t h[4], l[4];
+    split_f16(x.x, h[0], l[0]), split_f16(x.y, h[1], l[1]), split_f16(x.z, h[2], l[2]), split_f16(x.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(hi + (size_t)m * K + k) =
+        make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+    *reinterpret_cast<uint2*>(lo + (size_t)m * K + k) =
+        make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+}
+
+__global__ void transpose_split_f16_kernel(const float* __restrict__ B, int ldb, int K, int N, uint16_t* __restrict__ hi,
+                                           uint16_t* __restrict__ lo) {
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int k = k0 + r, n = n0 + threadIdx.x;
+        tile[r][threadIdx.x] = (k < K && n < N) ? B[(size_t)k * ldb + n] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int n = n0 + r, k = k0 + threadIdx.x;
+        if (n < N && k < K) {
+            uint16_t h, l;
+            split_f16(tile[threadIdx.x][r], h, l);
+            hi[(size_t)n * K + k] = h;
+            lo[(size_t)n * K + k] = l;
+        }
+    }
+}
+
+// One CTA per row: x = hi (+ lo) in fp32  ->  the row's power-of-two scale 2^e that brings max|x| to ~2^10, and
+// the fp16 split of x 2^e.  Gradient rows can be arbitrarily small (1e-7 near convergence); unscaled they would
+// fall into fp16's subnormals and keep only an absolute 2^-35.
+__global__ void __launch_bounds__(256) rowscale_split_f16_kernel(const float* __restrict__ xh, const float* __restrict__ xl,
+                                                                 int K, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                                 int32_t* __restrict__ row_exp) {
+    __shared__ float red[8];
+    const size_t row = blockIdx.x;
+    const float* ph = xh + row * K;
+    const float* pl = xl ? xl + row * K : nullptr;
+    float mx = 0.f;
+    for (int k = threadIdx.x * 4; k < K; k += 256 * 4) {
+        float4 v = *reinterpret_cast<const float4*>(ph + k);
+        if (pl) {
+            const float4 w = *reinterpret_cast<const float4*>(pl + k);
+            v.x += w.x, v.y += w.y, v.z += w.z, v.w += w.w;
+        }
+        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    int e = 0;
+    if (mx > 0.f && mx < 3.0e38f) {
+        e = 10 - ilogbf(mx);
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    }
+    const float sc = exp2f((float)e);
+    if (threadIdx.x == 0) row_exp[row] = e;
+    for (int k = threadIdx.x * 4; k < K; k += 256 * 4) {
+        float4 v = *reinterpret_cast<const float4*>(ph + k);
+        if (pl) {
+            const float4 w = *reinterpret_cast<const float4*>(pl + k);
+            v.x += w.x, v.y += w.y, v.z += w.z, v.w += w.w;      // hi + lo is exact
+        }
+        uint16_t h[4], l[4];
+        split_f16(v.x * sc, h[0], l[0]), split_f16(v.y * sc, h[1], l[1]);
+        split_f16(v.z * sc, h[2], l[2]), split_f16(v.w * sc, h[3], l[3]);
+        *reinterpret_cast<uint2*>(hi + row * K + k) =
+            make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+        *reinterpret_cast<uint2*>(lo + row * K + k) =
+            make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+    }
+}
+
 // ---------------------------------------------------------------- host side
-// rows x K fp32 row-major (pitch K), box = 128 rows x 32 floats, 128-byte swizzle, OOB rows read zero
-int make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t K, uint64_t pitch = 0, int box_rows = BM) {
+// rows x K row-major (pitch in elements), box = box_rows x one 128-byte row, 128-byte swizzle, OOB rows read zero
+int make_map(CUtensorMap* map, const void* base, bool f16, uint64_t rows, uint64_t K, uint64_t pitch = 0,
+             int box_rows = BM) {
+    const uint64_t esz = f16 ? 2 : 4;
     const uint64_t dims[2] = {K, rows};
-    const uint64_t strides[1] = {(pitch ? pitch : K) * sizeof(float)};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)box_rows};
-    return make_map_f32(map, base, 2, dims, strides, box);
+    const uint64_t strides[1] = {(pitch ? pitch : K) * esz};
+    const uint32_t box[2] = {(uint32_t)(128 / esz), (uint32_t)box_rows};
+    return f16 ? make_map_u16(map, base, 2, dims, strides, box)
+               : make_map_f32(map, static_cast<const float*>(base), 2, dims, strides, box);
 }
 
 constexpr int kNumBN = 4;
 constexpr int kBNs[kNumBN] = {112, 128, 144, 160};
 struct WeightSplit {
-    float *hi = nullptr, *lo = nullptr;
+    void *hi = nullptr, *lo = nullptr;                 // K-major [N][K], fp32 (TF32 scheme) or fp16
     int K = 0, N = 0;
     CUtensorMap map_hi[kNumBN], map_lo[kNumBN];       // one box height per N-tile width
 };
+struct KeyHash {
+    size_t operator()(const std::pair<const float*, int>& k) const {
+        return std::hash<const void*>()(k.first) ^ ((size_t)k.second * 0x9E3779B97F4A7C15ull);
+    }
+};
 struct TcState {
-    std::unordered_map<const float*, WeightSplit> weights;   // keyed by the caller's weight pointer
-    float *a_hi = nullptr, *a_lo = nullptr;
-    size_t a_capacity = 0;                                    // floats in each of a_hi / a_lo
+    std::unordered_map<std::pair<const float*, int>, WeightSplit, KeyHash> weights;   // (caller's weight pointer, scheme)
+    void *a_hi = nullptr, *a_lo = nullptr;
+    size_t a_capacity = 0;                                    // bytes in each of a_hi / a_lo
 };
 std::mutex g_mu;
 std::unordered_map<void*, TcState*> g_states;                // one per workspace owner (ctx)
@@ -298,8 +424,8 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int make_map_f32(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                 const uint32_t* box) {
+static int make_map_any(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -309,7 +435,7 @@ int make_map_f32(CUtensorMap* map, const float* base, int rank, const uint64_t* 
     cuuint32_t bx[5], estr[5];
     for (int i = 0; i < rank; ++i) d[i] = dims[i], bx[i] = box[i], estr[i] = 1;
     for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), d, st, bx, estr,
+    CUresult r = enc(map, dt, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -319,69 +445,98 @@ int make_map_f32(CUtensorMap* map, const float* base, int rank, const uint64_t* 
     return GEM_OK;
 }
 
+int make_map_f32(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box) {
+    return make_map_any(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
+}
+int make_map_u16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box) {
+    return make_map_any(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, base, rank, dims, strides_bytes, box);
+}
+
 }  // namespace tc
 
 bool tc_gemm_available() { return true; }
 
 // `owner` identifies the ctx; scratch grows on demand and lives until tc_gemm_release(owner).
-template <int BN>
+template <int BN, bool F16>
 static int launch_bn(cudaStream_t stream, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const WeightSplit& w, int idx,
                      const TcArgs& a) {
     static bool attr_set = false;
     if (!attr_set) {
-        GEM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GEM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)GemmCfg<BN>::kSmemBytes));
         attr_set = true;
     }
     dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN);
-    tc_gemm_kernel<BN><<<grid, kThreads, GemmCfg<BN>::kSmemBytes, stream>>>(a_hi, a_lo, w.map_hi[idx], w.map_lo[idx], a);
+    tc_gemm_kernel<BN, F16><<<grid, kThreads, GemmCfg<BN>::kSmemBytes, stream>>>(a_hi, a_lo, w.map_hi[idx], w.map_lo[idx], a);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }
-
-// `owner` identifies the ctx; scratch grows on demand and lives until tc_gemm_release(owner).
-int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, size_t) {
-    if (g.M <= 0) return GEM_OK;
-    GEM_REQUIRE(g.taps == 1, "tcgen05 path handles plain GEMMs only");
-    GEM_REQUIRE(g.K % BK == 0 && g.N % 128 == 0, "K must be a multiple of 32 and N of 128 for the tcgen05 path");
-    GEM_REQUIRE(g.lda % 4 == 0 && g.ldc % 4 == 0, "lda/ldc must be multiples of 4");
-    GEM_REQUIRE(g.epi == EPI_NONE || g.epi == EPI_LRELU, "unsupported epilogue on the tcgen05 path");
-    TcState* st;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        auto it = g_states.find(owner);
-        if (it == g_states.end()) it = g_states.emplace(owner, new TcState()).first;
-        st = it->second;
+template <bool F16>
+static int launch_scheme(int bn, cudaStream_t stream, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const WeightSplit& w,
+                         int idx, const TcArgs& a) {
+    switch (bn) {
+        case 112: return launch_bn<112, F16>(stream, a_hi, a_lo, w, idx, a);
+        case 144: return launch_bn<144, F16>(stream, a_hi, a_lo, w, idx, a);
+        case 160: return launch_bn<160, F16>(stream, a_hi, a_lo, w, idx, a);
+        default: return launch_bn<128, F16>(stream, a_hi, a_lo, w, idx, a);
     }
+}
+
+static TcState* state_of(void* owner) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_states.find(owner);
+    if (it == g_states.end()) it = g_states.emplace(owner, new TcState()).first;
+    return it->second;
+}
+
+// scheme: 1 = 3xTF32 (fp32 hi / lo operands), 2 = fp16 hi + scaled fp16 lo operands
+int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, size_t scheme) {
+    if (g.M <= 0) return GEM_OK;
+    const bool f16 = scheme == 2;
+    const int bk = f16 ? 64 : 32;
+    const size_t esz = f16 ? 2 : 4;
+    GEM_REQUIRE(g.taps == 1, "tcgen05 path handles plain GEMMs only");
+    GEM_REQUIRE(g.K % bk == 0 && g.N % 128 == 0, "K must be a multiple of the 128-byte K block and N of 128");
+    GEM_REQUIRE(g.lda % 8 == 0 && g.ldc % 4 == 0, "lda must be a multiple of 8, ldc of 4");
+    GEM_REQUIRE(g.epi == EPI_NONE || g.epi == EPI_LRELU, "unsupported epilogue on the tcgen05 path");
+    TcState* st = state_of(owner);
     // weights: K-major hi/lo copies registered by tc_gemm_prepare_weight
-    auto wit = st->weights.find(g.B);
+    auto wit = st->weights.find(std::make_pair(g.B, (int)(f16 ? 2 : 1)));
     if (wit == st->weights.end() || wit->second.K != g.K || wit->second.N != g.N) {
         set_error("tcgen05 path: weight matrix was not prepared (tc_gemm_prepare_weight)");
         return GEM_ERR_STATE;
     }
     // activations: already split by the producing kernel, or split here into the ctx-owned scratch
-    const float *a_hi = g.A_hi, *a_lo = g.A_lo;
+    const void *a_hi = g.A_hi, *a_lo = g.A_lo;
     uint64_t pitch = (uint64_t)g.lda;
     if (!a_hi) {
-        const size_t need = (size_t)g.M * g.K;
+        const size_t need = (size_t)g.M * g.K * esz;
         if (need > st->a_capacity) {
             GEM_CUDA(cudaStreamSynchronize(stream));
             if (st->a_hi) cudaFree(st->a_hi), cudaFree(st->a_lo);
-            GEM_CUDA(cudaMalloc(&st->a_hi, need * sizeof(float)));
-            GEM_CUDA(cudaMalloc(&st->a_lo, need * sizeof(float)));
+            GEM_CUDA(cudaMalloc(&st->a_hi, need));
+            GEM_CUDA(cudaMalloc(&st->a_lo, need));
             st->a_capacity = need;
         }
         const size_t n4 = (size_t)g.M * (g.K / 4);
-        split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(g.A, g.lda, g.M, g.K, st->a_hi, st->a_lo);
+        if (f16)
+            split_f16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(g.A, g.lda, g.M, g.K, g.row_exp,
+                                                                            (uint16_t*)st->a_hi, (uint16_t*)st->a_lo);
+        else
+            split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(g.A, g.lda, g.M, g.K, (float*)st->a_hi,
+                                                                             (float*)st->a_lo);
         GEM_CHECK_LAUNCH();
         a_hi = st->a_hi, a_lo = st->a_lo, pitch = (uint64_t)g.K;
     }
     CUtensorMap map_a_hi, map_a_lo;
-    int rc = make_map(&map_a_hi, a_hi, (uint64_t)g.M, (uint64_t)g.K, pitch);
-    if (rc == GEM_OK) rc = make_map(&map_a_lo, a_lo, (uint64_t)g.M, (uint64_t)g.K, pitch);
+    int rc = make_map(&map_a_hi, a_hi, f16, (uint64_t)g.M, (uint64_t)g.K, pitch);
+    if (rc == GEM_OK) rc = make_map(&map_a_lo, a_lo, f16, (uint64_t)g.M, (uint64_t)g.K, pitch);
     if (rc != GEM_OK) return rc;
     TcArgs a;
-    a.bias = g.bias, a.C = g.C, a.C_lo = g.C_lo, a.sign = g.C_sign, a.M = g.M, a.N = g.N, a.K = g.K, a.ldc = g.ldc, a.epi = g.epi;
+    a.bias = g.bias, a.C = g.C, a.C_lo = (float*)g.C_lo, a.sign = g.C_sign, a.M = g.M, a.N = g.N, a.K = g.K, a.ldc = g.ldc;
+    a.epi = g.epi, a.row_exp = f16 ? g.row_exp : nullptr;
     // N-tile width.  Up to one wave of 128-wide tiles: keep 128 (kernels of concurrent slices share the SMs, the
     // least padded tiling wins).  Beyond: the fewest waves x columns over the 148 SMs (sign words need
     // 32-column alignment).
@@ -400,12 +555,8 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
         for (int i = 0; i < kNumBN; ++i)
             if (atoi(env) == kBNs[i] && !(g.C_sign && kBNs[i] % 32 != 0)) best = i;
     }
-    switch (kBNs[best]) {
-        case 112: return launch_bn<112>(stream, map_a_hi, map_a_lo, wit->second, best, a);
-        case 144: return launch_bn<144>(stream, map_a_hi, map_a_lo, wit->second, best, a);
-        case 160: return launch_bn<160>(stream, map_a_hi, map_a_lo, wit->second, best, a);
-        default: return launch_bn<128>(stream, map_a_hi, map_a_lo, wit->second, best, a);
-    }
+    return f16 ? launch_scheme<true>(kBNs[best], stream, map_a_hi, map_a_lo, wit->second, best, a)
+               : launch_scheme<false>(kBNs[best], stream, map_a_hi, map_a_lo, wit->second, best, a);
 }
 
 // x -> (hi, lo) TF32 parts for M rows of K floats (K % 4 == 0; output pitch K)
@@ -417,19 +568,35 @@ int launch_split_tf32(cudaStream_t stream, const float* A, int lda, int M, int K
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }
+// x -> fp16 (hi, scaled lo) for M rows of K floats, rows optionally pre-scaled by 2^row_exp[m]
+int launch_split_f16(cudaStream_t stream, const float* A, int lda, int M, int K, const int32_t* row_exp, uint16_t* hi,
+                     uint16_t* lo) {
+    if (M <= 0) return GEM_OK;
+    GEM_REQUIRE(K % 4 == 0 && lda % 4 == 0, "K and lda must be multiples of 4");
+    const size_t n4 = (size_t)M * (K / 4);
+    split_f16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(A, lda, M, K, row_exp, hi, lo);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
 
-// Transposes B [K][ldb] to K-major [N][K] and splits it into TF32 hi / lo parts; replaces any earlier
-// registration of the same pointer (the caller may have refilled the buffer).
-int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N) {
-    GEM_REQUIRE(K % BK == 0 && N % 128 == 0, "K must be a multiple of 32 and N of 128 for the tcgen05 path");
-    TcState* st;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        auto it = g_states.find(owner);
-        if (it == g_states.end()) it = g_states.emplace(owner, new TcState()).first;
-        st = it->second;
-    }
-    auto old = st->weights.find(B);
+// rows of x = xh (+ xl) -> per-row power-of-two scale + fp16 split of the scaled row (K % 4 == 0, dense rows)
+int launch_rowscale_split_f16(cudaStream_t stream, const float* xh, const float* xl, int M, int K, uint16_t* hi,
+                              uint16_t* lo, int32_t* row_exp) {
+    if (M <= 0) return GEM_OK;
+    GEM_REQUIRE(K % 4 == 0, "K must be a multiple of 4");
+    rowscale_split_f16_kernel<<<M, 256, 0, stream>>>(xh, xl, K, hi, lo, row_exp);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+// Transposes B [K][ldb] to K-major [N][K] and splits it into hi / lo parts for one scheme (1 = 3xTF32, 2 = fp16);
+// replaces any earlier registration of the same pointer (the caller may have refilled the buffer).
+int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N, int scheme) {
+    const bool f16 = scheme == 2;
+    GEM_REQUIRE(K % (f16 ? 64 : 32) == 0 && N % 128 == 0, "K must be a multiple of the 128-byte K block and N of 128");
+    TcState* st = state_of(owner);
+    const auto key = std::make_pair(B, (int)(f16 ? 2 : 1));
+    auto old = st->weights.find(key);
     if (old != st->weights.end()) {
         GEM_CUDA(cudaStreamSynchronize(stream));
         cudaFree(old->second.hi), cudaFree(old->second.lo);
@@ -437,17 +604,21 @@ int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int
     }
     WeightSplit ws;
     ws.K = K, ws.N = N;
-    GEM_CUDA(cudaMalloc(&ws.hi, (size_t)N * K * sizeof(float)));
-    GEM_CUDA(cudaMalloc(&ws.lo, (size_t)N * K * sizeof(float)));
+    const size_t bytes = (size_t)N * K * (f16 ? 2 : 4);
+    GEM_CUDA(cudaMalloc(&ws.hi, bytes));
+    GEM_CUDA(cudaMalloc(&ws.lo, bytes));
     dim3 grid((K + 31) / 32, (N + 31) / 32), block(32, 8);
-    transpose_split_kernel<<<grid, block, 0, stream>>>(B, ldb, K, N, ws.hi, ws.lo);
+    if (f16)
+        transpose_split_f16_kernel<<<grid, block, 0, stream>>>(B, ldb, K, N, (uint16_t*)ws.hi, (uint16_t*)ws.lo);
+    else
+        transpose_split_kernel<<<grid, block, 0, stream>>>(B, ldb, K, N, (float*)ws.hi, (float*)ws.lo);
     GEM_CHECK_LAUNCH();
     for (int i = 0; i < kNumBN; ++i) {
-        int rc = make_map(&ws.map_hi[i], ws.hi, (uint64_t)N, (uint64_t)K, 0, kBNs[i]);
-        if (rc == GEM_OK) rc = make_map(&ws.map_lo[i], ws.lo, (uint64_t)N, (uint64_t)K, 0, kBNs[i]);
+        int rc = make_map(&ws.map_hi[i], ws.hi, f16, (uint64_t)N, (uint64_t)K, 0, kBNs[i]);
+        if (rc == GEM_OK) rc = make_map(&ws.map_lo[i], ws.lo, f16, (uint64_t)N, (uint64_t)K, 0, kBNs[i]);
         if (rc != GEM_OK) return rc;
     }
-    st->weights.emplace(B, ws);
+    st->weights.emplace(key, ws);
     return GEM_OK;
 }
 

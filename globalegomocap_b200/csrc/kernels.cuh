@@ -15,8 +15,9 @@ int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, 
 enum { EPI_NONE = 0, EPI_LRELU = 1, EPI_MASK = 2 };
 struct TapGemmArgs {
     const float* A;      // [M][lda]
-    const float* A_hi = nullptr;   // tensor-core path only: A already split into TF32 hi / lo parts ([M][lda] each)
-    const float* A_lo = nullptr;
+    const void* A_hi = nullptr;    // tensor-core path only: A already split into hi / lo parts ([M][lda] each; fp32 TF32
+    const void* A_lo = nullptr;    //   values, or fp16 with the fp16 scheme)
+    const int32_t* row_exp = nullptr;   // fp16 scheme: row m of A carries a factor 2^row_exp[m] that the epilogue removes
     float* C_lo = nullptr;         // tensor-core path only: write the result split (hi to C, lo to C_lo)
     uint32_t* C_sign = nullptr;    // tensor-core path only: packed sign bits of the result [M][N/32]
     const float* B;      // [taps][K][ldb]
@@ -28,8 +29,13 @@ struct TapGemmArgs {
     int epi;
 };
 int launch_tap_gemm_simt(cudaStream_t stream, const TapGemmArgs& g);
-int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, size_t reserved);
-int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N);
+// scheme: 1 = 3xTF32, 2 = fp16 hi + scaled fp16 lo (kind::f16, cross terms in their own accumulator)
+int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, size_t scheme);
+int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N, int scheme = 1);
+int launch_split_f16(cudaStream_t stream, const float* A, int lda, int M, int K, const int32_t* row_exp, uint16_t* hi,
+                     uint16_t* lo);
+int launch_rowscale_split_f16(cudaStream_t stream, const float* xh, const float* xl, int M, int K, uint16_t* hi,
+                              uint16_t* lo, int32_t* row_exp);
 int launch_split_tf32(cudaStream_t stream, const float* A, int lda, int M, int K, float* hi, float* lo);
 void tc_gemm_release(void* owner);
 bool tc_gemm_available();
@@ -59,7 +65,8 @@ struct LbfgsWin;
 struct LbfgsBuffers {
     LbfgsWin* st;
     float *X, *D, *G, *GP, *BG0, *BG1, *ZT;   // [W][n]  (prev_flat_grad is G itself, see lbfgs.cu)
-    float *ZT_hi, *ZT_lo;                           // optional [W][n]: the trial point as TF32 hi / lo parts
+    float *ZT_hi, *ZT_lo;                           // optional [W][n]: the trial point as TF32 hi / lo parts, or,
+    int zt_f16;                                     //   when zt_f16, as fp16 hi / scaled lo (uint16 [W][n] in the same buffers)
     float *Y, *S;                                   // [W][m][n]
     float* RO;                                      // [W][m]
     float* trace;                                   // [W][trace_stride] or NULL

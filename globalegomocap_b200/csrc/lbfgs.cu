@@ -96,9 +96,32 @@ __device__ __forceinline__ void st8(float* __restrict__ p, const float (&r)[kPer
 }
 // trial point: plain (host-driven closures read it) and, when requested, split into TF32 hi / lo parts so the
 // decoder's first tensor-core GEMM can consume it without a separate split pass
+__device__ __forceinline__ void split_f16_dev(float x, uint16_t& hi, uint16_t& lo) {     // = tc::split_f16
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hi) : "f"(x));
+    float hf;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(hi));
+    const float r = (x - hf) * 2048.f;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(lo) : "f"(r));
+}
 __device__ __forceinline__ void st_trial(const LbfgsBuffers& b, size_t off, const float (&r)[kPer], int tid, int n4) {
     st8(b.ZT + off, r, tid, n4);
-    if (b.ZT_hi) {
+    if (!b.ZT_hi) return;
+    if (b.zt_f16) {
+        uint16_t* zh = reinterpret_cast<uint16_t*>(b.ZT_hi) + off;
+        uint16_t* zl = reinterpret_cast<uint16_t*>(b.ZT_lo) + off;
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+            const int c = tid + i * kLbThreads;
+            if (c >= n4) continue;
+            uint16_t h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_f16_dev(r[4 * i + j], h[j], l[j]);
+            *reinterpret_cast<uint2*>(zh + 4 * c) =
+                make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+            *reinterpret_cast<uint2*>(zl + 4 * c) =
+                make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+        }
+    } else {
         float h[kPer], l[kPer];
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
@@ -180,7 +203,12 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_begin_kernel(LbfgsBuffers b,
         const float v = z0[off + i];
         b.X[off + i] = v;
         b.ZT[off + i] = v;
-        if (b.ZT_hi) {
+        if (b.ZT_hi && b.zt_f16) {
+            uint16_t h, l;
+            split_f16_dev(v, h, l);
+            reinterpret_cast<uint16_t*>(b.ZT_hi)[off + i] = h;
+            reinterpret_cast<uint16_t*>(b.ZT_lo)[off + i] = l;
+        } else if (b.ZT_hi) {
             const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
             b.ZT_hi[off + i] = h;
             b.ZT_lo[off + i] = v - h;

@@ -34,6 +34,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// same with fp16 inputs (kind::f16, K = 16 per instruction)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when they complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -92,6 +100,24 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// kind::f16 descriptor: fp16 A and B (format 0; mixing fp16 with bf16 operands in one instruction is illegal on
+// sm_100a), fp32 accumulate, K-major
+__host__ __device__ constexpr uint32_t instr_desc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// fp16 split of an fp32 value: hi = fp16(x), lo = fp16((x - hi) * 2^11), both saturating (no infinities).
+// x ~ hi + lo * 2^-11 carries 22 significant bits for 2^-14 <= |x| <= 65504 and an absolute precision of
+// 2^-35 below that (fp16 subnormals); products with lo go to a separate accumulator that is scaled by 2^-11.
+constexpr float kF16LoScale = 2048.f;
+__device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(hi) : "f"(x));
+    float hf;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(hi));
+    const float r = (x - hf) * kF16LoScale;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(lo) : "f"(r));
+}
+
 // x = hi + lo with hi = x with the 13 low mantissa bits cleared (an exact TF32 value), lo = x - hi (exact)
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
@@ -105,6 +131,9 @@ EncodeTiledFn get_encode_fn();
 // fp32 tensor of `rank` dims (dims[0] innermost), strides in bytes for dims 1.., box per dim; 128-byte swizzle,
 // out-of-bounds elements read as zero
 int make_map_f32(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box);
+// the same for 2-byte elements (fp16 operands of the kind::f16 scheme); dims and box in elements
+int make_map_u16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                  const uint32_t* box);
 
 }  // namespace tc

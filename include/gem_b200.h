@@ -100,8 +100,10 @@ int gem_ctx_set_skeleton(gem_ctx* ctx, const int32_t* parents_h, int num_joints)
 int gem_ctx_set_vae(gem_ctx* ctx, int which, const gem_vae_weights* weights_h);
 /* bytes of device scratch owned by the ctx */
 int64_t gem_ctx_scratch_bytes(const gem_ctx* ctx);
-/* 0: hand-written SIMT fp32 GEMM everywhere; 1: tcgen05/TMEM 3xTF32 GEMM for the latent<->T*256
- * contraction (default when available) */
+/* 0: hand-written SIMT fp32 layers everywhere; 1: tcgen05/TMEM, 3xTF32 arithmetic in every layer; 2 (default):
+ * like 1 but the plain GEMMs (latent<->T*256, encoder fc) use the fp16 scheme: x ~ fp16 hi + 2^-11 fp16 lo, three
+ * kind::f16 MMAs per product with the cross terms in their own accumulator, gradient rows rescaled by a power of
+ * two — twice the tensor rate of 3xTF32 and (measured) a smaller error against float64 */
 int gem_ctx_set_gemm_mode(gem_ctx* ctx, int mode);
 
 /* A stage's windows are independent: gem_solve_stage splits them into n_chunks slices (boundaries at
@@ -134,7 +136,7 @@ int gem_ctx_texel_cache_stats(gem_ctx* ctx, int enable, uint64_t* lookups_h, uin
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* kernel classes reported by gem_ctx_read_profile */
 #define GEM_TAG_DEC 100           /* +i: decoder forward layer i (0 = latent -> T*256 GEMM) */
-#define GEM_TAG_DEC_BWD 200       /* +i: decoder bwd-data layer i (5 = T*256 -> latent GEMM) */
+#define GEM_TAG_DEC_BWD 200       /* +i: decoder bwd-data layer i (5 = T*256 -> latent GEMM, 6 = its row-scaled fp16 split) */
 #define GEM_TAG_ENC 300           /* +i: encoder layer i (5 = T*512 -> 2*latent GEMM) */
 #define GEM_TAG_ENERGY 1
 #define GEM_TAG_LBFGS_BEGIN 2

@@ -106,3 +106,23 @@ def test_tc_tap_chain_ragged_window_counts(engine, W):
     torch.cuda.synchronize()
     assert _rel(pose_tc, pose_simt) < 1e-5, (W, _rel(pose_tc, pose_simt))
     assert _rel(dz_tc, dz_simt) < 2e-5, (W, _rel(dz_tc, dz_simt))   # six tensor-core layers in a row
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 128, 64), (300, 256, 128), (1870, 2560, 2048), (641, 2048, 2560), (130, 4096, 5120)])
+def test_fp16_scheme_gemm_against_float64(engine, M, N, K):
+    """tensor_cores=2: x ~ fp16 hi + 2^-11 fp16 lo, three kind::f16 MMAs, cross terms in their own accumulator.
+    Inputs with a spread of magnitudes (columns scaled by 1e-4 and 300) must come out at the same 1e-5 level
+    as the 3xTF32 scheme."""
+    g = torch.Generator(device="cpu").manual_seed(7 * M + N + K)
+    a = torch.randn(M, K, generator=g)
+    a[:, ::7] *= 1e-4
+    a[:, 3::11] *= 300.0
+    b = torch.randn(K, N, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    ref = a.double() @ b.double() + bias.double()
+    errs = {}
+    for mode in (1, 2):
+        c = engine.gemm(a, b, bias, leaky_relu=False, tensor_cores=mode).cpu()
+        errs[mode] = _rel(c, ref)
+    print((M, N, K), "relative max error vs float64: 3xTF32", errs[1], " fp16 scheme", errs[2])
+    assert errs[2] < 1e-5, errs
