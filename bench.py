@@ -66,7 +66,8 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=3000, help="frames per sequence per GPU")
     ap.add_argument("--max-iter", type=int, default=25)
     ap.add_argument("--gemm-mode", type=int, default=-1,
-                    help="-1 library default (2), 0 SIMT fp32, 1 tcgen05 3xTF32, 2 tcgen05 with fp16-scheme GEMMs")
+                    help="-1 library default (3), 0 SIMT fp32, 1 tcgen05 3xTF32, 2 fp16-scheme GEMMs + 3xTF32 convolutions, "
+                         "3 fp16 scheme everywhere")
     ap.add_argument("--cpu-windows", type=int, default=4, help="windows timed for cpu_baseline (after 1 warm-up)")
     ap.add_argument("--chunks", type=int, default=-1, help="window slices run concurrently per stage (-1 library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -122,7 +122,8 @@ static int timed(gem_ctx* c, cudaStream_t s, int tag, F&& f) {
 }
 
 static const int kDecC[6] = {256, 128, 64, 64, 64, 0};   // channels after dec[0..4]; dec[5] -> J*3
-static int pose_pad(const gem_ctx* c) { return (c->J * 3 + 3) & ~3; }   // row pitch of the split d pose (TMA: 16-byte pitch)
+// row pitch (elements) of the split d pose: 16-byte multiples for TMA; a whole 64-element K block with fp16 elements
+static int pose_pad(const gem_ctx* c) { return c->gemm_mode == 3 ? (c->J * 3 + 63) & ~63 : (c->J * 3 + 3) & ~3; }
 static const int kEncC[5] = {64, 64, 128, 256, 512};
 
 static int ensure_streams(gem_ctx* c, int n) {
@@ -222,10 +223,10 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
         gem_ctx_destroy(c);
         return rc;
     }
-    // default: tcgen05 everywhere, the plain GEMMs in the fp16 scheme (2); GEM_GEMM_MODE / gem_ctx_set_gemm_mode select
-    // 1 (3xTF32 GEMMs) or 0 (fp32 CUDA cores)
-    c->gemm_mode = 2;
-    if (const char* env = getenv("GEM_GEMM_MODE")) c->gemm_mode = (env[0] == '0') ? 0 : (env[0] == '2' ? 2 : 1);
+    // default: tcgen05 everywhere in the fp16 scheme (3); GEM_GEMM_MODE / gem_ctx_set_gemm_mode select 2 (fp16-scheme
+    // GEMMs, 3xTF32 convolutions), 1 (3xTF32 everywhere) or 0 (fp32 CUDA cores)
+    c->gemm_mode = 3;
+    if (const char* env = getenv("GEM_GEMM_MODE")) c->gemm_mode = (env[0] >= '0' && env[0] <= '3') ? env[0] - '0' : 3;
     c->n_chunks = 4;
     if (const char* env = getenv("GEM_CHUNKS")) c->n_chunks = atoi(env) >= 1 ? atoi(env) : 1;
     if (c->n_chunks > 16) c->n_chunks = 16;
@@ -263,7 +264,7 @@ int64_t gem_ctx_scratch_bytes(const gem_ctx* c) { return c ? c->scratch_bytes : 
 
 int gem_ctx_set_gemm_mode(gem_ctx* c, int mode) {
     GEM_REQUIRE(c != nullptr, "ctx is NULL");
-    GEM_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+    GEM_REQUIRE(mode >= 0 && mode <= 3, "mode must be 0, 1, 2 or 3");
     if (mode >= 1 && !tc_gemm_available()) {
         set_error("tcgen05 GEMM path not available in this build");
         return GEM_ERR_STATE;
@@ -403,11 +404,13 @@ int gem_ctx_set_vae(gem_ctx* c, int which, const gem_vae_weights* w) {
     for (int i = 0; i <= 4 && tap_ok; ++i) tap_ok = tc_tap_supported(w->dec_bwd[i].k, w->dec_bwd[i].n, c->T);
     tap_ok = tap_ok && c->vae[which].dec[0].k % 32 == 0 && c->vae[which].dec[0].n % 128 == 0;
     if (tap_ok) {
-        for (int i = 1; i <= 5; ++i)
-            GEM_TRY(tc_tap_prepare_weight(c, 0, w->dec[i].w_d, (w->dec[i].n + 3) & ~3, w->dec[i].k, w->dec[i].n));
-        for (int i = 0; i <= 4; ++i)
-            GEM_TRY(tc_tap_prepare_weight(c, 0, w->dec_bwd[i].w_d, (w->dec_bwd[i].n + 3) & ~3, w->dec_bwd[i].k,
-                                          w->dec_bwd[i].n));
+        for (int scheme = 1; scheme <= 2; ++scheme) {
+            for (int i = 1; i <= 5; ++i)
+                GEM_TRY(tc_tap_prepare_weight(c, 0, w->dec[i].w_d, (w->dec[i].n + 3) & ~3, w->dec[i].k, w->dec[i].n, scheme));
+            for (int i = 0; i <= 4; ++i)
+                GEM_TRY(tc_tap_prepare_weight(c, 0, w->dec_bwd[i].w_d, (w->dec_bwd[i].n + 3) & ~3, w->dec_bwd[i].k,
+                                              w->dec_bwd[i].n, scheme));
+        }
     }
     c->tap_tc[which] = tap_ok;
     GEM_CUDA(cudaStreamSynchronize(0));
@@ -419,25 +422,28 @@ int gem_ctx_set_vae(gem_ctx* c, int which, const gem_vae_weights* w) {
 // ---- layer runner ----------------------------------------------------------------------------
 static int run_layer(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, const float* A, int lda, int M, float* C,
                      int ldc, int epi, const float* aux, const void* A_hi = nullptr, const void* A_lo = nullptr,
-                     float* C_lo = nullptr, uint32_t* C_sign = nullptr, const int32_t* row_exp = nullptr) {
+                     float* C_lo = nullptr, uint32_t* C_sign = nullptr, const int32_t* row_exp = nullptr, int out16 = 0,
+                     const uint32_t* aux_bits = nullptr) {
     TapGemmArgs g;
-    g.A = A, g.B = L.w_d, g.bias = L.bias_d, g.aux = aux, g.C = C;
-    g.A_hi = A_hi, g.A_lo = A_lo, g.C_lo = C_lo, g.C_sign = C_sign, g.row_exp = row_exp;
+    g.A = A, g.B = L.w_d, g.bias = L.bias_d, g.aux = aux, g.C = C, g.aux_bits = aux_bits;
+    g.A_hi = A_hi, g.A_lo = A_lo, g.C_lo = C_lo, g.C_sign = C_sign, g.row_exp = row_exp, g.out16 = out16;
     g.M = M, g.N = L.n, g.K = L.k, g.taps = L.taps, g.T = c->T;
     g.lda = lda, g.ldb = (L.n + 3) & ~3, g.ldc = ldc, g.ldaux = L.n, g.epi = epi;
     return timed(c, s, tag, [&]() {
-        if (c->gemm_mode >= 1 && L.taps == 1 && (M >= 64 || A_hi || C_lo) && L.k % (c->gemm_mode == 2 ? 64 : 32) == 0 &&
+        if (c->gemm_mode >= 1 && L.taps == 1 && (M >= 64 || A_hi || C_lo) && L.k % (c->gemm_mode >= 2 ? 64 : 32) == 0 &&
             L.n % 128 == 0)
-            return launch_tap_gemm_tc(s, g, c, (size_t)c->gemm_mode);
+            return launch_tap_gemm_tc(s, g, c, (size_t)(c->gemm_mode >= 2 ? 2 : 1));
         return launch_tap_gemm_simt(s, g);
     });
 }
 
-// one k=3 convolution on the tcgen05 tap kernel; activations are TF32 hi / lo pairs
+// one k=3 convolution on the tcgen05 tap kernel; activations are TF32 hi / lo pairs (gemm_mode 1, 2) or fp16 hi /
+// scaled fp16 lo pairs held in the same buffers (gemm_mode 3)
 static int run_tap_tc(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, const float* A_hi, const float* A_lo, int lda,
                       int W, float* out_hi, float* out_lo, int ldo, int epi, const float* aux,
                       const uint32_t* aux_bits = nullptr, uint32_t* sign_out = nullptr) {
     TapTcLaunch t;
+    t.scheme = c->gemm_mode == 3 ? 2 : 1;
     t.aux_bits = aux_bits, t.sign_out = sign_out;
     t.B = L.w_d, t.A_hi = A_hi, t.A_lo = A_lo, t.lda = lda, t.Kreal = lda;
     t.bias = L.bias_d, t.aux = aux, t.ldaux = L.n, t.out_hi = out_hi, t.out_lo = out_lo, t.ldo = ldo;
@@ -478,7 +484,8 @@ static Slice slice_of(gem_ctx* c, int w0) {
     }
     const size_t P = (size_t)c->J * 3, n = c->n, m = c->m;
     v.pose = c->pose + v.tok0 * P, v.gpose = c->gpose + v.tok0 * P;
-    v.gp_hi = c->gp_hi + v.tok0 * pose_pad(c), v.gp_lo = c->gp_lo + v.tok0 * pose_pad(c);
+    const size_t gp_stride = (size_t)((c->J * 3 + 3) & ~3);      // floats per token the buffers were allocated with
+    v.gp_hi = c->gp_hi + v.tok0 * gp_stride, v.gp_lo = c->gp_lo + v.tok0 * gp_stride;   // (64 fp16 fit in 48 floats)
     v.f_new = c->f_new + w0, v.g_new = c->g_new + (size_t)w0 * n;
     v.g0_h16 = c->g0_h16 + v.tok0 * kDecC[0], v.g0_l16 = c->g0_l16 + v.tok0 * kDecC[0], v.row_exp = c->row_exp + w0;
     for (int i = 0; i < 5; ++i) v.eact[i] = c->eact[i] + v.tok0 * kEncC[i];
@@ -506,7 +513,7 @@ static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice
     if (use_tc_chain(c, which, W)) {
         // latent -> [T][256] on the tcgen05 GEMM, its epilogue writes the activation already split
         GEM_TRY(run_layer(c, s, GEM_TAG_DEC + 0, v.dec[0], z, c->n, W, v_.act_hi[0], T * 256, EPI_LRELU, nullptr, z_hi,
-                          z_lo, v_.act_lo[0], v_.act_sign[0]));
+                          z_lo, v_.act_lo[0], v_.act_sign[0], nullptr, c->gemm_mode == 3));
         for (int i = 1; i <= 4; ++i)
             GEM_TRY(run_tap_tc(c, s, GEM_TAG_DEC + i, v.dec[i], v_.act_hi[i - 1], v_.act_lo[i - 1], v.dec[i].k, W,
                                v_.act_hi[i], v_.act_lo[i], v.dec[i].n, EPI_LRELU, nullptr, nullptr, v_.act_sign[i]));
@@ -534,9 +541,16 @@ static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const S
     // dec_bwd[i] is the bwd-data of dec[5-i]; its output is d(pre-activation of dec[4-i])
     if (use_tc_chain(c, which, W)) {
         const int pp = pose_pad(c);
-        if (!dpose_is_split)
-            GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 0,
-                          [&]() { return launch_split_pad(s, dpose, P, (size_t)M, pp, v_.gp_hi, v_.gp_lo); }));
+        if (!dpose_is_split) {
+            if (c->gemm_mode == 3)
+                GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 0, [&]() {
+                    return launch_rowscale_split_pad_f16(s, dpose, P, T, W, pp, (uint16_t*)v_.gp_hi, (uint16_t*)v_.gp_lo,
+                                                         v_.row_exp);
+                }));
+            else
+                GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 0,
+                              [&]() { return launch_split_pad(s, dpose, P, (size_t)M, pp, v_.gp_hi, v_.gp_lo); }));
+        }
         const float *in_hi = v_.gp_hi, *in_lo = v_.gp_lo;
         int lda = pp;
         for (int i = 0; i < 5; ++i) {
@@ -546,6 +560,9 @@ static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const S
             in_hi = v_.gact_hi[a], in_lo = v_.gact_lo[a];
             lda = v.dec_bwd[i].n;
         }
+        if (c->gemm_mode == 3)      // the chain is fp16 end to end; the rows still carry the energy kernel's 2^row_exp
+            return run_layer(c, s, GEM_TAG_DEC_BWD + 5, v.dec_bwd[5], nullptr, T * 256, W, dz, c->n, EPI_NONE, nullptr,
+                             v_.gact_hi[0], v_.gact_lo[0], nullptr, nullptr, v_.row_exp);
         if (c->gemm_mode == 2) {
             // fp16 scheme: gradient rows are rescaled to ~2^10 before the split (they shrink to 1e-7 near convergence)
             GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 6, [&]() {
@@ -562,7 +579,8 @@ static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const S
     for (int i = 0; i < 5; ++i) {
         const int a = 4 - i;   // activation whose LeakyReLU derivative masks this output
         GEM_TRY(run_layer(c, s, GEM_TAG_DEC_BWD + i, v.dec_bwd[i], in, lda, M, v_.gact[a], v.dec_bwd[i].n, EPI_MASK,
-                          saved[a]));
+                          saved[a], nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                          c->act_split ? v_.act_sign[a] : nullptr));
         in = v_.gact[a];
         lda = v.dec_bwd[i].n;
     }
@@ -581,7 +599,7 @@ static int encode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice
         lda = v.enc[i].n;
     }
     const gem_layer& fcL = v.enc[5];
-    if (c->gemm_mode == 2 && fcL.k % 64 == 0 && fcL.n % 128 == 0) {
+    if (c->gemm_mode >= 2 && fcL.k % 64 == 0 && fcL.n % 128 == 0) {
         GEM_TRY(timed(c, s, GEM_TAG_ENC + 5, [&]() {
             return launch_split_f16(s, in, T * 512, W, T * 512, nullptr, (uint16_t*)v_.e4_hi, (uint16_t*)v_.e4_lo);
         }));
@@ -794,7 +812,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     LbfgsBuffers& lb = v.lb;
     lb.lr = a.p.lr, lb.tol_grad = a.p.tolerance_grad, lb.tol_change = a.p.tolerance_change;
     lb.max_iter = a.p.max_iter, lb.max_eval = a.p.max_eval;
-    lb.zt_f16 = c->gemm_mode == 2;
+    lb.zt_f16 = c->gemm_mode >= 2;
     lb.trace = a.trace ? v.trace_own : nullptr;
     lb.trace_stride = a.trace ? c->trace_cap : 0;
     if (a.trace) GEM_CUDA(cudaMemsetAsync(v.trace_own, 0xff, (size_t)Wk * c->trace_cap * sizeof(float), q));   // NaN
@@ -815,7 +833,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             return launch_energy_grad(q, Wk, c->T, c->J, c->H, c->Wd, v.pose, v.pose0_own, a.heat, v.fb_own, v.clip_own,
                                       v.mb_own, a.wt, v.f_new, nullptr, v.gpose, v.status_own, tc ? v.gp_hi : nullptr,
                                       v.gp_lo, pose_pad(c), a.texel_cache ? v.patch : nullptr, v.patch_origin,
-                                      c->patch_stats_on ? c->patch_stats : nullptr);
+                                      c->patch_stats_on ? c->patch_stats : nullptr, c->gemm_mode == 3, v.row_exp);
         }));
         GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, v.gpose, v.g_new, tc));
         return timed(c, q, GEM_TAG_LBFGS_ADVANCE, [&]() { return launch_lbfgs_advance(q, lb, v.f_new, v.g_new, Wk); });

@@ -52,6 +52,12 @@ struct EnergyArgs {
     // tensor-core bwd-data layers read (saves a separate split pass)
     float *gp_hi, *gp_lo;
     int pp;
+    // gp_f16: the split is the fp16 scheme's instead (uint16 arrays in the same buffers): the window's gradient is
+    // first scaled by the power of two that brings its largest entry to ~2^4 (gradients shrink to 1e-7 near
+    // convergence, far below fp16's normal range); the exponent goes to row_exp[w] and is removed again, exactly,
+    // by the epilogue of the T*256 -> latent GEMM at the end of the (linear) bwd-data chain
+    int gp_f16;
+    int32_t* row_exp;
     // optional texel cache (used when the heat maps stay in pinned HOST memory and are read over PCIe): per joint
     // a 4x4 neighbourhood of its map, 64 contiguous bytes in HBM, and the map coordinate of its corner.  The same
     // few texels are read by every evaluation of a stage (joints move by a fraction of a texel per step), so only
@@ -73,7 +79,7 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
     __shared__ __align__(16) float s_x[kWinPerCta * kSlot * 3];
     __shared__ __align__(16) float s_x0[kWinPerCta * kSlot * 3];
     __shared__ __align__(16) float s_g[kWinPerCta * kSlot * 3];
-    __shared__ float s_red[kThreads / 32][5];
+    __shared__ float s_red[kThreads / 32][6];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) float s_gh[kWinPerCta * kSplitMax];
     __shared__ __align__(16) float s_gl[kWinPerCta * kSplitMax];
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
     if (wl < kWinPerCta && k < TJ) {
         float* G = s_g + wl * n;
         G[k * 3 + 0] = gx, G[k * 3 + 1] = gy, G[k * 3 + 2] = gz;
-        if (a.gp_hi) {
+        if (a.gp_hi && !a.gp_f16) {
             const int t = k / a.J, j = k - t * a.J;
             const int o = wl * a.T * a.pp + t * a.pp + j * 3;
             const float g3[3] = {gx, gy, gz};
@@ -285,9 +291,10 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
 
     // ---- per-window energy reduction: shuffle inside each warp, then kSlot/32 partials --------
     const float r0 = warp_sum(e3d), r1 = warp_sum(esm), r2 = warp_sum(ebn), r3 = warp_sum(eva), r4 = warp_sum(erp);
+    const float r5 = warp_max(fmaxf(fabsf(gx), fmaxf(fabsf(gy), fabsf(gz))));      // (inactive threads hold zeros)
     if ((tid & 31) == 0) {
         float* d = s_red[tid >> 5];
-        d[0] = r0, d[1] = r1, d[2] = r2, d[3] = r3, d[4] = r4;
+        d[0] = r0, d[1] = r1, d[2] = r2, d[3] = r3, d[4] = r4, d[5] = r5;
     }
     if (bulk) fence_proxy_async_smem();           // make s_g visible to the bulk-copy engine
     __syncthreads();
@@ -308,7 +315,40 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
         if (a.wr != 0.f) E += a.wr * t5[4];
         a.energy[ww] = E;
     }
-    const int ns = a.T * a.pp;                     // floats per window of the split tile
+    int ns = a.T * a.pp;                           // floats per window of the split tile
+    if (a.gp_hi && a.gp_f16) {
+        // fp16 scheme: scale the window by 2^e (max entry -> ~2^4), split, stage as uint16
+        constexpr int wpw = kSlot / 32;
+        if (wl < kWinPerCta && k < TJ) {
+            float mx = 0.f;
+            for (int q = 0; q < wpw; ++q) mx = fmaxf(mx, s_red[wl * wpw + q][5]);
+            int e = 0;
+            if (mx > 0.f && mx < 3.0e38f) {
+                e = 4 - ilogbf(mx);
+                e = e > 100 ? 100 : (e < -100 ? -100 : e);
+            }
+            const float sc = exp2f((float)e);
+            if (k == 0 && wl < nwin) a.row_exp[w] = e;
+            const int t = k / a.J, j = k - t * a.J;
+            uint16_t* gh = reinterpret_cast<uint16_t*>(s_gh) + wl * a.T * a.pp + t * a.pp;
+            uint16_t* gl = reinterpret_cast<uint16_t*>(s_gl) + wl * a.T * a.pp + t * a.pp;
+            const float g3[3] = {gx * sc, gy * sc, gz * sc};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint16_t h, l;
+                asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(g3[c]));
+                float hf;
+                asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(h));
+                asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"((g3[c] - hf) * 2048.f));
+                gh[j * 3 + c] = h, gl[j * 3 + c] = l;
+            }
+            if (j == 0)
+                for (int c = a.J * 3; c < a.pp; ++c) gh[c] = 0, gl[c] = 0;
+        }
+        if (bulk) fence_proxy_async_smem();
+        __syncthreads();
+        ns = ns / 2;                               // staged as 16-bit: the copies below count 4-byte words
+    }
     if (bulk) {
         if (tid == 0) {
             bulk_s2g(a.grad + (size_t)w0 * n, s_g, (uint32_t)(kWinPerCta * n * sizeof(float)));
@@ -333,7 +373,7 @@ int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, 
                        const float* pose0, const float* heat, const int64_t* frame_base, const int32_t* clip,
                        const float* mean_bone, const gem_energy_weights& wt, float* energy, float* terms,
                        float* grad, uint32_t* status, float* gp_hi, float* gp_lo, int pp, float* patch,
-                       short2* patch_origin, unsigned long long* patch_stats) {
+                       short2* patch_origin, unsigned long long* patch_stats, int gp_f16, int32_t* row_exp) {
     if (W <= 0) return GEM_OK;
     GEM_REQUIRE(T * J <= kSlot, "T*J must be <= 160");
     GEM_REQUIRE(T >= 3, "seq_len must be >= 3");
@@ -342,8 +382,11 @@ int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, 
     a.pose = pose, a.pose0 = pose0, a.heat = heat, a.frame_base = frame_base, a.clip = clip, a.mean_bone = mean_bone;
     a.energy = energy, a.terms = terms, a.grad = grad, a.status = status;
     a.gp_hi = gp_hi, a.gp_lo = gp_hi ? gp_lo : nullptr, a.pp = gp_hi ? pp : 0;
+    a.gp_f16 = gp_hi ? gp_f16 : 0, a.row_exp = row_exp;
+    GEM_REQUIRE(!a.gp_f16 || (row_exp && (T * pp) % 8 == 0), "fp16 gradient output needs row_exp and T*pp % 8 == 0");
     a.patch = patch, a.patch_origin = patch ? patch_origin : nullptr, a.patch_stats = patch ? patch_stats : nullptr;
-    GEM_REQUIRE(!gp_hi || (gp_lo && pp >= J * 3 && T * pp <= kSplitMax && (T * pp) % 4 == 0), "bad split gradient layout");
+    GEM_REQUIRE(!gp_hi || (gp_lo && pp >= J * 3 && T * pp <= (gp_f16 ? 2 : 1) * kSplitMax && (T * pp) % 4 == 0),
+                "bad split gradient layout");
     a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd;
     a.w3d = wt.w3d, a.ws = wt.smooth, a.wb = wt.bone, a.wv = wt.vae, a.wr = wt.reproj;
     const size_t pair_bytes = (size_t)kWinPerCta * T * J * 3 * sizeof(float);

@@ -149,8 +149,10 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) tap_gemm_kernel(TapGemm
             if (g.epi == EPI_LRELU) {
                 v = v > 0.f ? v : v * 0.01f;
             } else if (g.epi == EPI_MASK) {
-                const float s = g.aux[(size_t)m * g.ldaux + n];
-                v = s > 0.f ? v : v * 0.01f;
+                bool pos;
+                if (g.aux_bits) pos = (g.aux_bits[(size_t)m * (g.N >> 5) + (n >> 5)] >> (n & 31)) & 1u;
+                else pos = g.aux[(size_t)m * g.ldaux + n] > 0.f;
+                v = pos ? v : v * 0.01f;
             }
             g.C[(size_t)m * g.ldc + n] = v;
         }

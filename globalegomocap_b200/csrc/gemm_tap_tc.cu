@@ -18,6 +18,13 @@
 // adds stay at the 1e-6 level, see gemm_tc.cu).  Activations travel between layers already split: the
 // epilogue of the producing kernel writes hi and lo, so no separate split pass touches HBM.
 //
+// Second scheme, same kernel (template parameter F16), twice the tensor rate and half the operand bytes:
+// activations x ~ hi + 2^-11 lo as two fp16 arrays (tc_common.cuh: split_f16); weights pre-multiplied by 2^8 and
+// stored as THREE fp16 slabs  hi' = fp16(256 w),  lo = fp16(256 w - hi')  (unscaled: normal numbers thanks to the
+// 2^8)  and  hs = hi' 2^-11,  so that  hi_a hi'_b + hi_a lo_b + lo_a hs_b  all carry the same scale and share ONE
+// accumulator (a second accumulator for scaled cross terms would not fit two CTAs' TMEM); the epilogue multiplies
+// by 2^-8.  A 128-byte row holds 64 fp16: the K = 64 layers are a single K block.
+//
 // CTA anatomy (320 threads, one stage of shared memory; two CTAs share an SM and overlap each other's
 // load / MMA / epilogue phases): warp 0 = TMA producer, warp 1 = TMEM allocation + single-thread
 // tcgen05.mma issue (M128, N = 3*NCTA, K8, kind::tf32), warps 2-9 = epilogue, two per TMEM lane quarter
@@ -37,17 +44,19 @@ using namespace tc;
 namespace {
 
 constexpr int kRows = 128;                 // UMMA M
-constexpr int BK = 32;                     // fp32 per 128-byte swizzle row
-constexpr int kATile = kRows * BK * 4;     // 16 KB
-constexpr int kQuarterBytes = 32 * BK * 4; // 4 KB: one warp's 32 rows
+constexpr int kATile = kRows * 128;        // 16 KB: 128 rows of one 128-byte swizzle row (32 fp32 or 64 fp16)
+constexpr int kQuarterBytes = 32 * 128;    // 4 KB: one warp's 32 rows
+constexpr float kWScale16 = 256.f;         // fp16 scheme: weights are stored times 2^8
 constexpr int kThreads = 320;              // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kTmemCols = 256;
 
-template <int NCTA>
+template <int NCTA, bool F16>
 struct Cfg {
     static constexpr int NP = 3 * NCTA;                       // accumulator columns: the taps side by side
-    static constexpr int kBTile = NP * BK * 4;
-    static constexpr int kStage = 2 * kATile + 2 * kBTile;    // A_hi, A_lo, B_hi, B_lo
+    static constexpr int BK = F16 ? 64 : 32;                  // elements per 128-byte row
+    static constexpr int kBTile = NP * 128;
+    static constexpr int kNB = F16 ? 3 : 2;                   // weight slabs per K block
+    static constexpr int kStage = 2 * kATile + kNB * kBTile;  // A_hi, A_lo, B slabs
     static constexpr size_t kSmem = (size_t)kStage + 1024 /*align slack*/ + 128 /*barriers*/;
     static_assert(NP % 16 == 0 && NP <= 256, "UMMA N");
     static_assert(kBTile % 1024 == 0, "B tile must keep the swizzle atom alignment");
@@ -58,8 +67,8 @@ struct TapTcArgs {
     const float* aux;    // [tokens][ldaux]: sign of the saved activation (EPI_MASK) ...
     const uint32_t* aux_bits;   // ... or, preferred, its packed sign bits [tokens][N/32]
     uint32_t* sign_out;  // optional: packed sign bits of this layer's output [tokens][N/32]
-    float* out_hi;       // [tokens][ldo]: TF32 hi part, or the plain result when out_lo is NULL
-    float* out_lo;
+    float* out_hi;       // [tokens][ldo]: hi part (fp32 TF32 value / fp16), or the plain fp32 result when out_lo is NULL
+    void* out_lo;
     int W, T, wpq;       // windows, frames per window, windows per 32-lane quarter
     int N, ldo, ldaux, epi, num_kb;
     long long* dbg;      // optional per-CTA phase timestamps (SM clock), 16 slots per CTA; NULL in production
@@ -69,18 +78,21 @@ struct TapTcArgs {
         if (g.dbg) g.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64();          \
     } while (0)
 
-template <int NCTA>
+template <int NCTA, bool F16>
 __global__ void __launch_bounds__(kThreads)
 tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+              const __grid_constant__ CUtensorMap map_b_hs,
               const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo, TapTcArgs g) {
-    using C = Cfg<NCTA>;
+    using C = Cfg<NCTA, F16>;
+    constexpr int BK = C::BK;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA_hi = smem;
     uint8_t* sA_lo = smem + kATile;
     uint8_t* sB_hi = smem + 2 * kATile;
     uint8_t* sB_lo = sB_hi + C::kBTile;
+    uint8_t* sB_hs = sB_lo + C::kBTile;              // fp16 scheme only
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStage);
     uint64_t* empty_bar = full_bar + 1;
     uint64_t* tmem_full_bar = full_bar + 2;
@@ -124,10 +136,10 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const uint32_t box_bytes = (uint32_t)rows_q * BK * 4;
+            const uint32_t box_bytes = (uint32_t)rows_q * 128;
             for (int kb = 0; kb < g.num_kb; ++kb) {
                 mbar_wait(empty_bar, (uint32_t)((kb & 1) ^ 1));
-                mbar_arrive_expect_tx(full_bar, 8 * box_bytes + 2 * C::kBTile);
+                mbar_arrive_expect_tx(full_bar, 8 * box_bytes + C::kNB * C::kBTile);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     tma_load_3d(sA_hi + q * kQuarterBytes, &map_a_hi, kb * BK, 0, win0 + q * g.wpq, full_bar);
@@ -135,24 +147,33 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 }
                 tma_load_2d(sB_hi, &map_b_hi, kb * BK, y * C::NP, full_bar);
                 tma_load_2d(sB_lo, &map_b_lo, kb * BK, y * C::NP, full_bar);
+                if (F16) tma_load_2d(sB_hs, &map_b_hs, kb * BK, y * C::NP, full_bar);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = instr_desc_tf32(kRows, C::NP);
+            constexpr uint32_t idesc = F16 ? instr_desc_f16(kRows, C::NP) : instr_desc_tf32(kRows, C::NP);
             const uint64_t a_hi = make_smem_desc(smem_u32(sA_hi)), a_lo = make_smem_desc(smem_u32(sA_lo));
             const uint64_t b_hi = make_smem_desc(smem_u32(sB_hi)), b_lo = make_smem_desc(smem_u32(sB_lo));
+            const uint64_t b_hs = make_smem_desc(smem_u32(sB_hs));
             for (int kb = 0; kb < g.num_kb; ++kb) {
                 mbar_wait(full_bar, (uint32_t)(kb & 1));
                 tc_fence_after();
                 if (kb < 2) TAP_DBG(2 + kb);
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
-                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);     // 32 bytes per K=8 step inside the 128-B row
-                    umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb > 0) || (k != 0));   // small terms first
-                    umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
-                    umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 32) >> 4);        // 32 bytes per MMA K step inside the 128-B row
+                    const uint32_t first = (kb > 0) || (k != 0);
+                    if (F16) {                                             // small terms first
+                        umma_f16(tmem_base, a_lo + adv, b_hs + adv, idesc, first);
+                        umma_f16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+                        umma_f16(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
+                    } else {
+                        umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, first);
+                        umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+                        umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1);
+                    }
                 }
                 umma_commit(empty_bar);              // the stage may be refilled once these MMAs have read it
             }
@@ -199,7 +220,7 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 float v = __uint_as_float(p1[j]);
                 v += has_prev ? up : 0.f;
                 v += has_next ? dn : 0.f;
-                o[j] = v;
+                o[j] = F16 ? v * (1.f / kWScale16) : v;          // fp16 scheme: the weights carry a factor 2^8
             }
             if (g.bias) {
 #pragma unroll
@@ -233,7 +254,24 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     sbits = 0;
                 }
             }
-            if (g.out_lo) {
+            if (g.out_lo && F16) {
+                // one 64-channel block of fp16: 128-byte rows, this chunk is two 16-byte pieces of them
+                uint8_t* th = smem + q * kQuarterBytes + lane * 128;
+                uint8_t* tl = th + kATile;
+#pragma unroll
+                for (int j = 0; j < 16; j += 8) {
+                    uint16_t h[8], l[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) split_f16(o[j + e], h[e], l[e]);
+                    const int off = (((c * 2 + (j >> 3)) ^ (lane & 7)) << 4);            // SWIZZLE_128B
+                    *reinterpret_cast<uint4*>(th + off) =
+                        make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                                   (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
+                    *reinterpret_cast<uint4*>(tl + off) =
+                        make_uint4((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16),
+                                   (uint32_t)l[4] | ((uint32_t)l[5] << 16), (uint32_t)l[6] | ((uint32_t)l[7] << 16));
+                }
+            } else if (g.out_lo) {
                 uint8_t* th = smem + ((c >> 1) * 2 + 0) * kATile + q * kQuarterBytes + lane * 128;
                 uint8_t* tl = th + kATile;
 #pragma unroll
@@ -253,7 +291,17 @@ tc_tap_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             }
         }
         if (threadIdx.x == 64) TAP_DBG(7);
-        if (g.out_lo) {
+        if (g.out_lo && F16) {
+            // the quarter's two warps fill one 64-channel block together: meet, then one of them stores it
+            fence_proxy_async_smem();
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            if (half == 0 && lane == 0 && winq < g.W) {
+                tma_store_3d(&map_o_hi, smem + q * kQuarterBytes, y * NCTA, 0, winq);
+                tma_store_3d(&map_o_lo, smem + kATile + q * kQuarterBytes, y * NCTA, 0, winq);
+                bulk_commit();
+                bulk_wait_read0();
+            }
+        } else if (g.out_lo) {
             fence_proxy_async_smem();             // generic-proxy writes -> visible to the TMA store
             __syncwarp();
             if (lane == 0 && winq < g.W) {
@@ -308,6 +356,27 @@ __global__ void tap_weight_prep_kernel(const float* __restrict__ B, int ldb, int
     hi[i] = h, lo[i] = l;
 }
 
+// the fp16 scheme's three slabs: hi' = fp16(2^8 w), lo = fp16(2^8 w - hi'), hs = hi' 2^-11
+__global__ void tap_weight_prep_f16_kernel(const float* __restrict__ B, int ldb, int K, int N, int Kp, int ncta, int gridy,
+                                           uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, uint16_t* __restrict__ hs) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)gridy * 3 * ncta * Kp;
+    if (i >= total) return;
+    const int k = (int)(i % Kp);
+    const size_t row = i / Kp;
+    const int np = (int)(row % ncta), tap = (int)((row / ncta) % 3), yy = (int)(row / (3 * (size_t)ncta));
+    const int n = yy * ncta + np;
+    float x = 0.f;
+    if (k < K && n < N) x = B[((size_t)tap * K + k) * ldb + n] * kWScale16;
+    uint16_t h, l, s;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+    float hf;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(h));
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(x - hf));
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(s) : "f"(hf * (1.f / kF16LoScale)));
+    hi[i] = h, lo[i] = l, hs[i] = s;
+}
+
 // [tokens][C] -> zero-padded [tokens][ldo] hi / lo (the bwd-data entry: d pose with 45 -> 48 columns)
 __global__ void split_pad_kernel(const float* __restrict__ src, int C, size_t tokens, int ldo, float* __restrict__ hi,
                                  float* __restrict__ lo) {
@@ -320,17 +389,51 @@ __global__ void split_pad_kernel(const float* __restrict__ src, int C, size_t to
     hi[i] = h, lo[i] = l;
 }
 
+// fp16 scheme: one CTA per window; the window's gradient [T*C] is scaled by the power of two that brings its
+// largest entry to ~2^4, split into fp16 hi / lo and zero-padded to [T][ldo]; the exponent goes to row_exp[w]
+__global__ void __launch_bounds__(128) rowscale_split_pad_f16_kernel(const float* __restrict__ src, int C, int T, int ldo,
+                                                                     uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                                     int32_t* __restrict__ row_exp) {
+    __shared__ float red[4];
+    const size_t w = blockIdx.x;
+    const float* p = src + w * T * C;
+    float mx = 0.f;
+    for (int i = threadIdx.x; i < T * C; i += 128) mx = fmaxf(mx, fabsf(p[i]));
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    int e = 0;
+    if (mx > 0.f && mx < 3.0e38f) {
+        e = 4 - ilogbf(mx);
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    }
+    const float sc = exp2f((float)e);
+    if (threadIdx.x == 0) row_exp[w] = e;
+    for (int i = threadIdx.x; i < T * ldo; i += 128) {
+        const int t = i / ldo, c = i - t * ldo;
+        uint16_t h = 0, l = 0;
+        if (c < C) split_f16(p[t * C + c] * sc, h, l);
+        hi[w * T * ldo + i] = h, lo[w * T * ldo + i] = l;
+    }
+}
+
 struct TapWeight {
-    float *hi = nullptr, *lo = nullptr;
+    void *hi = nullptr, *lo = nullptr, *hs = nullptr;
     int K = 0, Kp = 0, N = 0, ncta = 0, gridy = 0;
-    CUtensorMap map_hi, map_lo;
+    CUtensorMap map_hi, map_lo, map_hs;
 };
 struct AMaps {
     CUtensorMap hi, lo;
 };
+struct KeyHash {
+    size_t operator()(const std::pair<const float*, int>& k) const {
+        return std::hash<const void*>()(k.first) ^ ((size_t)k.second * 0x9E3779B97F4A7C15ull);
+    }
+};
 struct TapState {
-    std::unordered_map<const float*, TapWeight> weights;                       // keyed by the layer's weight pointer
-    std::map<std::tuple<const float*, const float*, int, int, int, int>, AMaps> amaps;   // (hi, lo, lda, K, W, T)
+    std::unordered_map<std::pair<const float*, int>, TapWeight, KeyHash> weights;     // (layer's weight pointer, scheme)
+    std::map<std::tuple<const void*, const void*, int, int, int, int, int>, AMaps> amaps;   // (hi, lo, ld, K, W, T, f16)
     bool attr_set = false;
 };
 std::mutex g_mu;
@@ -349,32 +452,52 @@ bool tc_tap_supported(int K, int N, int T) {
     return T >= 1 && T <= 32 && K >= 1 && K <= 1024 && N >= 1 && (N <= 48 || N % 64 == 0);
 }
 
-int tc_tap_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N) {
+// scheme: 1 = 3xTF32 (fp32 hi / lo slabs), 2 = fp16 (three fp16 slabs)
+int tc_tap_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N, int scheme) {
     GEM_REQUIRE(tc_tap_supported(K, N, 1), "layer shape not supported by the tcgen05 tap kernel");
+    const bool f16 = scheme == 2;
+    const int bk = f16 ? 64 : 32;
     TapState* st = state_of(owner);
-    auto old = st->weights.find(B);
+    const auto key = std::make_pair(B, f16 ? 2 : 1);
+    auto old = st->weights.find(key);
     if (old != st->weights.end()) {
         GEM_CUDA(cudaStreamSynchronize(stream));
         cudaFree(old->second.hi), cudaFree(old->second.lo);
+        if (old->second.hs) cudaFree(old->second.hs);
         st->weights.erase(old);
     }
     TapWeight w;
-    w.K = K, w.N = N, w.Kp = (K + BK - 1) / BK * BK;
+    w.K = K, w.N = N, w.Kp = (K + bk - 1) / bk * bk;
     w.ncta = N <= 48 ? 48 : 64;
     w.gridy = N <= 48 ? 1 : N / 64;
     const size_t total = (size_t)w.gridy * 3 * w.ncta * w.Kp;
-    GEM_CUDA(cudaMalloc(&w.hi, total * sizeof(float)));
-    GEM_CUDA(cudaMalloc(&w.lo, total * sizeof(float)));
-    tap_weight_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(B, ldb, K, N, w.Kp, w.ncta, w.gridy, w.hi,
-                                                                              w.lo);
+    const size_t esz = f16 ? 2 : 4;
+    GEM_CUDA(cudaMalloc(&w.hi, total * esz));
+    GEM_CUDA(cudaMalloc(&w.lo, total * esz));
+    if (f16) {
+        GEM_CUDA(cudaMalloc(&w.hs, total * esz));
+        tap_weight_prep_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+            B, ldb, K, N, w.Kp, w.ncta, w.gridy, (uint16_t*)w.hi, (uint16_t*)w.lo, (uint16_t*)w.hs);
+    } else {
+        tap_weight_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(B, ldb, K, N, w.Kp, w.ncta, w.gridy,
+                                                                                  (float*)w.hi, (float*)w.lo);
+    }
     GEM_CHECK_LAUNCH();
     const uint64_t dims[2] = {(uint64_t)w.Kp, (uint64_t)w.gridy * 3 * w.ncta};
-    const uint64_t strides[1] = {(uint64_t)w.Kp * sizeof(float)};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(3 * w.ncta)};
-    int rc = make_map_f32(&w.map_hi, w.hi, 2, dims, strides, box);
-    if (rc == GEM_OK) rc = make_map_f32(&w.map_lo, w.lo, 2, dims, strides, box);
+    const uint64_t strides[1] = {(uint64_t)w.Kp * esz};
+    const uint32_t box[2] = {(uint32_t)bk, (uint32_t)(3 * w.ncta)};
+    int rc;
+    if (f16) {
+        rc = make_map_u16(&w.map_hi, w.hi, 2, dims, strides, box);
+        if (rc == GEM_OK) rc = make_map_u16(&w.map_lo, w.lo, 2, dims, strides, box);
+        if (rc == GEM_OK) rc = make_map_u16(&w.map_hs, w.hs, 2, dims, strides, box);
+    } else {
+        rc = make_map_f32(&w.map_hi, (float*)w.hi, 2, dims, strides, box);
+        if (rc == GEM_OK) rc = make_map_f32(&w.map_lo, (float*)w.lo, 2, dims, strides, box);
+        w.map_hs = w.map_hi;
+    }
     if (rc != GEM_OK) return rc;
-    st->weights.emplace(B, w);
+    st->weights.emplace(key, w);
     return GEM_OK;
 }
 
@@ -386,40 +509,67 @@ int launch_split_pad(cudaStream_t stream, const float* src, int C, size_t tokens
     return GEM_OK;
 }
 
+int launch_rowscale_split_pad_f16(cudaStream_t stream, const float* src, int C, int T, int W, int ldo, uint16_t* hi,
+                                  uint16_t* lo, int32_t* row_exp) {
+    if (W <= 0) return GEM_OK;
+    rowscale_split_pad_f16_kernel<<<W, 128, 0, stream>>>(src, C, T, ldo, hi, lo, row_exp);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
 long long* g_tap_dbg = nullptr;   // set by gem_debug_tap_timestamps (tests / profiling only)
+
+template <int NCTA, bool F16>
+static int launch_tap_cfg(cudaStream_t stream, dim3 grid, const AMaps& am, const TapWeight& w, const AMaps& om,
+                          const TapTcArgs& a) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GEM_CUDA(cudaFuncSetAttribute(tc_tap_kernel<NCTA, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)Cfg<NCTA, F16>::kSmem));
+        attr_set = true;
+    }
+    tc_tap_kernel<NCTA, F16><<<grid, kThreads, Cfg<NCTA, F16>::kSmem, stream>>>(am.hi, am.lo, w.map_hi, w.map_lo, w.map_hs,
+                                                                                 om.hi, om.lo, a);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
 
 int launch_tap_tc(cudaStream_t stream, void* owner, const TapTcLaunch& L) {
     if (L.W <= 0) return GEM_OK;
+    const bool f16 = L.scheme == 2;
+    const int bk = f16 ? 64 : 32;
+    const size_t esz = f16 ? 2 : 4;
     TapState* st = state_of(owner);
-    auto wit = st->weights.find(L.B);
+    auto wit = st->weights.find(std::make_pair(L.B, f16 ? 2 : 1));
     if (wit == st->weights.end()) {
         set_error("tcgen05 tap path: weights were not prepared (tc_tap_prepare_weight)");
         return GEM_ERR_STATE;
     }
     const TapWeight& w = wit->second;
     GEM_REQUIRE(L.T >= 1 && L.T <= 32, "seq_len must be <= 32 on the tcgen05 tap path");
-    GEM_REQUIRE(L.lda % 4 == 0 && L.Kreal <= L.lda && L.Kreal <= w.Kp && L.Kreal >= w.K, "bad activation layout");
-    GEM_REQUIRE(L.out_lo == nullptr || (L.ldo % 4 == 0 && w.ncta == 64), "split output needs N % 64 == 0");
+    GEM_REQUIRE((L.lda * esz) % 16 == 0 && L.Kreal <= L.lda && L.Kreal <= w.Kp && L.Kreal >= w.K, "bad activation layout");
+    GEM_REQUIRE(L.out_lo == nullptr || ((L.ldo * esz) % 16 == 0 && w.ncta == 64), "split output needs N % 64 == 0");
     GEM_REQUIRE(L.epi != EPI_MASK || L.aux_bits || (L.aux && L.ldaux % 4 == 0 && w.N % 16 == 0),
                 "mask epilogue needs sign bits or an aligned aux");
     GEM_REQUIRE((!L.aux_bits && !L.sign_out) || w.N % 32 == 0, "sign bits need N % 32 == 0");
     GEM_REQUIRE(L.out_lo != nullptr || (L.ldo == w.N && w.N <= 48), "plain output must be dense and N <= 48");
-    if (!st->attr_set) {
-        GEM_CUDA(cudaFuncSetAttribute(tc_tap_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<64>::kSmem));
-        GEM_CUDA(cudaFuncSetAttribute(tc_tap_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<48>::kSmem));
-        st->attr_set = true;
-    }
     const int wpq = 32 / L.T;
-    auto maps_for = [&](const float* hi, const float* lo, int ld, int cols, AMaps** out) -> int {
-        const auto key = std::make_tuple(hi, lo, ld, cols, L.W, L.T);
+    auto maps_for = [&](const void* hi, const void* lo, int ld, int cols, AMaps** out) -> int {
+        const auto key = std::make_tuple(hi, lo, ld, cols, L.W, L.T, (int)f16);
         auto mit = st->amaps.find(key);
         if (mit == st->amaps.end()) {
             AMaps m;
             const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)L.T, (uint64_t)L.W};
-            const uint64_t strides[2] = {(uint64_t)ld * sizeof(float), (uint64_t)L.T * ld * sizeof(float)};
-            const uint32_t box[3] = {(uint32_t)BK, (uint32_t)L.T, (uint32_t)wpq};
-            int rc = make_map_f32(&m.hi, hi, 3, dims, strides, box);
-            if (rc == GEM_OK) rc = make_map_f32(&m.lo, lo, 3, dims, strides, box);
+            const uint64_t strides[2] = {(uint64_t)ld * esz, (uint64_t)L.T * ld * esz};
+            const uint32_t box[3] = {(uint32_t)bk, (uint32_t)L.T, (uint32_t)wpq};
+            int rc;
+            if (f16) {
+                rc = make_map_u16(&m.hi, hi, 3, dims, strides, box);
+                if (rc == GEM_OK) rc = make_map_u16(&m.lo, lo, 3, dims, strides, box);
+            } else {
+                rc = make_map_f32(&m.hi, (const float*)hi, 3, dims, strides, box);
+                if (rc == GEM_OK) rc = make_map_f32(&m.lo, (const float*)lo, 3, dims, strides, box);
+            }
             if (rc != GEM_OK) return rc;
             mit = st->amaps.emplace(key, m).first;
         }
@@ -435,17 +585,15 @@ int launch_tap_tc(cudaStream_t stream, void* owner, const TapTcLaunch& L) {
         if (!om) om = am;      // unused by the kernel when the output is plain
     }
     TapTcArgs a;
-    a.bias = L.bias, a.aux = L.aux, a.aux_bits = L.aux_bits, a.sign_out = L.sign_out, a.out_hi = L.out_hi, a.out_lo = L.out_lo;
+    a.bias = L.bias, a.aux = L.aux, a.aux_bits = L.aux_bits, a.sign_out = L.sign_out;
+    a.out_hi = (float*)L.out_hi, a.out_lo = L.out_lo;
     a.W = L.W, a.T = L.T, a.wpq = wpq, a.N = w.N, a.ldo = L.ldo, a.ldaux = L.ldaux, a.epi = L.epi;
-    a.num_kb = w.Kp / BK;
+    a.num_kb = w.Kp / bk;
     a.dbg = g_tap_dbg;
     dim3 grid((L.W + 4 * wpq - 1) / (4 * wpq), w.gridy);
     if (w.ncta == 64)
-        tc_tap_kernel<64><<<grid, kThreads, Cfg<64>::kSmem, stream>>>(am->hi, am->lo, w.map_hi, w.map_lo, om->hi, om->lo, a);
-    else
-        tc_tap_kernel<48><<<grid, kThreads, Cfg<48>::kSmem, stream>>>(am->hi, am->lo, w.map_hi, w.map_lo, om->hi, om->lo, a);
-    GEM_CHECK_LAUNCH();
-    return GEM_OK;
+        return f16 ? launch_tap_cfg<64, true>(stream, grid, *am, w, *om, a) : launch_tap_cfg<64, false>(stream, grid, *am, w, *om, a);
+    return f16 ? launch_tap_cfg<48, true>(stream, grid, *am, w, *om, a) : launch_tap_cfg<48, false>(stream, grid, *am, w, *om, a);
 }
 
 void tc_tap_release(void* owner) {
@@ -453,7 +601,10 @@ void tc_tap_release(void* owner) {
     auto it = g_states.find(owner);
     if (it == g_states.end()) return;
     TapState* st = it->second;
-    for (auto& kv : st->weights) cudaFree(kv.second.hi), cudaFree(kv.second.lo);
+    for (auto& kv : st->weights) {
+        cudaFree(kv.second.hi), cudaFree(kv.second.lo);
+        if (kv.second.hs) cudaFree(kv.second.hs);
+    }
     delete st;
     g_states.erase(it);
 }

@@ -61,6 +61,7 @@ struct GemmCfg {
     static constexpr int kMain16 = (kAcc - 1) < 2 ? (kAcc - 1) : 2;            // fp16 scheme: main accumulators ...
     static constexpr int kCross16 = kMain16;                                   // ... and the index of the cross one
     static constexpr int kPitch = BN + 4;                                      // staging row pitch (floats)
+    static constexpr int kPitch16 = BN + 8;                                    // ... of fp16 outputs (elements)
     static constexpr int kStageOut = 32 * kPitch * 4;                          // one warp's staged 32 x BN block
     static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert(BN % 16 == 0 && BN <= 256, "UMMA N");
@@ -74,6 +75,7 @@ struct TcArgs {
     float* C_lo;     // optional: the epilogue writes the result already split for the next tensor-core layer
     uint32_t* sign;  // optional: packed sign bits of the result, [M][N/32] (needs BN % 32 == 0)
     const int32_t* row_exp;   // optional: row m of A was scaled by 2^row_exp[m]; the result row is scaled back
+    int out16;                // C / C_lo are fp16 hi / scaled fp16 lo arrays (uint16), not TF32 hi / lo floats
     int M, N, K, ldc, epi;
 };
 
@@ -210,35 +212,63 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     sbits = 0;
                 }
             }
-            float* sh_row = stage_hi + lane * C::kPitch + c * 16;
-            if (g.C_lo) {
-                float* sl_row = stage_lo + lane * C::kPitch + c * 16;
+            if (g.out16) {
+                uint16_t* sh_row = reinterpret_cast<uint16_t*>(stage_hi) + lane * C::kPitch16 + c * 16;
+                uint16_t* sl_row = reinterpret_cast<uint16_t*>(stage_lo) + lane * C::kPitch16 + c * 16;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    float4 h, l;
-                    split_tf32(o[j + 0], h.x, l.x), split_tf32(o[j + 1], h.y, l.y);
-                    split_tf32(o[j + 2], h.z, l.z), split_tf32(o[j + 3], h.w, l.w);
-                    *reinterpret_cast<float4*>(sh_row + j) = h;
-                    *reinterpret_cast<float4*>(sl_row + j) = l;
+                for (int j = 0; j < 16; j += 2) {
+                    uint16_t h0, l0, h1, l1;
+                    split_f16(o[j], h0, l0), split_f16(o[j + 1], h1, l1);
+                    *reinterpret_cast<uint32_t*>(sh_row + j) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                    *reinterpret_cast<uint32_t*>(sl_row + j) = (uint32_t)l0 | ((uint32_t)l1 << 16);
                 }
             } else {
+                float* sh_row = stage_hi + lane * C::kPitch + c * 16;
+                if (g.C_lo) {
+                    float* sl_row = stage_lo + lane * C::kPitch + c * 16;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(sh_row + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 h, l;
+                        split_tf32(o[j + 0], h.x, l.x), split_tf32(o[j + 1], h.y, l.y);
+                        split_tf32(o[j + 2], h.z, l.z), split_tf32(o[j + 3], h.w, l.w);
+                        *reinterpret_cast<float4*>(sh_row + j) = h;
+                        *reinterpret_cast<float4*>(sl_row + j) = l;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(sh_row + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                }
             }
         }
         __syncwarp();
-        // coalesced write-out of this warp's 32 x BN block (N, ldc multiples of 4)
-        constexpr int kV4 = BN / 4;
+        // coalesced write-out of this warp's 32 x BN block in 16-byte vectors along the rows
         const int rows = min(32, g.M - (m0 + q * 32));
-        const int ncols4 = min(kV4, (g.N - n0) / 4);
-        for (int i = lane; i < rows * kV4; i += 32) {
-            const int r = i / kV4, c4 = i - r * kV4;
-            if (c4 >= ncols4) continue;
-            const size_t off = (size_t)(m0 + q * 32 + r) * g.ldc + n0 + c4 * 4;
-            *reinterpret_cast<float4*>(g.C + off) = *reinterpret_cast<const float4*>(stage_hi + r * C::kPitch + c4 * 4);
-            if (g.C_lo)
-                *reinterpret_cast<float4*>(g.C_lo + off) = *reinterpret_cast<const float4*>(stage_lo + r * C::kPitch + c4 * 4);
+        if (g.out16) {
+            constexpr int kV = BN / 8;                                    // 8 halves per vector (N, ldc % 8 == 0)
+            const int ncols = min(kV, (g.N - n0) / 8);
+            const uint16_t* sh = reinterpret_cast<const uint16_t*>(stage_hi);
+            const uint16_t* sl = reinterpret_cast<const uint16_t*>(stage_lo);
+            for (int i = lane; i < rows * kV; i += 32) {
+                const int r = i / kV, cv = i - r * kV;
+                if (cv >= ncols) continue;
+                const size_t off = (size_t)(m0 + q * 32 + r) * g.ldc + n0 + cv * 8;
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(g.C) + off) =
+                    *reinterpret_cast<const uint4*>(sh + r * C::kPitch16 + cv * 8);
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(g.C_lo) + off) =
+                    *reinterpret_cast<const uint4*>(sl + r * C::kPitch16 + cv * 8);
+            }
+        } else {
+            constexpr int kV4 = BN / 4;
+            const int ncols4 = min(kV4, (g.N - n0) / 4);
+            for (int i = lane; i < rows * kV4; i += 32) {
+                const int r = i / kV4, c4 = i - r * kV4;
+                if (c4 >= ncols4) continue;
+                const size_t off = (size_t)(m0 + q * 32 + r) * g.ldc + n0 + c4 * 4;
+                *reinterpret_cast<float4*>(g.C + off) = *reinterpret_cast<const float4*>(stage_hi + r * C::kPitch + c4 * 4);
+                if (g.C_lo)
+                    *reinterpret_cast<float4*>(g.C_lo + off) = *reinterpret_cast<const float4*>(stage_lo + r * C::kPitch + c4 * 4);
+            }
         }
     }
     tc_fence_before();
@@ -536,7 +566,8 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
     if (rc != GEM_OK) return rc;
     TcArgs a;
     a.bias = g.bias, a.C = g.C, a.C_lo = (float*)g.C_lo, a.sign = g.C_sign, a.M = g.M, a.N = g.N, a.K = g.K, a.ldc = g.ldc;
-    a.epi = g.epi, a.row_exp = f16 ? g.row_exp : nullptr;
+    a.epi = g.epi, a.row_exp = f16 ? g.row_exp : nullptr, a.out16 = (g.C_lo && g.out16) ? 1 : 0;
+    GEM_REQUIRE(!a.out16 || g.ldc % 8 == 0, "fp16 outputs need ldc % 8 == 0");
     // N-tile width.  Up to one wave of 128-wide tiles: keep 128 (kernels of concurrent slices share the SMs, the
     // least padded tiling wins).  Beyond: the fewest waves x columns over the 148 SMs (sign words need
     // 32-column alignment).

@@ -10,7 +10,8 @@ int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, 
                        const float* heat, const int64_t* frame_base, const int32_t* clip, const float* mean_bone,
                        const gem_energy_weights& wt, float* energy, float* terms, float* grad, uint32_t* status,
                        float* gp_hi = nullptr, float* gp_lo = nullptr, int pp = 0, float* patch = nullptr,
-                       short2* patch_origin = nullptr, unsigned long long* patch_stats = nullptr);
+                       short2* patch_origin = nullptr, unsigned long long* patch_stats = nullptr, int gp_f16 = 0,
+                       int32_t* row_exp = nullptr);
 
 enum { EPI_NONE = 0, EPI_LRELU = 1, EPI_MASK = 2 };
 struct TapGemmArgs {
@@ -20,9 +21,11 @@ struct TapGemmArgs {
     const int32_t* row_exp = nullptr;   // fp16 scheme: row m of A carries a factor 2^row_exp[m] that the epilogue removes
     float* C_lo = nullptr;         // tensor-core path only: write the result split (hi to C, lo to C_lo)
     uint32_t* C_sign = nullptr;    // tensor-core path only: packed sign bits of the result [M][N/32]
+    int out16 = 0;                 // with C_lo: write the result as fp16 hi / scaled fp16 lo (uint16 arrays) instead
     const float* B;      // [taps][K][ldb]
     const float* bias;   // [N] or NULL
-    const float* aux;    // [M][ldaux] saved activation for EPI_MASK
+    const float* aux;    // [M][ldaux] saved activation for EPI_MASK ...
+    const uint32_t* aux_bits = nullptr;   // ... or its packed sign bits [M][N/32] (N % 32 == 0)
     float* C;            // [M][ldc]
     int M, N, K, taps, T;
     int lda, ldb, ldc, ldaux;   // ldb = row stride of B[tap][k][:] (N rounded up to a multiple of 4, zero padded)
@@ -43,19 +46,22 @@ bool tc_gemm_available();
 // tcgen05 kernel for the k=3 convolutions (gemm_tap_tc.cu); activations travel as TF32 hi / lo pairs
 struct TapTcLaunch {
     const float* B;                 // the layer's weight pointer (key of tc_tap_prepare_weight)
-    const float *A_hi, *A_lo;       // [W*T][lda]
+    int scheme = 1;                 // 1 = 3xTF32 (fp32 hi / lo activations), 2 = fp16 hi + scaled fp16 lo (uint16 arrays)
+    const void *A_hi, *A_lo;        // [W*T][lda]
     int lda, Kreal;                 // row pitch and valid columns (the rest of a 32-wide K block reads zero)
     const float* bias;              // [N] or NULL
     const float* aux;               // EPI_MASK: [W*T][ldaux], only the sign is used ...
     int ldaux;
     const uint32_t* aux_bits = nullptr;   // ... or its packed sign bits [W*T][N/32] (preferred)
     uint32_t* sign_out = nullptr;         // optional: packed sign bits of the output [W*T][N/32]
-    float *out_hi, *out_lo;         // [W*T][ldo]; out_lo == NULL writes the plain result to out_hi
+    void *out_hi, *out_lo;          // [W*T][ldo] (scheme's element type); out_lo == NULL writes the plain fp32 result to out_hi
     int ldo;
     int W, T, epi;
 };
 bool tc_tap_supported(int K, int N, int T);
-int tc_tap_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N);
+int tc_tap_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N, int scheme = 1);
+int launch_rowscale_split_pad_f16(cudaStream_t stream, const float* src, int C, int T, int W, int ldo, uint16_t* hi,
+                                  uint16_t* lo, int32_t* row_exp);
 int launch_tap_tc(cudaStream_t stream, void* owner, const TapTcLaunch& L);
 int launch_split_pad(cudaStream_t stream, const float* src, int C, size_t tokens, int ldo, float* hi, float* lo);
 void tc_tap_release(void* owner);

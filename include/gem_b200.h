@@ -100,10 +100,10 @@ int gem_ctx_set_skeleton(gem_ctx* ctx, const int32_t* parents_h, int num_joints)
 int gem_ctx_set_vae(gem_ctx* ctx, int which, const gem_vae_weights* weights_h);
 /* bytes of device scratch owned by the ctx */
 int64_t gem_ctx_scratch_bytes(const gem_ctx* ctx);
-/* 0: hand-written SIMT fp32 layers everywhere; 1: tcgen05/TMEM, 3xTF32 arithmetic in every layer; 2 (default):
- * like 1 but the plain GEMMs (latent<->T*256, encoder fc) use the fp16 scheme: x ~ fp16 hi + 2^-11 fp16 lo, three
- * kind::f16 MMAs per product with the cross terms in their own accumulator, gradient rows rescaled by a power of
- * two — twice the tensor rate of 3xTF32 and (measured) a smaller error against float64 */
+/* 0: hand-written SIMT fp32 layers everywhere; 1: tcgen05/TMEM, 3xTF32 arithmetic in every layer; 2: like 1 but the
+ * plain GEMMs (latent<->T*256, encoder fc) use the fp16 scheme: x ~ fp16 hi + 2^-11 fp16 lo, three kind::f16 MMAs
+ * per product, gradient rows rescaled by a power of two — twice the tensor rate of 3xTF32 and (measured) a smaller
+ * error against float64; 3 (default): the fp16 scheme in every tensor-core layer, activations travel as fp16 pairs */
 int gem_ctx_set_gemm_mode(gem_ctx* ctx, int mode);
 
 /* A stage's windows are independent: gem_solve_stage splits them into n_chunks slices (boundaries at

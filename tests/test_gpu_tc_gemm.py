@@ -126,3 +126,25 @@ def test_fp16_scheme_gemm_against_float64(engine, M, N, K):
         errs[mode] = _rel(c, ref)
     print((M, N, K), "relative max error vs float64: 3xTF32", errs[1], " fp16 scheme", errs[2])
     assert errs[2] < 1e-5, errs
+
+
+@pytest.mark.parametrize("W", [1, 13, 128, 300, 641])
+def test_fp16_chain_matches_fp32_path(engine, W):
+    """gemm_mode 3: every tensor-core layer in the fp16 scheme (fp16 hi + 2^-11 fp16 lo activations, three fp16 weight
+    slabs, gradient rows rescaled by a power of two in the energy kernel / the entry split) against the CUDA-core
+    layers, including gradients a million times smaller than the activations."""
+    g = torch.Generator(device="cpu").manual_seed(3000 + W)
+    z = torch.randn(W, 2048, generator=g)
+    for scale in (1.0, 1e-6):
+        up = torch.randn(W, 10, 15, 3, generator=g) * scale
+        engine.set_gemm_mode(3)
+        pose_tc = engine.decode(0, z).clone()
+        dz_tc = engine.decode_vjp(0, up).clone()
+        engine.set_gemm_mode(0)
+        dz_simt = engine.decode_vjp(0, up).clone()      # same masks: the signs the mode-3 decode left
+        pose_simt = engine.decode(0, z).clone()
+        torch.cuda.synchronize()
+        rp, rz = _rel(pose_tc, pose_simt), _rel(dz_tc, dz_simt)
+        print(W, scale, "fp16 chain vs fp32 CUDA cores: pose", rp, "dz", rz)
+        assert rp < 1e-5 and rz < 2e-5, (W, scale, rp, rz)
+    engine.set_gemm_mode(2)
