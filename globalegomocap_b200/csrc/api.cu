@@ -279,6 +279,16 @@ int gem_debug_tap_timestamps(long long* buf_d) {
     return GEM_OK;
 }
 
+/* debug hook (not in the public header): 1 = CTA-pair (cta_group::2) fp16-scheme GEMM, 0 = one CTA per tile, -1 = default */
+int gem_debug_gemm_timestamps(long long* buf_d) {
+    gem::g_gemm_dbg = buf_d;
+    return GEM_OK;
+}
+int gem_debug_gemm_pair(int mode) {
+    gem::g_gemm_pair = mode;
+    return GEM_OK;
+}
+
 int gem_ctx_set_chunks(gem_ctx* c, int n_chunks) {
     GEM_REQUIRE(c != nullptr && n_chunks >= 1 && n_chunks <= 16, "n_chunks must be in [1, 16]");
     c->n_chunks = n_chunks;

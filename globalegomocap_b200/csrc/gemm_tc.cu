@@ -15,12 +15,12 @@
 // K = 2560), so the K blocks are dealt round-robin to four TMEM accumulators that the epilogue adds
 // with ordinary round-to-nearest fp32 adds: a quarter of the steps, a quarter of the bias.
 //
-// Kernel anatomy (one 128x128 output tile per CTA, 192 threads):
+// Kernel anatomy (one 128 x BN output tile per CTA, 576 threads):
 //   warp 0   TMA producer: per 32-wide K block four cp.async.bulk.tensor loads (A_hi, A_lo, B_hi, B_lo;
 //            128 rows x 128 B each, SWIZZLE_128B) into a 3-stage shared-memory ring, mbarrier full/empty
 //   warp 1   allocates all 512 TMEM columns (4 accumulators); one elected lane issues 12 tcgen05.mma.kind::tf32 (M128 N128 K8)
 //            per stage and tcgen05.commit's the stage back to the producer
-//   warps 2-5 epilogue: tcgen05.ld the accumulator (32 lanes x 32 columns per instruction), bias /
+//   warps 2-17 epilogue (four per TMEM lane quarter): tcgen05.ld the accumulators (32 lanes x 16 columns per instruction), bias /
 //            LeakyReLU, 128-byte row segments straight to global memory
 // Weights are transposed to K-major [N][K] and split once per checkpoint; activations are split by a
 // small elementwise kernel before each GEMM, or arrive already split from the producing kernel.
@@ -47,7 +47,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int kStages = 3;
 constexpr int kATileBytes = BM * 128;             // 16 KB: 128 rows of one 128-byte swizzle row (32 fp32 or 64 fp16)
-constexpr int kThreads = 192;
+constexpr int kEpiSub = 4;                        // epilogue warps per TMEM lane quarter
+constexpr int kThreads = 64 + 4 * 32 * kEpiSub;   // TMA warp, MMA warp, 16 epilogue warps
 constexpr int kTmemCols = 512;                    // all of TMEM: up to four BN-column accumulators
 
 // The N tile is a template parameter chosen per launch (launch_tap_gemm_tc): with ~15 M tiles the tile count
@@ -77,7 +78,153 @@ struct TcArgs {
     const int32_t* row_exp;   // optional: row m of A was scaled by 2^row_exp[m]; the result row is scaled back
     int out16;                // C / C_lo are fp16 hi / scaled fp16 lo arrays (uint16), not TF32 hi / lo floats
     int M, N, K, ldc, epi;
+    long long* dbg;           // debug: per-CTA phase timestamps (gem_debug_gemm_timestamps), NULL in production
 };
+
+
+// debug timestamps: slot s of CTA (blockIdx.y * gridDim.x + blockIdx.x), 16 slots per CTA
+#define GEMM_TS(slot)                                                                                   \
+    do {                                                                                                \
+        if (g.dbg) g.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64();      \
+    } while (0)
+#define GEMM_TS_ADD(slot, v)                                                                            \
+    do {                                                                                                \
+        if (g.dbg) g.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = (v);            \
+    } while (0)
+
+// Epilogue of one 128 x BN accumulator tile, run by kEpiWarps = 16 warps: a warp can only read the TMEM lane
+// quarter (warp % 4), so four warps share each quarter and deal its 16-column chunks round-robin.  (With one warp
+// per quarter the epilogue was a single dependent instruction stream per scheduler — ~460 instructions per chunk
+// at an IPC of 0.2 — and took 23k of a tile's 63k cycles; per-CTA timestamps, scratch/dbg_gemm.py.)
+// The accumulators' sum, bias and activation are formed one row per thread, staged in the (now idle) pipeline
+// memory and, after a named barrier over the quarter's four warps, written out along the rows: 16-byte vectors,
+// whole row segments per instruction instead of 32 row segments of 16 bytes.
+template <int BN, bool F16>
+__device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint8_t* smem, uint32_t tmem_base, int m0, int n0, int warp,
+                                              int lane, int num_kb) {
+    using C = GemmCfg<BN>;
+    constexpr int kAcc = C::kAcc;
+    const int q = warp & 3;                         // TMEM lane quarter this warp may read
+    const int sub = (warp - 2) >> 2;                // 0 .. kEpiSub-1: which of the quarter's warps
+    const int m = m0 + q * 32 + lane;
+    float* stage_hi = reinterpret_cast<float*>(smem + (size_t)(q * 2 + 0) * C::kStageOut);
+    float* stage_lo = reinterpret_cast<float*>(smem + (size_t)(q * 2 + 1) * C::kStageOut);
+    const int nmain = F16 ? C::kMain16 : kAcc;
+    const int nacc = num_kb < nmain ? num_kb : nmain;
+    float row_scale = 1.f;
+    if (g.row_exp && m < g.M) row_scale = exp2f(-(float)g.row_exp[m]);      // exact: a power of two
+#pragma unroll 1
+    for (int c = sub; c < BN / 16; c += kEpiSub) {
+        const int nb = n0 + c * 16;
+        if (nb >= g.N) break;                       // N % 16 == 0: a chunk is inside the matrix or outside
+        uint32_t v[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16);
+        if (F16) {
+            // main accumulator(s) and the cross accumulator in flight together, one wait
+            uint32_t t1[16], tx[16];
+            tmem_ld_32x32b_x16(taddr, v);
+            if (C::kMain16 > 1 && nacc > 1) tmem_ld_32x32b_x16(taddr + (uint32_t)BN, t1);
+            tmem_ld_32x32b_x16(taddr + (uint32_t)(C::kCross16 * BN), tx);
+            tmem_ld_wait();
+            if (C::kMain16 > 1 && nacc > 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t1[j]));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)      // + 2^-11 (hi*lo + lo*hi)
+                v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(tx[j]) * (1.f / kF16LoScale));
+        } else {
+            tmem_ld_32x32b_x16(taddr, v);
+            tmem_ld_wait();
+            for (int a = 1; a < nacc; ++a) {
+                uint32_t t[16];
+                tmem_ld_32x32b_x16(taddr + (uint32_t)(a * BN), t);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t[j]));
+            }
+        }
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) * row_scale;
+        if (g.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + nb + j));
+                o[j] += bv.x, o[j + 1] += bv.y, o[j + 2] += bv.z, o[j + 3] += bv.w;
+            }
+        }
+        if (g.epi == EPI_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * 0.01f;
+        }
+        if (g.sign) {                               // bit (n % 32) of word [m][n / 32]: this chunk is one 16-bit half
+            uint32_t sbits = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sbits |= (o[j] > 0.f ? 1u : 0u) << j;
+            if (m < g.M) reinterpret_cast<uint16_t*>(g.sign)[(size_t)m * (g.N >> 4) + (nb >> 4)] = (uint16_t)sbits;
+        }
+        if (g.out16) {
+            uint16_t* sh_row = reinterpret_cast<uint16_t*>(stage_hi) + lane * C::kPitch16 + c * 16;
+            uint16_t* sl_row = reinterpret_cast<uint16_t*>(stage_lo) + lane * C::kPitch16 + c * 16;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                uint16_t h0, l0, h1, l1;
+                split_f16(o[j], h0, l0), split_f16(o[j + 1], h1, l1);
+                *reinterpret_cast<uint32_t*>(sh_row + j) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                *reinterpret_cast<uint32_t*>(sl_row + j) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+        } else {
+            float* sh_row = stage_hi + lane * C::kPitch + c * 16;
+            if (g.C_lo) {
+                float* sl_row = stage_lo + lane * C::kPitch + c * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 h, l;
+                    split_tf32(o[j + 0], h.x, l.x), split_tf32(o[j + 1], h.y, l.y);
+                    split_tf32(o[j + 2], h.z, l.z), split_tf32(o[j + 3], h.w, l.w);
+                    *reinterpret_cast<float4*>(sh_row + j) = h;
+                    *reinterpret_cast<float4*>(sl_row + j) = l;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(sh_row + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            }
+        }
+    }
+    // the quarter's four warps have staged their chunks of the same 32 rows
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * kEpiSub) : "memory");
+    // coalesced write-out of the quarter's 32 x BN block in 16-byte vectors along the rows
+    const int rows = min(32, g.M - (m0 + q * 32));
+    const int tq = sub * 32 + lane;                 // thread index within the quarter's warps
+    if (g.out16) {
+        constexpr int kV = BN / 8;                                    // 8 halves per vector (N, ldc % 8 == 0)
+        const int ncols = min(kV, (g.N - n0) / 8);
+        const uint16_t* sh = reinterpret_cast<const uint16_t*>(stage_hi);
+        const uint16_t* sl = reinterpret_cast<const uint16_t*>(stage_lo);
+        for (int i = tq; i < rows * kV; i += 32 * kEpiSub) {
+            const int r = i / kV, cv = i - r * kV;
+            if (cv >= ncols) continue;
+            const size_t off = (size_t)(m0 + q * 32 + r) * g.ldc + n0 + cv * 8;
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(g.C) + off) =
+                *reinterpret_cast<const uint4*>(sh + r * C::kPitch16 + cv * 8);
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(g.C_lo) + off) =
+                *reinterpret_cast<const uint4*>(sl + r * C::kPitch16 + cv * 8);
+        }
+    } else {
+        constexpr int kV4 = BN / 4;
+        const int ncols4 = min(kV4, (g.N - n0) / 4);
+        for (int i = tq; i < rows * kV4; i += 32 * kEpiSub) {
+            const int r = i / kV4, c4 = i - r * kV4;
+            if (c4 >= ncols4) continue;
+            const size_t off = (size_t)(m0 + q * 32 + r) * g.ldc + n0 + c4 * 4;
+            *reinterpret_cast<float4*>(g.C + off) = *reinterpret_cast<const float4*>(stage_hi + r * C::kPitch + c4 * 4);
+            if (g.C_lo)
+                *reinterpret_cast<float4*>(g.C_lo + off) = *reinterpret_cast<const float4*>(stage_lo + r * C::kPitch + c4 * 4);
+        }
+    }
+}
 
 template <int BN, bool F16>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -96,6 +243,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     constexpr int BK = F16 ? 64 : 32;             // elements per 128-byte row
     const int num_kb = g.K / BK;
+    if (threadIdx.x == 0 && g.dbg) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        GEMM_TS_ADD(14, (long long)gt);
+        GEMM_TS(0);
+    }
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a_hi), prefetch_tmap(&map_a_lo), prefetch_tmap(&map_b_hi), prefetch_tmap(&map_b_lo);
@@ -108,14 +261,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) GEMM_TS(1);
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            long long wait_empty = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t parity = ((kb / kStages) & 1) ^ 1;
+                const long long t0 = g.dbg ? clock64() : 0;
                 mbar_wait(&empty_bar[s], parity);
+                if (g.dbg) wait_empty += clock64() - t0;
                 uint8_t* st = smem + s * C::kStageBytes;
                 mbar_arrive_expect_tx(&full_bar[s], C::kStageBytes);
                 tma_load_2d(st, &map_a_hi, kb * BK, m0, &full_bar[s]);
@@ -123,14 +280,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 tma_load_2d(st + 2 * kATileBytes, &map_b_hi, kb * BK, n0, &full_bar[s]);
                 tma_load_2d(st + 2 * kATileBytes + C::kBTileBytes, &map_b_lo, kb * BK, n0, &full_bar[s]);
             }
+            GEMM_TS_ADD(8, wait_empty);
+            GEMM_TS(2);
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = F16 ? instr_desc_f16(BM, BN) : instr_desc_tf32(BM, BN);
+            long long wait_full = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kStages;
+                const long long t0 = g.dbg ? clock64() : 0;
                 mbar_wait(&full_bar[s], (kb / kStages) & 1);
+                if (g.dbg) wait_full += clock64() - t0;
+                if (kb == 0) GEMM_TS(3);
                 tc_fence_after();
                 const uint32_t base = smem_u32(smem + s * C::kStageBytes);
                 const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + kATileBytes);
@@ -156,126 +319,163 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 umma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs have read it
             }
             umma_commit(tmem_full_bar);              // accumulators complete
+            GEMM_TS_ADD(9, wait_full);
+            GEMM_TS(4);
         }
     } else {
-        // ===== epilogue warps 2..5: TMEM lane quarter = warp % 4 =====
-        // The accumulators' sum, bias and activation are formed one row per thread, staged in the (now idle)
-        // pipeline memory and written out by the whole warp along the rows: 128-byte segments per instruction
-        // instead of 32 row segments of 16 bytes.
-        const int q = warp & 3;
+        // ===== epilogue warps 2..17 =====
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        const int m = m0 + q * 32 + lane;
-        float* stage_hi = reinterpret_cast<float*>(smem + (size_t)(q * 2 + 0) * C::kStageOut);
-        float* stage_lo = reinterpret_cast<float*>(smem + (size_t)(q * 2 + 1) * C::kStageOut);
-        const int nmain = F16 ? C::kMain16 : kAcc;
-        const int nacc = num_kb < nmain ? num_kb : nmain;
-        float row_scale = 1.f;
-        if (g.row_exp && m < g.M) row_scale = exp2f(-(float)g.row_exp[m]);      // exact: a power of two
-        uint32_t sbits = 0;
-#pragma unroll 1
-        for (int c = 0; c < BN / 16; ++c) {
-            uint32_t v[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16);
-            tmem_ld_32x32b_x16(taddr, v);
-            tmem_ld_wait();
-            for (int a = 1; a < nacc; ++a) {
-                uint32_t t[16];
-                tmem_ld_32x32b_x16(taddr + (uint32_t)(a * BN), t);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t[j]));
-            }
-            if (F16) {                    // + 2^-11 (hi*lo + lo*hi)
-                uint32_t t[16];
-                tmem_ld_32x32b_x16(taddr + (uint32_t)(C::kCross16 * BN), t);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(t[j]) * (1.f / kF16LoScale));
-            }
-            const int nb = n0 + c * 16;
-            float o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float x = __uint_as_float(v[j]) * row_scale;
-                if (g.bias && nb + j < g.N) x += __ldg(g.bias + nb + j);
-                if (g.epi == EPI_LRELU) x = x > 0.f ? x : x * 0.01f;
-                o[j] = x;
-            }
-            if (g.sign) {
-                const int sh = (c & 1) * 16;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) sbits |= (o[j] > 0.f ? 1u : 0u) << (sh + j);
-                if (sh == 16 || c == BN / 16 - 1) {
-                    if (m < g.M && nb < g.N) g.sign[(size_t)m * (g.N >> 5) + (nb >> 5)] = sbits;
-                    sbits = 0;
-                }
-            }
-            if (g.out16) {
-                uint16_t* sh_row = reinterpret_cast<uint16_t*>(stage_hi) + lane * C::kPitch16 + c * 16;
-                uint16_t* sl_row = reinterpret_cast<uint16_t*>(stage_lo) + lane * C::kPitch16 + c * 16;
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    uint16_t h0, l0, h1, l1;
-                    split_f16(o[j], h0, l0), split_f16(o[j + 1], h1, l1);
-                    *reinterpret_cast<uint32_t*>(sh_row + j) = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                    *reinterpret_cast<uint32_t*>(sl_row + j) = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                }
-            } else {
-                float* sh_row = stage_hi + lane * C::kPitch + c * 16;
-                if (g.C_lo) {
-                    float* sl_row = stage_lo + lane * C::kPitch + c * 16;
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float4 h, l;
-                        split_tf32(o[j + 0], h.x, l.x), split_tf32(o[j + 1], h.y, l.y);
-                        split_tf32(o[j + 2], h.z, l.z), split_tf32(o[j + 3], h.w, l.w);
-                        *reinterpret_cast<float4*>(sh_row + j) = h;
-                        *reinterpret_cast<float4*>(sl_row + j) = l;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(sh_row + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                }
-            }
-        }
-        __syncwarp();
-        // coalesced write-out of this warp's 32 x BN block in 16-byte vectors along the rows
-        const int rows = min(32, g.M - (m0 + q * 32));
-        if (g.out16) {
-            constexpr int kV = BN / 8;                                    // 8 halves per vector (N, ldc % 8 == 0)
-            const int ncols = min(kV, (g.N - n0) / 8);
-            const uint16_t* sh = reinterpret_cast<const uint16_t*>(stage_hi);
-            const uint16_t* sl = reinterpret_cast<const uint16_t*>(stage_lo);
-            for (int i = lane; i < rows * kV; i += 32) {
-                const int r = i / kV, cv = i - r * kV;
-                if (cv >= ncols) continue;
-                const size_t off = (size_t)(m0 + q * 32 + r) * g.ldc + n0 + cv * 8;
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(g.C) + off) =
-                    *reinterpret_cast<const uint4*>(sh + r * C::kPitch16 + cv * 8);
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(g.C_lo) + off) =
-                    *reinterpret_cast<const uint4*>(sl + r * C::kPitch16 + cv * 8);
-            }
-        } else {
-            constexpr int kV4 = BN / 4;
-            const int ncols4 = min(kV4, (g.N - n0) / 4);
-            for (int i = lane; i < rows * kV4; i += 32) {
-                const int r = i / kV4, c4 = i - r * kV4;
-                if (c4 >= ncols4) continue;
-                const size_t off = (size_t)(m0 + q * 32 + r) * g.ldc + n0 + c4 * 4;
-                *reinterpret_cast<float4*>(g.C + off) = *reinterpret_cast<const float4*>(stage_hi + r * C::kPitch + c4 * 4);
-                if (g.C_lo)
-                    *reinterpret_cast<float4*>(g.C_lo + off) = *reinterpret_cast<const float4*>(stage_lo + r * C::kPitch + c4 * 4);
-            }
-        }
+        if (threadIdx.x == 64) GEMM_TS(5);
+        epilogue_tile<BN, F16>(g, smem, tmem_base, m0, n0, warp, lane, num_kb);
+        if (threadIdx.x == 64) GEMM_TS(6);
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
+    }
+    if (threadIdx.x == 0 && g.dbg) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        GEMM_TS_ADD(15, (long long)gt);
+        GEMM_TS(7);
+    }
+}
+
+// ---- CTA-pair variant of the fp16 scheme (tcgen05.mma.cta_group::2, M = 256) --------------------------------------
+// The 1-CTA kernel is bound by shared-memory bandwidth, not by the tensor pipe: an M128 x N160 x K16 MMA reads
+// 4 KB of A and 5 KB of B from shared memory every 80 cycles (112 B/clk of the SM's 128) while TMA writes the next
+// stage at 75 B/clk on top.  Two CTAs of one cluster (the two SMs of a TPC) run ONE M256 MMA: each keeps its own
+// 128 rows of A but only HALF of the B tile, the hardware feeds both tensor cores from the two halves, so per SM
+// the MMA reads 6.5 KB per 80 cycles and TMA writes 52 KB instead of 72 KB per K block (and L2 -> SM traffic drops
+// by the same 28 %).  Protocol: both CTAs' producers load into their own shared memory but signal the LEADER's
+// full barrier (which expects both CTAs' bytes); the leader's MMA thread issues for the pair and multicasts its
+// commits to the empty / accumulator barriers of both CTAs; each CTA's epilogue drains its own TMEM.
+template <int BN>
+struct PairCfg {
+    static constexpr int kStages = 4;
+    static constexpr int kBHalfBytes = (BN / 2) * 128;
+    static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBHalfBytes;      // A_hi, A_lo, half of B_hi, half of B_lo
+    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(BN % 16 == 0 && BN <= 256, "UMMA N (M = 256 needs N % 16 == 0; halves keep the 8-row swizzle atoms)");
+    static_assert(kBHalfBytes % 1024 == 0, "B half tile must keep the swizzle atom alignment");
+    static_assert(8 * GemmCfg<BN>::kStageOut <= kStages * kStageBytes, "epilogue staging must fit in the pipeline's memory");
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory");
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo, TcArgs g) {
+    using C = GemmCfg<BN>;
+    using P = PairCfg<BN>;
+    constexpr int kSt = P::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSt * P::kStageBytes);
+    uint64_t* empty_bar = full_bar + kSt;
+    uint64_t* tmem_full_bar = empty_bar + kSt;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                 // 0 = leader; the pair covers rows [m0 - rank*BM, +256)
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    constexpr int BK = 64;
+    const int num_kb = g.K / BK;
+    if (threadIdx.x == 0 && g.dbg) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        GEMM_TS_ADD(14, (long long)gt);
+        GEMM_TS(0);
+    }
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a_hi), prefetch_tmap(&map_a_lo), prefetch_tmap(&map_b_hi), prefetch_tmap(&map_b_lo);
+        for (int s = 0; s < kSt; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, kTmemCols);
+    tc_fence_before();
+    cluster_sync_all();                 // the peer's barriers exist before anything arrives on them remotely
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) GEMM_TS(1);
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (lane == 0) {
+            const int nb = n0 + (int)rank * (BN / 2);
+            long long wait_empty = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kSt;
+                const uint32_t parity = ((kb / kSt) & 1) ^ 1;
+                const long long t0 = g.dbg ? clock64() : 0;
+                mbar_wait(&empty_bar[s], parity);
+                if (g.dbg) wait_empty += clock64() - t0;
+                uint8_t* st = smem + s * P::kStageBytes;
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * P::kStageBytes);
+                const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+                tma_load_2d_pair(st, &map_a_hi, kb * BK, m0, lead_bar);
+                tma_load_2d_pair(st + kATileBytes, &map_a_lo, kb * BK, m0, lead_bar);
+                tma_load_2d_pair(st + 2 * kATileBytes, &map_b_hi, kb * BK, nb, lead_bar);
+                tma_load_2d_pair(st + 2 * kATileBytes + P::kBHalfBytes, &map_b_lo, kb * BK, nb, lead_bar);
+            }
+            GEMM_TS_ADD(8, wait_empty);
+            GEMM_TS(2);
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = instr_desc_f16(2 * BM, BN);
+            const uint32_t cross = tmem_base + (uint32_t)(C::kCross16 * BN);
+            long long wait_full = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kSt;
+                const long long t0 = g.dbg ? clock64() : 0;
+                mbar_wait(&full_bar[s], (kb / kSt) & 1);
+                if (g.dbg) wait_full += clock64() - t0;
+                if (kb == 0) GEMM_TS(3);
+                tc_fence_after();
+                const uint32_t base = smem_u32(smem + s * P::kStageBytes);
+                const uint64_t a_hi = make_smem_desc(base), a_lo = make_smem_desc(base + kATileBytes);
+                const uint64_t b_hi = make_smem_desc(base + 2 * kATileBytes);
+                const uint64_t b_lo = make_smem_desc(base + 2 * kATileBytes + P::kBHalfBytes);
+                const uint32_t acc = tmem_base + (uint32_t)((kb % C::kMain16) * BN);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t adv = (uint64_t)((k * 32) >> 4);        // 32 bytes per MMA K step inside the 128-B row
+                    umma_f16_pair(cross, a_lo + adv, b_hi + adv, idesc, (kb != 0) || (k != 0));
+                    umma_f16_pair(cross, a_hi + adv, b_lo + adv, idesc, 1);
+                    umma_f16_pair(acc, a_hi + adv, b_hi + adv, idesc, (kb >= C::kMain16) || (k != 0));
+                }
+                umma_commit_pair(&empty_bar[s], 3);      // frees the stage in both CTAs
+            }
+            umma_commit_pair(tmem_full_bar, 3);          // accumulators complete in both CTAs
+            GEMM_TS_ADD(9, wait_full);
+            GEMM_TS(4);
+        }
+    } else {
+        // ===== epilogue warps 2..17 (both CTAs, each its own 128 rows) =====
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        if (threadIdx.x == 64) GEMM_TS(5);
+        epilogue_tile<BN, true>(g, smem, tmem_base, m0, n0, warp, lane, num_kb);
+        if (threadIdx.x == 64) GEMM_TS(6);
+    }
+    tc_fence_before();
+    cluster_sync_all();                 // neither CTA leaves (or frees TMEM) while the pair's MMAs / reads are in flight
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, kTmemCols);
+    }
+    if (threadIdx.x == 0 && g.dbg) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        GEMM_TS_ADD(15, (long long)gt);
+        GEMM_TS(7);
     }
 }
 
@@ -423,6 +623,7 @@ struct WeightSplit {
     void *hi = nullptr, *lo = nullptr;                 // K-major [N][K], fp32 (TF32 scheme) or fp16
     int K = 0, N = 0;
     CUtensorMap map_hi[kNumBN], map_lo[kNumBN];       // one box height per N-tile width
+    CUtensorMap map_hi2[kNumBN], map_lo2[kNumBN];     // half-height boxes: each CTA of a pair loads half of the B tile
 };
 struct KeyHash {
     size_t operator()(const std::pair<const float*, int>& k) const {
@@ -487,6 +688,8 @@ int make_map_u16(CUtensorMap* map, const void* base, int rank, const uint64_t* d
 }  // namespace tc
 
 bool tc_gemm_available() { return true; }
+long long* g_gemm_dbg = nullptr;   // set by gem_debug_gemm_timestamps (profiling only)
+int g_gemm_pair = -1;      // debug override of GEM_GEMM_PAIR (gem_debug_gemm_pair): -1 = environment / default
 
 // `owner` identifies the ctx; scratch grows on demand and lives until tc_gemm_release(owner).
 template <int BN, bool F16>
@@ -500,6 +703,20 @@ static int launch_bn(cudaStream_t stream, const CUtensorMap& a_hi, const CUtenso
     }
     dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN);
     tc_gemm_kernel<BN, F16><<<grid, kThreads, GemmCfg<BN>::kSmemBytes, stream>>>(a_hi, a_lo, w.map_hi[idx], w.map_lo[idx], a);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+template <int BN>
+static int launch_pair_bn(cudaStream_t stream, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const WeightSplit& w, int idx,
+                          const TcArgs& a) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GEM_CUDA(cudaFuncSetAttribute(tc_gemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)PairCfg<BN>::kSmemBytes));
+        attr_set = true;
+    }
+    dim3 grid(2 * ((a.M + 2 * BM - 1) / (2 * BM)), (a.N + BN - 1) / BN);      // whole pairs along M
+    tc_gemm_pair_kernel<BN><<<grid, kThreads, PairCfg<BN>::kSmemBytes, stream>>>(a_hi, a_lo, w.map_hi2[idx], w.map_lo2[idx], a);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }
@@ -567,7 +784,9 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
     TcArgs a;
     a.bias = g.bias, a.C = g.C, a.C_lo = (float*)g.C_lo, a.sign = g.C_sign, a.M = g.M, a.N = g.N, a.K = g.K, a.ldc = g.ldc;
     a.epi = g.epi, a.row_exp = f16 ? g.row_exp : nullptr, a.out16 = (g.C_lo && g.out16) ? 1 : 0;
+    a.dbg = g_gemm_dbg;
     GEM_REQUIRE(!a.out16 || g.ldc % 8 == 0, "fp16 outputs need ldc % 8 == 0");
+    GEM_REQUIRE((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "bias must be 16-byte aligned");
     // N-tile width.  Up to one wave of 128-wide tiles: keep 128 (kernels of concurrent slices share the SMs, the
     // least padded tiling wins).  Beyond: the fewest waves x columns over the 148 SMs (sign words need
     // 32-column alignment).
@@ -585,6 +804,19 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
     if (const char* env = getenv("GEM_GEMM_BN")) {
         for (int i = 0; i < kNumBN; ++i)
             if (atoi(env) == kBNs[i] && !(g.C_sign && kBNs[i] % 32 != 0)) best = i;
+    }
+    // fp16 scheme: CTA pairs (cta_group::2) unless GEM_GEMM_PAIR=0; 160-wide tiles (the lowest shared-memory traffic
+    // per MMA that three accumulators allow), 128 on request
+    static const int pair_env = []() {
+        const char* env = getenv("GEM_GEMM_PAIR");
+        return env ? atoi(env) : 1;
+    }();
+    const int pair_mode = g_gemm_pair >= 0 ? g_gemm_pair : pair_env;
+    if (f16 && pair_mode) {
+        int bn = 160;
+        if (const char* env = getenv("GEM_GEMM_BN")) bn = atoi(env) == 128 ? 128 : 160;
+        return bn == 128 ? launch_pair_bn<128>(stream, map_a_hi, map_a_lo, wit->second, 1, a)
+                         : launch_pair_bn<160>(stream, map_a_hi, map_a_lo, wit->second, 3, a);
     }
     return f16 ? launch_scheme<true>(kBNs[best], stream, map_a_hi, map_a_lo, wit->second, best, a)
                : launch_scheme<false>(kBNs[best], stream, map_a_hi, map_a_lo, wit->second, best, a);
@@ -647,6 +879,8 @@ int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int
     for (int i = 0; i < kNumBN; ++i) {
         int rc = make_map(&ws.map_hi[i], ws.hi, f16, (uint64_t)N, (uint64_t)K, 0, kBNs[i]);
         if (rc == GEM_OK) rc = make_map(&ws.map_lo[i], ws.lo, f16, (uint64_t)N, (uint64_t)K, 0, kBNs[i]);
+        if (rc == GEM_OK && f16) rc = make_map(&ws.map_hi2[i], ws.hi, f16, (uint64_t)N, (uint64_t)K, 0, kBNs[i] / 2);
+        if (rc == GEM_OK && f16) rc = make_map(&ws.map_lo2[i], ws.lo, f16, (uint64_t)N, (uint64_t)K, 0, kBNs[i] / 2);
         if (rc != GEM_OK) return rc;
     }
     st->weights.emplace(key, ws);

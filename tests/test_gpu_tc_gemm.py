@@ -148,3 +148,29 @@ def test_fp16_chain_matches_fp32_path(engine, W):
         print(W, scale, "fp16 chain vs fp32 CUDA cores: pose", rp, "dz", rz)
         assert rp < 1e-5 and rz < 2e-5, (W, scale, rp, rz)
     engine.set_gemm_mode(2)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 128, 64), (300, 256, 128), (1870, 2560, 2048), (641, 2048, 2560), (130, 4096, 5120),
+                                   (257, 2560, 2048)])
+def test_fp16_scheme_cta_pair_matches_single_cta(engine, M, N, K):
+    """The CTA-pair kernel (tcgen05.mma.cta_group::2, M = 256, each CTA holding half of the B tile) runs the same
+    MMAs in the same order per output element as the one-CTA kernel: bit-identical results, for odd M-tile counts
+    (a pair whose second CTA is empty), ragged last rows and N tiles that stick out of the matrix."""
+    import ctypes as C
+    g = torch.Generator(device="cpu").manual_seed(11 * M + N + K)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(K, N, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    ref = a.double() @ b.double() + bias.double()
+    out = {}
+    lib = engine.lib
+    lib.gem_debug_gemm_pair.argtypes = [C.c_int]
+    try:
+        for pair in (0, 1):
+            lib.gem_debug_gemm_pair(pair)
+            out[pair] = engine.gemm(a, b, bias, leaky_relu=True, tensor_cores=2).cpu()
+    finally:
+        lib.gem_debug_gemm_pair(-1)
+    ref_act = torch.where(ref > 0, ref, ref * 0.01)
+    assert _rel(out[1], ref_act) < 1e-5
+    assert torch.equal(out[0], out[1]), float((out[0] - out[1]).abs().max())
