@@ -28,6 +28,7 @@ struct gem_ctx {
     int device = 0;
     int Wmax = 0, n = 0, T = 0, J = 0, H = 0, Wd = 0, m = 0;
     int gemm_mode = 0;
+    int tap_chain = 1;                           // mode 3: the four K<=128 tap layers of each direction in one launch
     bool have_camera = false, have_skeleton = false;
     bool have_vae[2] = {false, false};
     gem_vae_weights vae[2];
@@ -227,6 +228,7 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     // GEMMs, 3xTF32 convolutions), 1 (3xTF32 everywhere) or 0 (fp32 CUDA cores)
     c->gemm_mode = 3;
     if (const char* env = getenv("GEM_GEMM_MODE")) c->gemm_mode = (env[0] >= '0' && env[0] <= '3') ? env[0] - '0' : 3;
+    if (const char* env = getenv("GEM_TAP_CHAIN")) c->tap_chain = env[0] != '0';
     c->n_chunks = 4;
     if (const char* env = getenv("GEM_CHUNKS")) c->n_chunks = atoi(env) >= 1 ? atoi(env) : 1;
     if (c->n_chunks > 16) c->n_chunks = 16;
@@ -280,6 +282,12 @@ int gem_debug_tap_timestamps(long long* buf_d) {
 }
 
 /* debug hook (not in the public header): 1 = CTA-pair (cta_group::2) fp16-scheme GEMM, 0 = one CTA per tile, -1 = default */
+/* debug hook: 1 = fused tap-layer chains (default), 0 = one launch per layer */
+int gem_debug_tap_chain(gem_ctx* c, int on) {
+    GEM_REQUIRE(c != nullptr, "ctx is NULL");
+    c->tap_chain = on ? 1 : 0;
+    return GEM_OK;
+}
 int gem_debug_gemm_timestamps(long long* buf_d) {
     gem::g_gemm_dbg = buf_d;
     return GEM_OK;
@@ -524,10 +532,25 @@ static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice
         // latent -> [T][256] on the tcgen05 GEMM, its epilogue writes the activation already split
         GEM_TRY(run_layer(c, s, GEM_TAG_DEC + 0, v.dec[0], z, c->n, W, v_.act_hi[0], T * 256, EPI_LRELU, nullptr, z_hi,
                           z_lo, v_.act_lo[0], v_.act_sign[0], nullptr, c->gemm_mode == 3));
+        c->act_split = true;
+        if (c->gemm_mode == 3 && c->tap_chain) {
+            // 256 -> 128 on its own, then 128 -> 64 -> 64 -> 64 -> pose in ONE launch: the activation tile stays in
+            // shared memory, only the sign bits (the bwd-data masks) and the pose reach HBM
+            GEM_TRY(run_tap_tc(c, s, GEM_TAG_DEC + 1, v.dec[1], v_.act_hi[0], v_.act_lo[0], v.dec[1].k, W, v_.act_hi[1],
+                               v_.act_lo[1], v.dec[1].n, EPI_LRELU, nullptr, nullptr, v_.act_sign[1]));
+            TapChainLaunch t;
+            t.nl = 4;
+            for (int i = 2; i <= 5; ++i) {
+                t.B[i - 2] = v.dec[i].w_d, t.bias[i - 2] = v.dec[i].bias_d, t.aux_bits[i - 2] = nullptr;
+                t.sign_out[i - 2] = i <= 4 ? v_.act_sign[i] : nullptr, t.epi[i - 2] = i <= 4 ? EPI_LRELU : EPI_NONE;
+            }
+            t.A_hi = v_.act_hi[1], t.A_lo = v_.act_lo[1], t.lda = v.dec[2].k, t.Kreal = v.dec[2].k;
+            t.out_hi = pose_out, t.out_lo = nullptr, t.ldo = P, t.W = W, t.T = T;
+            return timed(c, s, GEM_TAG_DEC + 2, [&]() { return launch_tap_chain(s, c, t); });
+        }
         for (int i = 1; i <= 4; ++i)
             GEM_TRY(run_tap_tc(c, s, GEM_TAG_DEC + i, v.dec[i], v_.act_hi[i - 1], v_.act_lo[i - 1], v.dec[i].k, W,
                                v_.act_hi[i], v_.act_lo[i], v.dec[i].n, EPI_LRELU, nullptr, nullptr, v_.act_sign[i]));
-        c->act_split = true;
         return run_tap_tc(c, s, GEM_TAG_DEC + 5, v.dec[5], v_.act_hi[4], v_.act_lo[4], 64, W, pose_out, nullptr, P, EPI_NONE,
                           nullptr);
     }
@@ -563,7 +586,22 @@ static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const S
         }
         const float *in_hi = v_.gp_hi, *in_lo = v_.gp_lo;
         int lda = pp;
-        for (int i = 0; i < 5; ++i) {
+        int i0 = 0;
+        if (c->gemm_mode == 3 && c->tap_chain && c->act_split) {
+            // d pose -> 64 -> 64 -> 64 -> 128 in ONE launch (masks from the forward pass's sign bits), 128 -> 256 after it
+            TapChainLaunch t;
+            t.nl = 4;
+            for (int i = 0; i < 4; ++i) {
+                t.B[i] = v.dec_bwd[i].w_d, t.bias[i] = v.dec_bwd[i].bias_d, t.aux_bits[i] = v_.act_sign[4 - i];
+                t.sign_out[i] = nullptr, t.epi[i] = EPI_MASK;
+            }
+            t.A_hi = in_hi, t.A_lo = in_lo, t.lda = pp, t.Kreal = pp;
+            t.out_hi = v_.gact_hi[1], t.out_lo = v_.gact_lo[1], t.ldo = v.dec_bwd[3].n, t.W = W, t.T = T;
+            GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 0, [&]() { return launch_tap_chain(s, c, t); }));
+            in_hi = v_.gact_hi[1], in_lo = v_.gact_lo[1], lda = v.dec_bwd[3].n;
+            i0 = 4;
+        }
+        for (int i = i0; i < 5; ++i) {
             const int a = 4 - i;
             GEM_TRY(run_tap_tc(c, s, GEM_TAG_DEC_BWD + i, v.dec_bwd[i], in_hi, in_lo, lda, W, v_.gact_hi[a], v_.gact_lo[a],
                                v.dec_bwd[i].n, EPI_MASK, saved[a], c->act_split ? v_.act_sign[a] : nullptr));
@@ -854,7 +892,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     int round_launches = 0;
     if (graphs && a.p.max_eval >= 2) {
         for (auto& g : c->graphs) {
-            if (g.which == which && g.w0 == w0 && g.Wk == Wk && g.gemm_mode == c->gemm_mode && g.heat == a.heat &&
+            if (g.which == which && g.w0 == w0 && g.Wk == Wk && g.gemm_mode == (c->gemm_mode | (c->tap_chain << 8)) && g.heat == a.heat &&
                 g.has_heat == ((a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on) &&
                 g.trace_stride == lb.trace_stride &&
                 memcmp(&g.wt, &a.wt, sizeof(a.wt)) == 0 && g.p.lr == a.p.lr && g.p.max_iter == a.p.max_iter &&
@@ -878,7 +916,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             }
             GEM_CUDA(e);
             gem_ctx::RoundGraph g;
-            g.which = which, g.w0 = w0, g.Wk = Wk, g.gemm_mode = c->gemm_mode, g.heat = a.heat;
+            g.which = which, g.w0 = w0, g.Wk = Wk, g.gemm_mode = c->gemm_mode | (c->tap_chain << 8), g.heat = a.heat;
             g.has_heat = (a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on;
             g.trace_stride = lb.trace_stride, g.wt = a.wt, g.p = a.p;
             g.launches = round_launches;

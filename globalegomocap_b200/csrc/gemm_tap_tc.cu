@@ -30,6 +30,8 @@
 // tcgen05.mma issue (M128, N = 3*NCTA, K8, kind::tf32), warps 2-9 = epilogue, two per TMEM lane quarter
 // (tcgen05.ld, shuffle shift-add, bias / LeakyReLU / LeakyReLU-derivative mask, hi/lo split, staging in the
 // idle operand memory, 3-D TMA store).
+#include <string.h>
+
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -418,6 +420,287 @@ __global__ void __launch_bounds__(128) rowscale_split_pad_f16_kernel(const float
     }
 }
 
+
+// ---- chain of k=3 layers in one launch (fp16 scheme) ---------------------------------------------------------------
+// A K = 64 layer is latency, not work: 0.7 us of setup, 1.3 us until the first tile lands, 0.5 us of MMAs, an
+// epilogue, then the launch gap — per layer, ten times per closure round.  The epilogue already stages its result in
+// the 128-byte-swizzled layout the next layer's MMA reads, so a chain of layers can keep the activation tile in
+// shared memory: one setup, one activation load, and only sign bits (the bwd-data masks) plus the last layer's
+// output go to HBM.  Structure per CTA (12 windows = one M tile, 576 threads, one CTA per SM):
+//   warp 0    TMA: the first layer's activation tile (3-D boxes per TMEM lane quarter), then every layer's weight
+//             blocks (three fp16 slabs of 3*NCTA rows per K block) through a two-slot ring (full / empty mbarriers)
+//   warp 1    one thread issues the MMAs of layer l as soon as its operand tile is ready (act_ready: the previous
+//             layer's epilogue warps arrive after a proxy fence) and commits to acc_full
+//   warps 2-17  epilogue, four per TMEM lane quarter (one 16-column chunk each): shuffle shift-add of the three
+//             taps, bias / LeakyReLU / mask, sign bits, fp16 hi/lo split into the other activation buffer
+// Accumulators alternate between TMEM columns [0, 192) and [192, 384); activation buffers alternate likewise.
+constexpr int kChainThreads = 64 + 16 * 32;
+constexpr int kChainEpiWarps = 16;
+constexpr int kChainWSlot = 3 * 192 * 128;                    // 73,728 B: three slabs of 192 rows x 128 B
+constexpr size_t kChainSmem = 4 * kATile + 2 * kChainWSlot + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct ChainLayer {
+    const float* bias;
+    const uint32_t* aux_bits;
+    uint32_t* sign_out;
+    int ncta, gridy, num_kb, N, epi;
+    int out_kind;            // 0: operand of the next layer (shared memory only), 1: split fp16 to global (TMA store),
+};                           // 2: plain fp32 rows to global
+struct ChainMaps {
+    CUtensorMap a_hi, a_lo;
+    CUtensorMap w[kTapChainMax][3];
+    CUtensorMap o_hi, o_lo;
+};
+struct ChainArgs {
+    ChainLayer L[kTapChainMax];
+    int nl, W, T, wpq;
+    float* out_plain;
+    long long* dbg;
+};
+
+__global__ void __launch_bounds__(kChainThreads, 1)
+tc_tap_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* act = smem;                                   // two buffers of (hi 16 KB, lo 16 KB)
+    uint8_t* wring = smem + 4 * kATile;                    // two weight slots
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wring + 2 * kChainWSlot);
+    uint64_t* act_full = bars;                             // the first layer's activation tile has landed
+    uint64_t* w_full = bars + 1;                           // [2]
+    uint64_t* w_empty = bars + 3;                          // [2]
+    uint64_t* acc_full = bars + 5;                         // layer l's accumulators complete (phase l)
+    uint64_t* act_ready = bars + 6;                        // layer l's output tile is in shared memory (phase l)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) TAP_DBG(0);
+    if (threadIdx.x == 0 && g.dbg) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g.dbg[(size_t)blockIdx.x * 16 + 14] = (long long)gt;
+    }
+    const int win0 = blockIdx.x * 4 * g.wpq;
+    const int rows_q = g.wpq * g.T;
+    const int nkb0 = g.L[0].num_kb;
+    // buffer plan: layer 0 reads buffers 0 .. nkb0-1; layer l >= 1 reads what layer l-1 wrote and writes the other one
+    auto in_buf = [&](int l) { return l == 0 ? 0 : ((nkb0 == 2 ? 0 : 1) + (l - 1)) & 1; };
+    auto out_buf = [&](int l) { return ((nkb0 == 2 ? 0 : 1) + l) & 1; };
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&maps.a_hi), prefetch_tmap(&maps.a_lo);
+        for (int l = 0; l < g.nl; ++l) prefetch_tmap(&maps.w[l][0]), prefetch_tmap(&maps.w[l][1]), prefetch_tmap(&maps.w[l][2]);
+        mbar_init(act_full, 1);
+        mbar_init(&w_full[0], 1), mbar_init(&w_full[1], 1), mbar_init(&w_empty[0], 1), mbar_init(&w_empty[1], 1);
+        mbar_init(acc_full, 1), mbar_init(act_ready, kChainEpiWarps);
+        fence_barrier_init();
+    }
+    // the idle rows of each quarter are never written by TMA: clear them once so the first layer's MMA reads zeros
+    {
+        const int idle = 32 - rows_q;
+        const int total = 4 * 4 * idle * 8;                    // 16-byte slots in the four tiles
+        for (int i = threadIdx.x; i < total; i += kChainThreads) {
+            const int tile = i / (4 * idle * 8), r = i % (4 * idle * 8);
+            const int q = r / (idle * 8), rr = (r % (idle * 8)) / 8, c16 = r % 8;
+            uint8_t* p = act + tile * kATile + q * kQuarterBytes + (rows_q + rr) * 128 + c16 * 16;
+            *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TAP_DBG(1);
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const uint32_t box_bytes = (uint32_t)rows_q * 128;
+            mbar_arrive_expect_tx(act_full, (uint32_t)nkb0 * 8 * box_bytes);
+            for (int kb = 0; kb < nkb0; ++kb) {
+                uint8_t* dst = act + kb * 2 * kATile;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    tma_load_3d(dst + q * kQuarterBytes, &maps.a_hi, kb * 64, 0, win0 + q * g.wpq, act_full);
+                    tma_load_3d(dst + kATile + q * kQuarterBytes, &maps.a_lo, kb * 64, 0, win0 + q * g.wpq, act_full);
+                }
+            }
+            int b = 0;
+            for (int l = 0; l < g.nl; ++l) {
+                const int np = 3 * g.L[l].ncta;
+                const uint32_t bt = (uint32_t)np * 128;
+                for (int y = 0; y < g.L[l].gridy; ++y)
+                    for (int kb = 0; kb < g.L[l].num_kb; ++kb, ++b) {
+                        const int slot = b & 1;
+                        mbar_wait(&w_empty[slot], (uint32_t)(((b >> 1) & 1) ^ 1));
+                        uint8_t* dst = wring + slot * kChainWSlot;
+                        mbar_arrive_expect_tx(&w_full[slot], 3 * bt);
+                        tma_load_2d(dst, &maps.w[l][0], kb * 64, y * np, &w_full[slot]);
+                        tma_load_2d(dst + bt, &maps.w[l][1], kb * 64, y * np, &w_full[slot]);
+                        tma_load_2d(dst + 2 * bt, &maps.w[l][2], kb * 64, y * np, &w_full[slot]);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int b = 0;
+            for (int l = 0; l < g.nl; ++l) {
+                if (l == 0) mbar_wait(act_full, 0);
+                else mbar_wait(act_ready, (uint32_t)((l - 1) & 1));
+                tc_fence_after();
+                if (l < 4) TAP_DBG(2 + l);
+                const int np = 3 * g.L[l].ncta;
+                const uint32_t bt = (uint32_t)np * 128;
+                const uint32_t idesc = instr_desc_f16(kRows, np);
+                for (int y = 0; y < g.L[l].gridy; ++y) {
+                    const uint32_t acc = tmem_base + (uint32_t)(((l + y) & 1) * 192);
+                    for (int kb = 0; kb < g.L[l].num_kb; ++kb, ++b) {
+                        const int slot = b & 1;
+                        mbar_wait(&w_full[slot], (uint32_t)((b >> 1) & 1));
+                        tc_fence_after();
+                        const uint8_t* in = act + (l == 0 ? kb : in_buf(l)) * 2 * kATile;
+                        const uint32_t wb = smem_u32(wring + slot * kChainWSlot);
+                        const uint64_t a_hi = make_smem_desc(smem_u32(in)), a_lo = make_smem_desc(smem_u32(in + kATile));
+                        const uint64_t b_hi = make_smem_desc(wb), b_lo = make_smem_desc(wb + bt), b_hs = make_smem_desc(wb + 2 * bt);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            umma_f16(acc, a_lo + adv, b_hs + adv, idesc, (kb > 0) || (k != 0));      // small terms first
+                            umma_f16(acc, a_hi + adv, b_lo + adv, idesc, 1);
+                            umma_f16(acc, a_hi + adv, b_hi + adv, idesc, 1);
+                        }
+                        umma_commit(&w_empty[slot]);
+                    }
+                }
+                umma_commit(acc_full);
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..17: TMEM lane quarter = warp % 4, one 16-column chunk per warp =====
+        const int q = warp & 3;
+        const int sub = (warp - 2) >> 2;
+        const int wl = lane / g.T, t = lane - wl * g.T;         // window inside the quarter, frame
+        const int winq = win0 + q * g.wpq;
+        const int win = winq + wl;
+        const bool row_ok = lane < rows_q && win < g.W;
+        const bool has_prev = t > 0, has_next = t < g.T - 1;
+        const size_t token = (size_t)win * g.T + t;
+        for (int l = 0; l < g.nl; ++l) {
+            const ChainLayer& L = g.L[l];
+            mbar_wait(acc_full, (uint32_t)(l & 1));
+            tc_fence_after();
+            if (threadIdx.x == 64 && l < 4) TAP_DBG(8 + l);
+            const int halves = L.N >> 4;                        // 16-bit sign halves per token
+            for (int y = 0; y < L.gridy; ++y) {
+                uint8_t* stage = act + (y == 0 ? out_buf(l) : in_buf(l)) * 2 * kATile;
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((l + y) & 1) * 192);
+                const int c = sub;
+                if (c * 16 < L.ncta) {
+                    uint32_t p0[16], p1[16], p2[16];
+                    tmem_ld_32x32b_x16(trow + (uint32_t)(0 * L.ncta + c * 16), p0);
+                    tmem_ld_32x32b_x16(trow + (uint32_t)(1 * L.ncta + c * 16), p1);
+                    tmem_ld_32x32b_x16(trow + (uint32_t)(2 * L.ncta + c * 16), p2);
+                    const int nb = y * L.ncta + c * 16;
+                    uint32_t mbits = 0;
+                    if (L.epi == EPI_MASK && row_ok)
+                        mbits = __ldg(reinterpret_cast<const uint16_t*>(L.aux_bits) + token * halves + (nb >> 4));
+                    tmem_ld_wait();
+                    float o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(p0[j]), 1);     // P_0 of the previous frame
+                        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(p2[j]), 1);   // P_2 of the next frame
+                        float v = __uint_as_float(p1[j]);
+                        v += has_prev ? up : 0.f;
+                        v += has_next ? dn : 0.f;
+                        o[j] = v * (1.f / kWScale16);
+                    }
+                    if (L.bias) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (nb + j < L.N) o[j] += __ldg(L.bias + nb + j);
+                    }
+                    if (L.epi == EPI_LRELU) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * 0.01f;
+                    } else if (L.epi == EPI_MASK) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = ((mbits >> j) & 1u) ? o[j] : o[j] * 0.01f;
+                    }
+                    if (L.sign_out) {
+                        uint32_t sbits = 0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) sbits |= (o[j] > 0.f ? 1u : 0u) << j;
+                        if (row_ok) reinterpret_cast<uint16_t*>(L.sign_out)[token * halves + (nb >> 4)] = (uint16_t)sbits;
+                    }
+                    if (L.out_kind != 2) {
+                        uint8_t* th = stage + q * kQuarterBytes + lane * 128;
+                        uint8_t* tl = th + kATile;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 8) {
+                            uint16_t h[8], lo8[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) split_f16(o[j + e], h[e], lo8[e]);
+                            const int off = (((c * 2 + (j >> 3)) ^ (lane & 7)) << 4);            // SWIZZLE_128B
+                            *reinterpret_cast<uint4*>(th + off) =
+                                make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                                           (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
+                            *reinterpret_cast<uint4*>(tl + off) =
+                                make_uint4((uint32_t)lo8[0] | ((uint32_t)lo8[1] << 16), (uint32_t)lo8[2] | ((uint32_t)lo8[3] << 16),
+                                           (uint32_t)lo8[4] | ((uint32_t)lo8[5] << 16), (uint32_t)lo8[6] | ((uint32_t)lo8[7] << 16));
+                        }
+                    } else {
+                        float* sp = reinterpret_cast<float*>(stage + q * 2 * kQuarterBytes) + lane * L.N + c * 16;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (nb + j < L.N) sp[j] = o[j];
+                    }
+                }
+                if (L.out_kind == 0) {
+                    // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+                    fence_proxy_async_smem();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(act_ready);
+                } else if (L.out_kind == 1) {
+                    fence_proxy_async_smem();
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+                    if (sub == 0 && lane == 0 && winq < g.W) {
+                        tma_store_3d(&maps.o_hi, stage + q * kQuarterBytes, y * L.ncta, 0, winq);
+                        tma_store_3d(&maps.o_lo, stage + kATile + q * kQuarterBytes, y * L.ncta, 0, winq);
+                        bulk_commit();
+                        bulk_wait_read0();
+                    }
+                } else {
+                    // plain output (the pose): the quarter's windows are consecutive, dense rows in global memory
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+                    int nwin = g.W - winq;
+                    nwin = nwin < 0 ? 0 : (nwin > g.wpq ? g.wpq : nwin);
+                    const int count = nwin * g.T * L.N;
+                    const float* sp = reinterpret_cast<const float*>(stage + q * 2 * kQuarterBytes);
+                    float* dp = g.out_plain + (size_t)winq * g.T * L.N;
+                    for (int i = sub * 32 + lane; i < count; i += 128) dp[i] = sp[i];
+                }
+            }
+        }
+    }
+    if (threadIdx.x == 64) TAP_DBG(5);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+    if (threadIdx.x == 0) TAP_DBG(6);
+    if (threadIdx.x == 0 && g.dbg) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g.dbg[(size_t)blockIdx.x * 16 + 15] = (long long)gt;
+    }
+}
+
 struct TapWeight {
     void *hi = nullptr, *lo = nullptr, *hs = nullptr;
     int K = 0, Kp = 0, N = 0, ncta = 0, gridy = 0;
@@ -594,6 +877,69 @@ int launch_tap_tc(cudaStream_t stream, void* owner, const TapTcLaunch& L) {
     if (w.ncta == 64)
         return f16 ? launch_tap_cfg<64, true>(stream, grid, *am, w, *om, a) : launch_tap_cfg<64, false>(stream, grid, *am, w, *om, a);
     return f16 ? launch_tap_cfg<48, true>(stream, grid, *am, w, *om, a) : launch_tap_cfg<48, false>(stream, grid, *am, w, *om, a);
+}
+
+
+int launch_tap_chain(cudaStream_t stream, void* owner, const TapChainLaunch& L) {
+    if (L.W <= 0) return GEM_OK;
+    GEM_REQUIRE(L.nl >= 1 && L.nl <= kTapChainMax, "chain length");
+    GEM_REQUIRE(L.T >= 1 && L.T <= 32, "seq_len must be <= 32 on the tcgen05 tap path");
+    TapState* st = state_of(owner);
+    const TapWeight* w[kTapChainMax];
+    for (int l = 0; l < L.nl; ++l) {
+        auto wit = st->weights.find(std::make_pair(L.B[l], 2));
+        if (wit == st->weights.end()) {
+            set_error("tcgen05 tap chain: weights were not prepared in the fp16 scheme (tc_tap_prepare_weight)");
+            return GEM_ERR_STATE;
+        }
+        w[l] = &wit->second;
+        const bool last = l == L.nl - 1;
+        GEM_REQUIRE(w[l]->Kp / 64 <= (l == 0 ? 2 : 1), "chain layers after the first take one 64-channel K block");
+        GEM_REQUIRE(last || (w[l]->N == 64 && w[l]->gridy == 1), "inner chain layers must produce 64 channels");
+        GEM_REQUIRE(w[l]->gridy <= 2, "the last chain layer may have at most two output slabs");
+        GEM_REQUIRE(L.epi[l] != EPI_MASK || L.aux_bits[l], "mask epilogue needs sign bits");
+        GEM_REQUIRE((!L.aux_bits[l] && !L.sign_out[l]) || w[l]->N % 16 == 0, "sign bits need N % 16 == 0");
+    }
+    const TapWeight& wl = *w[L.nl - 1];
+    GEM_REQUIRE((L.lda * 2) % 16 == 0 && L.Kreal <= L.lda && L.Kreal <= w[0]->Kp && L.Kreal >= w[0]->K, "bad activation layout");
+    GEM_REQUIRE(L.out_lo == nullptr || ((L.ldo * 2) % 16 == 0 && wl.ncta == 64), "split output needs N % 64 == 0");
+    GEM_REQUIRE(L.out_lo != nullptr || (L.ldo == wl.N && wl.N <= 48 && wl.gridy == 1), "plain output must be dense and N <= 48");
+    const int wpq = 32 / L.T;
+    auto make3 = [&](CUtensorMap* m, const void* base, int ld, int cols) -> int {
+        const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)L.T, (uint64_t)L.W};
+        const uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)L.T * ld * 2};
+        const uint32_t box[3] = {64u, (uint32_t)L.T, (uint32_t)wpq};
+        return make_map_u16(m, base, 3, dims, strides, box);
+    };
+    ChainMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc = make3(&maps.a_hi, L.A_hi, L.lda, L.Kreal);
+    if (rc == GEM_OK) rc = make3(&maps.a_lo, L.A_lo, L.lda, L.Kreal);
+    if (rc == GEM_OK && L.out_lo) rc = make3(&maps.o_hi, L.out_hi, L.ldo, wl.N);
+    if (rc == GEM_OK && L.out_lo) rc = make3(&maps.o_lo, L.out_lo, L.ldo, wl.N);
+    if (rc != GEM_OK) return rc;
+    if (!L.out_lo) maps.o_hi = maps.a_hi, maps.o_lo = maps.a_lo;      // unused by the kernel
+    ChainArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int l = 0; l < L.nl; ++l) {
+        maps.w[l][0] = w[l]->map_hi, maps.w[l][1] = w[l]->map_lo, maps.w[l][2] = w[l]->map_hs;
+        ChainLayer& c = a.L[l];
+        c.bias = L.bias[l], c.aux_bits = L.aux_bits[l], c.sign_out = L.sign_out[l];
+        c.ncta = w[l]->ncta, c.gridy = w[l]->gridy, c.num_kb = w[l]->Kp / 64, c.N = w[l]->N, c.epi = L.epi[l];
+        c.out_kind = l < L.nl - 1 ? 0 : (L.out_lo ? 1 : 2);
+    }
+    for (int l = L.nl; l < kTapChainMax; ++l) maps.w[l][0] = maps.w[l][1] = maps.w[l][2] = maps.a_hi;
+    a.nl = L.nl, a.W = L.W, a.T = L.T, a.wpq = wpq, a.out_plain = L.out_lo ? nullptr : (float*)L.out_hi;
+    a.dbg = g_tap_dbg;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GEM_CUDA(cudaFuncSetAttribute(tc_tap_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem));
+        attr_set = true;
+    }
+    const int grid = (L.W + 4 * wpq - 1) / (4 * wpq);
+    tc_tap_chain_kernel<<<grid, kChainThreads, kChainSmem, stream>>>(maps, a);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
 }
 
 void tc_tap_release(void* owner) {

@@ -65,6 +65,25 @@ int tc_tap_prepare_weight(void* owner, cudaStream_t stream, const float* B, int 
 int launch_rowscale_split_pad_f16(cudaStream_t stream, const float* src, int C, int T, int W, int ldo, uint16_t* hi,
                                   uint16_t* lo, int32_t* row_exp);
 int launch_tap_tc(cudaStream_t stream, void* owner, const TapTcLaunch& L);
+// Up to four consecutive k=3 layers in ONE launch (fp16 scheme): the activation tile stays in shared memory between
+// the layers (the epilogue's staged output IS the next layer's swizzled operand), only sign bits and the last
+// layer's output reach HBM; weights stream through a two-slot ring.  Layers after the first must be 64 -> N with
+// N = 64 for every layer but the last (which may be 48-padded plain fp32 output, or N = 128 split output).
+constexpr int kTapChainMax = 4;
+struct TapChainLaunch {
+    int nl;
+    const float* B[kTapChainMax];               // weight pointers (keys of tc_tap_prepare_weight, scheme 2)
+    const float* bias[kTapChainMax];            // [N] or NULL
+    const uint32_t* aux_bits[kTapChainMax];     // EPI_MASK: packed sign bits of the saved activation [W*T][N/32]
+    uint32_t* sign_out[kTapChainMax];           // optional: packed sign bits of the layer's output [W*T][N/32]
+    int epi[kTapChainMax];
+    const void *A_hi, *A_lo;                    // first layer's input [W*T][lda] fp16 hi / lo
+    int lda, Kreal;
+    void *out_hi, *out_lo;                      // last layer's output [W*T][ldo]: split fp16, or plain fp32 when out_lo == NULL
+    int ldo;
+    int W, T;
+};
+int launch_tap_chain(cudaStream_t stream, void* owner, const TapChainLaunch& L);
 int launch_split_pad(cudaStream_t stream, const float* src, int C, size_t tokens, int ldo, float* hi, float* lo);
 void tc_tap_release(void* owner);
 extern long long* g_tap_dbg;   // debug: per-CTA phase timestamps of the tap kernel (NULL in production)

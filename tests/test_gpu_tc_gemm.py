@@ -174,3 +174,31 @@ def test_fp16_scheme_cta_pair_matches_single_cta(engine, M, N, K):
     ref_act = torch.where(ref > 0, ref, ref * 0.01)
     assert _rel(out[1], ref_act) < 1e-5
     assert torch.equal(out[0], out[1]), float((out[0] - out[1]).abs().max())
+
+
+@pytest.mark.parametrize("W", [1, 2, 11, 12, 13, 37, 149, 641])
+def test_tap_chain_matches_layer_by_layer(engine, W):
+    """gemm_mode 3 runs the four K <= 128 tap layers of each direction as ONE launch (the activation tile stays in
+    shared memory, weights stream through a ring).  Same MMAs, same epilogue arithmetic: pose and dz must be
+    bit-identical to one launch per layer, for window counts that leave TMEM quarters / tiles partly empty."""
+    import ctypes as C
+    g = torch.Generator(device="cpu").manual_seed(5000 + W)
+    z = torch.randn(W, 2048, generator=g)
+    up = torch.randn(W, 10, 15, 3, generator=g) * 1e-3
+    lib = engine.lib
+    lib.gem_debug_tap_chain.argtypes = [C.c_void_p, C.c_int]
+    out = {}
+    engine.set_gemm_mode(3)
+    try:
+        for chain in (0, 1):
+            lib.gem_debug_tap_chain(engine._ctx, chain)
+            pose = engine.decode(0, z).clone()
+            dz = engine.decode_vjp(0, up).clone()
+            torch.cuda.synchronize()
+            out[chain] = (pose, dz)
+    finally:
+        lib.gem_debug_tap_chain(engine._ctx, 1)
+        engine.set_gemm_mode(2)
+    assert torch.isfinite(out[1][0]).all() and torch.isfinite(out[1][1]).all()
+    assert torch.equal(out[0][0], out[1][0]), float((out[0][0] - out[1][0]).abs().max())
+    assert torch.equal(out[0][1], out[1][1]), float((out[0][1] - out[1][1]).abs().max())
