@@ -51,6 +51,9 @@ struct gem_ctx {
     // encoder activations, fc output
     float *eact[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *fc = nullptr, *z0 = nullptr;
     float *e4_hi = nullptr, *e4_lo = nullptr;    // last encoder conv activation split for the tcgen05 fc GEMM
+    uint16_t *e2_hi = nullptr, *e2_lo = nullptr, *e3_hi = nullptr, *e3_lo = nullptr;   // fp16 pairs: enc[2], enc[3] outputs (mode 3)
+    bool enc_tc[2] = {false, false};             // enc[3], enc[4] are prepared for the tcgen05 tap kernel
+    int enc_tc_on = 0;                           // opt-in (GEM_ENC_TC=1): see encode_impl
     // closure outputs
     float *f_new = nullptr, *g_new = nullptr;
     LbfgsBuffers lb;
@@ -197,6 +200,10 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     A(&c->pose, Weven * seq_len * num_joints * 3), A(&c->gpose, Weven * seq_len * num_joints * 3);
     for (int i = 0; i < 5; ++i) A(&c->eact[i], tok * kEncC[i]);
     A(&c->e4_hi, tok * kEncC[4]), A(&c->e4_lo, tok * kEncC[4]);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->e2_hi, tok * kEncC[2]);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->e2_lo, tok * kEncC[2]);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->e3_hi, tok * kEncC[3]);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->e3_lo, tok * kEncC[3]);
     A(&c->fc, W * 2 * n), A(&c->z0, W * n), A(&c->f_new, W), A(&c->g_new, W * n);
     A(&c->pose0_own, Weven * seq_len * num_joints * 3), A(&c->mb_own, W * num_joints);
     c->trace_cap = max_history + 8;              // max_eval + 1 <= (max_history + 1) * 5 / 4 + 1
@@ -229,6 +236,7 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     c->gemm_mode = 3;
     if (const char* env = getenv("GEM_GEMM_MODE")) c->gemm_mode = (env[0] >= '0' && env[0] <= '3') ? env[0] - '0' : 3;
     if (const char* env = getenv("GEM_TAP_CHAIN")) c->tap_chain = env[0] != '0';
+    if (const char* env = getenv("GEM_ENC_TC")) c->enc_tc_on = env[0] != '0';
     c->n_chunks = 4;
     if (const char* env = getenv("GEM_CHUNKS")) c->n_chunks = atoi(env) >= 1 ? atoi(env) : 1;
     if (c->n_chunks > 16) c->n_chunks = 16;
@@ -286,6 +294,12 @@ int gem_debug_tap_timestamps(long long* buf_d) {
 int gem_debug_tap_chain(gem_ctx* c, int on) {
     GEM_REQUIRE(c != nullptr, "ctx is NULL");
     c->tap_chain = on ? 1 : 0;
+    return GEM_OK;
+}
+/* debug hook: 1 = the encoder's 128 -> 256 -> 512 layers on the tcgen05 tap kernel (mode 3), 0 = CUDA cores (default) */
+int gem_debug_enc_tc(gem_ctx* c, int on) {
+    GEM_REQUIRE(c != nullptr, "ctx is NULL");
+    c->enc_tc_on = on ? 1 : 0;
     return GEM_OK;
 }
 int gem_debug_gemm_timestamps(long long* buf_d) {
@@ -431,6 +445,14 @@ int gem_ctx_set_vae(gem_ctx* c, int which, const gem_vae_weights* w) {
         }
     }
     c->tap_tc[which] = tap_ok;
+    // the encoder's two wide k=3 layers (128 -> 256 -> 512) in the fp16 scheme
+    c->enc_tc[which] = false;
+    if (tap_ok && tc_tap_supported(w->enc[3].k, w->enc[3].n, c->T) && tc_tap_supported(w->enc[4].k, w->enc[4].n, c->T) &&
+        w->enc[3].k % 64 == 0 && w->enc[3].n % 64 == 0 && w->enc[4].n % 64 == 0) {
+        for (int i = 3; i <= 4; ++i)
+            GEM_TRY(tc_tap_prepare_weight(c, 0, w->enc[i].w_d, (w->enc[i].n + 3) & ~3, w->enc[i].k, w->enc[i].n, 2));
+        c->enc_tc[which] = true;
+    }
     GEM_CUDA(cudaStreamSynchronize(0));
     return GEM_OK;
 }
@@ -482,6 +504,7 @@ struct Slice {
     uint16_t *g0_h16, *g0_l16;
     int32_t* row_exp;
     float *eact[5], *e4_hi, *e4_lo, *fc, *z0;    // encoder activations, fc output, initial latent
+    uint16_t *e2_hi, *e2_lo, *e3_hi, *e3_lo;
     float *pose0_own, *mb_own, *trace_own;       // staged inputs / outputs of this slice
     int64_t* fb_own;
     int32_t* clip_own;
@@ -508,6 +531,8 @@ static Slice slice_of(gem_ctx* c, int w0) {
     v.g0_h16 = c->g0_h16 + v.tok0 * kDecC[0], v.g0_l16 = c->g0_l16 + v.tok0 * kDecC[0], v.row_exp = c->row_exp + w0;
     for (int i = 0; i < 5; ++i) v.eact[i] = c->eact[i] + v.tok0 * kEncC[i];
     v.e4_hi = c->e4_hi + v.tok0 * kEncC[4], v.e4_lo = c->e4_lo + v.tok0 * kEncC[4];
+    v.e2_hi = c->e2_hi + v.tok0 * kEncC[2], v.e2_lo = c->e2_lo + v.tok0 * kEncC[2];
+    v.e3_hi = c->e3_hi + v.tok0 * kEncC[3], v.e3_lo = c->e3_lo + v.tok0 * kEncC[3];
     v.fc = c->fc + (size_t)w0 * 2 * n, v.z0 = c->z0 + (size_t)w0 * n;
     v.pose0_own = c->pose0_own + v.tok0 * P, v.mb_own = c->mb_own;     // (mean bones are indexed by absolute window)
     v.trace_own = c->trace_own + (size_t)w0 * c->trace_cap;
@@ -641,13 +666,29 @@ static int encode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice
     const int T = c->T, M = W * T, P = c->J * 3;
     const float* in = pose;
     int lda = P;
-    for (int i = 0; i < 5; ++i) {
+    const gem_layer& fcL = v.enc[5];
+    // Opt-in: the encoder runs once per stage (3 % of a step) and its output z0 seeds a chaotic line search
+    // (DESIGN.md section 2); the CUDA-core layers' plain fp32 sums land nearer to ATen's bits than the split-fp16
+    // sums do, and the free-running agreement statistics with the reference's recorded runs are better with them
+    // (21+ vs 19 of 42 strict cases), so the default keeps them although the tcgen05 layers are 6x faster.
+    const bool enc_tc = c->enc_tc_on && c->gemm_mode == 3 && c->enc_tc[which] && fcL.k % 64 == 0 && fcL.n % 128 == 0;
+    for (int i = 0; i < (enc_tc ? 3 : 5); ++i) {
         GEM_TRY(run_layer(c, s, GEM_TAG_ENC + i, v.enc[i], in, lda, M, v_.eact[i], v.enc[i].n, EPI_LRELU, nullptr));
         in = v_.eact[i];
         lda = v.enc[i].n;
     }
-    const gem_layer& fcL = v.enc[5];
-    if (c->gemm_mode >= 2 && fcL.k % 64 == 0 && fcL.n % 128 == 0) {
+    if (enc_tc) {
+        // 128 -> 256 -> 512 on the tcgen05 tap kernel (fp16 scheme); its last epilogue writes the fc GEMM's operand
+        GEM_TRY(timed(c, s, GEM_TAG_ENC + 3, [&]() {
+            return launch_split_f16(s, in, v.enc[3].k, M, v.enc[3].k, nullptr, v_.e2_hi, v_.e2_lo);
+        }));
+        GEM_TRY(run_tap_tc(c, s, GEM_TAG_ENC + 3, v.enc[3], (const float*)v_.e2_hi, (const float*)v_.e2_lo, v.enc[3].k, W,
+                           (float*)v_.e3_hi, (float*)v_.e3_lo, v.enc[3].n, EPI_LRELU, nullptr));
+        GEM_TRY(run_tap_tc(c, s, GEM_TAG_ENC + 4, v.enc[4], (const float*)v_.e3_hi, (const float*)v_.e3_lo, v.enc[4].k, W,
+                           v_.e4_hi, v_.e4_lo, v.enc[4].n, EPI_LRELU, nullptr));
+        GEM_TRY(run_layer(c, s, GEM_TAG_ENC + 5, fcL, nullptr, T * 512, W, v_.fc, 2 * c->n, EPI_NONE, nullptr, v_.e4_hi,
+                          v_.e4_lo));
+    } else if (c->gemm_mode >= 2 && fcL.k % 64 == 0 && fcL.n % 128 == 0) {
         GEM_TRY(timed(c, s, GEM_TAG_ENC + 5, [&]() {
             return launch_split_f16(s, in, T * 512, W, T * 512, nullptr, (uint16_t*)v_.e4_hi, (uint16_t*)v_.e4_lo);
         }));

@@ -107,8 +107,10 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint8_t* smem, ui
     const int q = warp & 3;                         // TMEM lane quarter this warp may read
     const int sub = (warp - 2) >> 2;                // 0 .. kEpiSub-1: which of the quarter's warps
     const int m = m0 + q * 32 + lane;
-    float* stage_hi = reinterpret_cast<float*>(smem + (size_t)(q * 2 + 0) * C::kStageOut);
-    float* stage_lo = reinterpret_cast<float*>(smem + (size_t)(q * 2 + 1) * C::kStageOut);
+    // staging regions, as small as the output format allows (the CTA-pair kernel keeps fewer pipeline bytes)
+    const size_t region = g.out16 ? (size_t)32 * C::kPitch16 * 2 : (size_t)C::kStageOut;
+    float* stage_hi = reinterpret_cast<float*>(smem + (size_t)(g.C_lo ? q * 2 : q) * region);
+    float* stage_lo = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stage_hi) + region);
     const int nmain = F16 ? C::kMain16 : kAcc;
     const int nacc = num_kb < nmain ? num_kb : nmain;
     float row_scale = 1.f;
@@ -353,15 +355,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 // by the same 28 %).  Protocol: both CTAs' producers load into their own shared memory but signal the LEADER's
 // full barrier (which expects both CTAs' bytes); the leader's MMA thread issues for the pair and multicasts its
 // commits to the empty / accumulator barriers of both CTAs; each CTA's epilogue drains its own TMEM.
+#ifndef GEM_PAIR_STAGES
+#define GEM_PAIR_STAGES 4
+#endif
 template <int BN>
 struct PairCfg {
-    static constexpr int kStages = 4;
+    static constexpr int kStages = GEM_PAIR_STAGES;
     static constexpr int kBHalfBytes = (BN / 2) * 128;
     static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBHalfBytes;      // A_hi, A_lo, half of B_hi, half of B_lo
     static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
     static_assert(BN % 16 == 0 && BN <= 256, "UMMA N (M = 256 needs N % 16 == 0; halves keep the 8-row swizzle atoms)");
     static_assert(kBHalfBytes % 1024 == 0, "B half tile must keep the swizzle atom alignment");
-    static_assert(8 * GemmCfg<BN>::kStageOut <= kStages * kStageBytes, "epilogue staging must fit in the pipeline's memory");
+    // the pair kernel writes fp16 hi/lo pairs or plain fp32 (never fp32 hi/lo pairs): at most 8 fp16 or 4 fp32 regions
+    static_assert(8 * 32 * GemmCfg<BN>::kPitch16 * 2 <= kStages * kStageBytes && 4 * GemmCfg<BN>::kStageOut <= kStages * kStageBytes,
+                  "epilogue staging must fit in the pipeline's memory");
     static_assert(kSmemBytes <= 227 * 1024, "shared memory");
 };
 
@@ -812,7 +819,7 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
         return env ? atoi(env) : 1;
     }();
     const int pair_mode = g_gemm_pair >= 0 ? g_gemm_pair : pair_env;
-    if (f16 && pair_mode) {
+    if (f16 && pair_mode && !(a.C_lo && !a.out16)) {      // (fp32 hi/lo outputs need the one-CTA kernel's larger staging area)
         int bn = 160;
         if (const char* env = getenv("GEM_GEMM_BN")) bn = atoi(env) == 128 ? 128 : 160;
         return bn == 128 ? launch_pair_bn<128>(stream, map_a_hi, map_a_lo, wit->second, 1, a)

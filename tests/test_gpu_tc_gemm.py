@@ -202,3 +202,29 @@ def test_tap_chain_matches_layer_by_layer(engine, W):
     assert torch.isfinite(out[1][0]).all() and torch.isfinite(out[1][1]).all()
     assert torch.equal(out[0][0], out[1][0]), float((out[0][0] - out[1][0]).abs().max())
     assert torch.equal(out[0][1], out[1][1]), float((out[0][1] - out[1][1]).abs().max())
+
+
+@pytest.mark.parametrize("W", [1, 13, 300, 641])
+def test_fp16_encoder_matches_fp32_path(engine, W):
+    """Opt-in (GEM_ENC_TC=1): the encoder's 128 -> 256 -> 512 k=3 layers on the tcgen05 tap kernel (fp16 scheme),
+    their split output fed straight to the fc GEMM; mu / std / z0 must match the CUDA-core layers."""
+    import ctypes as C
+    g = torch.Generator(device="cpu").manual_seed(7000 + W)
+    pose_in = torch.randn(W, 10, 45, generator=g) * 0.3
+    eps = torch.randn(W, 2048, generator=g)
+    out = {}
+    engine.lib.gem_debug_enc_tc.argtypes = [C.c_void_p, C.c_int]
+    engine.lib.gem_debug_enc_tc(engine._ctx, 1)         # opt-in path (default: CUDA-core encoder layers)
+    try:
+        for mode in (0, 3):
+            engine.set_gemm_mode(mode)
+            z0, mu, std = engine.encode(1, pose_in, eps)
+            torch.cuda.synchronize()
+            out[mode] = (z0.clone(), mu.clone(), std.clone())
+    finally:
+        engine.lib.gem_debug_enc_tc(engine._ctx, 0)
+        engine.set_gemm_mode(2)
+    for name, a, b in zip(("z0", "mu", "std"), out[3], out[0]):
+        r = _rel(a, b)
+        print(W, name, "fp16 encoder vs fp32 CUDA cores:", r)
+        assert r < 3e-5, (W, name, r)
