@@ -471,6 +471,7 @@ tc_tap_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
     uint64_t* acc_full = bars + 5;                         // layer l's accumulators complete (phase l)
     uint64_t* act_ready = bars + 6;                        // layer l's output tile is in shared memory (phase l)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    __shared__ float sbias[kTapChainMax * 128];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) TAP_DBG(0);
@@ -486,13 +487,45 @@ tc_tap_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
     auto in_buf = [&](int l) { return l == 0 ? 0 : ((nkb0 == 2 ? 0 : 1) + (l - 1)) & 1; };
     auto out_buf = [&](int l) { return ((nkb0 == 2 ? 0 : 1) + l) & 1; };
 
+    // weight blocks in issue order: (layer, slab, K block); block b goes to ring slot b & 1
+    auto issue_weight_block = [&](int b, int l, int y, int kb) {
+        const int np = 3 * g.L[l].ncta;
+        const uint32_t bt = (uint32_t)np * 128;
+        const int slot = b & 1;
+        uint8_t* dst = wring + slot * kChainWSlot;
+        mbar_arrive_expect_tx(&w_full[slot], 3 * bt);
+        tma_load_2d(dst, &maps.w[l][0], kb * 64, y * np, &w_full[slot]);
+        tma_load_2d(dst + bt, &maps.w[l][1], kb * 64, y * np, &w_full[slot]);
+        tma_load_2d(dst + 2 * bt, &maps.w[l][2], kb * 64, y * np, &w_full[slot]);
+    };
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&maps.a_hi), prefetch_tmap(&maps.a_lo);
-        for (int l = 0; l < g.nl; ++l) prefetch_tmap(&maps.w[l][0]), prefetch_tmap(&maps.w[l][1]), prefetch_tmap(&maps.w[l][2]);
         mbar_init(act_full, 1);
         mbar_init(&w_full[0], 1), mbar_init(&w_full[1], 1), mbar_init(&w_empty[0], 1), mbar_init(&w_empty[1], 1);
         mbar_init(acc_full, 1), mbar_init(act_ready, kChainEpiWarps);
         fence_barrier_init();
+        // the first tiles are requested before the CTA-wide setup barrier: the activation tile and the first two
+        // weight blocks (both ring slots are empty) travel while TMEM is allocated and the idle rows are cleared
+        const uint32_t box_bytes = (uint32_t)rows_q * 128;
+        mbar_arrive_expect_tx(act_full, (uint32_t)nkb0 * 8 * box_bytes);
+        for (int kb = 0; kb < nkb0; ++kb) {
+            uint8_t* dst = act + kb * 2 * kATile;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                tma_load_3d(dst + q * kQuarterBytes, &maps.a_hi, kb * 64, 0, win0 + q * g.wpq, act_full);
+                tma_load_3d(dst + kATile + q * kQuarterBytes, &maps.a_lo, kb * 64, 0, win0 + q * g.wpq, act_full);
+            }
+        }
+        int b = 0;
+        for (int l = 0; l < g.nl && b < 2; ++l)
+            for (int y = 0; y < g.L[l].gridy && b < 2; ++y)
+                for (int kb = 0; kb < g.L[l].num_kb && b < 2; ++kb, ++b) issue_weight_block(b, l, y, kb);
+        for (int l = 1; l < g.nl; ++l) prefetch_tmap(&maps.w[l][0]), prefetch_tmap(&maps.w[l][1]), prefetch_tmap(&maps.w[l][2]);
+    }
+    // biases of every layer, zero beyond N (the epilogue adds them unguarded)
+    for (int i = threadIdx.x; i < g.nl * 128; i += kChainThreads) {
+        const ChainLayer& L = g.L[i >> 7];
+        const int n = i & 127;
+        sbias[i] = (L.bias && n < L.N) ? __ldg(L.bias + n) : 0.f;
     }
     // the idle rows of each quarter are never written by TMA: clear them once so the first layer's MMA reads zeros
     {
@@ -516,31 +549,14 @@ tc_tap_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const uint32_t box_bytes = (uint32_t)rows_q * 128;
-            mbar_arrive_expect_tx(act_full, (uint32_t)nkb0 * 8 * box_bytes);
-            for (int kb = 0; kb < nkb0; ++kb) {
-                uint8_t* dst = act + kb * 2 * kATile;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    tma_load_3d(dst + q * kQuarterBytes, &maps.a_hi, kb * 64, 0, win0 + q * g.wpq, act_full);
-                    tma_load_3d(dst + kATile + q * kQuarterBytes, &maps.a_lo, kb * 64, 0, win0 + q * g.wpq, act_full);
-                }
-            }
-            int b = 0;
-            for (int l = 0; l < g.nl; ++l) {
-                const int np = 3 * g.L[l].ncta;
-                const uint32_t bt = (uint32_t)np * 128;
+            int b = 0;                                       // (blocks 0 and 1 were requested during setup)
+            for (int l = 0; l < g.nl; ++l)
                 for (int y = 0; y < g.L[l].gridy; ++y)
                     for (int kb = 0; kb < g.L[l].num_kb; ++kb, ++b) {
-                        const int slot = b & 1;
-                        mbar_wait(&w_empty[slot], (uint32_t)(((b >> 1) & 1) ^ 1));
-                        uint8_t* dst = wring + slot * kChainWSlot;
-                        mbar_arrive_expect_tx(&w_full[slot], 3 * bt);
-                        tma_load_2d(dst, &maps.w[l][0], kb * 64, y * np, &w_full[slot]);
-                        tma_load_2d(dst + bt, &maps.w[l][1], kb * 64, y * np, &w_full[slot]);
-                        tma_load_2d(dst + 2 * bt, &maps.w[l][2], kb * 64, y * np, &w_full[slot]);
+                        if (b < 2) continue;
+                        mbar_wait(&w_empty[b & 1], (uint32_t)(((b >> 1) & 1) ^ 1));
+                        issue_weight_block(b, l, y, kb);
                     }
-            }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
@@ -589,10 +605,16 @@ tc_tap_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         const size_t token = (size_t)win * g.T + t;
         for (int l = 0; l < g.nl; ++l) {
             const ChainLayer& L = g.L[l];
+            const int halves = L.N >> 4;                        // 16-bit sign halves per token
+            // the masks of this layer's chunks do not depend on the accumulators: fetch them while the MMAs run
+            uint32_t mbits_y[2] = {0u, 0u};
+            if (L.epi == EPI_MASK && row_ok && sub * 16 < L.ncta) {
+                for (int y = 0; y < L.gridy; ++y)
+                    mbits_y[y] = __ldg(reinterpret_cast<const uint16_t*>(L.aux_bits) + token * halves + ((y * L.ncta + sub * 16) >> 4));
+            }
             mbar_wait(acc_full, (uint32_t)(l & 1));
             tc_fence_after();
             if (threadIdx.x == 64 && l < 4) TAP_DBG(8 + l);
-            const int halves = L.N >> 4;                        // 16-bit sign halves per token
             for (int y = 0; y < L.gridy; ++y) {
                 uint8_t* stage = act + (y == 0 ? out_buf(l) : in_buf(l)) * 2 * kATile;
                 const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((l + y) & 1) * 192);
@@ -603,9 +625,7 @@ tc_tap_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                     tmem_ld_32x32b_x16(trow + (uint32_t)(1 * L.ncta + c * 16), p1);
                     tmem_ld_32x32b_x16(trow + (uint32_t)(2 * L.ncta + c * 16), p2);
                     const int nb = y * L.ncta + c * 16;
-                    uint32_t mbits = 0;
-                    if (L.epi == EPI_MASK && row_ok)
-                        mbits = __ldg(reinterpret_cast<const uint16_t*>(L.aux_bits) + token * halves + (nb >> 4));
+                    const uint32_t mbits = mbits_y[y];
                     tmem_ld_wait();
                     float o[16];
 #pragma unroll
@@ -618,9 +638,12 @@ tc_tap_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         o[j] = v * (1.f / kWScale16);
                     }
                     if (L.bias) {
+                        const float4* bp = reinterpret_cast<const float4*>(sbias + l * 128 + nb);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (nb + j < L.N) o[j] += __ldg(L.bias + nb + j);
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 bv = bp[j >> 2];
+                            o[j] += bv.x, o[j + 1] += bv.y, o[j + 2] += bv.z, o[j + 3] += bv.w;
+                        }
                     }
                     if (L.epi == EPI_LRELU) {
 #pragma unroll
