@@ -27,8 +27,25 @@ import time
 
 import numpy as np
 
-# stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+# stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr.  (NCCL prints its version
+# banner to the C-level stdout whatever NCCL_DEBUG_FILE says, so multi-rank runs also point file descriptor 1 at
+# stderr while they work and print the JSON line through a saved copy of the real stdout.)
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_JSON_OUT = None
+
+
+def _divert_stdout():
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
@@ -227,6 +244,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        _divert_stdout()
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic workload in pinned host memory -------------------------------------------------
@@ -479,7 +497,7 @@ def main():
                                         "on a single stream with a CUDA-event pair around every launch"},
                 "effective_tflops_reference_flop_count": evals * FLOPS_PER_WINDOW_EVAL_ALGORITHMIC / (ms_per_step / 1e3) / 1e12,
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
