@@ -28,7 +28,8 @@ struct gem_ctx {
     int device = 0;
     int Wmax = 0, n = 0, T = 0, J = 0, H = 0, Wd = 0, m = 0;
     int gemm_mode = 0;
-    int tap_chain = 1;                           // mode 3: the four K<=128 tap layers of each direction in one launch
+    int tap_chain = 2;                           // mode 3: 0 one launch per k=3 layer, 1 the four K<=128 layers of each direction
+                                                 // in one launch, 2 all five on CTA pairs (cta_group::2) in one launch
     bool have_camera = false, have_skeleton = false;
     bool have_vae[2] = {false, false};
     gem_vae_weights vae[2];
@@ -235,7 +236,7 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     // GEMMs, 3xTF32 convolutions), 1 (3xTF32 everywhere) or 0 (fp32 CUDA cores)
     c->gemm_mode = 3;
     if (const char* env = getenv("GEM_GEMM_MODE")) c->gemm_mode = (env[0] >= '0' && env[0] <= '3') ? env[0] - '0' : 3;
-    if (const char* env = getenv("GEM_TAP_CHAIN")) c->tap_chain = env[0] != '0';
+    if (const char* env = getenv("GEM_TAP_CHAIN")) c->tap_chain = (env[0] >= '0' && env[0] <= '2') ? env[0] - '0' : 2;
     if (const char* env = getenv("GEM_ENC_TC")) c->enc_tc_on = env[0] != '0';
     c->n_chunks = 4;
     if (const char* env = getenv("GEM_CHUNKS")) c->n_chunks = atoi(env) >= 1 ? atoi(env) : 1;
@@ -290,10 +291,10 @@ int gem_debug_tap_timestamps(long long* buf_d) {
 }
 
 /* debug hook (not in the public header): 1 = CTA-pair (cta_group::2) fp16-scheme GEMM, 0 = one CTA per tile, -1 = default */
-/* debug hook: 1 = fused tap-layer chains (default), 0 = one launch per layer */
-int gem_debug_tap_chain(gem_ctx* c, int on) {
-    GEM_REQUIRE(c != nullptr, "ctx is NULL");
-    c->tap_chain = on ? 1 : 0;
+/* debug hook: 0 = one launch per k=3 layer, 1 = one-CTA chains of four layers, 2 = CTA-pair chains of five (default) */
+int gem_debug_tap_chain(gem_ctx* c, int mode) {
+    GEM_REQUIRE(c != nullptr && mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+    c->tap_chain = mode;
     return GEM_OK;
 }
 /* debug hook: 1 = the encoder's 128 -> 256 -> 512 layers on the tcgen05 tap kernel (mode 3), 0 = CUDA cores (default) */
@@ -558,6 +559,18 @@ static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice
         GEM_TRY(run_layer(c, s, GEM_TAG_DEC + 0, v.dec[0], z, c->n, W, v_.act_hi[0], T * 256, EPI_LRELU, nullptr, z_hi,
                           z_lo, v_.act_lo[0], v_.act_sign[0], nullptr, c->gemm_mode == 3));
         c->act_split = true;
+        if (c->gemm_mode == 3 && c->tap_chain == 2) {
+            // 256 -> 128 -> 64 -> 64 -> 64 -> pose in ONE launch on CTA pairs
+            TapChainLaunch t;
+            t.nl = 5;
+            for (int i = 1; i <= 5; ++i) {
+                t.B[i - 1] = v.dec[i].w_d, t.bias[i - 1] = v.dec[i].bias_d, t.aux_bits[i - 1] = nullptr;
+                t.sign_out[i - 1] = i <= 4 ? v_.act_sign[i] : nullptr, t.epi[i - 1] = i <= 4 ? EPI_LRELU : EPI_NONE;
+            }
+            t.A_hi = v_.act_hi[0], t.A_lo = v_.act_lo[0], t.lda = v.dec[1].k, t.Kreal = v.dec[1].k;
+            t.out_hi = pose_out, t.out_lo = nullptr, t.ldo = P, t.W = W, t.T = T;
+            return timed(c, s, GEM_TAG_DEC + 1, [&]() { return launch_tap_chain_pair(s, c, t); });
+        }
         if (c->gemm_mode == 3 && c->tap_chain) {
             // 256 -> 128 on its own, then 128 -> 64 -> 64 -> 64 -> pose in ONE launch: the activation tile stays in
             // shared memory, only the sign bits (the bwd-data masks) and the pose reach HBM
@@ -612,7 +625,19 @@ static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const S
         const float *in_hi = v_.gp_hi, *in_lo = v_.gp_lo;
         int lda = pp;
         int i0 = 0;
-        if (c->gemm_mode == 3 && c->tap_chain && c->act_split) {
+        if (c->gemm_mode == 3 && c->tap_chain == 2 && c->act_split) {
+            // d pose -> 64 -> 64 -> 64 -> 128 -> 256 in ONE launch on CTA pairs (masks from the forward pass's sign bits)
+            TapChainLaunch t;
+            t.nl = 5;
+            for (int i = 0; i < 5; ++i) {
+                t.B[i] = v.dec_bwd[i].w_d, t.bias[i] = v.dec_bwd[i].bias_d, t.aux_bits[i] = v_.act_sign[4 - i];
+                t.sign_out[i] = nullptr, t.epi[i] = EPI_MASK;
+            }
+            t.A_hi = in_hi, t.A_lo = in_lo, t.lda = pp, t.Kreal = pp;
+            t.out_hi = v_.gact_hi[0], t.out_lo = v_.gact_lo[0], t.ldo = v.dec_bwd[4].n, t.W = W, t.T = T;
+            GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 0, [&]() { return launch_tap_chain_pair(s, c, t); }));
+            i0 = 5;
+        } else if (c->gemm_mode == 3 && c->tap_chain && c->act_split) {
             // d pose -> 64 -> 64 -> 64 -> 128 in ONE launch (masks from the forward pass's sign bits), 128 -> 256 after it
             TapChainLaunch t;
             t.nl = 4;

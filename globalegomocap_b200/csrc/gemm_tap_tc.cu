@@ -724,10 +724,315 @@ tc_tap_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
     }
 }
 
+
+// ---- CTA-pair chain: a whole direction of the decoder's k=3 layers in one launch -----------------------------------
+// The 256 <-> 128 channel layers do not fit the one-CTA chain (their input alone is four activation buffers) and, on
+// their own, they are bound by the 590 KB of weight slabs every 128-row tile has to pull through L2.  Two CTAs of a
+// cluster run each layer as ONE M = 256 MMA (tcgen05.mma.cta_group::2): each CTA keeps its own twelve windows'
+// activations but only HALF of every weight block (96 of the 192 slab rows), so the weight traffic per window halves,
+// the ring slots shrink to 36 KB, and four activation buffers fit beside them.  Chains:
+//   forward   256 -> 128 -> 64 -> 64 -> 64 -> pose        backward   d pose -> 64 -> 64 -> 64 -> 128 -> 256
+// A layer with more than two output slabs is split into pseudo-layers of at most two slabs (two accumulators of
+// 192 TMEM columns); every pseudo-layer but the last arrives on act_ready when its accumulators are drained and its
+// output (if it feeds the next layer) is in shared memory.  Barriers the peer signals live in the LEADER: act_full
+// and w_full (both CTAs' TMA bytes), act_ready (both CTAs' epilogue warps); the leader's commits are multicast to
+// the w_empty / acc_full barriers of both CTAs.
+constexpr int kChain2Max = 6;
+constexpr int kChain2WSlot = 3 * 96 * 128;                     // 36,864 B: three half slabs of 96 rows x 128 B
+constexpr size_t kChain2Smem = 8 * kATile + 2 * kChain2WSlot + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct Chain2Layer {
+    const float* bias;           // full-layer bias [N] or NULL
+    const uint32_t* aux_bits;
+    uint32_t* sign_out;
+    int ncta, y0, ny, num_kb, N, epi, out_kind;      // slabs y0 .. y0+ny-1 (ny <= 2) of a layer with N outputs
+    unsigned char in_buf[4], stage_buf[2];
+    int wmap;                    // index of the layer's weight maps
+};
+struct Chain2Maps {
+    CUtensorMap a_hi, a_lo;
+    CUtensorMap w[kChain2Max][3];
+    CUtensorMap o_hi, o_lo;
+};
+struct Chain2Args {
+    Chain2Layer L[kChain2Max];
+    int nl, W, T, wpq;
+    float* out_plain;
+    long long* dbg;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1)
+tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_constant__ Chain2Args g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* act = smem;                                   // four buffers of (hi 16 KB, lo 16 KB)
+    uint8_t* wring = smem + 8 * kATile;                    // two half-block slots
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wring + 2 * kChain2WSlot);
+    uint64_t* act_full = bars;                             // leader: both CTAs' first-layer activation tiles landed
+    uint64_t* w_full = bars + 1;                           // [2] leader: both halves of a weight block landed
+    uint64_t* w_empty = bars + 3;                          // [2] each CTA (multicast commit)
+    uint64_t* acc_full = bars + 5;                         // each CTA (multicast commit), phase = pseudo-layer
+    uint64_t* act_ready = bars + 6;                        // leader: 32 epilogue warps of the pair, phase = pseudo-layer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    __shared__ float sbias[kChain2Max * 128];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) TAP_DBG(0);
+    if (threadIdx.x == 0 && g.dbg) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g.dbg[(size_t)blockIdx.x * 16 + 14] = (long long)gt;
+    }
+    const int win0 = blockIdx.x * 4 * g.wpq;               // this CTA's twelve windows
+    const int rows_q = g.wpq * g.T;
+    const int nkb0 = g.L[0].num_kb;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&maps.a_hi), prefetch_tmap(&maps.a_lo);
+        mbar_init(act_full, 1);
+        mbar_init(&w_full[0], 1), mbar_init(&w_full[1], 1), mbar_init(&w_empty[0], 1), mbar_init(&w_empty[1], 1);
+        mbar_init(acc_full, 1), mbar_init(act_ready, 2 * kChainEpiWarps);
+        fence_barrier_init();
+    }
+    // biases of every pseudo-layer's slabs, zero beyond N (the epilogue adds them unguarded)
+    for (int i = threadIdx.x; i < g.nl * 128; i += kChainThreads) {
+        const Chain2Layer& L = g.L[i >> 7];
+        const int n = L.y0 * L.ncta + (i & 127);
+        sbias[i] = (L.bias && (i & 127) < L.ny * L.ncta && n < L.N) ? __ldg(L.bias + n) : 0.f;
+    }
+    // idle rows of each quarter are never written by TMA: clear them once so the first layer's MMA reads zeros
+    {
+        const int idle = 32 - rows_q;
+        const int total = 8 * 4 * idle * 8;                    // 16-byte slots in the eight tiles
+        for (int i = threadIdx.x; i < total; i += kChainThreads) {
+            const int tile = i / (4 * idle * 8), r = i % (4 * idle * 8);
+            const int q = r / (idle * 8), rr = (r % (idle * 8)) / 8, c16 = r % 8;
+            uint8_t* p = act + tile * kATile + q * kQuarterBytes + (rows_q + rr) * 128 + c16 * 16;
+            *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        fence_proxy_async_smem();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();                  // the peer's barriers exist before anything arrives on them remotely
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TAP_DBG(1);
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs: own activations, own half of every weight block) =====
+        if (lane == 0) {
+            const uint32_t box_bytes = (uint32_t)rows_q * 128;
+            const uint32_t act_bar = mapa_u32(smem_u32(act_full), 0);
+            if (rank == 0) mbar_arrive_expect_tx(act_full, 2u * (uint32_t)nkb0 * 8 * box_bytes);
+            for (int kb = 0; kb < nkb0; ++kb) {
+                uint8_t* dst = act + g.L[0].in_buf[kb] * 2 * kATile;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    tma_load_3d_pair(dst + q * kQuarterBytes, &maps.a_hi, kb * 64, 0, win0 + q * g.wpq, act_bar);
+                    tma_load_3d_pair(dst + kATile + q * kQuarterBytes, &maps.a_lo, kb * 64, 0, win0 + q * g.wpq, act_bar);
+                }
+            }
+            for (int l = 0; l < g.nl; ++l) prefetch_tmap(&maps.w[g.L[l].wmap][0]);
+            int b = 0;
+            for (int l = 0; l < g.nl; ++l) {
+                const Chain2Layer& L = g.L[l];
+                const int half = 3 * L.ncta / 2;                           // slab rows per CTA
+                const uint32_t bt = (uint32_t)half * 128;
+                for (int i = 0; i < L.ny; ++i)
+                    for (int kb = 0; kb < L.num_kb; ++kb, ++b) {
+                        const int slot = b & 1;
+                        mbar_wait(&w_empty[slot], (uint32_t)(((b >> 1) & 1) ^ 1));
+                        uint8_t* dst = wring + slot * kChain2WSlot;
+                        if (rank == 0) mbar_arrive_expect_tx(&w_full[slot], 2u * 3u * bt);
+                        const uint32_t bar = mapa_u32(smem_u32(&w_full[slot]), 0);
+                        const int row = (L.y0 + i) * 3 * L.ncta + (int)rank * half;
+                        tma_load_2d_pair(dst, &maps.w[L.wmap][0], kb * 64, row, bar);
+                        tma_load_2d_pair(dst + bt, &maps.w[L.wmap][1], kb * 64, row, bar);
+                        tma_load_2d_pair(dst + 2 * bt, &maps.w[L.wmap][2], kb * 64, row, bar);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (lane == 0 && rank == 0) {
+            int b = 0;
+            for (int l = 0; l < g.nl; ++l) {
+                const Chain2Layer& L = g.L[l];
+                if (l == 0) mbar_wait(act_full, 0);
+                else mbar_wait_cluster(act_ready, (uint32_t)((l - 1) & 1));
+                tc_fence_after();
+                if (l < 6) TAP_DBG(2 + l);
+                const int np = 3 * L.ncta;
+                const uint32_t bt = (uint32_t)(np / 2) * 128;
+                const uint32_t idesc = instr_desc_f16(2 * kRows, np);
+                for (int i = 0; i < L.ny; ++i) {
+                    const uint32_t acc = tmem_base + (uint32_t)(((l + i) & 1) * 192);
+                    for (int kb = 0; kb < L.num_kb; ++kb, ++b) {
+                        const int slot = b & 1;
+                        mbar_wait(&w_full[slot], (uint32_t)((b >> 1) & 1));
+                        tc_fence_after();
+                        const uint8_t* in = act + L.in_buf[kb] * 2 * kATile;
+                        const uint32_t wb = smem_u32(wring + slot * kChain2WSlot);
+                        const uint64_t a_hi = make_smem_desc(smem_u32(in)), a_lo = make_smem_desc(smem_u32(in + kATile));
+                        const uint64_t b_hi = make_smem_desc(wb), b_lo = make_smem_desc(wb + bt), b_hs = make_smem_desc(wb + 2 * bt);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                            umma_f16_pair(acc, a_lo + adv, b_hs + adv, idesc, (kb > 0) || (k != 0));      // small terms first
+                            umma_f16_pair(acc, a_hi + adv, b_lo + adv, idesc, 1);
+                            umma_f16_pair(acc, a_hi + adv, b_hi + adv, idesc, 1);
+                        }
+                        umma_commit_pair(&w_empty[slot], 3);
+                    }
+                }
+                umma_commit_pair(acc_full, 3);
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..17 (both CTAs): TMEM lane quarter = warp % 4, one 16-column chunk per warp =====
+        const int q = warp & 3;
+        const int sub = (warp - 2) >> 2;
+        const int wl = lane / g.T, t = lane - wl * g.T;
+        const int winq = win0 + q * g.wpq;
+        const int win = winq + wl;
+        const bool row_ok = lane < rows_q && win < g.W;
+        const bool has_prev = t > 0, has_next = t < g.T - 1;
+        const size_t token = (size_t)win * g.T + t;
+        const uint32_t ready_bar = mapa_u32(smem_u32(act_ready), 0);
+        const int c = sub;
+        for (int l = 0; l < g.nl; ++l) {
+            const Chain2Layer& L = g.L[l];
+            const int halves = L.N >> 4;
+            const bool has_chunk = c * 16 < L.ncta;
+            uint32_t mbits_i[2] = {0u, 0u};
+            if (L.epi == EPI_MASK && row_ok && has_chunk) {
+                for (int i = 0; i < L.ny; ++i)
+                    mbits_i[i] = __ldg(reinterpret_cast<const uint16_t*>(L.aux_bits) + token * halves +
+                                       (((L.y0 + i) * L.ncta + c * 16) >> 4));
+            }
+            mbar_wait(acc_full, (uint32_t)(l & 1));
+            tc_fence_after();
+            if (threadIdx.x == 64 && l < 6) TAP_DBG(8 + l);
+            for (int i = 0; i < L.ny; ++i) {
+                const int y = L.y0 + i;
+                uint8_t* stage = act + L.stage_buf[i] * 2 * kATile;
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((l + i) & 1) * 192);
+                if (has_chunk) {
+                    uint32_t p0[16], p1[16], p2[16];
+                    tmem_ld_32x32b_x16(trow + (uint32_t)(0 * L.ncta + c * 16), p0);
+                    tmem_ld_32x32b_x16(trow + (uint32_t)(1 * L.ncta + c * 16), p1);
+                    tmem_ld_32x32b_x16(trow + (uint32_t)(2 * L.ncta + c * 16), p2);
+                    const int nb = y * L.ncta + c * 16;
+                    const uint32_t mbits = mbits_i[i];
+                    tmem_ld_wait();
+                    float o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(p0[j]), 1);     // P_0 of the previous frame
+                        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(p2[j]), 1);   // P_2 of the next frame
+                        float v = __uint_as_float(p1[j]);
+                        v += has_prev ? up : 0.f;
+                        v += has_next ? dn : 0.f;
+                        o[j] = v * (1.f / kWScale16);
+                    }
+                    if (L.bias) {
+                        const float4* bp = reinterpret_cast<const float4*>(sbias + l * 128 + i * L.ncta + c * 16);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 bv = bp[j >> 2];
+                            o[j] += bv.x, o[j + 1] += bv.y, o[j + 2] += bv.z, o[j + 3] += bv.w;
+                        }
+                    }
+                    if (L.epi == EPI_LRELU) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * 0.01f;
+                    } else if (L.epi == EPI_MASK) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = ((mbits >> j) & 1u) ? o[j] : o[j] * 0.01f;
+                    }
+                    if (L.sign_out) {
+                        uint32_t sbits = 0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) sbits |= (o[j] > 0.f ? 1u : 0u) << j;
+                        if (row_ok) reinterpret_cast<uint16_t*>(L.sign_out)[token * halves + (nb >> 4)] = (uint16_t)sbits;
+                    }
+                    if (L.out_kind != 2) {
+                        uint8_t* th = stage + q * kQuarterBytes + lane * 128;
+                        uint8_t* tl = th + kATile;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 8) {
+                            uint16_t h[8], lo8[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) split_f16(o[j + e], h[e], lo8[e]);
+                            const int off = (((c * 2 + (j >> 3)) ^ (lane & 7)) << 4);            // SWIZZLE_128B
+                            *reinterpret_cast<uint4*>(th + off) =
+                                make_uint4((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16),
+                                           (uint32_t)h[4] | ((uint32_t)h[5] << 16), (uint32_t)h[6] | ((uint32_t)h[7] << 16));
+                            *reinterpret_cast<uint4*>(tl + off) =
+                                make_uint4((uint32_t)lo8[0] | ((uint32_t)lo8[1] << 16), (uint32_t)lo8[2] | ((uint32_t)lo8[3] << 16),
+                                           (uint32_t)lo8[4] | ((uint32_t)lo8[5] << 16), (uint32_t)lo8[6] | ((uint32_t)lo8[7] << 16));
+                        }
+                    } else {
+                        float* sp = reinterpret_cast<float*>(stage + q * 2 * kQuarterBytes) + lane * L.N + c * 16;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (nb + j < L.N) sp[j] = o[j];
+                    }
+                }
+            }
+            // accumulators drained, operand tiles (if any) written: the leader may issue the next pseudo-layer
+            if (l + 1 < g.nl) {
+                fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's operand reads
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(ready_bar);
+            }
+            if (L.out_kind == 1) {
+                fence_proxy_async_smem();
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+                if (sub == 0 && lane == 0 && winq < g.W) {
+                    for (int i = 0; i < L.ny; ++i) {
+                        const uint8_t* stage = act + L.stage_buf[i] * 2 * kATile;
+                        tma_store_3d(&maps.o_hi, stage + q * kQuarterBytes, (L.y0 + i) * L.ncta, 0, winq);
+                        tma_store_3d(&maps.o_lo, stage + kATile + q * kQuarterBytes, (L.y0 + i) * L.ncta, 0, winq);
+                    }
+                    bulk_commit();
+                    bulk_wait_read0();
+                }
+            } else if (L.out_kind == 2) {
+                // plain output (the pose): the quarter's windows are consecutive, dense rows in global memory
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+                int nwin = g.W - winq;
+                nwin = nwin < 0 ? 0 : (nwin > g.wpq ? g.wpq : nwin);
+                const int count = nwin * g.T * L.N;
+                const float* sp = reinterpret_cast<const float*>(act + L.stage_buf[0] * 2 * kATile + q * 2 * kQuarterBytes);
+                float* dp = g.out_plain + (size_t)winq * g.T * L.N;
+                for (int k = sub * 32 + lane; k < count; k += 128) dp[k] = sp[k];
+            }
+        }
+    }
+    if (threadIdx.x == 64) TAP_DBG(5);
+    tc_fence_before();
+    cluster_sync_all();                  // neither CTA leaves (or frees TMEM) while the pair's MMAs / reads are in flight
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+    if (threadIdx.x == 0) TAP_DBG(6);
+    if (threadIdx.x == 0 && g.dbg) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g.dbg[(size_t)blockIdx.x * 16 + 15] = (long long)gt;
+    }
+}
+
 struct TapWeight {
     void *hi = nullptr, *lo = nullptr, *hs = nullptr;
     int K = 0, Kp = 0, N = 0, ncta = 0, gridy = 0;
     CUtensorMap map_hi, map_lo, map_hs;
+    CUtensorMap map_hi2, map_lo2, map_hs2;     // half-height boxes (fp16 scheme): each CTA of a pair loads half a block
 };
 struct AMaps {
     CUtensorMap hi, lo;
@@ -797,6 +1102,10 @@ int tc_tap_prepare_weight(void* owner, cudaStream_t stream, const float* B, int 
         rc = make_map_u16(&w.map_hi, w.hi, 2, dims, strides, box);
         if (rc == GEM_OK) rc = make_map_u16(&w.map_lo, w.lo, 2, dims, strides, box);
         if (rc == GEM_OK) rc = make_map_u16(&w.map_hs, w.hs, 2, dims, strides, box);
+        const uint32_t box2[2] = {(uint32_t)bk, (uint32_t)(3 * w.ncta / 2)};
+        if (rc == GEM_OK) rc = make_map_u16(&w.map_hi2, w.hi, 2, dims, strides, box2);
+        if (rc == GEM_OK) rc = make_map_u16(&w.map_lo2, w.lo, 2, dims, strides, box2);
+        if (rc == GEM_OK) rc = make_map_u16(&w.map_hs2, w.hs, 2, dims, strides, box2);
     } else {
         rc = make_map_f32(&w.map_hi, (float*)w.hi, 2, dims, strides, box);
         if (rc == GEM_OK) rc = make_map_f32(&w.map_lo, (float*)w.lo, 2, dims, strides, box);
@@ -961,6 +1270,105 @@ int launch_tap_chain(cudaStream_t stream, void* owner, const TapChainLaunch& L) 
     }
     const int grid = (L.W + 4 * wpq - 1) / (4 * wpq);
     tc_tap_chain_kernel<<<grid, kChainThreads, kChainSmem, stream>>>(maps, a);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+
+// A whole direction of the decoder's k=3 layers on CTA pairs (see tc_tap_chain2_kernel).  Layers with more than two
+// output slabs are split into pseudo-layers; activation buffers are assigned here: a pseudo-layer's outputs go to
+// buffers that none of its own inputs occupy unless it is the layer's last pseudo-layer (whose MMAs have all
+// completed before its epilogue runs).
+int launch_tap_chain_pair(cudaStream_t stream, void* owner, const TapChainLaunch& L) {
+    if (L.W <= 0) return GEM_OK;
+    GEM_REQUIRE(L.nl >= 1 && L.nl <= kTapChainMax, "chain length");
+    GEM_REQUIRE(L.T >= 1 && L.T <= 32, "seq_len must be <= 32 on the tcgen05 tap path");
+    TapState* st = state_of(owner);
+    const TapWeight* w[kTapChainMax];
+    for (int l = 0; l < L.nl; ++l) {
+        auto wit = st->weights.find(std::make_pair(L.B[l], 2));
+        if (wit == st->weights.end()) {
+            set_error("tcgen05 tap chain: weights were not prepared in the fp16 scheme (tc_tap_prepare_weight)");
+            return GEM_ERR_STATE;
+        }
+        w[l] = &wit->second;
+        GEM_REQUIRE(w[l]->Kp / 64 <= 4 && w[l]->gridy <= 4, "chain layers take at most 256 channels in and out");
+        GEM_REQUIRE(l == 0 || w[l]->Kp == (w[l - 1]->N + 63) / 64 * 64, "chain layers must fit together");
+        GEM_REQUIRE(l == L.nl - 1 || w[l]->ncta == 64, "inner chain layers must produce multiples of 64 channels");
+        GEM_REQUIRE(L.epi[l] != EPI_MASK || L.aux_bits[l], "mask epilogue needs sign bits");
+        GEM_REQUIRE((!L.aux_bits[l] && !L.sign_out[l]) || w[l]->N % 16 == 0, "sign bits need N % 16 == 0");
+    }
+    const TapWeight& wl = *w[L.nl - 1];
+    GEM_REQUIRE((L.lda * 2) % 16 == 0 && L.Kreal <= L.lda && L.Kreal <= w[0]->Kp && L.Kreal >= w[0]->K, "bad activation layout");
+    GEM_REQUIRE(L.out_lo == nullptr || ((L.ldo * 2) % 16 == 0 && wl.ncta == 64), "split output needs N % 64 == 0");
+    GEM_REQUIRE(L.out_lo != nullptr || (L.ldo == wl.N && wl.N <= 48 && wl.gridy == 1), "plain output must be dense and N <= 48");
+    const int wpq = 32 / L.T;
+    auto make3 = [&](CUtensorMap* m, const void* base, int ld, int cols) -> int {
+        const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)L.T, (uint64_t)L.W};
+        const uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)L.T * ld * 2};
+        const uint32_t box[3] = {64u, (uint32_t)L.T, (uint32_t)wpq};
+        return make_map_u16(m, base, 3, dims, strides, box);
+    };
+    Chain2Maps maps;
+    memset(&maps, 0, sizeof(maps));
+    int rc = make3(&maps.a_hi, L.A_hi, L.lda, L.Kreal);
+    if (rc == GEM_OK) rc = make3(&maps.a_lo, L.A_lo, L.lda, L.Kreal);
+    if (rc == GEM_OK && L.out_lo) rc = make3(&maps.o_hi, L.out_hi, L.ldo, wl.N);
+    if (rc == GEM_OK && L.out_lo) rc = make3(&maps.o_lo, L.out_lo, L.ldo, wl.N);
+    if (rc != GEM_OK) return rc;
+    if (!L.out_lo) maps.o_hi = maps.a_hi, maps.o_lo = maps.a_lo;      // unused by the kernel
+    for (int l = 0; l < kChain2Max; ++l) maps.w[l][0] = maps.w[l][1] = maps.w[l][2] = maps.a_hi;
+    Chain2Args a;
+    memset(&a, 0, sizeof(a));
+    // buffer plan
+    int cur[4], ncur = w[0]->Kp / 64;                 // buffers holding the current layer's input K blocks
+    for (int i = 0; i < ncur; ++i) cur[i] = i;
+    int np = 0;
+    for (int l = 0; l < L.nl; ++l) {
+        maps.w[l][0] = w[l]->map_hi2, maps.w[l][1] = w[l]->map_lo2, maps.w[l][2] = w[l]->map_hs2;
+        const bool last = l == L.nl - 1;
+        const int gridy = w[l]->gridy;
+        int next[4], nnext = 0;
+        for (int y0 = 0; y0 < gridy; y0 += 2) {
+            GEM_REQUIRE(np < kChain2Max, "too many pseudo-layers in the chain");
+            Chain2Layer& c = a.L[np++];
+            c.bias = L.bias[l], c.aux_bits = L.aux_bits[l], c.sign_out = L.sign_out[l];
+            c.ncta = w[l]->ncta, c.y0 = y0, c.ny = gridy - y0 < 2 ? gridy - y0 : 2;
+            c.num_kb = w[l]->Kp / 64, c.N = w[l]->N, c.epi = L.epi[l], c.wmap = l;
+            c.out_kind = last ? (L.out_lo ? 1 : 2) : 0;
+            for (int i = 0; i < c.num_kb; ++i) c.in_buf[i] = (unsigned char)cur[i];
+            const bool last_pseudo = y0 + 2 >= gridy;
+            for (int i = 0; i < c.ny; ++i) {
+                // a free buffer: not an input (unless this is the layer's last pseudo-layer), not an output kept for
+                // the next layer, not one a TMA store of an earlier pseudo-layer of this layer may still be reading
+                int pick = -1;
+                for (int bfr = 0; bfr < 4 && pick < 0; ++bfr) {
+                    bool used = false;
+                    for (int k = 0; k < nnext; ++k) used |= next[k] == bfr;
+                    if (!last_pseudo)
+                        for (int k = 0; k < ncur; ++k) used |= cur[k] == bfr;
+                    for (int k = 0; k < i; ++k) used |= c.stage_buf[k] == bfr;
+                    if (!used) pick = bfr;
+                }
+                GEM_REQUIRE(pick >= 0, "no free activation buffer for the chain");
+                c.stage_buf[i] = (unsigned char)pick;
+                next[nnext++] = pick;
+            }
+        }
+        GEM_REQUIRE(nnext <= 4, "layer output does not fit the activation buffers");
+        for (int i = 0; i < nnext; ++i) cur[i] = next[i];
+        ncur = nnext;
+    }
+    a.nl = np, a.W = L.W, a.T = L.T, a.wpq = wpq, a.out_plain = L.out_lo ? nullptr : (float*)L.out_hi;
+    a.dbg = g_tap_dbg;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GEM_CUDA(cudaFuncSetAttribute(tc_tap_chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChain2Smem));
+        attr_set = true;
+    }
+    const int tiles = (L.W + 4 * wpq - 1) / (4 * wpq);
+    const int grid = 2 * ((tiles + 1) / 2);
+    tc_tap_chain2_kernel<<<grid, kChainThreads, kChain2Smem, stream>>>(maps, a);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }

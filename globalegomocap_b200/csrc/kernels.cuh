@@ -69,7 +69,7 @@ int launch_tap_tc(cudaStream_t stream, void* owner, const TapTcLaunch& L);
 // the layers (the epilogue's staged output IS the next layer's swizzled operand), only sign bits and the last
 // layer's output reach HBM; weights stream through a two-slot ring.  Layers after the first must be 64 -> N with
 // N = 64 for every layer but the last (which may be 48-padded plain fp32 output, or N = 128 split output).
-constexpr int kTapChainMax = 4;
+constexpr int kTapChainMax = 5;
 struct TapChainLaunch {
     int nl;
     const float* B[kTapChainMax];               // weight pointers (keys of tc_tap_prepare_weight, scheme 2)
@@ -84,6 +84,8 @@ struct TapChainLaunch {
     int W, T;
 };
 int launch_tap_chain(cudaStream_t stream, void* owner, const TapChainLaunch& L);
+// the same on CTA pairs (cta_group::2): up to five layers with up to 256 channels in and out (gemm_tap_tc.cu)
+int launch_tap_chain_pair(cudaStream_t stream, void* owner, const TapChainLaunch& L);
 int launch_split_pad(cudaStream_t stream, const float* src, int C, size_t tokens, int ldo, float* hi, float* lo);
 void tc_tap_release(void* owner);
 extern long long* g_tap_dbg;   // debug: per-CTA phase timestamps of the tap kernel (NULL in production)

@@ -114,6 +114,33 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
         : "memory");
 }
+// 3-D tile into the executing CTA's shared memory, completion bytes on an mbarrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                                 uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster_addr)
+        : "memory");
+}
+// arrive on an mbarrier of any CTA of the cluster (shared::cluster address), releasing this thread's writes cluster-wide
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+// wait on an own mbarrier that threads of the peer CTA arrive on: acquire at cluster scope (bounded like mbar_wait)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (spin > (1u << 26)) __trap();
+    }
+}
 // executed by the same warp of BOTH CTAs of the pair
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)

@@ -178,9 +178,11 @@ def test_fp16_scheme_cta_pair_matches_single_cta(engine, M, N, K):
 
 @pytest.mark.parametrize("W", [1, 2, 11, 12, 13, 37, 149, 641])
 def test_tap_chain_matches_layer_by_layer(engine, W):
-    """gemm_mode 3 runs the four K <= 128 tap layers of each direction as ONE launch (the activation tile stays in
-    shared memory, weights stream through a ring).  Same MMAs, same epilogue arithmetic: pose and dz must be
-    bit-identical to one launch per layer, for window counts that leave TMEM quarters / tiles partly empty."""
+    """gemm_mode 3 runs the k=3 layers of each direction as ONE launch (the activation tile stays in shared memory,
+    weights stream through a ring): four layers per one-CTA chain (mode 1) or all five on CTA pairs with
+    tcgen05.mma.cta_group::2 (mode 2, the default).  Same MMAs per output element, same epilogue arithmetic: pose
+    and dz must be bit-identical to one launch per layer, for window counts that leave TMEM quarters, tiles or the
+    second CTA of a pair partly or wholly empty."""
     import ctypes as C
     g = torch.Generator(device="cpu").manual_seed(5000 + W)
     z = torch.randn(W, 2048, generator=g)
@@ -190,18 +192,19 @@ def test_tap_chain_matches_layer_by_layer(engine, W):
     out = {}
     engine.set_gemm_mode(3)
     try:
-        for chain in (0, 1):
+        for chain in (0, 1, 2):
             lib.gem_debug_tap_chain(engine._ctx, chain)
             pose = engine.decode(0, z).clone()
             dz = engine.decode_vjp(0, up).clone()
             torch.cuda.synchronize()
             out[chain] = (pose, dz)
     finally:
-        lib.gem_debug_tap_chain(engine._ctx, 1)
+        lib.gem_debug_tap_chain(engine._ctx, 2)
         engine.set_gemm_mode(2)
-    assert torch.isfinite(out[1][0]).all() and torch.isfinite(out[1][1]).all()
-    assert torch.equal(out[0][0], out[1][0]), float((out[0][0] - out[1][0]).abs().max())
-    assert torch.equal(out[0][1], out[1][1]), float((out[0][1] - out[1][1]).abs().max())
+    for chain in (1, 2):        # 1: one-CTA chains of four layers, 2: CTA-pair chains of five (the default)
+        assert torch.isfinite(out[chain][0]).all() and torch.isfinite(out[chain][1]).all()
+        assert torch.equal(out[0][0], out[chain][0]), (chain, float((out[0][0] - out[chain][0]).abs().max()))
+        assert torch.equal(out[0][1], out[chain][1]), (chain, float((out[0][1] - out[chain][1]).abs().max()))
 
 
 @pytest.mark.parametrize("W", [1, 13, 300, 641])
