@@ -863,7 +863,7 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
                 if (l == 0) mbar_wait(act_full, 0);
                 else mbar_wait_cluster(act_ready, (uint32_t)((l - 1) & 1));
                 tc_fence_after();
-                if (l < 6) TAP_DBG(2 + l);
+                if (l < 3) TAP_DBG(2 + l);
                 const int np = 3 * L.ncta;
                 const uint32_t bt = (uint32_t)(np / 2) * 128;
                 const uint32_t idesc = instr_desc_f16(2 * kRows, np);

@@ -17,7 +17,8 @@ torch.cuda.synchronize()
 nct = (W + 11) // 12
 buf = torch.zeros(16 * 4096, dtype=torch.int64, device="cuda")
 eng.lib.gem_debug_tap_timestamps.argtypes = [C.c_void_p]
-names = {1: "setup", 2: "mma L0", 3: "mma L1", 4: "mma L2", 5: "epi done", 6: "end", 8: "acc L0", 9: "acc L1", 10: "acc L2", 11: "acc L3"}
+names = {1: "setup", 2: "mma L0", 3: "mma L1", 4: "mma L2", 5: "epi done", 6: "end", 8: "acc L0", 9: "acc L1", 10: "acc L2", 11: "acc L3", 12: "acc L4", 13: "acc L5"}
+nct = 2 * ((nct + 1) // 2) if True else nct
 def report(tag):
     t = buf.view(-1, 16)[:nct].cpu().numpy()
     d = {n: int(np.median(t[:, i] - t[:, 0])) for i, n in sorted(names.items())}
@@ -33,10 +34,7 @@ report("fwd chain")
 eng.decode(0, z); torch.cuda.synchronize()
 buf.zero_()
 eng.lib.gem_debug_tap_timestamps(C.c_void_p(buf.data_ptr()))
-eng.decode_vjp(0, up)     # bwd chain first, tap 204 (grid 156 x 4) overwrites: read only what the chain left? no: run chain alone
+eng.decode_vjp(0, up)
 torch.cuda.synchronize()
 eng.lib.gem_debug_tap_timestamps(C.c_void_p(0))
-t = buf.view(-1, 16)[:624].cpu().numpy()
-d = t[:, 1:8] - t[:, :1]
-print("tap 204 (grid x4) median cycles:", dict(zip(["setup", "kb0", "kb1", "acc", "epi done", "end", "chunks"], np.median(d, 0).astype(int))),
-      "span ns", int(t[:, 15].max() - t[:, 14].min()), "median life ns", int(np.median(t[:, 15] - t[:, 14])))
+report("bwd chain")
