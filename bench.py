@@ -54,11 +54,11 @@ if REPO not in sys.path:
 METRIC = "optimised frames/sec (windows x iters, device-timed)"
 FLOPS_PER_WINDOW_EVAL_ALGORITHMIC = 63.9e6   # decoder fwd + bwd-data as the reference runs it
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at W = 1870 from one `ncu --set full` capture of this
-# command in the default gemm mode (profiles/r01_ncu_full_fp16_summary.csv)
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 39.1e6              # mean of the latent->T*256 (37.5 MB) and T*256->latent (40.7 MB) layers;
+# command (--chunks 1) in the default gemm mode (profiles/r01_ncu_full_pair_summary.csv)
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 39.4e6              # mean of the latent->T*256 (37.5 MB) and T*256->latent (41.3 MB) layers;
                                                      # the fp16 operands are 15 MB activations + 21 MB weights
-NCU_LBFGS_DRAM_BYTES_PER_LAUNCH = 574.3e6            # a mid-stage round (the history grows with the iteration count)
-NCU_ENERGY_DRAM_BYTES_PER_LAUNCH_LOCAL = 104.7e6
+NCU_LBFGS_DRAM_BYTES_PER_LAUNCH = 492.4e6            # rounds 15-16 of the local stage (the history grows with the iteration count)
+NCU_ENERGY_DRAM_BYTES_PER_LAUNCH_LOCAL = 104.3e6
 
 
 def lbfgs_rows(sol):
@@ -433,10 +433,10 @@ def main():
         g_n = sum(per_tag[t]["launches"] for t in gemm_tags if t in per_tag)
         flop_per_launch = 2.0 * W * 2048 * 2560
         g_tf = flop_per_launch / (g_ms / max(g_n, 1) / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "tc_gemm_kernel: decoder latent<->T*256 GEMM (tags 100, 205)",
+        roof = {"bound": "tensor", "kernel": "tc_gemm_pair_kernel<160>: decoder latent<->T*256 GEMM (tags 100, 205)",
                 "achieved": g_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": g_tf / tf_peak,
                 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the two layers
-                # (profiles/r01_ncu_full_fp16_summary.csv)
+                # (profiles/r01_ncu_full_pair_summary.csv)
                 "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH if (W == 1870 and args.gemm_mode in (-1, 3)) else None,
                 "peak_source": peak_src + ", bf16 sustained",
                 "share_of_kernel_time": g_ms / max(kern_ms, 1e-9),
