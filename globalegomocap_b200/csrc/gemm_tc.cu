@@ -821,9 +821,10 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
     const int pair_mode = g_gemm_pair >= 0 ? g_gemm_pair : pair_env;
     if (f16 && pair_mode && !(a.C_lo && !a.out16)) {      // (fp32 hi/lo outputs need the one-CTA kernel's larger staging area)
         int bn = 160;
-        if (const char* env = getenv("GEM_GEMM_BN")) bn = atoi(env) == 128 ? 128 : 160;
-        return bn == 128 ? launch_pair_bn<128>(stream, map_a_hi, map_a_lo, wit->second, 1, a)
-                         : launch_pair_bn<160>(stream, map_a_hi, map_a_lo, wit->second, 3, a);
+        if (const char* env = getenv("GEM_GEMM_BN")) bn = atoi(env);
+        if (bn == 128) return launch_pair_bn<128>(stream, map_a_hi, map_a_lo, wit->second, 1, a);
+        if (bn == 144) return launch_pair_bn<144>(stream, map_a_hi, map_a_lo, wit->second, 2, a);
+        return launch_pair_bn<160>(stream, map_a_hi, map_a_lo, wit->second, 3, a);
     }
     return f16 ? launch_scheme<true>(kBNs[best], stream, map_a_hi, map_a_lo, wit->second, best, a)
                : launch_scheme<false>(kBNs[best], stream, map_a_hi, map_a_lo, wit->second, best, a);
