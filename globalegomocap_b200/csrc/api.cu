@@ -74,9 +74,11 @@ struct gem_ctx {
     // energy kernel's texel cache (heat maps read from pinned host memory): [W][T*J][16] + origins, and counters
     float* patch = nullptr;
     short2* patch_origin = nullptr;
-    unsigned long long* patch_stats = nullptr;   // {lookups, rebuilds}, counted while patch_stats_on
+    unsigned long long* patch_valid = nullptr;   // one bit per texel of a joint's window
+    unsigned long long* patch_stats = nullptr;   // {lookups, texels fetched}, counted while patch_stats_on
     bool patch_stats_on = false;
     int texel_cache = -1;                        // -1 auto (on when the maps are host memory), 0 off, 1 on
+    int texel_prefetch_ctas = 4;                 // CTAs of the texel prefetch kernel (0: the energy kernel fetches itself)
     int trace_cap = 0;                           // columns of trace_own
     bool use_graphs = true;
     struct RoundGraph {
@@ -212,8 +214,9 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     if (rc == GEM_OK) rc = ctx_alloc(c, &c->fb_own, W);
     if (rc == GEM_OK) rc = ctx_alloc(c, &c->clip_own, W);
     if (rc == GEM_OK) rc = ctx_alloc(c, &c->status_own, W);
-    A(&c->patch, Weven * seq_len * num_joints * 16);
+    A(&c->patch, Weven * seq_len * num_joints * (kPatchW * kPatchW));
     if (rc == GEM_OK) rc = ctx_alloc(c, &c->patch_origin, Weven * seq_len * num_joints);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->patch_valid, Weven * seq_len * num_joints);
     if (rc == GEM_OK) rc = ctx_alloc(c, &c->patch_stats, 2);
     if (rc == GEM_OK && cudaMemset(c->patch_stats, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) rc = GEM_ERR_CUDA;
     LbfgsBuffers& b = c->lb;
@@ -238,11 +241,12 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     if (const char* env = getenv("GEM_GEMM_MODE")) c->gemm_mode = (env[0] >= '0' && env[0] <= '3') ? env[0] - '0' : 3;
     if (const char* env = getenv("GEM_TAP_CHAIN")) c->tap_chain = (env[0] >= '0' && env[0] <= '2') ? env[0] - '0' : 2;
     if (const char* env = getenv("GEM_ENC_TC")) c->enc_tc_on = env[0] != '0';
-    c->n_chunks = 4;
-    if (const char* env = getenv("GEM_CHUNKS")) c->n_chunks = atoi(env) >= 1 ? atoi(env) : 1;
+    c->n_chunks = 0;      // automatic (slice_bounds)
+    if (const char* env = getenv("GEM_CHUNKS")) c->n_chunks = atoi(env) >= 0 ? atoi(env) : 0;
     if (c->n_chunks > 16) c->n_chunks = 16;
     if (const char* env = getenv("GEM_GRAPHS")) c->use_graphs = env[0] != '0';
     if (const char* env = getenv("GEM_TEXEL_CACHE")) c->texel_cache = atoi(env);
+    if (const char* env = getenv("GEM_TEXEL_PREFETCH_CTAS")) c->texel_prefetch_ctas = atoi(env) > 0 ? atoi(env) : 0;
     // default skeleton: the reference's 15-joint kinematic tree (optimizer.py:34)
     if (num_joints == 15) {
         static const int32_t parents[15] = {0, 0, 1, 2, 0, 4, 5, 1, 7, 8, 9, 4, 11, 12, 13};
@@ -313,7 +317,7 @@ int gem_debug_gemm_pair(int mode) {
 }
 
 int gem_ctx_set_chunks(gem_ctx* c, int n_chunks) {
-    GEM_REQUIRE(c != nullptr && n_chunks >= 1 && n_chunks <= 16, "n_chunks must be in [1, 16]");
+    GEM_REQUIRE(c != nullptr && n_chunks >= 0 && n_chunks <= 16, "n_chunks must be in [0, 16] (0 = automatic)");
     c->n_chunks = n_chunks;
     return GEM_OK;
 }
@@ -324,14 +328,14 @@ int gem_ctx_set_texel_cache(gem_ctx* c, int mode) {
     return GEM_OK;
 }
 
-int gem_ctx_texel_cache_stats(gem_ctx* c, int enable, uint64_t* lookups_h, uint64_t* rebuilds_h) {
+int gem_ctx_texel_cache_stats(gem_ctx* c, int enable, uint64_t* lookups_h, uint64_t* texels_fetched_h) {
     GEM_REQUIRE(c != nullptr, "ctx is NULL");
     GEM_CUDA(cudaSetDevice(c->device));
     GEM_CUDA(cudaDeviceSynchronize());
     unsigned long long v[2] = {0, 0};
     GEM_CUDA(cudaMemcpy(v, c->patch_stats, sizeof(v), cudaMemcpyDeviceToHost));
     if (lookups_h) *lookups_h = v[0];
-    if (rebuilds_h) *rebuilds_h = v[1];
+    if (texels_fetched_h) *texels_fetched_h = v[1];
     GEM_CUDA(cudaMemset(c->patch_stats, 0, sizeof(v)));
     c->patch_stats_on = enable != 0;
     return GEM_OK;
@@ -512,6 +516,7 @@ struct Slice {
     uint32_t* status_own;
     float* patch;
     short2* patch_origin;
+    unsigned long long* patch_valid;
     LbfgsBuffers lb;
 };
 static Slice slice_of(gem_ctx* c, int w0) {
@@ -538,7 +543,8 @@ static Slice slice_of(gem_ctx* c, int w0) {
     v.pose0_own = c->pose0_own + v.tok0 * P, v.mb_own = c->mb_own;     // (mean bones are indexed by absolute window)
     v.trace_own = c->trace_own + (size_t)w0 * c->trace_cap;
     v.fb_own = c->fb_own + w0, v.clip_own = c->clip_own + w0, v.status_own = c->status_own + w0;
-    v.patch = c->patch + v.tok0 * c->J * 16, v.patch_origin = c->patch_origin + v.tok0 * c->J;
+    v.patch = c->patch + v.tok0 * c->J * (kPatchW * kPatchW), v.patch_origin = c->patch_origin + v.tok0 * c->J;
+    v.patch_valid = c->patch_valid + v.tok0 * c->J;
     v.lb = c->lb;
     LbfgsBuffers& b = v.lb;
     const size_t on = (size_t)w0 * n;
@@ -739,14 +745,14 @@ __global__ void stage_inputs_kernel(int w_abs0, int TJ3, int J, const float* __r
                                     const int32_t* __restrict__ clip, const float* __restrict__ mean_bone,
                                     float* __restrict__ pose0_own, int64_t* __restrict__ fb_own,
                                     int32_t* __restrict__ clip_own, float* __restrict__ mb_own,
-                                    uint32_t* __restrict__ status_own, short2* __restrict__ patch_origin, int TJ) {
+                                    uint32_t* __restrict__ status_own, unsigned long long* __restrict__ patch_valid, int TJ) {
     // all pointers are the slice's (window blockIdx.x of the slice); mb_own is the ctx-wide table indexed by the
     // absolute window w_abs0 + blockIdx.x, which is what the staged clip index points at
     const int w = blockIdx.x;
     for (int i = threadIdx.x; i < TJ3; i += blockDim.x) pose0_own[(size_t)w * TJ3 + i] = pose0[(size_t)w * TJ3 + i];
     if (threadIdx.x < J) mb_own[(size_t)(w_abs0 + w) * J + threadIdx.x] = mean_bone[(size_t)clip[w] * J + threadIdx.x];
     // a new stage reads new maps: every joint's cached texel patch is stale
-    for (int i = threadIdx.x; i < TJ; i += blockDim.x) patch_origin[(size_t)w * TJ + i] = make_short2(-30000, -30000);
+    for (int i = threadIdx.x; i < TJ; i += blockDim.x) patch_valid[(size_t)w * TJ + i] = 0ull;      // empty window
     if (threadIdx.x == 0) {
         fb_own[w] = fb ? fb[w] : 0;
         clip_own[w] = w_abs0 + w;
@@ -932,7 +938,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     if (a.trace) GEM_CUDA(cudaMemsetAsync(v.trace_own, 0xff, (size_t)Wk * c->trace_cap * sizeof(float), q));   // NaN
     stage_inputs_kernel<<<Wk, 128, 0, q>>>(w0, TJ3, c->J, a.pose0 + w0 * P, a.frame_base ? a.frame_base + w0 : nullptr,
                                            a.clip + w0, a.mean_bone, v.pose0_own, v.fb_own, v.clip_own, v.mb_own,
-                                           v.status_own, v.patch_origin, c->T * c->J);
+                                           v.status_own, v.patch_valid, c->T * c->J);
     GEM_CHECK_LAUNCH();
     c->launches += 1;
     // z0 = mu + eps * std                                   optimizer.py:255-259
@@ -943,11 +949,18 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     // one closure round: decode -> fused energy/gradient -> decoder bwd-data -> L-BFGS advance
     auto enqueue_round = [&]() -> int {
         GEM_TRY(decode_impl(c, q, which, Wk, v, lb.ZT, v.pose, tc ? lb.ZT_hi : nullptr, tc ? lb.ZT_lo : nullptr));
+        if (a.texel_cache && c->texel_prefetch_ctas > 0)
+            // zero-copy maps: the wait for PCIe happens in a few CTAs, not in energy CTAs parked on every SM
+            GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
+                return launch_texel_prefetch(q, Wk, c->T, c->J, c->H, c->Wd, v.pose, a.heat, v.fb_own, v.patch, v.patch_origin,
+                                             v.patch_valid, c->patch_stats_on ? c->patch_stats : nullptr,
+                                             c->texel_prefetch_ctas);
+            }));
         GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
             return launch_energy_grad(q, Wk, c->T, c->J, c->H, c->Wd, v.pose, v.pose0_own, a.heat, v.fb_own, v.clip_own,
                                       v.mb_own, a.wt, v.f_new, nullptr, v.gpose, v.status_own, tc ? v.gp_hi : nullptr,
                                       v.gp_lo, pose_pad(c), a.texel_cache ? v.patch : nullptr, v.patch_origin,
-                                      c->patch_stats_on ? c->patch_stats : nullptr, c->gemm_mode == 3, v.row_exp);
+                                      c->patch_stats_on ? c->patch_stats : nullptr, c->gemm_mode == 3, v.row_exp, v.patch_valid);
         }));
         GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, v.gpose, v.g_new, tc));
         return timed(c, q, GEM_TAG_LBFGS_ADVANCE, [&]() { return launch_lbfgs_advance(q, lb, v.f_new, v.g_new, Wk); });
@@ -959,7 +972,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     if (graphs && a.p.max_eval >= 2) {
         for (auto& g : c->graphs) {
             if (g.which == which && g.w0 == w0 && g.Wk == Wk && g.gemm_mode == (c->gemm_mode | (c->tap_chain << 8)) && g.heat == a.heat &&
-                g.has_heat == ((a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on) &&
+                g.has_heat == ((a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * c->texel_prefetch_ctas) &&
                 g.trace_stride == lb.trace_stride &&
                 memcmp(&g.wt, &a.wt, sizeof(a.wt)) == 0 && g.p.lr == a.p.lr && g.p.max_iter == a.p.max_iter &&
                 g.p.max_eval == a.p.max_eval && g.p.tolerance_grad == a.p.tolerance_grad &&
@@ -983,7 +996,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             GEM_CUDA(e);
             gem_ctx::RoundGraph g;
             g.which = which, g.w0 = w0, g.Wk = Wk, g.gemm_mode = c->gemm_mode | (c->tap_chain << 8), g.heat = a.heat;
-            g.has_heat = (a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on;
+            g.has_heat = (a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * c->texel_prefetch_ctas;
             g.trace_stride = lb.trace_stride, g.wt = a.wt, g.p = a.p;
             g.launches = round_launches;
             e = cudaGraphInstantiate(&g.exec, graph, 0);
@@ -1021,14 +1034,15 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
 
 // Slice boundaries of a call over W windows: the caller's (gem_ctx_set_slices) when they fit, else n_chunks
 // equal parts at multiples of 12 windows (the tap kernel's M tile), at least 96 windows each.
-static std::vector<int> slice_bounds(const gem_ctx* c, int W) {
+static std::vector<int> slice_bounds(const gem_ctx* c, int W, bool zero_copy = false) {
     std::vector<int> w0;
     if (!c->prof_on && !c->user_slices.empty() && c->user_slices.back() < W) {
         w0 = c->user_slices;
         w0.push_back(W);
         return w0;
     }
-    int n = c->prof_on ? 1 : c->n_chunks;
+    // automatic: 4 slices; 8 when the maps are read over PCIe (more slices hide more of the transfers)
+    int n = c->prof_on ? 1 : (c->n_chunks > 0 ? c->n_chunks : (zero_copy ? 8 : 4));
     const int kAlign = 12, kMinChunk = 96;
     if (n > W / kMinChunk) n = W / kMinChunk;
     if (n < 1) n = 1;
@@ -1122,7 +1136,7 @@ int gem_solve_stage(gem_ctx* c, void* stream, int which, int W, const float* pos
     a.pose_out = pose_out_d, a.trace = energy_trace_d, a.n_iter = n_iter_d, a.func_evals = func_evals_d, a.status = status_d;
     a.texel_cache = want_texel_cache(c, heat_d, wt->reproj);
     const bool graphs = c->use_graphs && !c->prof_on;
-    const std::vector<int> w0 = slice_bounds(c, W);
+    const std::vector<int> w0 = slice_bounds(c, W, a.texel_cache);
     Fork f;
     GEM_TRY(fork_slices(c, s, w0, graphs, &f));
     for (size_t k = 0; k + 1 < w0.size(); ++k) GEM_TRY(enqueue_stage_slice(c, f.cs[k], a, w0[k], w0[k + 1] - w0[k], graphs));
@@ -1157,7 +1171,7 @@ int gem_solve_windows(gem_ctx* c, void* stream, int W, const float* pose0_d, con
     b.pose_out = global_pose_d, b.status = nullptr;
     b.n_iter = n_iter_d ? n_iter_d + W : nullptr, b.func_evals = func_evals_d ? func_evals_d + W : nullptr;
     const bool graphs = c->use_graphs && !c->prof_on;
-    const std::vector<int> w0 = slice_bounds(c, W);
+    const std::vector<int> w0 = slice_bounds(c, W, a.texel_cache);
     Fork f;
     GEM_TRY(fork_slices(c, s, w0, graphs, &f));
     const size_t P = (size_t)c->T * c->J * 3;

@@ -13,6 +13,8 @@
 //   * per-term energies are reduced with warp shuffles, combined in the reference's order.
 // Compiled with --fmad=false: the pixel-coordinate chain must round like ATen's separate
 // fp32 ops, because floor() of the pixel coordinate selects the texels.
+#include <string.h>
+
 #include "kernels.cuh"
 
 namespace gem {
@@ -59,20 +61,108 @@ struct EnergyArgs {
     int gp_f16;
     int32_t* row_exp;
     // optional texel cache (used when the heat maps stay in pinned HOST memory and are read over PCIe): per joint
-    // a 4x4 neighbourhood of its map, 64 contiguous bytes in HBM, and the map coordinate of its corner.  The same
-    // few texels are read by every evaluation of a stage (joints move by a fraction of a texel per step), so only
-    // the ~6 % of the maps the optimiser ever looks at cross the bus.  A joint that leaves its patch rebuilds it
-    // around the new cell (which is also how the first evaluation fills it); values are copies of the map's, so
-    // the energy is bit-identical with and without the cache.
-    float* patch;              // [W][T*J][16]
-    short2* patch_origin;      // [W][T*J]
-    unsigned long long* patch_stats;   // optional {lookups, rebuilds}
+    // an 8x8 window of its map, 256 contiguous bytes in HBM, the map coordinate of its corner and a valid bit per
+    // texel.  The same few texels are read by every evaluation of a stage (joints move by a fraction of a texel per
+    // step), so only the texels the optimiser actually samples cross the bus, once each while the joint stays in
+    // its window; values are copies of the map's, so the energy is bit-identical with and without the cache.
+    float* patch;              // [W][T*J][kPatchW * kPatchW]
+    short2* patch_origin;      // [W][T*J]: map coordinate of the window's corner
+    unsigned long long* patch_valid;   // [W][T*J]: one bit per texel of the window (0: empty window)
+    unsigned long long* patch_stats;   // optional {lookups, texels fetched}
 };
 
 __device__ __forceinline__ float texel(const float* __restrict__ heat, int64_t frame, int y, int x, int j, int H,
                                        int Wd, int J) {
     if (x < 0 || x >= Wd || y < 0 || y >= H) return 0.f;     // padding_mode='zeros'
     return __ldg(heat + ((frame * H + y) * (int64_t)Wd + x) * J + j);
+}
+
+
+// Demand-fetched 8x8 window of one joint's map: origin and a valid bit per texel; only texels of the bilinear footprint
+// (x0, y0) .. (x0+1, y0+1) that are not in the window yet are read from the map (over PCIe when it is host memory).
+// A footprint that leaves the window re-centres it (and empties it).
+__device__ __forceinline__ void cache_lookup(const EnergyArgs& a, size_t pk, int64_t frame, int j, int x0, int y0,
+                                             bool count_lookup, float& nw, float& ne, float& sw, float& se) {
+    float* pe = a.patch + pk * (kPatchW * kPatchW);
+    const short2 o = a.patch_origin[pk];
+    unsigned long long valid = a.patch_valid[pk];
+    int ox = o.x, oy = o.y;
+    int dx = x0 - ox, dy = y0 - oy;
+    if (valid == 0ull || dx < 0 || dx > kPatchW - 2 || dy < 0 || dy > kPatchW - 2)
+        ox = x0 - (kPatchW / 2 - 1), oy = y0 - (kPatchW / 2 - 1), dx = dy = kPatchW / 2 - 1, valid = 0ull;
+    const int b00 = dy * kPatchW + dx;
+    const unsigned long long foot = (3ull | (3ull << kPatchW)) << b00;
+    const unsigned long long missing = foot & ~valid;
+    if (a.patch_stats) {
+        if (count_lookup) atomicAdd(a.patch_stats, 1ull);
+        if (missing) atomicAdd(a.patch_stats + 1, (unsigned long long)__popcll(missing));
+    }
+    float* p0 = pe + b00;
+    if (missing) {                            // up to four independent loads in flight
+        const bool m0 = (missing >> b00) & 1ull, m1 = (missing >> (b00 + 1)) & 1ull;
+        const bool m2 = (missing >> (b00 + kPatchW)) & 1ull, m3 = (missing >> (b00 + kPatchW + 1)) & 1ull;
+        nw = m0 ? texel(a.heat, frame, y0, x0, j, a.H, a.Wd, a.J) : p0[0];
+        ne = m1 ? texel(a.heat, frame, y0, x0 + 1, j, a.H, a.Wd, a.J) : p0[1];
+        sw = m2 ? texel(a.heat, frame, y0 + 1, x0, j, a.H, a.Wd, a.J) : p0[kPatchW];
+        se = m3 ? texel(a.heat, frame, y0 + 1, x0 + 1, j, a.H, a.Wd, a.J) : p0[kPatchW + 1];
+        if (m0) p0[0] = nw;
+        if (m1) p0[1] = ne;
+        if (m2) p0[kPatchW] = sw;
+        if (m3) p0[kPatchW + 1] = se;
+        a.patch_origin[pk] = make_short2((short)ox, (short)oy);
+        a.patch_valid[pk] = valid | missing;
+    } else {
+        nw = p0[0], ne = p0[1], sw = p0[kPatchW], se = p0[kPatchW + 1];
+    }
+}
+
+// Fisheye projection of a joint and the map cell its bilinear footprint starts at (FishEyeCalibrated.py:96-129,
+// optimizer.py:139-149); the arithmetic (and this translation unit's --fmad=false) is what decides the cell, so the
+// energy kernel and the texel prefetch kernel share it.  Returns false when r == 0.
+struct Proj {
+    float r, inv, rho, drho, ix, iy, fx0, fy0;
+};
+__device__ __forceinline__ bool project_joint(float x, float y, float z, int H, int Wd, Proj& p) {
+    const float zn = -z;
+    p.r = sqrtf(x * x + y * y);
+    if (p.r == 0.f) return false;
+    const float theta = atanf(zn / p.r);
+    float rho = c_cam.poly[0], drho = 0.f, ti = 1.f;
+    for (int i = 1; i < c_cam.n_poly; ++i) {          // power accumulation, not Horner
+        drho += (float)i * c_cam.poly[i] * ti;
+        ti *= theta;
+        rho += ti * c_cam.poly[i];
+    }
+    p.rho = rho, p.drho = drho;
+    p.inv = 1.0f / p.r;
+    const float u = x * p.inv * rho + c_cam.cx;
+    const float v = y * p.inv * rho + c_cam.cy;
+    // pose_2d[:,0] -= 128; (pose_2d - 512)/512; grid_sample unnormalise (align_corners)
+    const float gxn = ((u - 128.f) - 512.f) / 512.f;
+    const float gyn = (v - 512.f) / 512.f;
+    p.ix = ((gxn + 1.f) / 2.f) * (float)(Wd - 1);
+    p.iy = ((gyn + 1.f) / 2.f) * (float)(H - 1);
+    p.fx0 = floorf(p.ix), p.fy0 = floorf(p.iy);
+    return true;
+}
+
+// Zero-copy maps: fetches the texels the next energy evaluation will sample into the joints' cache windows.  A
+// handful of CTAs (grid-stride over all joints) so that the wait for PCIe occupies a few SMs instead of every SM:
+// energy CTAs stalled on PCIe reads are small but sit on all SMs, and no 200 KB tensor-core CTA of another slice can
+// be scheduled beside them — the solve then serialises with the transfers instead of overlapping them.
+__global__ void __launch_bounds__(512) texel_prefetch_kernel(EnergyArgs a) {
+    const int TJ = a.T * a.J;
+    const size_t total = (size_t)a.W * TJ;
+    for (size_t i = (size_t)blockIdx.x * 512 + threadIdx.x; i < total; i += (size_t)gridDim.x * 512) {
+        const int w = (int)(i / TJ), k = (int)(i - (size_t)w * TJ);
+        const int t = k / a.J, j = k - t * a.J;
+        const float x = a.pose[i * 3 + 0], y = a.pose[i * 3 + 1], z = a.pose[i * 3 + 2];
+        Proj p;
+        if (!project_joint(x, y, z, a.H, a.Wd, p)) continue;
+        if (!(p.fx0 >= -1.f && p.fx0 <= (float)a.Wd && p.fy0 >= -1.f && p.fy0 <= (float)a.H)) continue;
+        float nw, ne, sw, se;
+        cache_lookup(a, i, a.frame_base[w] + t, j, (int)p.fx0, (int)p.fy0, false, nw, ne, sw, se);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
@@ -184,27 +274,12 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
         }
         // E_reproj = -sum bilinear(H_tj; pix(project(x)))            optimizer.py:139-149
         if (a.wr != 0.f) {
-            const float zn = -z;
-            const float r = sqrtf(x * x + y * y);
-            if (r == 0.f) {
+            Proj pj;
+            if (!project_joint(x, y, z, a.H, a.Wd, pj)) {
                 if (a.status) atomicOr(a.status + w, GEM_WIN_NORM_ZERO);
             } else {
-                const float theta = atanf(zn / r);
-                float rho = c_cam.poly[0], drho = 0.f, ti = 1.f;
-                for (int i = 1; i < c_cam.n_poly; ++i) {          // power accumulation, not Horner
-                    drho += (float)i * c_cam.poly[i] * ti;
-                    ti *= theta;
-                    rho += ti * c_cam.poly[i];
-                }
-                const float inv = 1.0f / r;
-                const float u = x * inv * rho + c_cam.cx;
-                const float v = y * inv * rho + c_cam.cy;
-                // pose_2d[:,0] -= 128; (pose_2d - 512)/512; grid_sample unnormalise (align_corners)
-                const float gxn = ((u - 128.f) - 512.f) / 512.f;
-                const float gyn = (v - 512.f) / 512.f;
-                const float ix = ((gxn + 1.f) / 2.f) * (float)(a.Wd - 1);
-                const float iy = ((gyn + 1.f) / 2.f) * (float)(a.H - 1);
-                const float fx0 = floorf(ix), fy0 = floorf(iy);
+                const float r = pj.r, inv = pj.inv, rho = pj.rho, drho = pj.drho;
+                const float ix = pj.ix, iy = pj.iy, fx0 = pj.fx0, fy0 = pj.fy0;
                 // Anything further than one texel outside contributes exactly 0.
                 if (fx0 >= -1.f && fx0 <= (float)a.Wd && fy0 >= -1.f && fy0 <= (float)a.H) {
                     const int x0 = (int)fx0, y0 = (int)fy0;
@@ -213,33 +288,7 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
                     const int64_t frame = a.frame_base[w] + t;
                     float nw, ne, sw, se;
                     if (a.patch) {
-                        const size_t pk = (size_t)w * TJ + k;
-                        float* pe = a.patch + pk * 16;
-                        short2 o = a.patch_origin[pk];
-                        const int dx = x0 - o.x, dy = y0 - o.y;
-                        const bool miss = dx < 0 || dx > 2 || dy < 0 || dy > 2;
-                        if (a.patch_stats) {
-                            atomicAdd(a.patch_stats, 1ull);
-                            if (miss) atomicAdd(a.patch_stats + 1, 1ull);
-                        }
-                        if (miss) {                               // (re)build around the current cell
-                            o.x = (short)(x0 - 1), o.y = (short)(y0 - 1);
-                            float4 rows[4];
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) {         // 16 independent loads in flight
-                                rows[r].x = texel(a.heat, frame, o.y + r, o.x + 0, j, a.H, a.Wd, a.J);
-                                rows[r].y = texel(a.heat, frame, o.y + r, o.x + 1, j, a.H, a.Wd, a.J);
-                                rows[r].z = texel(a.heat, frame, o.y + r, o.x + 2, j, a.H, a.Wd, a.J);
-                                rows[r].w = texel(a.heat, frame, o.y + r, o.x + 3, j, a.H, a.Wd, a.J);
-                            }
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) *reinterpret_cast<float4*>(pe + r * 4) = rows[r];
-                            a.patch_origin[pk] = o;
-                            nw = rows[1].y, ne = rows[1].z, sw = rows[2].y, se = rows[2].z;
-                        } else {
-                            const float* p0 = pe + dy * 4 + dx;
-                            nw = p0[0], ne = p0[1], sw = p0[4], se = p0[5];
-                        }
+                        cache_lookup(a, (size_t)w * TJ + k, frame, j, x0, y0, true, nw, ne, sw, se);
                     } else {
                         nw = texel(a.heat, frame, y0, x0, j, a.H, a.Wd, a.J);
                         ne = texel(a.heat, frame, y0, x0 + 1, j, a.H, a.Wd, a.J);
@@ -373,7 +422,8 @@ int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, 
                        const float* pose0, const float* heat, const int64_t* frame_base, const int32_t* clip,
                        const float* mean_bone, const gem_energy_weights& wt, float* energy, float* terms,
                        float* grad, uint32_t* status, float* gp_hi, float* gp_lo, int pp, float* patch,
-                       short2* patch_origin, unsigned long long* patch_stats, int gp_f16, int32_t* row_exp) {
+                       short2* patch_origin, unsigned long long* patch_stats, int gp_f16, int32_t* row_exp,
+                       unsigned long long* patch_valid) {
     if (W <= 0) return GEM_OK;
     GEM_REQUIRE(T * J <= kSlot, "T*J must be <= 160");
     GEM_REQUIRE(T >= 3, "seq_len must be >= 3");
@@ -384,7 +434,9 @@ int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, 
     a.gp_hi = gp_hi, a.gp_lo = gp_hi ? gp_lo : nullptr, a.pp = gp_hi ? pp : 0;
     a.gp_f16 = gp_hi ? gp_f16 : 0, a.row_exp = row_exp;
     GEM_REQUIRE(!a.gp_f16 || (row_exp && (T * pp) % 8 == 0), "fp16 gradient output needs row_exp and T*pp % 8 == 0");
-    a.patch = patch, a.patch_origin = patch ? patch_origin : nullptr, a.patch_stats = patch ? patch_stats : nullptr;
+    a.patch = patch && patch_valid ? patch : nullptr;
+    a.patch_origin = a.patch ? patch_origin : nullptr, a.patch_stats = a.patch ? patch_stats : nullptr;
+    a.patch_valid = a.patch ? patch_valid : nullptr;
     GEM_REQUIRE(!gp_hi || (gp_lo && pp >= J * 3 && T * pp <= (gp_f16 ? 2 : 1) * kSplitMax && (T * pp) % 4 == 0),
                 "bad split gradient layout");
     a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd;
@@ -395,6 +447,25 @@ int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, 
                  (!gp_hi || (al16(gp_hi) && al16(gp_lo)));
     const int grid = (W + kWinPerCta - 1) / kWinPerCta;
     energy_grad_kernel<<<grid, kThreads, 0, stream>>>(a);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+// fetches, into the joints' cache windows, the texels the energy evaluation of `pose` will sample (zero-copy maps)
+int launch_texel_prefetch(cudaStream_t stream, int W, int T, int J, int H, int Wd, const float* pose, const float* heat,
+                          const int64_t* frame_base, float* patch, short2* patch_origin, unsigned long long* patch_valid,
+                          unsigned long long* patch_stats, int ctas) {
+    if (W <= 0) return GEM_OK;
+    GEM_REQUIRE(heat && frame_base && patch && patch_origin && patch_valid, "texel prefetch needs the maps and the cache");
+    EnergyArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pose = pose, a.heat = heat, a.frame_base = frame_base;
+    a.patch = patch, a.patch_origin = patch_origin, a.patch_valid = patch_valid, a.patch_stats = patch_stats;
+    a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd;
+    const size_t total = (size_t)W * T * J;
+    int grid = (int)((total + 511) / 512);
+    if (grid > ctas) grid = ctas;
+    texel_prefetch_kernel<<<grid, 512, 0, stream>>>(a);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }

@@ -112,7 +112,7 @@ class Engine:
         check(self.lib.gem_ctx_set_texel_cache(self._ctx, int(mode)))
 
     def texel_cache_stats(self, enable: bool):
-        """(lookups, rebuilds) counted since the previous call; switches the counting on or off."""
+        """(lookups, texels fetched from the map) counted since the previous call; switches the counting on or off."""
         a, b = C.c_uint64(0), C.c_uint64(0)
         check(self.lib.gem_ctx_texel_cache_stats(self._ctx, int(bool(enable)), C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)

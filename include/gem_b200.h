@@ -109,7 +109,8 @@ int gem_ctx_set_gemm_mode(gem_ctx* ctx, int mode);
 /* A stage's windows are independent: gem_solve_stage splits them into n_chunks slices (boundaries at
  * multiples of 12 windows, at least 96 windows each) that run the same kernel sequence on internal streams,
  * forked from and joined to the caller's stream, so one slice's launch gaps and HBM-bound L-BFGS updates
- * overlap another's tensor-core layers.  Default 4 (env GEM_CHUNKS); 1 = everything on the caller's stream.
+ * overlap another's tensor-core layers.  Default 0 = automatic (4 slices, 8 when the heat maps are host memory read over
+ * PCIe; env GEM_CHUNKS); 1 = everything on the caller's stream.
  * Results do not depend on the setting.  Profiling (gem_ctx_set_profiling) forces 1.
  * Closure rounds 1.. of a stage replay a CUDA graph of round 0's launches (captured once per slice and
  * configuration, cached in the ctx; env GEM_GRAPHS=0 disables). */
@@ -125,13 +126,15 @@ int gem_ctx_set_slices(gem_ctx* ctx, int n, const int32_t* first_window_h);
 int gem_ctx_set_ready_events(gem_ctx* ctx, int n, const int32_t* first_window_h, void* const* events_h);
 
 /* heat_d may be pinned (or registered) HOST memory: the energy kernel then reads the maps over PCIe through a
- * per-joint 4x4 texel cache in HBM (64 bytes per joint, rebuilt when the joint leaves it), so only the few per
- * cent of the maps the optimiser ever samples cross the bus and no up-front copy is needed.  Values are copies:
+ * per-joint 8x8 texel window in HBM (256 bytes per joint and a valid bit per texel: a texel is fetched the first time
+ * the bilinear footprint needs it; the window is re-centred, empty, when the footprint leaves it), so only the few
+ * per cent of the maps the optimiser ever samples cross the bus and no up-front copy is needed.  Values are copies:
  * results are bit-identical.  mode -1 (default): cache on exactly when heat_d is host memory; 0 off; 1 on. */
 int gem_ctx_set_texel_cache(gem_ctx* ctx, int mode);
-/* synchronises; returns the cache's lookups and rebuilds (16 texels each) counted since the previous call while
- * counting was enabled, then clears them and sets counting on/off */
-int gem_ctx_texel_cache_stats(gem_ctx* ctx, int enable, uint64_t* lookups_h, uint64_t* rebuilds_h);
+/* synchronises; returns the cache's lookups (one per joint per evaluation) and the texels it fetched from the map
+ * (one 32-byte sector each) counted since the previous call while counting was enabled, then clears them and sets
+ * counting on/off */
+int gem_ctx_texel_cache_stats(gem_ctx* ctx, int enable, uint64_t* lookups_h, uint64_t* texels_fetched_h);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* kernel classes reported by gem_ctx_read_profile */

@@ -144,8 +144,8 @@ def test_slices_streams_graphs_and_pipelined_upload_do_not_change_results(vae_we
     host_heat = torch.cat([c["heatmap_list"] for c in pinned]).pin_memory()
     eng.texel_cache_stats(True)
     zero_copy = run(WindowBatch(eng, pinned, host_heat=host_heat))
-    lookups, rebuilds = eng.texel_cache_stats(False)
-    assert lookups > 0 and 0 < rebuilds < lookups / 2, (lookups, rebuilds)
+    lookups, fetched = eng.texel_cache_stats(False)
+    assert lookups > 0 and 0 < fetched < 2 * lookups, (lookups, fetched)      # without the cache: 4 per lookup
     eng.set_texel_cache(1)                       # the cache on device-resident maps
     cached = run(WindowBatch(eng, clips))
     eng.set_texel_cache(-1)
