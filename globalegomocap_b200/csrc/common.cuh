@@ -88,10 +88,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.  try_wait itself may
+// suspend the thread for a while, so the bound is wall-clock time (4 s), checked every 256 polls.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    unsigned long long t0 = 0;
     for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-        if (spin > (1u << 26)) __trap();
+        if ((spin & 255u) == 255u) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ull) __trap();
+        }
     }
 }
 // global -> shared bulk copy (cp.async.bulk, SASS UBLKCP); 16-byte aligned, size % 16 == 0

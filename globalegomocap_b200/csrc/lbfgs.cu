@@ -12,6 +12,8 @@
 // decision logic runs on thread 0.  torch mixes Python floats (double) with fp32 0-d tensors; `Num`
 // reproduces that typing so that step lengths round the way the reference's do.  Compiled with
 // --fmad=false.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace gem {
@@ -144,15 +146,19 @@ __device__ __forceinline__ float dot8(const float (&a)[kPer], const float (&b)[k
 struct RedBuf {
     float v[2][3][kWarps];
 };
+// barrier over the kLbThreads threads of one window group (group 0 of a one-group CTA: the same as __syncthreads)
+__device__ __forceinline__ void group_sync(int gid) {
+    asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "n"(kLbThreads) : "memory");
+}
 template <int NV, int MAXMASK>
-__device__ __forceinline__ void block_reduce(float (&x)[NV], RedBuf& red, int& par) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void block_reduce(float (&x)[NV], RedBuf& red, int& par, int tid, int gid) {
+    const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         x[j] = ((MAXMASK >> j) & 1) ? warp_max(x[j]) : warp_sum(x[j]);
         if (lane == 0) red.v[par][j][warp] = x[j];
     }
-    __syncthreads();
+    group_sync(gid);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         float r = red.v[par][j][0];
@@ -232,18 +238,32 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_begin_kernel(LbfgsBuffers b,
 //   * prev_flat_grad is G itself: y = g_new - G is formed before G is overwritten;
 //   * g_prev aliases G until the bracket phase interpolates (LbfgsWin::gp_is_g);
 //   * the bracket gradients are only stored while the line search is still running.
-__global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffers b, const float* __restrict__ loss_in,
-                                                                     const float* __restrict__ grad_in, int W) {
-    extern __shared__ __align__(16) float ring[];     // [kRing][n]
-    __shared__ RedBuf red;
-    __shared__ LbfgsWin s;                             // thread 0 mutates; others only read the snapshot below
-    __shared__ int sh_action, sh_code, sh_copy_gp, sh_gsrc, sh_gp_is_g, sh_stop, sh_done2;
-    __shared__ float sh_tf, sh_tf2;
-    __shared__ float al_s[kMaxHist], ro_s[kMaxHist];
-    __shared__ __align__(8) uint64_t full_bar[kRing];
+// everything the kLbThreads threads that advance one window share
+struct GroupSmem {
+    RedBuf red;
+    LbfgsWin s;                                        // thread 0 mutates; others only read the snapshot below
+    int sh_action, sh_code, sh_copy_gp, sh_gsrc, sh_gp_is_g, sh_stop, sh_done2;
+    float sh_tf, sh_tf2;
+    float al_s[kMaxHist], ro_s[kMaxHist];
+    __align__(8) uint64_t full_bar[kRing];
+};
 
-    const int tid = threadIdx.x, n = b.n, n4 = b.n >> 2;
-    const int w = blockIdx.x;
+// advances window w by one closure evaluation; called by one group of kLbThreads threads (tid = 0 .. kLbThreads-1,
+// barrier id gid + 1), `ring` = the group's [kRing][n] floats of shared memory
+template <bool kReuse>
+__device__ __forceinline__ void lbfgs_advance_window(const LbfgsBuffers& b, const float* __restrict__ loss_in,
+                                                     const float* __restrict__ grad_in, int w, int tid, int gid,
+                                                     GroupSmem& sm, float* ring, bool first_window, uint32_t& rows_done) {
+    RedBuf& red = sm.red;
+    LbfgsWin& s = sm.s;
+    int &sh_action = sm.sh_action, &sh_code = sm.sh_code, &sh_copy_gp = sm.sh_copy_gp, &sh_gsrc = sm.sh_gsrc;
+    int &sh_gp_is_g = sm.sh_gp_is_g, &sh_stop = sm.sh_stop, &sh_done2 = sm.sh_done2;
+    float &sh_tf = sm.sh_tf, &sh_tf2 = sm.sh_tf2;
+    float* al_s = sm.al_s;
+    float* ro_s = sm.ro_s;
+    uint64_t* full_bar = sm.full_bar;
+
+    const int n = b.n, n4 = b.n >> 2;
     const size_t off = (size_t)w * n;
     float *X = b.X + off, *D = b.D + off, *G = b.G + off, *GP = b.GP + off, *BG0 = b.BG0 + off, *BG1 = b.BG1 + off,
           *ZT = b.ZT + off;
@@ -252,11 +272,14 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
 
     if (tid == 0) {
         s = b.st[w];
+        // a persistent group keeps its barriers across windows (rows_done counts the rows they have carried)
+        if (!kReuse || first_window) {
 #pragma unroll
-        for (int i = 0; i < kRing; ++i) mbar_init(&full_bar[i], 1);
-        fence_barrier_init();
+            for (int i = 0; i < kRing; ++i) mbar_init(&full_bar[i], 1);
+            fence_barrier_init();
+        }
     }
-    __syncthreads();
+    group_sync(gid);
     const int phase0 = s.phase, hist0 = s.hist_len, n_iter0 = s.n_iter;
     const float h_diag0 = s.h_diag;
     if (phase0 == PH_DONE) return;
@@ -279,7 +302,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
         float r1[1] = {0.f};
 #pragma unroll
         for (int i = 0; i < kPer; ++i) r1[0] = fmaxf(r1[0], fabsf(gn[i]));
-        block_reduce<1, 1>(r1, red, par);
+        block_reduce<1, 1>(r1, red, par, tid, gid);
         if (tid == 0) {
             s.loss = f_new;
             s.evals = 1;
@@ -291,7 +314,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
                 b.st[w] = s;
             }
         }
-        __syncthreads();
+        group_sync(gid);
         if (sh_stop) return;
         first_iter = true;
     } else {
@@ -299,7 +322,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
         float d[kPer];
         ld8(d, D, tid, n4);
         float r1[1] = {dot8(gn, d)};
-        block_reduce<1, 0>(r1, red, par);
+        block_reduce<1, 0>(r1, red, par, tid, gid);
         const float gtd_new = r1[0];
         if (tid == 0) {
             const double c1 = 1e-4, c2 = 0.9;
@@ -430,7 +453,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
             if (copy_gp) s.gp_is_g = 0;
             if (act == ACT_EVAL) b.st[w] = s;     // (a finishing call stores the state after its stop test)
         }
-        __syncthreads();
+        group_sync(gid);
         const int code = sh_code;
         const float tf = sh_tf;
         if (sh_action == ACT_EVAL) {
@@ -486,7 +509,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
         }
         st8(G, g, tid, n4);
         st8(X, x, tid, n4);
-        block_reduce<2, 3>(r2, red, par);
+        block_reduce<2, 3>(r2, red, par, tid, gid);
         if (tid == 0) {
             s.t = s.br[s.low_pos];
             s.loss = s.br_f[s.low_pos];
@@ -503,7 +526,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
                 b.st[w] = s;
             }
         }
-        __syncthreads();
+        group_sync(gid);
         if (sh_stop) {
             st_trial(b, off, x, tid, n4);
             return;
@@ -536,7 +559,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
         auto issue_upto = [&](int limit) {
             limit = limit < total ? limit : total;
             while (issued < limit) {
-                const int slot = issued % kRing;
+                const int slot = (int)((rows_done + (uint32_t)issued) % kRing);
                 mbar_arrive_expect_tx(&full_bar[slot], row_bytes);
                 bulk_g2s(ring + (size_t)slot * n, row_src(issued), row_bytes, &full_bar[slot]);
                 ++issued;
@@ -545,7 +568,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
         if (tid == 0) issue_upto(kRing);
         if (tid < k) ro_s[tid] = ROw[tid];
         float r2[2] = {dot8(yv, sv), dot8(yv, yv)};
-        block_reduce<2, 0>(r2, red, par);
+        block_reduce<2, 0>(r2, red, par, tid, gid);
         const float ys = r2[0], yy = r2[1];
         // ys > 1e-10: keep the pair.  max_iter - 1 <= m (checked by the host), so the history never overflows.
         const bool pushed = (double)ys > (double)1e-10f;
@@ -565,14 +588,15 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
         int r = 0;                                    // rows consumed from the ring
         float row[kPer];
         auto next_row = [&]() {
-            const int slot = r % kRing;
-            mbar_wait(&full_bar[slot], (uint32_t)((r / kRing) & 1));
+            const uint32_t g = rows_done + (uint32_t)r;           // rows this group's ring has carried so far
+            const int slot = (int)(g % kRing);
+            mbar_wait(&full_bar[slot], (g / kRing) & 1u);
             ld8(row, ring + (size_t)slot * n, tid, n4);
             ++r;
         };
         if (pushed) {
             float r1[1] = {dot8(sv, q)};
-            block_reduce<1, 0>(r1, red, par);
+            block_reduce<1, 0>(r1, red, par, tid, gid);
             const float a = r1[0] * ro_new;
             if (tid == 0) al_s[k - 1] = a;
             const float na = -a;
@@ -582,7 +606,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
         for (int h = kr - 1; h >= 0; --h) {
             next_row();                               // s_h
             float r1[1] = {dot8(row, q)};
-            block_reduce<1, 0>(r1, red, par);
+            block_reduce<1, 0>(r1, red, par, tid, gid);
             if (tid == 0) issue_upto(r + kRing);      // every row < r has been consumed by the whole CTA
             const float a = r1[0] * ro_s[h];
             if (tid == 0) al_s[h] = a;
@@ -596,7 +620,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
         for (int h = 0; h < kr; ++h) {
             next_row();                               // y_h
             float r1[1] = {dot8(row, q)};
-            block_reduce<1, 0>(r1, red, par);
+            block_reduce<1, 0>(r1, red, par, tid, gid);
             if (tid == 0) issue_upto(r + kRing);
             const float c = al_s[h] - r1[0] * ro_s[h];
             next_row();                               // s_h
@@ -605,11 +629,12 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
         }
         if (pushed) {
             float r1[1] = {dot8(yv, q)};
-            block_reduce<1, 0>(r1, red, par);
+            block_reduce<1, 0>(r1, red, par, tid, gid);
             const float c = al_s[k - 1] - r1[0] * ro_new;
 #pragma unroll
             for (int i = 0; i < kPer; ++i) q[i] = q[i] + sv[i] * c;
         }
+        rows_done += (uint32_t)total;                 // every issued row was consumed
     }
     // d = q; prev_flat_grad = flat_grad (G itself); gtd = g.d; t
     st8(D, q, tid, n4);
@@ -629,7 +654,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
             r3[2] = fmaxf(r3[2], fabsf(q[i]));
         }
     }
-    block_reduce<3, 4>(r3, red, par);
+    block_reduce<3, 4>(r3, red, par, tid, gid);
     if (tid == 0) {
         const float gtd = r3[0], l1 = r3[1], dmax = r3[2];
         s.n_iter = n_iter0 + 1;
@@ -665,7 +690,7 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
         sh_tf2 = (float)t.v;
         b.st[w] = s;
     }
-    __syncthreads();
+    group_sync(gid);
     {
         float x[kPer];
         ld8(x, X, tid, n4);
@@ -675,6 +700,36 @@ __global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffe
             for (int i = 0; i < kPer; ++i) x[i] = x[i] + tf * q[i];
         }
         st_trial(b, off, x, tid, n4);
+    }
+}
+
+// One CTA per window (the original launch shape): four CTAs per SM, spread over every SM of the GPU.
+__global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffers b, const float* __restrict__ loss_in,
+                                                                     const float* __restrict__ grad_in, int W) {
+    extern __shared__ __align__(16) float ring[];     // [kRing][n]
+    __shared__ GroupSmem sm;
+    uint32_t rows_done = 0;
+    lbfgs_advance_window<false>(b, loss_in, grad_in, blockIdx.x, threadIdx.x, 0, sm, ring, true, rows_done);
+}
+
+// Persistent variant (opt-in, GEM_LBFGS_SMS): a CTA of kGroups independent groups fills one SM (1024 threads x 64
+// registers) and walks over windows, so a launch of G CTAs occupies exactly G SMs.  Small CTAs spread over every SM,
+// and an SM that holds even one of them has no room for a 200 KB tensor-core CTA of another slice: measured, the
+// L-BFGS update does not overlap the tensor-bound layers at all (a step without it is 7.1 ms shorter, its own time is
+// 8.2 ms).  Packing it onto fewer SMs does not pay either, see launch_lbfgs_advance.
+constexpr int kGroups = 4;
+__global__ void __launch_bounds__(kGroups * kLbThreads, 1)
+lbfgs_advance_persistent_kernel(LbfgsBuffers b, const float* __restrict__ loss_in, const float* __restrict__ grad_in, int W) {
+    extern __shared__ __align__(16) float ring[];     // [kGroups][kRing][n]
+    __shared__ GroupSmem sm[kGroups];
+    const int gid = threadIdx.x / kLbThreads, tid = threadIdx.x - gid * kLbThreads;
+    float* my_ring = ring + (size_t)gid * kRing * b.n;
+    bool first = true;
+    uint32_t rows_done = 0;
+    for (int w = blockIdx.x * kGroups + gid; w < W; w += gridDim.x * kGroups) {
+        lbfgs_advance_window<true>(b, loss_in, grad_in, w, tid, gid, sm[gid], my_ring, first, rows_done);
+        group_sync(gid);          // the group's shared state is reused by the next window
+        first = false;
     }
 }
 
@@ -702,8 +757,31 @@ int launch_lbfgs_begin(cudaStream_t stream, const LbfgsBuffers& b, const float* 
 }
 int launch_lbfgs_advance(cudaStream_t stream, const LbfgsBuffers& b, const float* loss, const float* grad, int W) {
     if (W <= 0) return GEM_OK;
+    static const bool dbg_skip = getenv("GEM_DBG_SKIP_LBFGS") != nullptr;      // timing experiments only: breaks the solve
+    if (dbg_skip) return GEM_OK;
+    // one small CTA per window spread over the whole GPU (default), or persistent CTAs on GEM_LBFGS_SMS SMs.  The
+    // persistent shape was meant to leave SMs to other slices' tensor-core CTAs; measured, it loses: a group moves one
+    // 8 KB row per ~1 us (its four-row ring against a loaded HBM latency of ~4 us), so the kernel needs the
+    // shared memory of ALL SMs in flight to reach 4.9 TB/s, and on 64 SMs it takes 2.3x as long (step 22.1 -> 23.2 ms).
+    static const int sms = []() {
+        const char* env = getenv("GEM_LBFGS_SMS");
+        const int v = env ? atoi(env) : 0;
+        return v < 0 ? 0 : (v > kNumSMs ? kNumSMs : v);
+    }();
     const size_t smem = (size_t)kRing * b.n * sizeof(float);
-    lbfgs_advance_kernel<<<W, kLbThreads, smem, stream>>>(b, loss, grad, W);
+    if (sms > 0) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            GEM_CUDA(cudaFuncSetAttribute(lbfgs_advance_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(kGroups * kRing * 2048 * sizeof(float))));
+            attr_set = true;
+        }
+        int grid = (W + kGroups - 1) / kGroups;
+        if (grid > sms) grid = sms;
+        lbfgs_advance_persistent_kernel<<<grid, kGroups * kLbThreads, kGroups * smem, stream>>>(b, loss, grad, W);
+    } else {
+        lbfgs_advance_kernel<<<W, kLbThreads, smem, stream>>>(b, loss, grad, W);
+    }
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }
