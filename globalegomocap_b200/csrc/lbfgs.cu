@@ -76,7 +76,10 @@ constexpr int kLbThreads = 256;
 constexpr int kWarps = kLbThreads / 32;
 constexpr int kChunks = 2;          // float4 chunks per thread: n <= 2048 keeps a vector in 8 registers
 constexpr int kPer = 4 * kChunks;
-constexpr int kRing = 4;            // rows (n floats each) of the (y, s) history in flight per CTA
+#ifndef GEM_LBFGS_RING
+#define GEM_LBFGS_RING 4
+#endif
+constexpr int kRing = GEM_LBFGS_RING;   // rows (n floats each) of the (y, s) history in flight per CTA
 constexpr int kMaxHist = 64;
 
 // ---- per-thread slices: chunk c = tid + i*kLbThreads covers elements [4c, 4c+4) ---------------
@@ -780,6 +783,12 @@ int launch_lbfgs_advance(cudaStream_t stream, const LbfgsBuffers& b, const float
         if (grid > sms) grid = sms;
         lbfgs_advance_persistent_kernel<<<grid, kGroups * kLbThreads, kGroups * smem, stream>>>(b, loss, grad, W);
     } else {
+        static bool attr1_set = false;
+        if (!attr1_set) {
+            GEM_CUDA(cudaFuncSetAttribute(lbfgs_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(kRing * 2048 * sizeof(float))));
+            attr1_set = true;
+        }
         lbfgs_advance_kernel<<<W, kLbThreads, smem, stream>>>(b, loss, grad, W);
     }
     GEM_CHECK_LAUNCH();
