@@ -25,6 +25,7 @@ SOURCES = {
     "energy.cu": ["--fmad=false"],
     "lbfgs.cu": ["--fmad=false"],
     "pose_ops.cu": ["--fmad=false"],
+    "lift.cu": ["--fmad=false"],
     "gemm_simt.cu": [],
     "gemm_tc.cu": [],
     "gemm_tap_tc.cu": [],

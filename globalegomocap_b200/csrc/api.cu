@@ -1223,4 +1223,12 @@ int gem_gaussian_smooth(gem_ctx* c, void* stream, int N, int row, double sigma, 
                  [&]() { return launch_gauss((cudaStream_t)stream, N, row, sigma, seq_d, out_d); });
 }
 
+int gem_lift_skeleton(void* stream, int n_frames, int H, int W, int J, const float* heat_d, const double* depth_d,
+                      const double* poly_c2w_h, int n_poly, double cx, double cy, int up, int pad_x, double* points_d,
+                      float* preds_d, float* maxvals_d, int32_t* argmax_d) {
+    GEM_REQUIRE(n_frames >= 0 && H > 0 && W > 0 && up >= 1 && pad_x >= 0, "bad arguments");
+    return launch_lift((cudaStream_t)stream, n_frames, H, W, J, heat_d, depth_d, poly_c2w_h, n_poly, cx, cy, up, pad_x,
+                       points_d, preds_d, maxvals_d, argmax_d);
+}
+
 }  // extern "C"

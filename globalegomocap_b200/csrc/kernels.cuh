@@ -113,6 +113,11 @@ int launch_lbfgs_advance(cudaStream_t stream, const LbfgsBuffers& b, const float
 int launch_lbfgs_stats(cudaStream_t stream, const LbfgsBuffers& b, int W, int32_t* n_iter, int32_t* evals,
                        int32_t* finished, double* t, double* loss);
 
+// initial 3-D lift (lift.cu): heat-map argmax + depth -> local skeleton
+int launch_lift(cudaStream_t stream, int N, int H, int Wd, int J, const float* heat, const double* depth,
+                const double* poly_c2w, int n_poly, double cx, double cy, int up, int pad_x, double* points, float* preds,
+                float* maxvals, int32_t* argmax);
+
 int launch_reparam(cudaStream_t stream, const float* fc, const float* eps, size_t eps_stride, float* z0, float* mu,
                    float* sd, int W, int n);
 int launch_transform(cudaStream_t stream, int W, int T, int J, const void* pose, int pose_is_f64, const double* cams,

@@ -238,6 +238,20 @@ int gem_merge_windows(gem_ctx* ctx, void* stream, int W, int overlap, const doub
 int gem_gaussian_smooth(gem_ctx* ctx, void* stream, int N, int row, double sigma, const double* seq_d,
                         double* out_d);
 
+
+/* ---- initial 3-D lift (the step that produces the optimiser's `estimated_local_skeleton`) --------
+ * Skeleton.set_skeleton for n_frames frames (utils/skeleton.py:33-46): get_max_preds (:176-204) on the maps as
+ * set_skeleton_from_file prepares them (:80-82: nearest resize by `up` = 16, `pad_x` = 128 zero columns left and
+ * right) followed by FishEyeCameraCalibrated.camera2world (FishEyeCalibrated.py:18-33, float64).  heat_d float32
+ * [n_frames][H][W][J] in the pickle's HWC layout (H*W a multiple of 512, J <= 16, 16-byte aligned), depth_d float64
+ * [n_frames][J], poly_c2w_h = the calibration's polynomialC2W (constant term first, host memory), (cx, cy) =
+ * intrinsic[0][2], intrinsic[1][2].  points_d float64 [n_frames][J][3]; optional outputs (NULL to skip): preds_d
+ * float32 [n_frames][J][2] image coordinates, maxvals_d float32 [n_frames][J], argmax_d int32 [n_frames][J] = y0*W+x0
+ * of the source map's first row-major maximum.  No ctx: the call only needs the current device. */
+int gem_lift_skeleton(void* stream, int n_frames, int H, int W, int J, const float* heat_d, const double* depth_d,
+                      const double* poly_c2w_h, int n_poly, double cx, double cy, int up, int pad_x, double* points_d,
+                      float* preds_d, float* maxvals_d, int32_t* argmax_d);
+
 #ifdef __cplusplus
 }
 #endif
