@@ -73,6 +73,7 @@ _SIGNATURES = {
     "gem_to_global": (C.c_int, [_P, _P, _I, _P, _I, _P, _P]),
     "gem_merge_windows": (C.c_int, [_P, _P, _I, _I, _P, _P]),
     "gem_gaussian_smooth": (C.c_int, [_P, _P, _I, _I, C.c_double, _P, _P]),
+    "gem_pose_align_errors": (C.c_int, [_P, _I, _I, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_double), _P, _P, _P]),
     "gem_lift_skeleton": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, C.POINTER(C.c_double), _I, C.c_double, C.c_double, _I, _I,
                                     _P, _P, _P, _P]),
 }

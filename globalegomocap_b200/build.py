@@ -26,6 +26,7 @@ SOURCES = {
     "lbfgs.cu": ["--fmad=false"],
     "pose_ops.cu": ["--fmad=false"],
     "lift.cu": ["--fmad=false"],
+    "metrics.cu": [],
     "gemm_simt.cu": [],
     "gemm_tc.cu": [],
     "gemm_tap_tc.cu": [],

@@ -1231,4 +1231,12 @@ int gem_lift_skeleton(void* stream, int n_frames, int H, int W, int J, const flo
                        points_d, preds_d, maxvals_d, argmax_d);
 }
 
+int gem_pose_align_errors(void* stream, int n_frames, int J, const double* est_d, const double* gt_d,
+                          const int32_t* parents_h, const double* bone_len_mm_h, double* aligned_d, double* gt_out_d,
+                          double* err_d) {
+    GEM_REQUIRE(n_frames >= 0, "bad arguments");
+    return launch_pose_align((cudaStream_t)stream, n_frames, J, est_d, gt_d, parents_h, bone_len_mm_h, aligned_d, gt_out_d,
+                             err_d);
+}
+
 }  // extern "C"

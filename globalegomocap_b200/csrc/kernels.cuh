@@ -118,6 +118,10 @@ int launch_lift(cudaStream_t stream, int N, int H, int Wd, int J, const float* h
                 const double* poly_c2w, int n_poly, double cx, double cy, int up, int pad_x, double* points, float* preds,
                 float* maxvals, int32_t* argmax);
 
+// per-pose similarity alignment of the error metrics (metrics.cu)
+int launch_pose_align(cudaStream_t stream, int N, int J, const double* est, const double* gt, const int32_t* parents_h,
+                      const double* bone_len_mm_h, double* aligned, double* gt_out, double* err);
+
 int launch_reparam(cudaStream_t stream, const float* fc, const float* eps, size_t eps_stride, float* z0, float* mu,
                    float* sd, int W, int n);
 int launch_transform(cudaStream_t stream, int W, int T, int J, const void* pose, int pose_is_f64, const double* cams,

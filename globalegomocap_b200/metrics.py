@@ -1,7 +1,11 @@
 """Error metrics returned by ``main`` (reference calculate_errors.py:114-179):
 MPJPE variants with no / per-sequence / per-pose similarity alignment and with
-bone-length normalisation.  Host-side numpy (called once per clip; SURVEY.md §8f
-row N2 — not part of the optimisation hot path).
+bone-length normalisation (SURVEY.md §8f row N2 — not part of the optimisation hot path).
+
+The per-pose alignments — one 3x3 SVD per frame and variant, six Python loops over the frames in the
+reference — run on the GPU (`gem_pose_align_errors`, csrc/metrics.cu) when ``on_device=True`` (what ``main``
+uses); the handful of whole-sequence reductions stay in numpy.  ``on_device=False`` is the same arithmetic in
+numpy for callers that only hold host arrays.
 """
 from __future__ import annotations
 
@@ -68,7 +72,7 @@ def resize_to_mean_bones(joints):
     return out
 
 
-def _align_per_pose(est, gt, resize):
+def _align_per_pose_host(est, gt, resize):
     est, gt = np.array(est, dtype=np.float64), np.array(gt, dtype=np.float64)
     if resize:
         est = np.stack([resize_to_mean_bones(p) for p in est])
@@ -80,9 +84,38 @@ def _align_per_pose(est, gt, resize):
     return out, gt
 
 
-def calculate_errors(final_estimated_seq, mid_estimated_seq, final_optimized_seq, final_gt_seq):
+def _align_per_pose_device(est, gt, resize):
+    """`_align_per_pose` on the GPU: one thread per frame (csrc/metrics.cu); raises GemError without the CUDA library."""
+    import ctypes as C
+
+    import torch
+
+    from ._lib import GemError, check, load
+    if not torch.cuda.is_available():
+        raise GemError("no CUDA device: use calculate_errors(..., on_device=False) for host arrays")
+    lib = load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    e = torch.as_tensor(np.ascontiguousarray(est, dtype=np.float64), device=dev)
+    g = torch.as_tensor(np.ascontiguousarray(gt, dtype=np.float64), device=dev)
+    n, j = e.shape[0], e.shape[1]
+    aligned, gt_out = torch.empty_like(e), torch.empty_like(g)
+    err = torch.empty((n, j), dtype=torch.float64, device=dev)
+    parents = (C.c_int32 * j)(*PARENTS[:j])
+    bone = None
+    if resize:
+        bl = np.linalg.norm(MEAN3D_MM - MEAN3D_MM[PARENTS], axis=1)
+        bone = (C.c_double * j)(*bl[:j])
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(lib.gem_pose_align_errors(stream, n, j, C.c_void_p(e.data_ptr()), C.c_void_p(g.data_ptr()), parents, bone,
+                                    C.c_void_p(aligned.data_ptr()), C.c_void_p(gt_out.data_ptr()),
+                                    C.c_void_p(err.data_ptr())))
+    return aligned.cpu().numpy(), gt_out.cpu().numpy()
+
+
+def calculate_errors(final_estimated_seq, mid_estimated_seq, final_optimized_seq, final_gt_seq, on_device=False):
     est, mid, opt, gt = (np.asarray(a, dtype=np.float64) for a in
                          (final_estimated_seq, mid_estimated_seq, final_optimized_seq, final_gt_seq))
+    _align_per_pose = _align_per_pose_device if on_device else _align_per_pose_host
     res = OrderedDict()
     res["original_global_mpjpe"] = _mpjpe(est, gt)
     res["mid_global_mpjpe"] = _mpjpe(mid, gt)

@@ -186,5 +186,5 @@ def main(data_id, camera_model_path, vae_weight, gmm_weight, smoothness_weight, 
         with open(os.path.join(out_dir, "result_pose.pkl"), "wb") as f:
             pickle.dump({"estimated_pose": final_estimated_seq, "optimized_pose": final_optimized_seq,
                          "mid_optimized_pose": mid_estimated_seq, "gt_pose": final_gt_seq}, f)
-    errors = calculate_errors(final_estimated_seq, mid_estimated_seq, final_optimized_seq, final_gt_seq)
+    errors = calculate_errors(final_estimated_seq, mid_estimated_seq, final_optimized_seq, final_gt_seq, on_device=True)
     return errors, final_estimated_seq, mid_local_pose_seq, final_optimized_seq, final_gt_seq

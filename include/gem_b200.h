@@ -252,6 +252,18 @@ int gem_lift_skeleton(void* stream, int n_frames, int H, int W, int J, const flo
                       const double* poly_c2w_h, int n_poly, double cx, double cy, int up, int pad_x, double* points_d,
                       float* preds_d, float* maxvals_d, int32_t* argmax_d);
 
+
+/* ---- error metrics ---------------------------------------------------------------------------
+ * The per-pose part of calculate_errors (calculate_errors.py:114-179): every estimated pose est_d[f] is aligned to
+ * its ground truth gt_d[f] by the similarity transform of umeyama (utils/rigid_transform_with_scale.py:18-43); with
+ * bone_len_mm_h != NULL both poses are first rescaled bone by bone along the kinematic chain parents_h
+ * (Skeleton._skeleton_resize, utils/skeleton.py:123-135; lengths in millimetres, host memory).  est_d, gt_d float64
+ * [n_frames][J][3] (3 <= J <= 32); err_d float64 [n_frames][J] = |aligned - gt|; optional aligned_d / gt_out_d
+ * float64 [n_frames][J][3] = the aligned estimate and the (rescaled) ground truth it is compared with.  No ctx. */
+int gem_pose_align_errors(void* stream, int n_frames, int J, const double* est_d, const double* gt_d,
+                          const int32_t* parents_h, const double* bone_len_mm_h, double* aligned_d, double* gt_out_d,
+                          double* err_d);
+
 #ifdef __cplusplus
 }
 #endif

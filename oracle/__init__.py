@@ -24,4 +24,8 @@ installed torch on toy problems and on the reference's own traces),
 ``torch.nn.functional.grid_sample`` (bilinear, zeros padding,
 align_corners=True), ``scipy.ndimage.gaussian_filter1d`` (scipy 1.18.1;
 restated in ``pipeline_np.gaussian_filter1d_reflect``).
+
+``lift_np.py`` restates the step before the optimiser (heat-map argmax + depth -> local
+skeleton, reference ``utils/skeleton.py`` / ``FishEyeCalibrated.camera2world``) and is pinned the same way
+(``tests/golden/make_golden_lift.py`` -> ``lift.npz``, ``tests/test_oracle_lift.py``).
 """
