@@ -156,6 +156,8 @@ class Engine:
     def set_vae(self, which: int, state_dict):
         prep = state_dict if isinstance(state_dict, PreparedVae) else PreparedVae(
             state_dict, self.device, seq_len=self.T, latent_dim=self.n, channels=self.J * 3)
+        if self._vae.get(which) is prep:          # the same prepared weights are already in the ctx
+            return prep
         vw = VaeWeights()
         for name in ("dec", "dec_bwd", "enc"):
             arr = getattr(vw, name)

@@ -146,13 +146,21 @@ def load_clip(data_id):
                                              "heatmap_list")}
 
 
-def main(data_id, camera_model_path, vae_weight, gmm_weight, smoothness_weight, bone_length_weight, weight_3d,
-         reproj_weight, visualization=False, final_smooth=False, merge=True, save=False, save_pose=False,
-         max_iter=25, eps=None, local_vae_path=LOCAL_VAE_PATH, global_vae_path=GLOBAL_VAE_PATH, engine=None):
-    clip = load_clip(data_id)
+def main_batch(data_ids, camera_model_path, vae_weight, gmm_weight, smoothness_weight, bone_length_weight, weight_3d,
+               reproj_weight, visualization=False, final_smooth=False, merge=True, save=False, save_pose=False,
+               max_iter=25, eps=None, local_vae_path=LOCAL_VAE_PATH, global_vae_path=GLOBAL_VAE_PATH, engine=None):
+    """`main` for several clips at once: every window of every clip is optimised in ONE batched
+    solve instead of one `main` call per 100-frame clip (optimize_whole_sequence.py:48-63 loops over the clips, and
+    each call reloads both checkpoints, optimizer.py:332-350).  Returns the list of `main`'s return tuples, clip by
+    clip.  The reparameterisation noise is drawn as one (sum W, 2, latent) block, which consumes the global torch
+    generator exactly like consecutive `main` calls do, so batched and per-clip runs see the same z0."""
+    clips = [load_clip(d) for d in data_ids]
     seq_len, overlap = 10, 2
-    n_windows = len(range(0, len(clip["estimated_local_skeleton"]) - seq_len + 1, seq_len - overlap))
-    eng = engine if engine is not None else shared_engine(n_windows, max(max_iter - 1, 1))
+    n_win = [len(range(0, len(c["estimated_local_skeleton"]) - seq_len + 1, seq_len - overlap)) for c in clips]
+    for d, n in zip(data_ids, n_win):
+        if n <= 0:
+            raise ValueError("clip {} is shorter than one window ({} frames)".format(d, seq_len))
+    eng = engine if engine is not None else shared_engine(sum(n_win), max(max_iter - 1, 1))
     eng.set_camera_json(camera_model_path)
     eng.set_vae(0, load_vae(local_vae_path, eng.device))
     eng.set_vae(1, load_vae(global_vae_path, eng.device))
@@ -163,28 +171,39 @@ def main(data_id, camera_model_path, vae_weight, gmm_weight, smoothness_weight, 
         # the reference draws torch.randn_like(std) of shape (1, 2048) in the order local(w0),
         # global(w0), local(w1), ... from the global generator; one CPU draw of (W, 2, 2048)
         # consumes the same stream
-        eps = torch.randn(n_windows, 2, eng.n)
-    batch, sol, merged = seq_opt.run([clip], eps=eps, final_smooth=final_smooth is True)
+        eps = torch.randn(sum(n_win), 2, eng.n)
+    batch, sol, merged = seq_opt.run(clips, eps=eps, final_smooth=final_smooth is True)
     _raise_on_status(sol["local"]["status"])
-    m = merged[0]
-    if m is None:
-        raise ValueError("clip shorter than one window ({} frames)".format(seq_len))
-    final_estimated_seq = list(m["final_estimated_seq"].cpu().numpy())
-    mid_estimated_seq = list(m["mid_estimated_seq"].cpu().numpy())
-    mid_local_pose_seq = list(m["mid_local_pose_seq"].cpu().numpy())
-    final_gt_seq = list(m["final_gt_seq"].cpu().numpy())
-    final_optimized_seq = m["final_optimized_seq"].cpu().numpy()
-    if final_smooth is not True:
-        final_optimized_seq = list(final_optimized_seq)
     if visualization is True or save:
         raise NotImplementedError("mesh visualisation / .ply export need open3d and are outside this path")
-    if save_pose:
-        dataset_dir, seq_name = os.path.split(data_id)
-        dataset_name = os.path.split(dataset_dir)[1]
-        out_dir = "out/{}/{}".format(dataset_name, seq_name)
-        os.makedirs(out_dir, exist_ok=True)
-        with open(os.path.join(out_dir, "result_pose.pkl"), "wb") as f:
-            pickle.dump({"estimated_pose": final_estimated_seq, "optimized_pose": final_optimized_seq,
-                         "mid_optimized_pose": mid_estimated_seq, "gt_pose": final_gt_seq}, f)
-    errors = calculate_errors(final_estimated_seq, mid_estimated_seq, final_optimized_seq, final_gt_seq, on_device=True)
-    return errors, final_estimated_seq, mid_local_pose_seq, final_optimized_seq, final_gt_seq
+    results = []
+    for data_id, m in zip(data_ids, merged):
+        final_estimated_seq = list(m["final_estimated_seq"].cpu().numpy())
+        mid_estimated_seq = list(m["mid_estimated_seq"].cpu().numpy())
+        mid_local_pose_seq = list(m["mid_local_pose_seq"].cpu().numpy())
+        final_gt_seq = list(m["final_gt_seq"].cpu().numpy())
+        final_optimized_seq = m["final_optimized_seq"].cpu().numpy()
+        if final_smooth is not True:
+            final_optimized_seq = list(final_optimized_seq)
+        if save_pose:
+            dataset_dir, seq_name = os.path.split(data_id)
+            dataset_name = os.path.split(dataset_dir)[1]
+            out_dir = "out/{}/{}".format(dataset_name, seq_name)
+            os.makedirs(out_dir, exist_ok=True)
+            with open(os.path.join(out_dir, "result_pose.pkl"), "wb") as f:
+                pickle.dump({"estimated_pose": final_estimated_seq, "optimized_pose": final_optimized_seq,
+                             "mid_optimized_pose": mid_estimated_seq, "gt_pose": final_gt_seq}, f)
+        errors = calculate_errors(final_estimated_seq, mid_estimated_seq, final_optimized_seq, final_gt_seq,
+                                  on_device=True)
+        results.append((errors, final_estimated_seq, mid_local_pose_seq, final_optimized_seq, final_gt_seq))
+    return results
+
+
+def main(data_id, camera_model_path, vae_weight, gmm_weight, smoothness_weight, bone_length_weight, weight_3d,
+         reproj_weight, visualization=False, final_smooth=False, merge=True, save=False, save_pose=False,
+         max_iter=25, eps=None, local_vae_path=LOCAL_VAE_PATH, global_vae_path=GLOBAL_VAE_PATH, engine=None):
+    """The reference's `optimizer.main` (optimizer.py:311-507) for one clip."""
+    return main_batch([data_id], camera_model_path, vae_weight, gmm_weight, smoothness_weight, bone_length_weight,
+                      weight_3d, reproj_weight, visualization=visualization, final_smooth=final_smooth, merge=merge,
+                      save=save, save_pose=save_pose, max_iter=max_iter, eps=eps, local_vae_path=local_vae_path,
+                      global_vae_path=global_vae_path, engine=engine)[0]

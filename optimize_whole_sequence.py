@@ -3,7 +3,8 @@
 optimize_whole_sequence.py:5-117): same flags and defaults, same iteration over the
 natural-sorted sub-directories of --data_path, same printed summary, running on the B200 path.
 
-Added flags (not in the reference): --max_iter, --seed, --local_vae, --global_vae.
+Added flags (not in the reference): --max_iter, --seed, --local_vae, --global_vae, --batch_clips (default True: all
+clips of the dataset are optimised in one batched solve; False = one `main` call per clip, as the reference loops).
 """
 import argparse
 import os
@@ -52,17 +53,23 @@ def run(args):
         torch.manual_seed(args.seed)
     collected = {k[1]: [] for k in SUMMARY if k}
     joints_error = []
+    kwargs = dict(camera_model_path=args.camera, vae_weight=args.vae, gmm_weight=args.gmm, smoothness_weight=args.smooth,
+                  visualization=False, save=args.save, bone_length_weight=args.bone_length, weight_3d=args.weight_3d,
+                  reproj_weight=args.reproj_weight, merge=args.merge, final_smooth=args.final_smooth,
+                  max_iter=args.max_iter, local_vae_path=args.local_vae, global_vae_path=args.global_vae)
+    data_paths = []
     for name in natsorted(os.listdir(args.data_path)):
         data_path = os.path.join(args.data_path, name)
         print("running data: {}".format(data_path))
         if not os.path.isdir(data_path):
             continue
-        res, _est, _mid, _opt, _gt = gem.main(
-            data_path, camera_model_path=args.camera, vae_weight=args.vae, gmm_weight=args.gmm,
-            smoothness_weight=args.smooth, visualization=False, save=args.save, bone_length_weight=args.bone_length,
-            weight_3d=args.weight_3d, reproj_weight=args.reproj_weight, merge=args.merge,
-            final_smooth=args.final_smooth, max_iter=args.max_iter, local_vae_path=args.local_vae,
-            global_vae_path=args.global_vae)
+        data_paths.append(data_path)
+    if args.batch_clips:
+        # every window of every clip in one batched solve (a 100-frame clip alone is 12 windows: far too few to fill a GPU)
+        results = gem.main_batch(data_paths, **kwargs)
+    else:
+        results = [gem.main(p, **kwargs) for p in data_paths]
+    for res, _est, _mid, _opt, _gt in results:
         for k in collected:
             collected[k].append(res[k])
         joints_error.append(res["joints_error"])
@@ -97,6 +104,7 @@ if __name__ == "__main__":
     parser.add_argument("--merge", required=False, default=True, type=boolean)
     parser.add_argument("--max_iter", required=False, default=25, type=int)
     parser.add_argument("--seed", required=False, default=None, type=int)
+    parser.add_argument("--batch_clips", required=False, default=True, type=boolean)
     parser.add_argument("--local_vae", required=False, default=LOCAL_VAE_PATH, type=str)
     parser.add_argument("--global_vae", required=False, default=GLOBAL_VAE_PATH, type=str)
     run(parser.parse_args())

@@ -159,3 +159,29 @@ def test_slices_streams_graphs_and_pipelined_upload_do_not_change_results(vae_we
         for a, b in zip(ref, other):
             assert torch.equal(a, b), name
     eng.close()
+
+
+def test_main_batch_equals_per_clip_main(workdir, monkeypatch):
+    """`main_batch` (every window of every clip of a dataset in ONE batched solve) returns, clip by
+    clip, exactly what consecutive `main` calls return: windows are independent, the mean bone lengths are per
+    clip, and one (sum W, 2, latent) noise draw consumes the torch generator like the per-clip draws do."""
+    from globalegomocap_b200 import optimizer as gem
+    monkeypatch.chdir(workdir)
+    names = []
+    for i, frames in enumerate((42, 26, 34)):
+        d = os.path.join("data", "batch", "clip%d" % i)
+        syn.write_clip_pickle(syn.make_clip(frames, seed=40 + i), str(workdir / d))
+        names.append(d)
+    kw = dict(camera_model_path=syn.DEFAULT_CAMERA_JSON, vae_weight=0.0, gmm_weight=0.0, smoothness_weight=0.001,
+              bone_length_weight=0.01, weight_3d=0.01, reproj_weight=0.01, visualization=False, save=False, merge=True,
+              final_smooth=True, max_iter=3)
+    torch.manual_seed(5)
+    single = [gem.main(d, **kw) for d in names]
+    torch.manual_seed(5)
+    batched = gem.main_batch(names, **kw)
+    assert len(batched) == 3
+    for (e1, est1, mid1, opt1, gt1), (e2, est2, mid2, opt2, gt2) in zip(single, batched):
+        assert np.array_equal(np.asarray(mid1), np.asarray(mid2)) and np.array_equal(opt1, opt2)
+        assert np.array_equal(np.asarray(est1), np.asarray(est2)) and np.array_equal(np.asarray(gt1), np.asarray(gt2))
+        for k in e1:
+            np.testing.assert_array_equal(e1[k], e2[k])
