@@ -499,6 +499,44 @@ def main():
                               "kernel is issue-bound, see DESIGN.md section 5"}
             energy["frac"] = energy["achieved"] / hbm_peak
             others.append(energy)
+        # the step before the optimiser: heat-map argmax + depth -> local skeleton, one streaming pass
+        # over the resident maps (a pure HBM kernel; 245,760 algorithmic bytes per frame)
+        try:
+            import ctypes as C
+            from globalegomocap_b200.lift import load_camera_c2w
+            poly_c2w, lcx, lcy = load_camera_c2w(syn.DEFAULT_CAMERA_JSON)
+            lheat = resident.heat
+            nf, lh, lw, lj = lheat.shape
+            ldepth = torch.rand((nf, lj), dtype=torch.float64, device=dev) + 0.5
+            lpts = torch.empty((nf, lj, 3), dtype=torch.float64, device=dev)
+            lstream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+            def lift_once():
+                rc = eng.lib.gem_lift_skeleton(lstream, nf, lh, lw, lj, C.c_void_p(lheat.data_ptr()),
+                                               C.c_void_p(ldepth.data_ptr()), poly_c2w.ctypes.data_as(C.POINTER(C.c_double)),
+                                               int(poly_c2w.size), lcx, lcy, 16, 128, C.c_void_p(lpts.data_ptr()), None, None, None)
+                if rc != 0:
+                    raise RuntimeError("gem_lift_skeleton failed")
+            for _ in range(3):
+                lift_once()
+            torch.cuda.synchronize()
+            la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            la.record()
+            for _ in range(5):
+                lift_once()
+            lb.record()
+            torch.cuda.synchronize()
+            lms = la.elapsed_time(lb) / 5
+            lbytes = nf * (lh * lw * lj * 4 + lj * 8 + lj * 24)
+            others.append({"bound": "hbm", "kernel": "lift_kernel (gem_lift_skeleton: heat-map argmax + back-projection, "
+                           "the step that produces the optimiser's input)", "achieved": lbytes / (lms / 1e3) / 1e9,
+                           "peak": hbm_peak, "unit": "GB/s", "frac": lbytes / (lms / 1e3) / 1e9 / hbm_peak, "ms_avg": lms,
+                           "launches": 5, "traffic": 3.688e9 * nf / 15000.0,
+                           "note": "algorithmic bytes = the maps once (245,760 B per frame) + depths and results; traffic = "
+                                   "ncu DRAM reads per launch scaled from the 15 000-frame capture "
+                                   "(profiles/r01_ncu_full_lift_summary.csv); frames/s = %.3g" % (nf / (lms / 1e3))})
+        except Exception as exc:                                  # never lose the bench line to the extra measurement
+            sys.stderr.write("lift measurement skipped: %r\n" % (exc,))
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
