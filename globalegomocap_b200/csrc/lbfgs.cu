@@ -76,6 +76,9 @@ constexpr int kLbThreads = 256;
 constexpr int kWarps = kLbThreads / 32;
 constexpr int kChunks = 2;          // float4 chunks per thread: n <= 2048 keeps a vector in 8 registers
 constexpr int kPer = 4 * kChunks;
+#ifndef GEM_LBFGS_OCC
+#define GEM_LBFGS_OCC 4     // resident CTAs per SM the register budget is compiled for
+#endif
 #ifndef GEM_LBFGS_RING
 #define GEM_LBFGS_RING 4
 #endif
@@ -707,7 +710,7 @@ __device__ __forceinline__ void lbfgs_advance_window(const LbfgsBuffers& b, cons
 }
 
 // One CTA per window (the original launch shape): four CTAs per SM, spread over every SM of the GPU.
-__global__ void __launch_bounds__(kLbThreads, 4) lbfgs_advance_kernel(LbfgsBuffers b, const float* __restrict__ loss_in,
+__global__ void __launch_bounds__(kLbThreads, GEM_LBFGS_OCC) lbfgs_advance_kernel(LbfgsBuffers b, const float* __restrict__ loss_in,
                                                                      const float* __restrict__ grad_in, int W) {
     extern __shared__ __align__(16) float ring[];     // [kRing][n]
     __shared__ GroupSmem sm;
