@@ -985,7 +985,8 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             cudaGraph_t graph = nullptr;
             GEM_CUDA(cudaStreamBeginCapture(q, cudaStreamCaptureModeRelaxed));
             const int64_t launches_before = c->launches;
-            const int rc_round = enqueue_round();
+            int rc_round = GEM_OK;
+            for (int round = 1; round <= a.p.max_eval && rc_round == GEM_OK; ++round) rc_round = enqueue_round();   // ONE graph of all replayed rounds: kernel-to-kernel edges instead of graph-to-graph launch gaps
             round_launches = (int)(c->launches - launches_before);
             c->launches = launches_before;               // captured, not executed
             cudaError_t e = cudaStreamEndCapture(q, &graph);
@@ -1010,13 +1011,11 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             exec = g.exec;
         }
     }
-    for (int round = 1; round <= a.p.max_eval; ++round) {
-        if (exec) {
-            GEM_CUDA(cudaGraphLaunch(exec, q));
-            c->launches += round_launches;
-        } else {
-            GEM_TRY(enqueue_round());
-        }
+    if (exec) {
+        GEM_CUDA(cudaGraphLaunch(exec, q));                   // rounds 1 .. max_eval
+        c->launches += round_launches;
+    } else {
+        for (int round = 1; round <= a.p.max_eval; ++round) GEM_TRY(enqueue_round());
     }
     // final decode of the optimum (every window is parked with its trial point = x)      optimizer.py:273-276
     GEM_TRY(decode_impl(c, q, which, Wk, v, lb.X, a.pose_out + w0 * P, tc ? lb.ZT_hi : nullptr, tc ? lb.ZT_lo : nullptr));

@@ -112,7 +112,7 @@ int gem_ctx_set_gemm_mode(gem_ctx* ctx, int mode);
  * overlap another's tensor-core layers.  Default 0 = automatic (4 slices, 8 when the heat maps are host memory read over
  * PCIe; env GEM_CHUNKS); 1 = everything on the caller's stream.
  * Results do not depend on the setting.  Profiling (gem_ctx_set_profiling) forces 1.
- * Closure rounds 1.. of a stage replay a CUDA graph of round 0's launches (captured once per slice and
+ * Closure rounds 1.. of a stage are one CUDA graph of round 0's launches (captured once per slice and
  * configuration, cached in the ctx; env GEM_GRAPHS=0 disables). */
 int gem_ctx_set_chunks(gem_ctx* ctx, int n_chunks);
 /* Explicit slice boundaries instead of n_chunks equal parts: first_window_h[0] = 0 < first_window_h[1] < ...
