@@ -36,3 +36,24 @@ def test_bench_lbfgs_row_accounting():
     # window 2: 25 iterations (250 + 4*(24*23/2)) + 6 evaluations
     per_stage = (10 + 5) + (30 + 4 + 5) + (250 + 4 * 276 + 30)
     assert bench.lbfgs_rows(sol) == 2 * per_stage
+
+
+def test_lift_host_pieces_match_reference_vectors(golden_dir):
+    """The host-side parts of the initial 3-D lift (calibration loader, bone-length normalisation) against the
+    vectors recorded from the unmodified reference; the kernel itself is checked in tests/test_gpu_lift.py."""
+    import os
+
+    import numpy as np
+
+    from globalegomocap_b200 import synthetic as syn
+    from globalegomocap_b200.lift import load_camera_c2w, skeleton_resize
+    g = np.load(os.path.join(golden_dir, "lift.npz"))
+    poly, cx, cy = load_camera_c2w(syn.DEFAULT_CAMERA_JSON)
+    assert np.array_equal(poly, g["poly_c2w"]) and (cx, cy) == tuple(g["center"])
+    for f in range(g["points"].shape[0]):
+        out = skeleton_resize(g["points"][f], g["bone_length"])
+        assert np.abs(out - g["resized"][f]).max() < 1e-12
+    # the input is not modified (the reference's version works in place on its own copy)
+    p0 = g["points"][0].copy()
+    skeleton_resize(p0, g["bone_length"])
+    assert np.array_equal(p0, g["points"][0])
