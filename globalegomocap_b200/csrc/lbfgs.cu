@@ -763,8 +763,6 @@ int launch_lbfgs_begin(cudaStream_t stream, const LbfgsBuffers& b, const float* 
 }
 int launch_lbfgs_advance(cudaStream_t stream, const LbfgsBuffers& b, const float* loss, const float* grad, int W) {
     if (W <= 0) return GEM_OK;
-    static const bool dbg_skip = getenv("GEM_DBG_SKIP_LBFGS") != nullptr;      // timing experiments only: breaks the solve
-    if (dbg_skip) return GEM_OK;
     // one small CTA per window spread over the whole GPU (default), or persistent CTAs on GEM_LBFGS_SMS SMs.  The
     // persistent shape was meant to leave SMs to other slices' tensor-core CTAs; measured, it loses: a group moves one
     // 8 KB row per ~1 us (its four-row ring against a loaded HBM latency of ~4 us), so the kernel needs the
