@@ -217,6 +217,30 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
         const int t = k / a.J, j = k - t * a.J;
         const float x = X[k * 3 + 0], y = X[k * 3 + 1], z = X[k * 3 + 2];
 
+        // E_reproj, first half: the projection and the four texel loads are issued before the other terms so that
+        // their DRAM latency overlaps that arithmetic (the terms are still added to the gradient in the old order)
+        bool rp = false;
+        Proj pj;
+        float nw = 0.f, ne = 0.f, sw = 0.f, se = 0.f;
+        if (a.wr != 0.f) {
+            if (!project_joint(x, y, z, a.H, a.Wd, pj)) {
+                if (a.status) atomicOr(a.status + w, GEM_WIN_NORM_ZERO);
+            } else if (pj.fx0 >= -1.f && pj.fx0 <= (float)a.Wd && pj.fy0 >= -1.f && pj.fy0 <= (float)a.H) {
+                // (anything further than one texel outside contributes exactly 0)
+                rp = true;
+                const int x0 = (int)pj.fx0, y0 = (int)pj.fy0;
+                const int64_t frame = a.frame_base[w] + t;
+                if (a.patch) {
+                    cache_lookup(a, (size_t)w * TJ + k, frame, j, x0, y0, true, nw, ne, sw, se);
+                } else {
+                    nw = texel(a.heat, frame, y0, x0, j, a.H, a.Wd, a.J);
+                    ne = texel(a.heat, frame, y0, x0 + 1, j, a.H, a.Wd, a.J);
+                    sw = texel(a.heat, frame, y0 + 1, x0, j, a.H, a.Wd, a.J);
+                    se = texel(a.heat, frame, y0 + 1, x0 + 1, j, a.H, a.Wd, a.J);
+                }
+            }
+        }
+
         // E_3d = sum (x - x0)^2                                     optimizer.py:210-213
         {
             const float dx = x - X0[k * 3 + 0], dy = y - X0[k * 3 + 1], dz = z - X0[k * 3 + 2];
@@ -273,28 +297,13 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
             }
         }
         // E_reproj = -sum bilinear(H_tj; pix(project(x)))            optimizer.py:139-149
-        if (a.wr != 0.f) {
-            Proj pj;
-            if (!project_joint(x, y, z, a.H, a.Wd, pj)) {
-                if (a.status) atomicOr(a.status + w, GEM_WIN_NORM_ZERO);
-            } else {
+        if (rp) {
+            {
                 const float r = pj.r, inv = pj.inv, rho = pj.rho, drho = pj.drho;
                 const float ix = pj.ix, iy = pj.iy, fx0 = pj.fx0, fy0 = pj.fy0;
-                // Anything further than one texel outside contributes exactly 0.
-                if (fx0 >= -1.f && fx0 <= (float)a.Wd && fy0 >= -1.f && fy0 <= (float)a.H) {
-                    const int x0 = (int)fx0, y0 = (int)fy0;
+                {
                     const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix;
                     const float wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
-                    const int64_t frame = a.frame_base[w] + t;
-                    float nw, ne, sw, se;
-                    if (a.patch) {
-                        cache_lookup(a, (size_t)w * TJ + k, frame, j, x0, y0, true, nw, ne, sw, se);
-                    } else {
-                        nw = texel(a.heat, frame, y0, x0, j, a.H, a.Wd, a.J);
-                        ne = texel(a.heat, frame, y0, x0 + 1, j, a.H, a.Wd, a.J);
-                        sw = texel(a.heat, frame, y0 + 1, x0, j, a.H, a.Wd, a.J);
-                        se = texel(a.heat, frame, y0 + 1, x0 + 1, j, a.H, a.Wd, a.J);
-                    }
                     erp = -(nw * (wx0 * wy0) + ne * (wx1 * wy0) + sw * (wx0 * wy1) + se * (wx1 * wy1));
                     const float ds_dix = -nw * wy0 + ne * wy0 - sw * wy1 + se * wy1;
                     const float ds_diy = -nw * wx0 - ne * wx1 + sw * wx0 + se * wx1;
