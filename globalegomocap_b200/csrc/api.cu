@@ -31,6 +31,8 @@ struct gem_ctx {
     int tap_chain = 2;                           // mode 3: 0 one launch per k=3 layer, 1 the four K<=128 layers of each direction
                                                  // in one launch, 2 all five on CTA pairs (cta_group::2) in one launch
     bool have_camera = false, have_skeleton = false;
+    CameraConst cam;                             // this ctx's calibration and kinematic tree: kernel parameters of the energy
+    SkeletonConst skel;                          // kernels (captured graphs bake them in, so setting either drops the graphs)
     bool have_vae[2] = {false, false};
     gem_vae_weights vae[2];
     int64_t scratch_bytes = 0;
@@ -126,6 +128,13 @@ static int timed(gem_ctx* c, cudaStream_t s, int tag, F&& f) {
     const int rc = f();
     GEM_CUDA(cudaEventRecord(e.b, s));
     return rc;
+}
+
+// Captured rounds bake in kernel parameters (weight pointers, TMA descriptors, camera, skeleton): whenever one of
+// those changes the cached graphs are dropped and re-captured by the next solve.
+static void drop_graphs(gem_ctx* c) {
+    for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
 }
 
 static const int kDecC[6] = {256, 128, 64, 64, 64, 0};   // channels after dec[0..4]; dec[5] -> J*3
@@ -264,7 +273,7 @@ int gem_ctx_destroy(gem_ctx* c) {
     if (!c) return GEM_OK;
     cudaSetDevice(c->device);
     for (void* p : c->allocs) cudaFree(p);
-    for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+    drop_graphs(c);
     for (cudaStream_t st : c->streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : c->join_ev) cudaEventDestroy(ev);
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
@@ -381,7 +390,11 @@ int gem_ctx_set_camera(gem_ctx* c, const double* poly_h, int n_poly, double cx, 
     for (int i = 0; i < n_poly; ++i) cam.poly[i] = (float)poly_h[i];   // python scalars are cast to the tensor dtype
     cam.n_poly = n_poly, cam.cx = (float)cx, cam.cy = (float)cy;
     GEM_CUDA(cudaSetDevice(c->device));
-    GEM_TRY(upload_camera(cam));
+    if (!c->have_camera || memcmp(&c->cam, &cam, sizeof(cam)) != 0) {
+        GEM_CUDA(cudaDeviceSynchronize());       // (replayed graphs of an earlier solve may still be running)
+        drop_graphs(c);
+        c->cam = cam;
+    }
     c->have_camera = true;
     return GEM_OK;
 }
@@ -403,7 +416,11 @@ int gem_ctx_set_skeleton(gem_ctx* c, const int32_t* parents_h, int num_joints) {
     }
     for (int j = num_joints; j <= kMaxJoints; ++j) sk.child_start[j] = nc;
     GEM_CUDA(cudaSetDevice(c->device));
-    GEM_TRY(upload_skeleton(sk));
+    if (!c->have_skeleton || memcmp(&c->skel, &sk, sizeof(sk)) != 0) {
+        GEM_CUDA(cudaDeviceSynchronize());
+        drop_graphs(c);
+        c->skel = sk;
+    }
     c->have_skeleton = true;
     return GEM_OK;
 }
@@ -424,10 +441,30 @@ int gem_ctx_set_vae(gem_ctx* c, int which, const gem_vae_weights* w) {
         GEM_REQUIRE(w->enc[i].w_d && w->enc[i].k == ek[i] && w->enc[i].n == en_[i] && w->enc[i].taps == et[i],
                     "encoder layer shape mismatch");
     }
+    GEM_CUDA(cudaSetDevice(c->device));
+    // New weights: every captured round still points at the old matrices and their prepared slabs — wait
+    // for work in flight, drop the graphs, and free the prepared copies of matrices no slot uses any more.
+    GEM_CUDA(cudaDeviceSynchronize());
+    drop_graphs(c);
+    if (c->have_vae[which]) {
+        const gem_vae_weights old = c->vae[which];
+        auto still_used = [&](const float* p) {
+            for (int i = 0; i < 6; ++i) {
+                if (w->dec[i].w_d == p || w->dec_bwd[i].w_d == p || w->enc[i].w_d == p) return true;
+                if (c->have_vae[1 - which]) {
+                    const gem_vae_weights& o = c->vae[1 - which];
+                    if (o.dec[i].w_d == p || o.dec_bwd[i].w_d == p || o.enc[i].w_d == p) return true;
+                }
+            }
+            return false;
+        };
+        for (int i = 0; i < 6; ++i)
+            for (const gem_layer* L : {&old.dec[i], &old.dec_bwd[i], &old.enc[i]})
+                if (!still_used(L->w_d)) tc_gemm_forget_weight(c, L->w_d), tc_tap_forget_weight(c, L->w_d);
+    }
     c->vae[which] = *w;
     c->have_vae[which] = true;
     // K-major TF32 hi/lo copies of the three plain-GEMM weight matrices for the tcgen05 path
-    GEM_CUDA(cudaSetDevice(c->device));
     const gem_layer* big[3] = {&w->dec[0], &w->dec_bwd[5], &w->enc[5]};
     for (const gem_layer* L : big)
         if (L->k % 32 == 0 && L->n % 128 == 0)
@@ -468,10 +505,11 @@ int gem_ctx_set_vae(gem_ctx* c, int which, const gem_vae_weights* w) {
 static int run_layer(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, const float* A, int lda, int M, float* C,
                      int ldc, int epi, const float* aux, const void* A_hi = nullptr, const void* A_lo = nullptr,
                      float* C_lo = nullptr, uint32_t* C_sign = nullptr, const int32_t* row_exp = nullptr, int out16 = 0,
-                     const uint32_t* aux_bits = nullptr) {
+                     const uint32_t* aux_bits = nullptr, uint32_t* row_flag = nullptr) {
     TapGemmArgs g;
     g.A = A, g.B = L.w_d, g.bias = L.bias_d, g.aux = aux, g.C = C, g.aux_bits = aux_bits;
     g.A_hi = A_hi, g.A_lo = A_lo, g.C_lo = C_lo, g.C_sign = C_sign, g.row_exp = row_exp, g.out16 = out16;
+    g.row_flag = row_flag;
     g.M = M, g.N = L.n, g.K = L.k, g.taps = L.taps, g.T = c->T;
     g.lda = lda, g.ldb = (L.n + 3) & ~3, g.ldc = ldc, g.ldaux = L.n, g.epi = epi;
     return timed(c, s, tag, [&]() {
@@ -556,14 +594,15 @@ static Slice slice_of(gem_ctx* c, int w0) {
 }
 
 // z: plain latent [W][n]; or, when z_hi/z_lo are given, the same already split into TF32 parts
+// status: optional per-window status words of the slice (GEM_WIN_F16_RANGE is raised when an fp16 operand saturates)
 static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice& v_, const float* z, float* pose_out,
-                       const void* z_hi = nullptr, const void* z_lo = nullptr) {
+                       const void* z_hi = nullptr, const void* z_lo = nullptr, uint32_t* status = nullptr) {
     const gem_vae_weights& v = c->vae[which];
     const int T = c->T, M = W * T, P = c->J * 3;
     if (use_tc_chain(c, which, W)) {
         // latent -> [T][256] on the tcgen05 GEMM, its epilogue writes the activation already split
         GEM_TRY(run_layer(c, s, GEM_TAG_DEC + 0, v.dec[0], z, c->n, W, v_.act_hi[0], T * 256, EPI_LRELU, nullptr, z_hi,
-                          z_lo, v_.act_lo[0], v_.act_sign[0], nullptr, c->gemm_mode == 3));
+                          z_lo, v_.act_lo[0], v_.act_sign[0], nullptr, c->gemm_mode == 3, nullptr, status));
         c->act_split = true;
         if (c->gemm_mode == 3 && c->tap_chain == 2) {
             // 256 -> 128 -> 64 -> 64 -> 64 -> pose in ONE launch on CTA pairs
@@ -574,7 +613,7 @@ static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice
                 t.sign_out[i - 1] = i <= 4 ? v_.act_sign[i] : nullptr, t.epi[i - 1] = i <= 4 ? EPI_LRELU : EPI_NONE;
             }
             t.A_hi = v_.act_hi[0], t.A_lo = v_.act_lo[0], t.lda = v.dec[1].k, t.Kreal = v.dec[1].k;
-            t.out_hi = pose_out, t.out_lo = nullptr, t.ldo = P, t.W = W, t.T = T;
+            t.out_hi = pose_out, t.out_lo = nullptr, t.ldo = P, t.W = W, t.T = T, t.status = status;
             return timed(c, s, GEM_TAG_DEC + 1, [&]() { return launch_tap_chain_pair(s, c, t); });
         }
         if (c->gemm_mode == 3 && c->tap_chain) {
@@ -589,7 +628,7 @@ static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice
                 t.sign_out[i - 2] = i <= 4 ? v_.act_sign[i] : nullptr, t.epi[i - 2] = i <= 4 ? EPI_LRELU : EPI_NONE;
             }
             t.A_hi = v_.act_hi[1], t.A_lo = v_.act_lo[1], t.lda = v.dec[2].k, t.Kreal = v.dec[2].k;
-            t.out_hi = pose_out, t.out_lo = nullptr, t.ldo = P, t.W = W, t.T = T;
+            t.out_hi = pose_out, t.out_lo = nullptr, t.ldo = P, t.W = W, t.T = T, t.status = status;
             return timed(c, s, GEM_TAG_DEC + 2, [&]() { return launch_tap_chain(s, c, t); });
         }
         for (int i = 1; i <= 4; ++i)
@@ -610,7 +649,7 @@ static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice
 
 // dpose_is_split: the slice's gp_hi / gp_lo already hold dpose (written by the energy kernel)
 static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice& v_, const float* dpose, float* dz,
-                           bool dpose_is_split = false) {
+                           bool dpose_is_split = false, uint32_t* status = nullptr) {
     const gem_vae_weights& v = c->vae[which];
     const int T = c->T, M = W * T, P = c->J * 3;
     // the LeakyReLU derivative only needs the sign of the saved activation, which its TF32 hi part keeps
@@ -640,7 +679,7 @@ static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const S
                 t.sign_out[i] = nullptr, t.epi[i] = EPI_MASK;
             }
             t.A_hi = in_hi, t.A_lo = in_lo, t.lda = pp, t.Kreal = pp;
-            t.out_hi = v_.gact_hi[0], t.out_lo = v_.gact_lo[0], t.ldo = v.dec_bwd[4].n, t.W = W, t.T = T;
+            t.out_hi = v_.gact_hi[0], t.out_lo = v_.gact_lo[0], t.ldo = v.dec_bwd[4].n, t.W = W, t.T = T, t.status = status;
             GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 0, [&]() { return launch_tap_chain_pair(s, c, t); }));
             i0 = 5;
         } else if (c->gemm_mode == 3 && c->tap_chain && c->act_split) {
@@ -652,7 +691,7 @@ static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const S
                 t.sign_out[i] = nullptr, t.epi[i] = EPI_MASK;
             }
             t.A_hi = in_hi, t.A_lo = in_lo, t.lda = pp, t.Kreal = pp;
-            t.out_hi = v_.gact_hi[1], t.out_lo = v_.gact_lo[1], t.ldo = v.dec_bwd[3].n, t.W = W, t.T = T;
+            t.out_hi = v_.gact_hi[1], t.out_lo = v_.gact_lo[1], t.ldo = v.dec_bwd[3].n, t.W = W, t.T = T, t.status = status;
             GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 0, [&]() { return launch_tap_chain(s, c, t); }));
             in_hi = v_.gact_hi[1], in_lo = v_.gact_lo[1], lda = v.dec_bwd[3].n;
             i0 = 4;
@@ -692,7 +731,7 @@ static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const S
 }
 
 static int encode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice& v_, const float* pose, const float* eps,
-                       float* z0, float* mu, float* sd, size_t eps_stride = 0) {
+                       float* z0, float* mu, float* sd, size_t eps_stride = 0, uint32_t* status = nullptr) {
     const gem_vae_weights& v = c->vae[which];
     const int T = c->T, M = W * T, P = c->J * 3;
     const float* in = pose;
@@ -721,7 +760,7 @@ static int encode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice
                           v_.e4_lo));
     } else if (c->gemm_mode >= 2 && fcL.k % 64 == 0 && fcL.n % 128 == 0) {
         GEM_TRY(timed(c, s, GEM_TAG_ENC + 5, [&]() {
-            return launch_split_f16(s, in, T * 512, W, T * 512, nullptr, (uint16_t*)v_.e4_hi, (uint16_t*)v_.e4_lo);
+            return launch_split_f16(s, in, T * 512, W, T * 512, nullptr, (uint16_t*)v_.e4_hi, (uint16_t*)v_.e4_lo, status);
         }));
         GEM_TRY(run_layer(c, s, GEM_TAG_ENC + 5, fcL, nullptr, T * 512, W, v_.fc, 2 * c->n, EPI_NONE, nullptr, v_.e4_hi,
                           v_.e4_lo));
@@ -781,7 +820,8 @@ int gem_energy_grad(gem_ctx* c, void* stream, int W, const float* pose_d, const 
         return GEM_ERR_STATE;
     }
     return timed(c, (cudaStream_t)stream, GEM_TAG_ENERGY, [&]() {
-        return launch_energy_grad((cudaStream_t)stream, W, c->T, c->J, c->H, c->Wd, pose_d, pose0_d, heat_d,
+        return launch_energy_grad((cudaStream_t)stream, c->have_camera ? &c->cam : nullptr, &c->skel, W, c->T, c->J, c->H,
+                                  c->Wd, pose_d, pose0_d, heat_d,
                                   frame_base_d, clip_d, mean_bone_d, *wt, energy_d, terms_d, grad_d, status_d);
     });
 }
@@ -906,8 +946,14 @@ struct StageCall {
     float* trace;               // [W][max_eval + 1] or NULL
     int32_t *n_iter, *func_evals;
     uint32_t* status;
+    bool status_or = false;     // OR this stage's status bits into `status` instead of overwriting it
     bool texel_cache;           // read the maps through the per-joint texel cache
 };
+
+__global__ void or_status_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] |= src[i];
+}
 
 // The texel cache pays when the maps are read over PCIe from (pinned / registered) host memory
 static bool want_texel_cache(const gem_ctx* c, const void* heat, float reproj) {
@@ -933,6 +979,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     lb.lr = a.p.lr, lb.tol_grad = a.p.tolerance_grad, lb.tol_change = a.p.tolerance_change;
     lb.max_iter = a.p.max_iter, lb.max_eval = a.p.max_eval;
     lb.zt_f16 = c->gemm_mode >= 2;
+    lb.status = v.status_own;
     lb.trace = a.trace ? v.trace_own : nullptr;
     lb.trace_stride = a.trace ? c->trace_cap : 0;
     if (a.trace) GEM_CUDA(cudaMemsetAsync(v.trace_own, 0xff, (size_t)Wk * c->trace_cap * sizeof(float), q));   // NaN
@@ -943,26 +990,27 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     c->launches += 1;
     // z0 = mu + eps * std                                   optimizer.py:255-259
     GEM_TRY(encode_impl(c, q, which, Wk, v, a.pose0 + w0 * P, a.eps + (size_t)w0 * a.eps_stride, v.z0, nullptr, nullptr,
-                        a.eps_stride));
+                        a.eps_stride, v.status_own));
     GEM_TRY(timed(c, q, GEM_TAG_LBFGS_BEGIN, [&]() { return launch_lbfgs_begin(q, lb, v.z0, Wk); }));
     const bool tc = use_tc_chain(c, which, Wk);
     // one closure round: decode -> fused energy/gradient -> decoder bwd-data -> L-BFGS advance
     auto enqueue_round = [&]() -> int {
-        GEM_TRY(decode_impl(c, q, which, Wk, v, lb.ZT, v.pose, tc ? lb.ZT_hi : nullptr, tc ? lb.ZT_lo : nullptr));
+        GEM_TRY(decode_impl(c, q, which, Wk, v, lb.ZT, v.pose, tc ? lb.ZT_hi : nullptr, tc ? lb.ZT_lo : nullptr, v.status_own));
         if (a.texel_cache && c->texel_prefetch_ctas > 0)
             // zero-copy maps: the wait for PCIe happens in a few CTAs, not in energy CTAs parked on every SM
             GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
-                return launch_texel_prefetch(q, Wk, c->T, c->J, c->H, c->Wd, v.pose, a.heat, v.fb_own, v.patch, v.patch_origin,
+                return launch_texel_prefetch(q, &c->cam, Wk, c->T, c->J, c->H, c->Wd, v.pose, a.heat, v.fb_own, v.patch, v.patch_origin,
                                              v.patch_valid, c->patch_stats_on ? c->patch_stats : nullptr,
                                              c->texel_prefetch_ctas);
             }));
         GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
-            return launch_energy_grad(q, Wk, c->T, c->J, c->H, c->Wd, v.pose, v.pose0_own, a.heat, v.fb_own, v.clip_own,
+            return launch_energy_grad(q, c->have_camera ? &c->cam : nullptr, &c->skel, Wk, c->T, c->J, c->H, c->Wd, v.pose,
+                                      v.pose0_own, a.heat, v.fb_own, v.clip_own,
                                       v.mb_own, a.wt, v.f_new, nullptr, v.gpose, v.status_own, tc ? v.gp_hi : nullptr,
                                       v.gp_lo, pose_pad(c), a.texel_cache ? v.patch : nullptr, v.patch_origin,
                                       c->patch_stats_on ? c->patch_stats : nullptr, c->gemm_mode == 3, v.row_exp, v.patch_valid);
         }));
-        GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, v.gpose, v.g_new, tc));
+        GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, v.gpose, v.g_new, tc, v.status_own));
         return timed(c, q, GEM_TAG_LBFGS_ADVANCE, [&]() { return launch_lbfgs_advance(q, lb, v.f_new, v.g_new, Wk); });
     };
     // LBFGS.step: at most max_eval + 1 closure evaluations per window (lbfgs.py:478-487, App. B)
@@ -1018,13 +1066,19 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
         for (int round = 1; round <= a.p.max_eval; ++round) GEM_TRY(enqueue_round());
     }
     // final decode of the optimum (every window is parked with its trial point = x)      optimizer.py:273-276
-    GEM_TRY(decode_impl(c, q, which, Wk, v, lb.X, a.pose_out + w0 * P, tc ? lb.ZT_hi : nullptr, tc ? lb.ZT_lo : nullptr));
+    GEM_TRY(decode_impl(c, q, which, Wk, v, lb.X, a.pose_out + w0 * P, tc ? lb.ZT_hi : nullptr, tc ? lb.ZT_lo : nullptr,
+                        v.status_own));
     GEM_TRY(timed(c, q, GEM_TAG_OTHER, [&]() {
         return launch_lbfgs_stats(q, lb, Wk, a.n_iter ? a.n_iter + w0 : nullptr, a.func_evals ? a.func_evals + w0 : nullptr,
                                   nullptr, nullptr, nullptr);
     }));
-    if (a.status)
+    if (a.status && a.status_or) {
+        or_status_kernel<<<(Wk + 255) / 256, 256, 0, q>>>(a.status + w0, v.status_own, Wk);
+        GEM_CHECK_LAUNCH();
+        c->launches += 1;
+    } else if (a.status) {
         GEM_CUDA(cudaMemcpyAsync(a.status + w0, v.status_own, (size_t)Wk * sizeof(uint32_t), cudaMemcpyDeviceToDevice, q));
+    }
     if (a.trace)
         GEM_CUDA(cudaMemcpy2DAsync(a.trace + (size_t)w0 * trace_cols, trace_cols * sizeof(float), v.trace_own,
                                    c->trace_cap * sizeof(float), trace_cols * sizeof(float), Wk, cudaMemcpyDeviceToDevice, q));
@@ -1033,8 +1087,14 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
 
 // Slice boundaries of a call over W windows: the caller's (gem_ctx_set_slices) when they fit, else n_chunks
 // equal parts at multiples of 12 windows (the tap kernel's M tile), at least 96 windows each.
-static std::vector<int> slice_bounds(const gem_ctx* c, int W, bool zero_copy = false) {
+static std::vector<int> slice_bounds(const gem_ctx* c, int W, bool zero_copy, bool shared_scratch) {
     std::vector<int> w0;
+    // layer shapes the chain / tap kernels do not take (T > 32, odd channel counts) fall back to GEMM launches that
+    // split their operand into ONE ctx-wide scratch buffer: concurrent slices would overwrite each other's operand
+    if (shared_scratch) {
+        w0 = {0, W};
+        return w0;
+    }
     if (!c->prof_on && !c->user_slices.empty() && c->user_slices.back() < W) {
         w0 = c->user_slices;
         w0.push_back(W);
@@ -1135,7 +1195,7 @@ int gem_solve_stage(gem_ctx* c, void* stream, int which, int W, const float* pos
     a.pose_out = pose_out_d, a.trace = energy_trace_d, a.n_iter = n_iter_d, a.func_evals = func_evals_d, a.status = status_d;
     a.texel_cache = want_texel_cache(c, heat_d, wt->reproj);
     const bool graphs = c->use_graphs && !c->prof_on;
-    const std::vector<int> w0 = slice_bounds(c, W, a.texel_cache);
+    const std::vector<int> w0 = slice_bounds(c, W, a.texel_cache, c->gemm_mode >= 1 && !c->tap_tc[which]);
     Fork f;
     GEM_TRY(fork_slices(c, s, w0, graphs, &f));
     for (size_t k = 0; k + 1 < w0.size(); ++k) GEM_TRY(enqueue_stage_slice(c, f.cs[k], a, w0[k], w0[k + 1] - w0[k], graphs));
@@ -1167,10 +1227,10 @@ int gem_solve_windows(gem_ctx* c, void* stream, int W, const float* pose0_d, con
     b = a;
     b.texel_cache = false;
     b.which = 1, b.pose0 = rel_f32_d, b.heat = nullptr, b.frame_base = nullptr, b.eps = eps_d + c->n, b.wt = *wt_global;
-    b.pose_out = global_pose_d, b.status = nullptr;
+    b.pose_out = global_pose_d, b.status_or = true;      // (status_d keeps the local stage's bits, the global stage ORs its own in)
     b.n_iter = n_iter_d ? n_iter_d + W : nullptr, b.func_evals = func_evals_d ? func_evals_d + W : nullptr;
     const bool graphs = c->use_graphs && !c->prof_on;
-    const std::vector<int> w0 = slice_bounds(c, W, a.texel_cache);
+    const std::vector<int> w0 = slice_bounds(c, W, a.texel_cache, c->gemm_mode >= 1 && !(c->tap_tc[0] && c->tap_tc[1]));
     Fork f;
     GEM_TRY(fork_slices(c, s, w0, graphs, &f));
     const size_t P = (size_t)c->T * c->J * 3;

@@ -28,6 +28,16 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         }                                            \
     } while (0)
 
+// cudaFuncSetAttribute applies to the current device only: one flag per device and call site
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool* flag() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return &done[d & 63];
+    }
+};
+
 constexpr int kMaxJoints = 32;
 constexpr int kMaxPoly = 24;
 constexpr int kNumSMs = 148;

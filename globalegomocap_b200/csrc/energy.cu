@@ -19,18 +19,6 @@
 
 namespace gem {
 
-__constant__ CameraConst c_cam;
-__constant__ SkeletonConst c_skel;
-
-int upload_camera(const CameraConst& cam) {
-    GEM_CUDA(cudaMemcpyToSymbol(c_cam, &cam, sizeof(cam)));
-    return GEM_OK;
-}
-int upload_skeleton(const SkeletonConst& sk) {
-    GEM_CUDA(cudaMemcpyToSymbol(c_skel, &sk, sizeof(sk)));
-    return GEM_OK;
-}
-
 constexpr int kSlot = 160;             // threads per window (>= T*J, multiple of 32)
 constexpr int kWinPerCta = 2;
 constexpr int kThreads = kSlot * kWinPerCta;
@@ -69,6 +57,10 @@ struct EnergyArgs {
     short2* patch_origin;      // [W][T*J]: map coordinate of the window's corner
     unsigned long long* patch_valid;   // [W][T*J]: one bit per texel of the window (0: empty window)
     unsigned long long* patch_stats;   // optional {lookups, texels fetched}
+    // camera and skeleton of the calling ctx: they travel as kernel parameters (constant bank), so two ctxs with
+    // different calibrations never see each other's (FishEyeCalibrated.py:8-14 is per optimiser in the reference too)
+    CameraConst cam;
+    SkeletonConst skel;
 };
 
 __device__ __forceinline__ float texel(const float* __restrict__ heat, int64_t frame, int y, int x, int j, int H,
@@ -122,7 +114,7 @@ __device__ __forceinline__ void cache_lookup(const EnergyArgs& a, size_t pk, int
 struct Proj {
     float r, inv, rho, drho, ix, iy, fx0, fy0;
 };
-__device__ __forceinline__ bool project_joint(float x, float y, float z, int H, int Wd, Proj& p) {
+__device__ __forceinline__ bool project_joint(const CameraConst& c_cam, float x, float y, float z, int H, int Wd, Proj& p) {
     const float zn = -z;
     p.r = sqrtf(x * x + y * y);
     if (p.r == 0.f) return false;
@@ -150,7 +142,7 @@ __device__ __forceinline__ bool project_joint(float x, float y, float z, int H, 
 // handful of CTAs (grid-stride over all joints) so that the wait for PCIe occupies a few SMs instead of every SM:
 // energy CTAs stalled on PCIe reads are small but sit on all SMs, and no 200 KB tensor-core CTA of another slice can
 // be scheduled beside them — the solve then serialises with the transfers instead of overlapping them.
-__global__ void __launch_bounds__(512) texel_prefetch_kernel(EnergyArgs a) {
+__global__ void __launch_bounds__(512) texel_prefetch_kernel(const __grid_constant__ EnergyArgs a) {
     const int TJ = a.T * a.J;
     const size_t total = (size_t)a.W * TJ;
     for (size_t i = (size_t)blockIdx.x * 512 + threadIdx.x; i < total; i += (size_t)gridDim.x * 512) {
@@ -158,14 +150,14 @@ __global__ void __launch_bounds__(512) texel_prefetch_kernel(EnergyArgs a) {
         const int t = k / a.J, j = k - t * a.J;
         const float x = a.pose[i * 3 + 0], y = a.pose[i * 3 + 1], z = a.pose[i * 3 + 2];
         Proj p;
-        if (!project_joint(x, y, z, a.H, a.Wd, p)) continue;
+        if (!project_joint(a.cam, x, y, z, a.H, a.Wd, p)) continue;
         if (!(p.fx0 >= -1.f && p.fx0 <= (float)a.Wd && p.fy0 >= -1.f && p.fy0 <= (float)a.H)) continue;
         float nw, ne, sw, se;
         cache_lookup(a, i, a.frame_base[w] + t, j, (int)p.fx0, (int)p.fy0, false, nw, ne, sw, se);
     }
 }
 
-__global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
+__global__ void __launch_bounds__(kThreads) energy_grad_kernel(const __grid_constant__ EnergyArgs a) {
     __shared__ __align__(16) float s_x[kWinPerCta * kSlot * 3];
     __shared__ __align__(16) float s_x0[kWinPerCta * kSlot * 3];
     __shared__ __align__(16) float s_g[kWinPerCta * kSlot * 3];
@@ -223,7 +215,7 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
         Proj pj;
         float nw = 0.f, ne = 0.f, sw = 0.f, se = 0.f;
         if (a.wr != 0.f) {
-            if (!project_joint(x, y, z, a.H, a.Wd, pj)) {
+            if (!project_joint(a.cam, x, y, z, a.H, a.Wd, pj)) {
                 if (a.status) atomicOr(a.status + w, GEM_WIN_NORM_ZERO);
             } else if (pj.fx0 >= -1.f && pj.fx0 <= (float)a.Wd && pj.fy0 >= -1.f && pj.fy0 <= (float)a.H) {
                 // (anything further than one texel outside contributes exactly 0)
@@ -275,7 +267,7 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
         // E_bone = sum (|x_j - x_parent| - Lbar_j)^2                 optimizer.py:172-177, 89-94
         {
             const float* mb = a.mean_bone + (size_t)a.clip[w] * a.J;
-            const int p = c_skel.parent[j];
+            const int p = a.skel.parent[j];
             const float bx = x - X[(t * a.J + p) * 3 + 0], by = y - X[(t * a.J + p) * 3 + 1],
                         bz = z - X[(t * a.J + p) * 3 + 2];
             const float len = sqrtf(bx * bx + by * by + bz * bz);
@@ -285,8 +277,8 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
                 const float c = a.wb * (2.f * diff) / len;
                 gx += c * bx, gy += c * by, gz += c * bz;
             }
-            for (int ci = c_skel.child_start[j]; ci < c_skel.child_start[j + 1]; ++ci) {   // this joint as a parent
-                const int cj = c_skel.child_list[ci];
+            for (int ci = a.skel.child_start[j]; ci < a.skel.child_start[j + 1]; ++ci) {   // this joint as a parent
+                const int cj = a.skel.child_list[ci];
                 const float cx = X[(t * a.J + cj) * 3 + 0] - x, cy = X[(t * a.J + cj) * 3 + 1] - y,
                             cz = X[(t * a.J + cj) * 3 + 2] - z;
                 const float cl = sqrtf(cx * cx + cy * cy + cz * cz);
@@ -427,17 +419,22 @@ __global__ void __launch_bounds__(kThreads) energy_grad_kernel(EnergyArgs a) {
     }
 }
 
-int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, const float* pose,
-                       const float* pose0, const float* heat, const int64_t* frame_base, const int32_t* clip,
+int launch_energy_grad(cudaStream_t stream, const CameraConst* cam, const SkeletonConst* skel, int W, int T, int J, int H,
+                       int Wd, const float* pose, const float* pose0, const float* heat, const int64_t* frame_base, const int32_t* clip,
                        const float* mean_bone, const gem_energy_weights& wt, float* energy, float* terms,
                        float* grad, uint32_t* status, float* gp_hi, float* gp_lo, int pp, float* patch,
                        short2* patch_origin, unsigned long long* patch_stats, int gp_f16, int32_t* row_exp,
                        unsigned long long* patch_valid) {
     if (W <= 0) return GEM_OK;
+    GEM_REQUIRE(skel != nullptr && skel->num_joints == J, "skeleton not set for this joint count");
+    GEM_REQUIRE(wt.reproj == 0.f || cam != nullptr, "camera not set");
     GEM_REQUIRE(T * J <= kSlot, "T*J must be <= 160");
     GEM_REQUIRE(T >= 3, "seq_len must be >= 3");
     GEM_REQUIRE(wt.reproj == 0.f || (heat != nullptr && frame_base != nullptr), "heatmaps required when reproj != 0");
     EnergyArgs a;
+    memset(&a.cam, 0, sizeof(a.cam));
+    if (cam) a.cam = *cam;
+    a.skel = *skel;
     a.pose = pose, a.pose0 = pose0, a.heat = heat, a.frame_base = frame_base, a.clip = clip, a.mean_bone = mean_bone;
     a.energy = energy, a.terms = terms, a.grad = grad, a.status = status;
     a.gp_hi = gp_hi, a.gp_lo = gp_hi ? gp_lo : nullptr, a.pp = gp_hi ? pp : 0;
@@ -461,13 +458,14 @@ int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, 
 }
 
 // fetches, into the joints' cache windows, the texels the energy evaluation of `pose` will sample (zero-copy maps)
-int launch_texel_prefetch(cudaStream_t stream, int W, int T, int J, int H, int Wd, const float* pose, const float* heat,
-                          const int64_t* frame_base, float* patch, short2* patch_origin, unsigned long long* patch_valid,
-                          unsigned long long* patch_stats, int ctas) {
+int launch_texel_prefetch(cudaStream_t stream, const CameraConst* cam, int W, int T, int J, int H, int Wd, const float* pose,
+                          const float* heat, const int64_t* frame_base, float* patch, short2* patch_origin,
+                          unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas) {
     if (W <= 0) return GEM_OK;
-    GEM_REQUIRE(heat && frame_base && patch && patch_origin && patch_valid, "texel prefetch needs the maps and the cache");
+    GEM_REQUIRE(cam && heat && frame_base && patch && patch_origin && patch_valid, "texel prefetch needs the camera, the maps and the cache");
     EnergyArgs a;
     memset(&a, 0, sizeof(a));
+    a.cam = *cam;
     a.pose = pose, a.heat = heat, a.frame_base = frame_base;
     a.patch = patch, a.patch_origin = patch_origin, a.patch_valid = patch_valid, a.patch_stats = patch_stats;
     a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd;

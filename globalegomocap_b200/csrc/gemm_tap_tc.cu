@@ -455,6 +455,7 @@ struct ChainArgs {
     ChainLayer L[kTapChainMax];
     int nl, W, T, wpq;
     float* out_plain;
+    uint32_t* status;            // optional [W]: GEM_WIN_F16_RANGE is OR-ed in when a split activation saturates
     long long* dbg;
 };
 
@@ -659,6 +660,12 @@ tc_tap_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         if (row_ok) reinterpret_cast<uint16_t*>(L.sign_out)[token * halves + (nb >> 4)] = (uint16_t)sbits;
                     }
                     if (L.out_kind != 2) {
+                        if (g.status) {             // fp16 range check (the split saturates silently)
+                            float amax = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) amax = fmaxf(amax, fabsf(o[j]));
+                            if (amax > 65504.f && row_ok) atomicOr(g.status + win, GEM_WIN_F16_RANGE);
+                        }
                         uint8_t* th = stage + q * kQuarterBytes + lane * 128;
                         uint8_t* tl = th + kATile;
 #pragma unroll
@@ -758,6 +765,7 @@ struct Chain2Args {
     Chain2Layer L[kChain2Max];
     int nl, W, T, wpq;
     float* out_plain;
+    uint32_t* status;            // optional [W]: GEM_WIN_F16_RANGE is OR-ed in when a split activation saturates
     long long* dbg;
 };
 
@@ -959,6 +967,12 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
                         if (row_ok) reinterpret_cast<uint16_t*>(L.sign_out)[token * halves + (nb >> 4)] = (uint16_t)sbits;
                     }
                     if (L.out_kind != 2) {
+                        if (g.status) {             // fp16 range check (the split saturates silently)
+                            float amax = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) amax = fmaxf(amax, fabsf(o[j]));
+                            if (amax > 65504.f && row_ok) atomicOr(g.status + win, GEM_WIN_F16_RANGE);
+                        }
                         uint8_t* th = stage + q * kQuarterBytes + lane * 128;
                         uint8_t* tl = th + kATile;
 #pragma unroll
@@ -1137,11 +1151,11 @@ long long* g_tap_dbg = nullptr;   // set by gem_debug_tap_timestamps (tests / pr
 template <int NCTA, bool F16>
 static int launch_tap_cfg(cudaStream_t stream, dim3 grid, const AMaps& am, const TapWeight& w, const AMaps& om,
                           const TapTcArgs& a) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (bool* once_ = attr_set.flag(); !*once_) {
         GEM_CUDA(cudaFuncSetAttribute(tc_tap_kernel<NCTA, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)Cfg<NCTA, F16>::kSmem));
-        attr_set = true;
+        *once_ = true;
     }
     tc_tap_kernel<NCTA, F16><<<grid, kThreads, Cfg<NCTA, F16>::kSmem, stream>>>(am.hi, am.lo, w.map_hi, w.map_lo, w.map_hs,
                                                                                  om.hi, om.lo, a);
@@ -1263,10 +1277,11 @@ int launch_tap_chain(cudaStream_t stream, void* owner, const TapChainLaunch& L) 
     for (int l = L.nl; l < kTapChainMax; ++l) maps.w[l][0] = maps.w[l][1] = maps.w[l][2] = maps.a_hi;
     a.nl = L.nl, a.W = L.W, a.T = L.T, a.wpq = wpq, a.out_plain = L.out_lo ? nullptr : (float*)L.out_hi;
     a.dbg = g_tap_dbg;
-    static bool attr_set = false;
-    if (!attr_set) {
+    a.status = L.status;
+    static PerDeviceOnce attr_set;
+    if (bool* once_ = attr_set.flag(); !*once_) {
         GEM_CUDA(cudaFuncSetAttribute(tc_tap_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem));
-        attr_set = true;
+        *once_ = true;
     }
     const int grid = (L.W + 4 * wpq - 1) / (4 * wpq);
     tc_tap_chain_kernel<<<grid, kChainThreads, kChainSmem, stream>>>(maps, a);
@@ -1361,16 +1376,29 @@ int launch_tap_chain_pair(cudaStream_t stream, void* owner, const TapChainLaunch
     }
     a.nl = np, a.W = L.W, a.T = L.T, a.wpq = wpq, a.out_plain = L.out_lo ? nullptr : (float*)L.out_hi;
     a.dbg = g_tap_dbg;
-    static bool attr_set = false;
-    if (!attr_set) {
+    a.status = L.status;
+    static PerDeviceOnce attr_set;
+    if (bool* once_ = attr_set.flag(); !*once_) {
         GEM_CUDA(cudaFuncSetAttribute(tc_tap_chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChain2Smem));
-        attr_set = true;
+        *once_ = true;
     }
     const int tiles = (L.W + 4 * wpq - 1) / (4 * wpq);
     const int grid = 2 * ((tiles + 1) / 2);
     tc_tap_chain2_kernel<<<grid, kChainThreads, kChain2Smem, stream>>>(maps, a);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
+}
+
+// frees the prepared slabs of one layer's weights (every scheme); the caller has synchronised the device
+void tc_tap_forget_weight(void* owner, const float* B) {
+    TapState* st = state_of(owner);
+    for (int scheme = 1; scheme <= 2; ++scheme) {
+        auto it = st->weights.find(std::make_pair(B, scheme));
+        if (it == st->weights.end()) continue;
+        cudaFree(it->second.hi), cudaFree(it->second.lo);
+        if (it->second.hs) cudaFree(it->second.hs);
+        st->weights.erase(it);
+    }
 }
 
 void tc_tap_release(void* owner) {

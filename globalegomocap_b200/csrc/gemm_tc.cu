@@ -77,6 +77,7 @@ struct TcArgs {
     uint32_t* sign;  // optional: packed sign bits of the result, [M][N/32] (needs BN % 32 == 0)
     const int32_t* row_exp;   // optional: row m of A was scaled by 2^row_exp[m]; the result row is scaled back
     int out16;                // C / C_lo are fp16 hi / scaled fp16 lo arrays (uint16), not TF32 hi / lo floats
+    uint32_t* row_flag;       // optional [M]: GEM_WIN_F16_RANGE is OR-ed in when a row's fp16 output saturates
     int M, N, K, ldc, epi;
     long long* dbg;           // debug: per-CTA phase timestamps (gem_debug_gemm_timestamps), NULL in production
 };
@@ -167,6 +168,12 @@ __device__ __forceinline__ void epilogue_tile(const TcArgs& g, uint8_t* smem, ui
             if (m < g.M) reinterpret_cast<uint16_t*>(g.sign)[(size_t)m * (g.N >> 4) + (nb >> 4)] = (uint16_t)sbits;
         }
         if (g.out16) {
+            if (g.row_flag) {                       // fp16 range check (the conversions below saturate silently)
+                float amax = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) amax = fmaxf(amax, fabsf(o[j]));
+                if (amax > 65504.f && m < g.M) atomicOr(g.row_flag + m, GEM_WIN_F16_RANGE);
+            }
             uint16_t* sh_row = reinterpret_cast<uint16_t*>(stage_hi) + lane * C::kPitch16 + c * 16;
             uint16_t* sl_row = reinterpret_cast<uint16_t*>(stage_lo) + lane * C::kPitch16 + c * 16;
 #pragma unroll
@@ -526,7 +533,7 @@ __global__ void transpose_split_kernel(const float* __restrict__ B, int ldb, int
 
 // the fp16 scheme's split (tc_common.cuh: split_f16), optionally of rows pre-scaled by 2^row_exp[m]
 __global__ void split_f16_kernel(const float* __restrict__ A, int lda, int M, int K, const int32_t* __restrict__ row_exp,
-                                 uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+                                 uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, uint32_t* __restrict__ row_flag) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // one float4 per thread
     const int kv = K / 4;
     if (i >= (size_t)M * kv) return;
@@ -536,6 +543,8 @@ __global__ void split_f16_kernel(const float* __restrict__ A, int lda, int M, in
         const float sc = exp2f((float)row_exp[m]);
         x.x *= sc, x.y *= sc, x.z *= sc, x.w *= sc;
     }
+    if (row_flag && fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))) > 65504.f)
+        atomicOr(row_flag + m, GEM_WIN_F16_RANGE);
     uint16_t h[4], l[4];
     split_f16(x.x, h[0], l[0]), split_f16(x.y, h[1], l[1]), split_f16(x.z, h[2], l[2]), split_f16(x.w, h[3], l[3]);
     *reinterpret_cast<uint2*>(hi + (size_t)m * K + k) =
@@ -702,11 +711,11 @@ int g_gemm_pair = -1;      // debug override of GEM_GEMM_PAIR (gem_debug_gemm_pa
 template <int BN, bool F16>
 static int launch_bn(cudaStream_t stream, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const WeightSplit& w, int idx,
                      const TcArgs& a) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (bool* once_ = attr_set.flag(); !*once_) {
         GEM_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)GemmCfg<BN>::kSmemBytes));
-        attr_set = true;
+        *once_ = true;
     }
     dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN);
     tc_gemm_kernel<BN, F16><<<grid, kThreads, GemmCfg<BN>::kSmemBytes, stream>>>(a_hi, a_lo, w.map_hi[idx], w.map_lo[idx], a);
@@ -716,11 +725,11 @@ static int launch_bn(cudaStream_t stream, const CUtensorMap& a_hi, const CUtenso
 template <int BN>
 static int launch_pair_bn(cudaStream_t stream, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const WeightSplit& w, int idx,
                           const TcArgs& a) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (bool* once_ = attr_set.flag(); !*once_) {
         GEM_CUDA(cudaFuncSetAttribute(tc_gemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)PairCfg<BN>::kSmemBytes));
-        attr_set = true;
+        *once_ = true;
     }
     dim3 grid(2 * ((a.M + 2 * BM - 1) / (2 * BM)), (a.N + BN - 1) / BN);      // whole pairs along M
     tc_gemm_pair_kernel<BN><<<grid, kThreads, PairCfg<BN>::kSmemBytes, stream>>>(a_hi, a_lo, w.map_hi2[idx], w.map_lo2[idx], a);
@@ -777,7 +786,7 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
         const size_t n4 = (size_t)g.M * (g.K / 4);
         if (f16)
             split_f16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(g.A, g.lda, g.M, g.K, g.row_exp,
-                                                                            (uint16_t*)st->a_hi, (uint16_t*)st->a_lo);
+                                                                            (uint16_t*)st->a_hi, (uint16_t*)st->a_lo, nullptr);
         else
             split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(g.A, g.lda, g.M, g.K, (float*)st->a_hi,
                                                                              (float*)st->a_lo);
@@ -792,6 +801,7 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
     a.bias = g.bias, a.C = g.C, a.C_lo = (float*)g.C_lo, a.sign = g.C_sign, a.M = g.M, a.N = g.N, a.K = g.K, a.ldc = g.ldc;
     a.epi = g.epi, a.row_exp = f16 ? g.row_exp : nullptr, a.out16 = (g.C_lo && g.out16) ? 1 : 0;
     a.dbg = g_gemm_dbg;
+    a.row_flag = a.out16 ? g.row_flag : nullptr;
     GEM_REQUIRE(!a.out16 || g.ldc % 8 == 0, "fp16 outputs need ldc % 8 == 0");
     GEM_REQUIRE((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "bias must be 16-byte aligned");
     // N-tile width.  Up to one wave of 128-wide tiles: keep 128 (kernels of concurrent slices share the SMs, the
@@ -841,11 +851,11 @@ int launch_split_tf32(cudaStream_t stream, const float* A, int lda, int M, int K
 }
 // x -> fp16 (hi, scaled lo) for M rows of K floats, rows optionally pre-scaled by 2^row_exp[m]
 int launch_split_f16(cudaStream_t stream, const float* A, int lda, int M, int K, const int32_t* row_exp, uint16_t* hi,
-                     uint16_t* lo) {
+                     uint16_t* lo, uint32_t* row_flag) {
     if (M <= 0) return GEM_OK;
     GEM_REQUIRE(K % 4 == 0 && lda % 4 == 0, "K and lda must be multiples of 4");
     const size_t n4 = (size_t)M * (K / 4);
-    split_f16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(A, lda, M, K, row_exp, hi, lo);
+    split_f16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(A, lda, M, K, row_exp, hi, lo, row_flag);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }
@@ -893,6 +903,17 @@ int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int
     }
     st->weights.emplace(key, ws);
     return GEM_OK;
+}
+
+// frees the prepared copies of one weight matrix (every scheme); the caller has synchronised the device
+void tc_gemm_forget_weight(void* owner, const float* B) {
+    TcState* st = state_of(owner);
+    for (int scheme = 1; scheme <= 2; ++scheme) {
+        auto it = st->weights.find(std::make_pair(B, scheme));
+        if (it == st->weights.end()) continue;
+        cudaFree(it->second.hi), cudaFree(it->second.lo);
+        st->weights.erase(it);
+    }
 }
 
 void tc_gemm_release(void* owner) {

@@ -4,17 +4,17 @@
 
 namespace gem {
 
-int upload_camera(const CameraConst& cam);
-int upload_skeleton(const SkeletonConst& sk);
-int launch_energy_grad(cudaStream_t stream, int W, int T, int J, int H, int Wd, const float* pose, const float* pose0,
+// cam / skel: host copies owned by the calling ctx (passed to the kernel by value; cam may be NULL when reproj == 0)
+int launch_energy_grad(cudaStream_t stream, const CameraConst* cam, const SkeletonConst* skel, int W, int T, int J, int H,
+                       int Wd, const float* pose, const float* pose0,
                        const float* heat, const int64_t* frame_base, const int32_t* clip, const float* mean_bone,
                        const gem_energy_weights& wt, float* energy, float* terms, float* grad, uint32_t* status,
                        float* gp_hi = nullptr, float* gp_lo = nullptr, int pp = 0, float* patch = nullptr,
                        short2* patch_origin = nullptr, unsigned long long* patch_stats = nullptr, int gp_f16 = 0,
                        int32_t* row_exp = nullptr, unsigned long long* patch_valid = nullptr);
-int launch_texel_prefetch(cudaStream_t stream, int W, int T, int J, int H, int Wd, const float* pose, const float* heat,
-                          const int64_t* frame_base, float* patch, short2* patch_origin, unsigned long long* patch_valid,
-                          unsigned long long* patch_stats, int ctas);
+int launch_texel_prefetch(cudaStream_t stream, const CameraConst* cam, int W, int T, int J, int H, int Wd, const float* pose,
+                          const float* heat, const int64_t* frame_base, float* patch, short2* patch_origin,
+                          unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas);
 constexpr int kPatchW = 8;      // side of the per-joint texel window of the energy kernel's cache (at most 8: 64 valid bits)
 
 enum { EPI_NONE = 0, EPI_LRELU = 1, EPI_MASK = 2 };
@@ -26,6 +26,7 @@ struct TapGemmArgs {
     float* C_lo = nullptr;         // tensor-core path only: write the result split (hi to C, lo to C_lo)
     uint32_t* C_sign = nullptr;    // tensor-core path only: packed sign bits of the result [M][N/32]
     int out16 = 0;                 // with C_lo: write the result as fp16 hi / scaled fp16 lo (uint16 arrays) instead
+    uint32_t* row_flag = nullptr;  // optional [M]: OR-ed with GEM_WIN_F16_RANGE when a row's fp16 output left fp16's range
     const float* B;      // [taps][K][ldb]
     const float* bias;   // [N] or NULL
     const float* aux;    // [M][ldaux] saved activation for EPI_MASK ...
@@ -42,10 +43,11 @@ extern int g_gemm_pair;
 extern long long* g_gemm_dbg;
 int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N, int scheme = 1);
 int launch_split_f16(cudaStream_t stream, const float* A, int lda, int M, int K, const int32_t* row_exp, uint16_t* hi,
-                     uint16_t* lo);
+                     uint16_t* lo, uint32_t* row_flag = nullptr);
 int launch_rowscale_split_f16(cudaStream_t stream, const float* xh, const float* xl, int M, int K, uint16_t* hi,
                               uint16_t* lo, int32_t* row_exp);
 int launch_split_tf32(cudaStream_t stream, const float* A, int lda, int M, int K, float* hi, float* lo);
+void tc_gemm_forget_weight(void* owner, const float* B);
 void tc_gemm_release(void* owner);
 bool tc_gemm_available();
 
@@ -86,11 +88,13 @@ struct TapChainLaunch {
     void *out_hi, *out_lo;                      // last layer's output [W*T][ldo]: split fp16, or plain fp32 when out_lo == NULL
     int ldo;
     int W, T;
+    uint32_t* status = nullptr;                 // optional [W]: OR-ed with GEM_WIN_F16_RANGE when a split output saturates
 };
 int launch_tap_chain(cudaStream_t stream, void* owner, const TapChainLaunch& L);
 // the same on CTA pairs (cta_group::2): up to five layers with up to 256 channels in and out (gemm_tap_tc.cu)
 int launch_tap_chain_pair(cudaStream_t stream, void* owner, const TapChainLaunch& L);
 int launch_split_pad(cudaStream_t stream, const float* src, int C, size_t tokens, int ldo, float* hi, float* lo);
+void tc_tap_forget_weight(void* owner, const float* B);
 void tc_tap_release(void* owner);
 extern long long* g_tap_dbg;   // debug: per-CTA phase timestamps of the tap kernel (NULL in production)
 
@@ -100,6 +104,7 @@ struct LbfgsBuffers {
     float *X, *D, *G, *GP, *BG0, *BG1, *ZT;   // [W][n]  (prev_flat_grad is G itself, see lbfgs.cu)
     float *ZT_hi, *ZT_lo;                           // optional [W][n]: the trial point as TF32 hi / lo parts, or,
     int zt_f16;                                     //   when zt_f16, as fp16 hi / scaled lo (uint16 [W][n] in the same buffers)
+    uint32_t* status;                               // optional [W]: OR-ed with GEM_WIN_F16_RANGE when a trial point saturates
     float *Y, *S;                                   // [W][m][n]
     float* RO;                                      // [W][m]
     float* trace;                                   // [W][trace_stride] or NULL

@@ -117,6 +117,12 @@ __device__ __forceinline__ void st_trial(const LbfgsBuffers& b, size_t off, cons
     if (b.zt_f16) {
         uint16_t* zh = reinterpret_cast<uint16_t*>(b.ZT_hi) + off;
         uint16_t* zl = reinterpret_cast<uint16_t*>(b.ZT_lo) + off;
+        if (b.status) {                     // fp16 range check (the split saturates silently)
+            float amax = 0.f;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) amax = fmaxf(amax, fabsf(r[i]));
+            if (amax > 65504.f) atomicOr(b.status + off / (size_t)b.n, GEM_WIN_F16_RANGE);
+        }
 #pragma unroll
         for (int i = 0; i < kChunks; ++i) {
             const int c = tid + i * kLbThreads;
@@ -217,6 +223,7 @@ __global__ void __launch_bounds__(kLbThreads) lbfgs_begin_kernel(LbfgsBuffers b,
         b.ZT[off + i] = v;
         if (b.ZT_hi && b.zt_f16) {
             uint16_t h, l;
+            if (b.status && fabsf(v) > 65504.f) atomicOr(b.status + w, GEM_WIN_F16_RANGE);
             split_f16_dev(v, h, l);
             reinterpret_cast<uint16_t*>(b.ZT_hi)[off + i] = h;
             reinterpret_cast<uint16_t*>(b.ZT_lo)[off + i] = l;
@@ -774,21 +781,21 @@ int launch_lbfgs_advance(cudaStream_t stream, const LbfgsBuffers& b, const float
     }();
     const size_t smem = (size_t)kRing * b.n * sizeof(float);
     if (sms > 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr_set;
+        if (bool* once_ = attr_set.flag(); !*once_) {
             GEM_CUDA(cudaFuncSetAttribute(lbfgs_advance_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(kGroups * kRing * 2048 * sizeof(float))));
-            attr_set = true;
+            *once_ = true;
         }
         int grid = (W + kGroups - 1) / kGroups;
         if (grid > sms) grid = sms;
         lbfgs_advance_persistent_kernel<<<grid, kGroups * kLbThreads, kGroups * smem, stream>>>(b, loss, grad, W);
     } else {
-        static bool attr1_set = false;
-        if (!attr1_set) {
+        static PerDeviceOnce attr1_set;
+        if (bool* once_ = attr1_set.flag(); !*once_) {
             GEM_CUDA(cudaFuncSetAttribute(lbfgs_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(kRing * 2048 * sizeof(float))));
-            attr1_set = true;
+            *once_ = true;
         }
         lbfgs_advance_kernel<<<W, kLbThreads, smem, stream>>>(b, loss, grad, W);
     }

@@ -153,11 +153,11 @@ int launch_lift(cudaStream_t stream, int N, int H, int Wd, int J, const float* h
     a.n_poly = n_poly, a.cx = cx, a.cy = cy;
     a.N = N, a.HW = H * Wd, a.Wd = Wd, a.J = J, a.up = up, a.pad_x = pad_x;
     const size_t smem = (size_t)kLiftBuf * kLiftPix * J * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (bool* once_ = attr_set.flag(); !*once_) {
         GEM_CUDA(cudaFuncSetAttribute(lift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(kLiftBuf * kLiftPix * kLiftMaxJ * sizeof(float))));
-        attr_set = true;
+        *once_ = true;
     }
     lift_kernel<<<N, kLiftThreads, smem, stream>>>(a);
     GEM_CHECK_LAUNCH();

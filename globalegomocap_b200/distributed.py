@@ -28,15 +28,19 @@ def owned_frames(lo: int, hi: int, n_windows: int, stride: int, overlap: int):
     return stride * lo, stride * hi + (overlap if hi == n_windows else 0)
 
 
-def exchange_boundary_windows(windows: torch.Tensor, group=None):
-    """windows: this rank's results [S, Wr, T, J, 3] float64 for S sequences (Wr >= 1).
+def exchange_boundary_windows(windows, group=None):
+    """windows: this rank's results [S, Wr, T, J, 3] float64 for S sequences (Wr >= 1), or a list of S tensors
+    [Wr_s, T, J, 3] when the sequences differ in length.
     Returns (left, right): [S, T, J, 3] tensors holding the left neighbour's last window and the
     right neighbour's first window (None at the ends of the rank line)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     if world == 1:
         return None, None
-    mine = torch.stack([windows[:, 0], windows[:, -1]], dim=1).contiguous()        # [S,2,T,J,3]
+    if isinstance(windows, torch.Tensor):
+        mine = torch.stack([windows[:, 0], windows[:, -1]], dim=1).contiguous()    # [S,2,T,J,3]
+    else:
+        mine = torch.stack([torch.stack([w[0], w[-1]]) for w in windows]).contiguous()
     gathered = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(gathered, mine, group=group)
     left = gathered[rank - 1][:, 1] if rank > 0 else None
@@ -60,3 +64,19 @@ def stitch_shard(windows, left, right, merge_fn, smooth_fn, stride: int, overlap
     start = stride if left is not None else 0
     n_own = stride * windows.shape[0] + (overlap if right is None else 0)
     return seq[start:start + n_own]
+
+
+def stitch_optimized(engine, windows_per_sequence, final_smooth=True, group=None):
+    """The optimised global sequence of every clip from this rank's windows (reference optimizer.py:421-450: merge
+    with overlap averaging, then the sigma = 1 Gaussian), one all-gather of boundary windows when the clips' windows
+    are sharded over ranks.  windows_per_sequence: list of float64 CUDA tensors [Wr_s, T, J, 3] in the global frame.
+    Returns the list of this rank's owned frames per sequence (the whole sequence in a single process)."""
+    stride, overlap = engine.T - 2, 2
+    sharded = dist.is_initialized() and dist.get_world_size(group) > 1
+    left, right = exchange_boundary_windows(windows_per_sequence, group) if sharded else (None, None)
+    outs = []
+    for s, wins in enumerate(windows_per_sequence):
+        outs.append(stitch_shard(wins, None if left is None else left[s], None if right is None else right[s],
+                                 lambda w, ov: engine.merge_windows(w, ov), lambda q: engine.gaussian_smooth(q, 1.0),
+                                 stride, overlap, final_smooth=final_smooth))
+    return outs

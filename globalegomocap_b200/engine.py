@@ -127,6 +127,23 @@ class Engine:
             return heat
         return self._dev(heat, torch.float32)
 
+    def _check_heat(self, heat, frame_base):
+        """The C ABI takes a raw map pointer and indexes it with the ctx's (H, Wd, J): a pickle with another map
+        resolution / joint count, or a window that runs past the last frame, must not reach the kernel."""
+        if heat is None:
+            return
+        if tuple(heat.shape[-3:]) != (self.H, self.Wd, self.J):
+            raise GemError(f"heat maps are {tuple(heat.shape[-3:])}, the engine was created for "
+                           f"{(self.H, self.Wd, self.J)} (H, W, joints)")
+        if frame_base is None or (isinstance(frame_base, torch.Tensor) and frame_base.is_cuda):
+            return          # device-resident indices were range-checked by whoever built them (WindowBatch does)
+        fb = np.asarray(frame_base)
+        if fb.size:
+            n_frames = int(np.prod(heat.shape)) // (self.H * self.Wd * self.J)
+            lo, hi = int(fb.min()), int(fb.max())
+            if lo < 0 or hi + self.T > n_frames:
+                raise GemError(f"window frame range [{lo}, {hi + self.T}) leaves the {n_frames} heat-map frames")
+
     def _dev(self, t, dtype):
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(np.asarray(t))
@@ -174,6 +191,7 @@ class Engine:
         W = pose.shape[0]
         self._check_w(W)
         heat = None if heat is None else self._dev(heat, torch.float32)
+        self._check_heat(heat, frame_base)
         frame_base = None if frame_base is None else self._dev(frame_base, torch.int64)
         clip = self._dev(clip, torch.int32)
         mean_bone = self._dev(mean_bone, torch.float32).reshape(-1, self.J)
@@ -259,6 +277,7 @@ class Engine:
         W = pose0.shape[0]
         self._check_w(W)
         heat = self._heat(heat)
+        self._check_heat(heat, frame_base)
         frame_base = None if frame_base is None else self._dev(frame_base, torch.int64)
         clip = self._dev(clip, torch.int32)
         mean_bone = self._dev(mean_bone, torch.float32).reshape(-1, self.J)
@@ -282,6 +301,7 @@ class Engine:
         W = pose0.shape[0]
         self._check_w(W)
         heat = self._heat(heat)
+        self._check_heat(heat, frame_base)
         frame_base = None if frame_base is None else self._dev(frame_base, torch.int64)
         clip = self._dev(clip, torch.int32)
         mean_bone = self._dev(mean_bone, torch.float32).reshape(-1, self.J)

@@ -31,6 +31,7 @@ from .vae_prep import PreparedVae
 LOCAL_VAE_PATH = "networks/logs/only_local_full_dataset_latent_2048_len_10_kl_0.5_2/checkpoints/19.pth.tar"
 GLOBAL_VAE_PATH = "networks/logs/real_full_dataset_latent_2048_len_10_slide_window_step_1_kl_0.5/checkpoints/19.pth.tar"
 GEM_WIN_NORM_ZERO = 1
+GEM_WIN_F16_RANGE = 2
 
 _vae_cache = {}
 _engine_cache = {}
@@ -46,23 +47,33 @@ def load_vae(vae_path, device, seq_len=10, latent_dim=2048):
     return _vae_cache[key]
 
 
-def shared_engine(max_windows, max_history=24, latent_dim=2048, seq_len=10):
-    """One Engine per process, grown when a clip needs more windows / a longer history."""
-    key = (latent_dim, seq_len, torch.cuda.current_device() if torch.cuda.is_available() else -1)
+def shared_engine(max_windows, max_history=24, latent_dim=2048, seq_len=10, heat_hw=(64, 64), num_joints=15):
+    """One Engine per process (and heat-map geometry), grown when a clip needs more windows / a longer history."""
+    key = (latent_dim, seq_len, tuple(heat_hw), num_joints,
+           torch.cuda.current_device() if torch.cuda.is_available() else -1)
     eng = _engine_cache.get(key)
     if eng is None or eng.max_windows < max_windows or eng.max_history < max_history:
         if eng is not None:
             max_windows, max_history = max(max_windows, eng.max_windows), max(max_history, eng.max_history)
             eng.close()
         eng = Engine(max_windows=max(max_windows, 128), latent_dim=latent_dim, seq_len=seq_len,
-                     max_history=max_history)
+                     num_joints=num_joints, heat_hw=tuple(heat_hw), max_history=max_history)
         _engine_cache[key] = eng
     return eng
 
 
 def _raise_on_status(status):
-    if int((status & GEM_WIN_NORM_ZERO).sum()) != 0:
+    bits = 0
+    if status.numel():
+        for b in (GEM_WIN_NORM_ZERO, GEM_WIN_F16_RANGE):
+            if int((status & b).sum()) != 0:
+                bits |= b
+    if bits & GEM_WIN_NORM_ZERO:
         raise Exception("norm is zero!")          # FishEyeCalibrated.py:124-127
+    if bits & GEM_WIN_F16_RANGE:
+        raise GemError("an activation or latent entry left fp16's finite range (65504): the split-fp16 tensor-core "
+                       "operands saturated and the result is not fp32-faithful; re-run with "
+                       "Engine.set_gemm_mode(1) (3xTF32, fp32 range)")
 
 
 class BodyPoseOptimizer:
@@ -138,46 +149,195 @@ class BodyPoseOptimizer:
         return E[0]
 
 
-def load_clip(data_id):
-    """'<data_id>/test_data.pkl' -> dict of ndarrays (optimizer.py:315-324); extra keys are ignored."""
+CLIP_KEYS = ("estimated_local_skeleton", "gt_global_skeleton", "camera_pose_list", "heatmap_list")
+_CLIP_DTYPES = {"estimated_local_skeleton": np.float64, "gt_global_skeleton": np.float64, "camera_pose_list": np.float64,
+                "heatmap_list": np.float32}
+_pinned_pool = {}
+
+
+def _pinned(name, shape, np_dtype):
+    """A pinned host array of the process-wide staging pool (grown when needed, reused across calls: page-locking
+    gigabytes costs about as long as copying them).  Falls back to pageable memory without CUDA."""
+    nbytes = int(np.prod(shape)) * np.dtype(np_dtype).itemsize
+    if not torch.cuda.is_available():
+        return torch.from_numpy(np.empty(shape, np_dtype))
+    buf = _pinned_pool.get(name)
+    if buf is None or buf.numel() < nbytes:
+        _pinned_pool.pop(name, None)
+        buf = torch.empty(max(nbytes, 16), dtype=torch.uint8, pin_memory=True)
+        _pinned_pool[name] = buf
+    return buf[:nbytes].view({np.float32: torch.float32, np.float64: torch.float64}[np_dtype]).view(*shape)
+
+
+class ClipSet(list):
+    """The clips of one call: a list of per-clip dicts of (pinned) host tensors, plus `heat_all`, the ONE pinned tensor
+    [total frames, H, W, J] every clip's heat maps are a view of (what the zero-copy path reads in place)."""
+    heat_all = None
+
+
+def _unpickle(data_id):
     with open("{}/test_data.pkl".format(data_id), "rb") as f:
-        data = pickle.load(f)
-    return {k: np.asarray(data[k]) for k in ("estimated_local_skeleton", "gt_global_skeleton", "camera_pose_list",
-                                             "heatmap_list")}
+        return pickle.load(f)
+
+
+def load_clips(data_ids, pinned=True):
+    """'<data_id>/test_data.pkl' of every clip (optimizer.py:315-324; extra keys are ignored) unpickled and landed
+    ONCE in page-locked host memory: each per-frame list is stacked straight into its slice of one pinned buffer
+    per key, so the solver can read the heat maps where they are (or DMA them) without another host copy."""
+    raws = [_unpickle(d) for d in data_ids]
+    n_frames = [len(r["estimated_local_skeleton"]) for r in raws]
+    offs = np.concatenate([[0], np.cumsum(n_frames)]).astype(np.int64)
+    total = int(offs[-1])
+    clips = ClipSet({} for _ in raws)
+    for key in CLIP_KEYS:
+        if any(key not in r for r in raws):
+            if key == "gt_global_skeleton":
+                continue
+            raise KeyError("test_data.pkl lacks the key {!r}".format(key))
+        shape = tuple(np.asarray(next(r[key][0] for r in raws if len(r[key]))).shape) if total else ()
+        dt = _CLIP_DTYPES[key]
+        buf = _pinned("clip_" + key, (total,) + shape, dt) if pinned else torch.from_numpy(np.empty((total,) + shape, dt))
+        view = buf.numpy()
+        for i, r in enumerate(raws):
+            frames = r[key]
+            if len(frames) != n_frames[i]:
+                raise ValueError("{}: {} has {} frames, expected {}".format(data_ids[i], key, len(frames), n_frames[i]))
+            dst = view[offs[i]:offs[i + 1]]
+            if n_frames[i]:
+                if isinstance(frames, np.ndarray):
+                    np.copyto(dst, frames, casting="same_kind")
+                else:
+                    np.stack(frames, out=dst, casting="same_kind")
+            clips[i][key] = buf[offs[i]:offs[i + 1]]
+        if key == "heatmap_list":
+            clips.heat_all = buf
+    return clips
+
+
+def load_clip(data_id, pinned=True):
+    """'<data_id>/test_data.pkl' -> dict of (pinned) host tensors (optimizer.py:315-324); extra keys are ignored."""
+    return load_clips([data_id], pinned=pinned)[0]
+
+
+def _n_windows(n_frames, seq_len=10, overlap=2):
+    return len(range(0, n_frames - seq_len + 1, seq_len - overlap))
+
+
+def solve_clips(clips, camera_model_path, vae_weight=0.0, gmm_weight=0.0, smoothness_weight=0.001, bone_length_weight=0.01,
+                weight_3d=0.01, reproj_weight=0.01, final_smooth=False, max_iter=25, eps=None,
+                local_vae_path=LOCAL_VAE_PATH, global_vae_path=GLOBAL_VAE_PATH, engine=None, ingest="auto",
+                outputs="all", copy_stream=None, group=None):
+    """The batched path behind `main` / `main_batch`, for clips that are already in memory: every window of every clip
+    through local stage -> SLAM transform -> global stage -> stitching in ONE batched solve.  Nothing here
+    synchronises with the host; the results are device tensors.
+
+    clips   : list of dicts (reference pickle keys) of numpy arrays / host tensors / CUDA tensors, a `ClipSet` from
+              `load_clips`, or an already built `pipeline.WindowBatch` (inputs resident in HBM).
+    ingest  : how host heat maps reach the GPU.  "zero_copy": they stay in ONE pinned host tensor (`ClipSet.heat_all`)
+              and the energy kernel fetches the texels it samples over PCIe (about 2 % of the maps);
+              "upload": piecewise host-to-device copies on `copy_stream`, the solve starts on the first pieces while the
+              rest is in flight; "auto": zero_copy when `clips.heat_all` is pinned, else upload.
+    outputs : "all" = the six stitched sequences of optimizer.py:442-450 per clip; "optimized" = only the final
+              optimised global sequence (with torch.distributed initialised: this rank's frames of it, the clips'
+              windows being sharded over the ranks; `globalegomocap_b200.distributed.stitch_optimized`).
+    Returns dict(batch, sol, merged); `merged[i]` is a dict of device tensors for clip i (None for a clip shorter
+    than one window)."""
+    from . import distributed as gdist
+    from .pipeline import WindowBatch
+    if ingest not in ("auto", "zero_copy", "upload"):
+        raise ValueError("ingest must be 'auto', 'zero_copy' or 'upload'")
+    if outputs not in ("all", "optimized"):
+        raise ValueError("outputs must be 'all' or 'optimized'")
+    prebuilt = isinstance(clips, WindowBatch)
+    if prebuilt:
+        batch_W = clips.W
+        heat_shape = tuple(clips.heat.shape[-3:])
+    else:
+        batch_W = sum(_n_windows(len(c["estimated_local_skeleton"])) for c in clips)
+        heat_shape = tuple(np.shape(clips[0]["heatmap_list"])[-3:]) if len(clips) else (64, 64, 15)
+    eng = engine if engine is not None else shared_engine(batch_W, max(max_iter - 1, 1), heat_hw=heat_shape[:2],
+                                                          num_joints=heat_shape[2])
+    eng.set_camera_json(camera_model_path) if isinstance(camera_model_path, str) else eng.set_camera(*camera_model_path)
+    for which, path in ((0, local_vae_path), (1, global_vae_path)):
+        eng.set_vae(which, load_vae(path, eng.device) if isinstance(path, str) else path)
+    seq_opt = SequenceOptimizer(eng, vae_weight=vae_weight, smoothness_weight=smoothness_weight,
+                                bone_length_weight=bone_length_weight, weight_3d=weight_3d,
+                                reproj_weight=reproj_weight, lr=2, max_iter=max_iter)
+    if prebuilt:
+        batch = clips
+    else:
+        heat_all = getattr(clips, "heat_all", None)
+        zero_copy_ok = (heat_all is not None and isinstance(heat_all, torch.Tensor) and not heat_all.is_cuda and
+                        heat_all.is_pinned() and reproj_weight != 0)
+        if ingest == "zero_copy" and not zero_copy_ok:
+            raise ValueError("ingest='zero_copy' needs the clips' heat maps in one pinned host tensor (load_clips)")
+        if zero_copy_ok and ingest in ("auto", "zero_copy"):
+            batch = WindowBatch(eng, clips, host_heat=heat_all)
+        else:
+            host_side = len(clips) > 0 and not (isinstance(clips[0]["heatmap_list"], torch.Tensor) and
+                                                clips[0]["heatmap_list"].is_cuda)
+            if host_side and copy_stream is None:
+                copy_stream = _copy_stream(eng.device)
+            batch = WindowBatch(eng, clips, copy_stream=copy_stream if host_side else None)
+    sol = seq_opt.solve(batch, eps=eps)
+    if batch.ready_events:
+        eng.set_slices(None)
+    if outputs == "all":
+        merged = seq_opt.stitch(batch, sol, final_smooth=final_smooth is True)
+    else:
+        opt_global = eng.to_global(sol["glob"]["pose"], sol["cams"])                  # optimizer.py:421
+        wo = batch.window_offsets
+        live = [i for i, n in enumerate(batch.n_windows) if n > 0]
+        seqs = gdist.stitch_optimized(eng, [opt_global[wo[i]:wo[i + 1]] for i in live],
+                                      final_smooth=final_smooth is True, group=group)
+        merged = [None] * len(batch.n_windows)
+        for i, q in zip(live, seqs):
+            merged[i] = {"final_optimized_seq": q}
+    return dict(batch=batch, sol=sol, merged=merged, engine=eng)
+
+
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    key = str(device)
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=device)
+    return _copy_streams[key]
 
 
 def main_batch(data_ids, camera_model_path, vae_weight, gmm_weight, smoothness_weight, bone_length_weight, weight_3d,
                reproj_weight, visualization=False, final_smooth=False, merge=True, save=False, save_pose=False,
-               max_iter=25, eps=None, local_vae_path=LOCAL_VAE_PATH, global_vae_path=GLOBAL_VAE_PATH, engine=None):
-    """`main` for several clips at once: every window of every clip is optimised in ONE batched
-    solve instead of one `main` call per 100-frame clip (optimize_whole_sequence.py:48-63 loops over the clips, and
+               max_iter=25, eps=None, local_vae_path=LOCAL_VAE_PATH, global_vae_path=GLOBAL_VAE_PATH, engine=None,
+               ingest="auto"):
+    """`main` for several clips at once: every window of every clip is optimised in ONE batched solve
+    instead of one `main` call per 100-frame clip (optimize_whole_sequence.py:48-63 loops over the clips, and
     each call reloads both checkpoints, optimizer.py:332-350).  Returns the list of `main`'s return tuples, clip by
-    clip.  The reparameterisation noise is drawn as one (sum W, 2, latent) block, which consumes the global torch
-    generator exactly like consecutive `main` calls do, so batched and per-clip runs see the same z0."""
-    clips = [load_clip(d) for d in data_ids]
-    seq_len, overlap = 10, 2
-    n_win = [len(range(0, len(c["estimated_local_skeleton"]) - seq_len + 1, seq_len - overlap)) for c in clips]
+    clip.  The pickles are landed once in pinned host memory (`load_clips`) and the heat maps are read from there by
+    the GPU (`solve_clips`, ingest).  The reparameterisation noise is drawn as one (sum W, 2, latent) block, which
+    consumes the global torch generator exactly like consecutive `main` calls do, so batched and per-clip runs see the
+    same z0."""
+    if visualization is True or save:
+        # (checked before any work is done: the reference's open3d mesh export is outside this path)
+        raise NotImplementedError("mesh visualisation / .ply export need open3d and are outside this path")
+    clips = load_clips(data_ids)
+    n_win = [_n_windows(len(c["estimated_local_skeleton"])) for c in clips]
     for d, n in zip(data_ids, n_win):
         if n <= 0:
-            raise ValueError("clip {} is shorter than one window ({} frames)".format(d, seq_len))
-    eng = engine if engine is not None else shared_engine(sum(n_win), max(max_iter - 1, 1))
-    eng.set_camera_json(camera_model_path)
-    eng.set_vae(0, load_vae(local_vae_path, eng.device))
-    eng.set_vae(1, load_vae(global_vae_path, eng.device))
-    seq_opt = SequenceOptimizer(eng, vae_weight=vae_weight, smoothness_weight=smoothness_weight,
-                                bone_length_weight=bone_length_weight, weight_3d=weight_3d,
-                                reproj_weight=reproj_weight, lr=2, max_iter=max_iter)
+            raise ValueError("clip {} is shorter than one window ({} frames)".format(d, 10))
+    if "gt_global_skeleton" not in clips[0]:
+        raise KeyError("test_data.pkl lacks the key 'gt_global_skeleton' (optimizer.py:318)")
     if eps is None:
         # the reference draws torch.randn_like(std) of shape (1, 2048) in the order local(w0),
         # global(w0), local(w1), ... from the global generator; one CPU draw of (W, 2, 2048)
         # consumes the same stream
-        eps = torch.randn(sum(n_win), 2, eng.n)
-    batch, sol, merged = seq_opt.run(clips, eps=eps, final_smooth=final_smooth is True)
-    _raise_on_status(sol["local"]["status"])
-    if visualization is True or save:
-        raise NotImplementedError("mesh visualisation / .ply export need open3d and are outside this path")
+        eps = torch.randn(sum(n_win), 2, 2048)
+    out = solve_clips(clips, camera_model_path, vae_weight, gmm_weight, smoothness_weight, bone_length_weight, weight_3d,
+                      reproj_weight, final_smooth=final_smooth, max_iter=max_iter, eps=eps,
+                      local_vae_path=local_vae_path, global_vae_path=global_vae_path, engine=engine, ingest=ingest)
+    _raise_on_status(out["sol"]["local"]["status"])
     results = []
-    for data_id, m in zip(data_ids, merged):
+    for data_id, m in zip(data_ids, out["merged"]):
         final_estimated_seq = list(m["final_estimated_seq"].cpu().numpy())
         mid_estimated_seq = list(m["mid_estimated_seq"].cpu().numpy())
         mid_local_pose_seq = list(m["mid_local_pose_seq"].cpu().numpy())
@@ -201,9 +361,10 @@ def main_batch(data_ids, camera_model_path, vae_weight, gmm_weight, smoothness_w
 
 def main(data_id, camera_model_path, vae_weight, gmm_weight, smoothness_weight, bone_length_weight, weight_3d,
          reproj_weight, visualization=False, final_smooth=False, merge=True, save=False, save_pose=False,
-         max_iter=25, eps=None, local_vae_path=LOCAL_VAE_PATH, global_vae_path=GLOBAL_VAE_PATH, engine=None):
+         max_iter=25, eps=None, local_vae_path=LOCAL_VAE_PATH, global_vae_path=GLOBAL_VAE_PATH, engine=None,
+         ingest="auto"):
     """The reference's `optimizer.main` (optimizer.py:311-507) for one clip."""
     return main_batch([data_id], camera_model_path, vae_weight, gmm_weight, smoothness_weight, bone_length_weight,
                       weight_3d, reproj_weight, visualization=visualization, final_smooth=final_smooth, merge=merge,
                       save=save, save_pose=save_pose, max_iter=max_iter, eps=eps, local_vae_path=local_vae_path,
-                      global_vae_path=global_vae_path, engine=engine)[0]
+                      global_vae_path=global_vae_path, engine=engine, ingest=ingest)[0]

@@ -150,10 +150,30 @@ class WindowBatch:
                 if t is not None:
                     t.record_stream(copy_stream)
         # mean bone length per clip from the fp32 cast of the whole clip's local estimate
-        # (BodyPoseOptimizer.__init__, optimizer.py:42-43, 333, 343)
+        # (BodyPoseOptimizer.__init__, optimizer.py:42-43, 333, 343); a clip that is one rank's shard of a longer
+        # sequence brings the whole sequence's lengths along ("mean_bone_length", computed before sharding)
         est32 = self.est.to(torch.float32)
         bone = torch.linalg.vector_norm(est32 - est32[:, parents, :], dim=-1)   # [F,15]
-        self.mean_bone = torch.stack([bone[offs[i]:offs[i + 1]].mean(0) for i in range(len(clips))])
+        self.mean_bone = torch.stack([
+            torch.as_tensor(np.asarray(clips[i]["mean_bone_length"], dtype=np.float32), device=dev)
+            if "mean_bone_length" in clips[i] else bone[offs[i]:offs[i + 1]].mean(0) for i in range(len(clips))])
+
+    def replicate(self, R):
+        """Every window R times (independent solves from their own noise that share the clips' inputs in HBM):
+        the 1e5-window point of BASELINE configs[4] without 200 GB of heat maps.  Replica r of clip i becomes
+        clip r * n_clips + i."""
+        R = int(R)
+        if R <= 1:
+            return self
+        n_clips = len(self.n_windows)
+        self.frame_base, self.clip_idx = self.frame_base.repeat(R), self.clip_idx.repeat(R)
+        self.frame_idx = self.frame_idx.repeat(R, 1)
+        self.n_windows = list(self.n_windows) * R
+        self.starts = list(self.starts) * R
+        self.window_offsets = np.concatenate([[0], np.cumsum(self.n_windows)]).astype(np.int64)
+        self.W = int(self.window_offsets[-1])
+        self.n_clips_unique = n_clips
+        return self
 
     def clip_slices(self, min_windows=96):
         """Slice starts for the library: the upload pieces when the batch was uploaded on a copy stream, else

@@ -274,6 +274,14 @@ def mean_pose_bias(clip) -> np.ndarray:
     return np.asarray(clip["estimated_local_skeleton"], dtype=np.float64).mean(axis=0).reshape(45).astype(np.float32)
 
 
+def mean_bone_length(skeleton) -> np.ndarray:
+    """(15,) fp32 mean bone lengths over all frames of a clip's local estimate, cast to fp32 first
+    (BodyPoseOptimizer.__init__, reference optimizer.py:42-43, 89-94, 333)."""
+    s = np.asarray(skeleton).astype(np.float32).reshape(-1, NUM_JOINTS, 3)
+    b = s - s[:, list(KINEMATIC_PARENTS), :]
+    return np.sqrt((b * b).sum(-1)).mean(0, dtype=np.float32)
+
+
 def window_starts(n_frames: int, seq_len: int = SEQ_LEN, overlap: int = OVERLAP):
     """Bit-exact window partition of reference optimizer.py:370."""
     return list(range(0, n_frames - seq_len + 1, seq_len - overlap))

@@ -44,9 +44,12 @@ enum gem_status {
     GEM_ERR_CAPACITY = -4   /* more windows than the ctx was created for */
 };
 
-/* per-window status bits written by the energy kernel */
+/* per-window status bits */
 #define GEM_WIN_NORM_ZERO 1u /* a joint had x = y = 0 in the camera frame: the reference raises
                                 Exception("norm is zero!") (FishEyeCalibrated.py:108,124-127) */
+#define GEM_WIN_F16_RANGE 2u /* an activation or latent entry of the window exceeded fp16's finite range (65504) while the
+                                tensor-core layers ran in the split-fp16 scheme (gemm modes 2, 3): operands saturate, the
+                                result is no longer fp32-faithful.  Re-run with gem_ctx_set_gemm_mode(ctx, 1) (3xTF32). */
 
 /* weights of total_loss in the reference's order of appearance (optimizer.py:239-240) */
 typedef struct gem_energy_weights {
@@ -213,7 +216,7 @@ int gem_solve_stage(gem_ctx* ctx, void* stream, int which, int W, const float* p
  * gem_relative_global of its result with cams_d [W][T][4][4] float64, then gem_solve_stage(which = 1) with
  * weights_global_h (reproj must be 0) anchored at the transformed pose.  eps_d is [W][2][latent] (local, global).
  * Outputs: local_pose_d, global_pose_d [W][T][J][3] fp32; rel_f32_d (required) / rel_f64_d (optional) the
- * transformed local result; n_iter_d, func_evals_d [2][W] (optional); status_d [W] (optional, local stage). */
+ * transformed local result; n_iter_d, func_evals_d [2][W] (optional); status_d [W] (optional: GEM_WIN_* bits of both stages OR-ed). */
 int gem_solve_windows(gem_ctx* ctx, void* stream, int W, const float* pose0_d, const float* heat_d,
                       const int64_t* frame_base_d, const int32_t* clip_d, const float* mean_bone_d,
                       const double* cams_d, const float* eps_d, const gem_energy_weights* weights_local_h,

@@ -185,3 +185,64 @@ def test_main_batch_equals_per_clip_main(workdir, monkeypatch):
         assert np.array_equal(np.asarray(est1), np.asarray(est2)) and np.array_equal(np.asarray(gt1), np.asarray(gt2))
         for k in e1:
             np.testing.assert_array_equal(e1[k], e2[k])
+
+
+def test_main_batch_ingest_modes_are_bit_identical(workdir, monkeypatch, vae_weights):
+    """`main_batch` lands the pickles in pinned memory once (load_clips) and solves with the heat maps
+    read in place over PCIe (ingest 'zero_copy', the default), or uploaded piecewise on a copy stream ('upload');
+    both give exactly what `solve_clips` gives on clips already resident in HBM, and `outputs='optimized'` is the
+    same optimised sequence."""
+    from globalegomocap_b200 import optimizer as gem
+    from globalegomocap_b200.pipeline import WindowBatch
+    monkeypatch.chdir(workdir)
+    names = []
+    for i, frames in enumerate((810, 26, 402)):              # 101 + 3 + 50 windows: several slices, ragged clips
+        d = os.path.join("data", "ingest", "clip%d" % i)
+        syn.write_clip_pickle(syn.make_clip(frames, seed=60 + i), str(workdir / d))
+        names.append(d)
+    kw = dict(camera_model_path=syn.DEFAULT_CAMERA_JSON, vae_weight=0.0, gmm_weight=0.0, smoothness_weight=0.001,
+              bone_length_weight=0.01, weight_3d=0.01, reproj_weight=0.01, final_smooth=True, max_iter=4)
+    W = 101 + 3 + 50
+    eps = torch.randn(W, 2, 2048, generator=torch.Generator().manual_seed(8))
+    zero = gem.main_batch(names, eps=eps, ingest="zero_copy", **kw)
+    auto = gem.main_batch(names, eps=eps, **kw)
+    up = gem.main_batch(names, eps=eps, ingest="upload", **kw)
+    clips = gem.load_clips(names)
+    assert clips.heat_all.is_pinned()
+    eng = gem.shared_engine(W, 3)
+    resident = WindowBatch(eng, [{k: v.cuda() for k, v in c.items()} for c in clips])
+    res = gem.solve_clips(resident, eps=eps, **kw)
+    opt_only = gem.solve_clips(resident, eps=eps, outputs="optimized", **kw)
+    torch.cuda.synchronize()
+    for i in range(3):
+        want = res["merged"][i]
+        for other in (zero, auto, up):
+            errors, est, mid, opt, gt = other[i]
+            assert np.array_equal(opt, want["final_optimized_seq"].cpu().numpy())
+            assert np.array_equal(np.asarray(mid), want["mid_local_pose_seq"].cpu().numpy())
+            assert np.array_equal(np.asarray(est), want["final_estimated_seq"].cpu().numpy())
+        assert torch.equal(opt_only["merged"][i]["final_optimized_seq"], want["final_optimized_seq"])
+    with pytest.raises(NotImplementedError):                 # rejected before any work is done
+        gem.main_batch(names, eps=eps, save=True, **kw)
+
+
+def test_replicated_windows_share_inputs(vae_weights, camera):
+    """WindowBatch.replicate (the 1e5-window sweep point of BASELINE configs[4]): replicas fed the same noise give
+    the same result as the original windows; each replica is stitched as its own clip."""
+    from globalegomocap_b200 import optimizer as gem
+    from globalegomocap_b200.engine import Engine
+    from globalegomocap_b200.pipeline import WindowBatch
+    from globalegomocap_b200.vae_prep import PreparedVae
+    clips = [syn.make_clip(50, seed=70), syn.make_clip(26, seed=71)]
+    eng = Engine(max_windows=64)
+    prep = (PreparedVae(vae_weights[0], eng.device), PreparedVae(vae_weights[1], eng.device))
+    kw = dict(camera_model_path=camera, final_smooth=True, max_iter=3, local_vae_path=prep[0], global_vae_path=prep[1],
+              engine=eng, outputs="optimized")
+    eps = torch.randn(9, 2, 2048, generator=torch.Generator().manual_seed(2))
+    one = gem.solve_clips(WindowBatch(eng, clips), eps=eps, **kw)
+    rep = gem.solve_clips(WindowBatch(eng, clips).replicate(3), eps=eps.repeat(3, 1, 1), **kw)
+    assert len(rep["merged"]) == 6 and rep["batch"].W == 27
+    for r in range(3):
+        for i in range(2):
+            assert torch.equal(rep["merged"][2 * r + i]["final_optimized_seq"], one["merged"][i]["final_optimized_seq"])
+    eng.close()

@@ -57,3 +57,64 @@ def test_lift_host_pieces_match_reference_vectors(golden_dir):
     p0 = g["points"][0].copy()
     skeleton_resize(p0, g["bone_length"])
     assert np.array_equal(p0, g["points"][0])
+
+
+def test_load_clips_lands_every_clip_in_one_staging_buffer(tmp_path):
+    """optimizer.load_clips (reference optimizer.py:315-324): the pickles' per-frame lists are stacked into one buffer
+    per key (pinned when there is a GPU), the clips are views of it, extra keys are ignored, dtypes are the
+    reference's.  Without CUDA the same code runs on pageable memory."""
+    import pickle
+
+    from globalegomocap_b200 import optimizer as gem
+    from globalegomocap_b200 import synthetic as syn
+    clips = [syn.make_clip(n, seed=40 + i) for i, n in enumerate((18, 26))]
+    dirs = []
+    for i, c in enumerate(clips):
+        d = tmp_path / f"data_start_{i}_end_{i + 1}"
+        syn.write_clip_pickle(c, str(d))
+        with open(d / "test_data.pkl", "rb") as f:          # an extra key like the data-prep script writes
+            raw = pickle.load(f)
+        raw["estimated_global_skeleton"] = raw["gt_global_skeleton"]
+        with open(d / "test_data.pkl", "wb") as f:
+            pickle.dump(raw, f)
+        dirs.append(str(d))
+    cs = gem.load_clips(dirs)
+    assert isinstance(cs, gem.ClipSet) and len(cs) == 2
+    assert tuple(cs.heat_all.shape) == (18 + 26, 64, 64, 15) and cs.heat_all.dtype == torch.float32
+    off = 0
+    for c, got in zip(clips, cs):
+        assert set(got) == set(gem.CLIP_KEYS)
+        for k in gem.CLIP_KEYS:
+            assert np.array_equal(got[k].numpy(), c[k]), k
+        n = len(c["heatmap_list"])
+        assert got["heatmap_list"].data_ptr() == cs.heat_all[off:off + n].data_ptr()      # a view, not a copy
+        assert got["estimated_local_skeleton"].dtype == torch.float64
+        off += n
+    one = gem.load_clip(dirs[1])
+    assert np.array_equal(one["camera_pose_list"].numpy(), clips[1]["camera_pose_list"])
+
+
+def test_bench_workload_resolution_and_strong_shards():
+    """bench.py --windows tiles BASELINE configs[4]'s sweep points; --scaling strong cuts every sequence's windows
+    into contiguous per-rank blocks whose frames cover each window once."""
+    import argparse
+
+    import bench
+    from globalegomocap_b200 import distributed as gd
+    ns = argparse.Namespace(windows=0, sequences=5, frames=3000)
+    assert bench.resolve_workload(ns) == (5, 3000, 1)
+    for want, got in ((1000, (3, 3000, 1)), (10000, (27, 3000, 1)), (100000, (27, 3000, 10))):
+        ns.windows = want
+        assert bench.resolve_workload(ns) == got
+        n_seq, frames, rep = got
+        assert abs(n_seq * 374 * rep - want) / want < 0.15
+    world, frames = 4, 250
+    n_win = len(range(0, frames - 10 + 1, 8))
+    seen = []
+    for r in range(world):
+        part = bench.make_strong_clips(1, frames, r, world)[0]
+        lo, hi = gd.shard_range(n_win, r, world)
+        assert len(part["estimated_local_skeleton"]) == 8 * (hi - lo - 1) + 10
+        assert part["mean_bone_length"].shape == (15,)
+        seen += list(range(lo, hi))
+    assert seen == list(range(n_win))
