@@ -36,8 +36,8 @@ class ReferenceRunner:
 
     def __init__(self, root, clip, weights, camera_json, max_iter=25):
         import torch
-        os.environ.setdefault("CUDA_VISIBLE_DEVICES", "")            # (set before the reference picks its device)
-        self.torch = torch
+        self.torch = torch            # (the reference runs on cuda when torch sees one, optimizer.py:39: callers that want
+                                      #  its CPU path hide the GPUs with CUDA_VISIBLE_DEVICES before importing torch)
         self.root = root
         self.scratch = tempfile.mkdtemp(prefix="gem_ref_run_")
         from globalegomocap_b200 import synthetic as syn
@@ -80,16 +80,39 @@ class ReferenceRunner:
         self._cls.reparameterize = self._orig
         os.chdir(self._cwd)
 
+    def solve_stage(self, which, x0, heat, eps):
+        """One optimize_pose_seq_pytorch_LBFGS call of the local (0) or global (1) optimiser with the energies of every
+        closure evaluation recorded: (pose (10,15,3) float32, [E_0, E_1, ...])."""
+        torch = self.torch
+        opt = self.local if which == 0 else self.glob
+        energies = []
+        cls = type(opt)
+        orig = cls.total_loss
+
+        def traced(self_, hidden):
+            e = orig(self_, hidden)
+            energies.append(float(e.detach()))
+            return e
+
+        cls.total_loss = traced
+        try:
+            self.queue.append(torch.from_numpy(np.asarray(eps, np.float32)).view(1, -1).to(opt.device))
+            x0 = np.asarray(x0)
+            pose = opt.optimize_pose_seq_pytorch_LBFGS(x0, np.asarray(heat), x0.copy())
+        finally:
+            cls.total_loss = orig
+        return pose, energies
+
     def window(self, start, eps):
         """One iteration of the reference's window loop (optimizer.py:372-419): local stage, SLAM transform, global stage."""
         torch = self.torch
         est = np.asarray(self.clip["estimated_local_skeleton"])[start:start + 10]
         heat = np.asarray(self.clip["heatmap_list"])[start:start + 10]
         cams = np.asarray(self.clip["camera_pose_list"])[start:start + 10]
-        self.queue.append(torch.from_numpy(np.asarray(eps[0], np.float32)).view(1, -1))
+        self.queue.append(torch.from_numpy(np.asarray(eps[0], np.float32)).view(1, -1).to(self.local.device))
         local = self.local.optimize_pose_seq_pytorch_LBFGS(est, heat, est.copy())
         rel = self.ref.get_relative_global_pose_with_camera_matrix(local, cams)
-        self.queue.append(torch.from_numpy(np.asarray(eps[1], np.float32)).view(1, -1))
+        self.queue.append(torch.from_numpy(np.asarray(eps[1], np.float32)).view(1, -1).to(self.glob.device))
         return self.glob.optimize_pose_seq_pytorch_LBFGS(rel, heat, rel.copy())
 
     def time_windows(self, first_window, n_windows, seed=0):
