@@ -29,7 +29,7 @@ SOURCES = {
     "metrics.cu": [],
     "gemm_simt.cu": [],
     "gemm_tc.cu": [],
-    "gemm_tap_tc.cu": [],
+    "gemm_tap_tc.cu": ["--fmad=false"],       # includes energy_device.cuh (the chain kernel's energy prologue)
 }
 
 

@@ -28,6 +28,7 @@ struct gem_ctx {
     int device = 0;
     int Wmax = 0, n = 0, T = 0, J = 0, H = 0, Wd = 0, m = 0;
     int gemm_mode = 0;
+    int fuse_energy = 1;                         // mode 3 + CTA-pair chains: the backward chain evaluates the energy itself (GEM_FUSE_ENERGY)
     int tap_chain = 2;                           // mode 3: 0 one launch per k=3 layer, 1 the four K<=128 layers of each direction
                                                  // in one launch, 2 all five on CTA pairs (cta_group::2) in one launch
     bool have_camera = false, have_skeleton = false;
@@ -250,6 +251,7 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     if (const char* env = getenv("GEM_GEMM_MODE")) c->gemm_mode = (env[0] >= '0' && env[0] <= '3') ? env[0] - '0' : 3;
     if (const char* env = getenv("GEM_TAP_CHAIN")) c->tap_chain = (env[0] >= '0' && env[0] <= '2') ? env[0] - '0' : 2;
     if (const char* env = getenv("GEM_ENC_TC")) c->enc_tc_on = env[0] != '0';
+    if (const char* env = getenv("GEM_FUSE_ENERGY")) c->fuse_energy = env[0] != '0';
     c->n_chunks = 0;      // automatic (slice_bounds)
     if (const char* env = getenv("GEM_CHUNKS")) c->n_chunks = atoi(env) >= 0 ? atoi(env) : 0;
     if (c->n_chunks > 16) c->n_chunks = 16;
@@ -311,6 +313,12 @@ int gem_debug_tap_chain(gem_ctx* c, int mode) {
     return GEM_OK;
 }
 /* debug hook: 1 = the encoder's 128 -> 256 -> 512 layers on the tcgen05 tap kernel (mode 3), 0 = CUDA cores (default) */
+/* debug hook: 1 = the backward chain evaluates the energy in its prologue (default), 0 = separate energy kernel */
+int gem_debug_fuse_energy(gem_ctx* c, int on) {
+    GEM_REQUIRE(c != nullptr, "ctx is NULL");
+    c->fuse_energy = on ? 1 : 0;
+    return GEM_OK;
+}
 int gem_debug_enc_tc(gem_ctx* c, int on) {
     GEM_REQUIRE(c != nullptr, "ctx is NULL");
     c->enc_tc_on = on ? 1 : 0;
@@ -535,6 +543,11 @@ static int run_tap_tc(gem_ctx* c, cudaStream_t s, int tag, const gem_layer& L, c
 }
 
 static bool use_tc_chain(const gem_ctx* c, int which, int W) { return c->gemm_mode >= 1 && c->tap_tc[which] && W >= 1; }
+// the backward chain on CTA pairs can evaluate the energy terms in its prologue (gemm_tap_tc.cu: Chain2Energy)
+static bool fused_energy_ok(const gem_ctx* c, int which, int W) {
+    return c->fuse_energy && use_tc_chain(c, which, W) && c->gemm_mode == 3 && c->tap_chain == 2 &&
+           tap_chain_energy_supported(c->T, c->J, pose_pad(c));
+}
 
 // Scratch of the windows [w0, w0 + W): every per-window buffer of the ctx shifted by w0.  Chunks of one
 // stage run concurrently on different streams, each on its own slice.
@@ -648,8 +661,9 @@ static int decode_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice
 }
 
 // dpose_is_split: the slice's gp_hi / gp_lo already hold dpose (written by the energy kernel)
+// en: the chain kernel evaluates the energy itself (fused_energy_ok) and no d pose exists anywhere
 static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const Slice& v_, const float* dpose, float* dz,
-                           bool dpose_is_split = false, uint32_t* status = nullptr) {
+                           bool dpose_is_split = false, uint32_t* status = nullptr, const ChainEnergyLaunch* en = nullptr) {
     const gem_vae_weights& v = c->vae[which];
     const int T = c->T, M = W * T, P = c->J * 3;
     // the LeakyReLU derivative only needs the sign of the saved activation, which its TF32 hi part keeps
@@ -680,6 +694,7 @@ static int decode_vjp_impl(gem_ctx* c, cudaStream_t s, int which, int W, const S
             }
             t.A_hi = in_hi, t.A_lo = in_lo, t.lda = pp, t.Kreal = pp;
             t.out_hi = v_.gact_hi[0], t.out_lo = v_.gact_lo[0], t.ldo = v.dec_bwd[4].n, t.W = W, t.T = T, t.status = status;
+            t.energy = en;
             GEM_TRY(timed(c, s, GEM_TAG_DEC_BWD + 0, [&]() { return launch_tap_chain_pair(s, c, t); }));
             i0 = 5;
         } else if (c->gemm_mode == 3 && c->tap_chain && c->act_split) {
@@ -993,6 +1008,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
                         a.eps_stride, v.status_own));
     GEM_TRY(timed(c, q, GEM_TAG_LBFGS_BEGIN, [&]() { return launch_lbfgs_begin(q, lb, v.z0, Wk); }));
     const bool tc = use_tc_chain(c, which, Wk);
+    const bool fused = fused_energy_ok(c, which, Wk);
     // one closure round: decode -> fused energy/gradient -> decoder bwd-data -> L-BFGS advance
     auto enqueue_round = [&]() -> int {
         GEM_TRY(decode_impl(c, q, which, Wk, v, lb.ZT, v.pose, tc ? lb.ZT_hi : nullptr, tc ? lb.ZT_lo : nullptr, v.status_own));
@@ -1003,14 +1019,28 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
                                              v.patch_valid, c->patch_stats_on ? c->patch_stats : nullptr,
                                              c->texel_prefetch_ctas);
             }));
-        GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
-            return launch_energy_grad(q, c->have_camera ? &c->cam : nullptr, &c->skel, Wk, c->T, c->J, c->H, c->Wd, v.pose,
-                                      v.pose0_own, a.heat, v.fb_own, v.clip_own,
-                                      v.mb_own, a.wt, v.f_new, nullptr, v.gpose, v.status_own, tc ? v.gp_hi : nullptr,
-                                      v.gp_lo, pose_pad(c), a.texel_cache ? v.patch : nullptr, v.patch_origin,
-                                      c->patch_stats_on ? c->patch_stats : nullptr, c->gemm_mode == 3, v.row_exp, v.patch_valid);
-        }));
-        GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, v.gpose, v.g_new, tc, v.status_own));
+        if (fused) {
+            // the backward chain evaluates the energy in its prologue: no energy launch, no d pose in memory
+            ChainEnergyLaunch en;
+            en.cam = c->have_camera ? &c->cam : nullptr, en.skel = &c->skel;
+            en.pose = v.pose, en.pose0 = v.pose0_own, en.heat = a.heat, en.frame_base = v.fb_own, en.clip = v.clip_own;
+            en.mean_bone = v.mb_own, en.wt = a.wt, en.energy = v.f_new, en.status = v.status_own, en.row_exp = v.row_exp;
+            en.J = c->J, en.H = c->H, en.Wd = c->Wd;
+            if (a.texel_cache) {
+                en.patch = v.patch, en.patch_origin = v.patch_origin, en.patch_valid = v.patch_valid;
+                en.patch_stats = c->patch_stats_on ? c->patch_stats : nullptr;
+            }
+            GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, nullptr, v.g_new, true, v.status_own, &en));
+        } else {
+            GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
+                return launch_energy_grad(q, c->have_camera ? &c->cam : nullptr, &c->skel, Wk, c->T, c->J, c->H, c->Wd, v.pose,
+                                          v.pose0_own, a.heat, v.fb_own, v.clip_own,
+                                          v.mb_own, a.wt, v.f_new, nullptr, v.gpose, v.status_own, tc ? v.gp_hi : nullptr,
+                                          v.gp_lo, pose_pad(c), a.texel_cache ? v.patch : nullptr, v.patch_origin,
+                                          c->patch_stats_on ? c->patch_stats : nullptr, c->gemm_mode == 3, v.row_exp, v.patch_valid);
+            }));
+            GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, v.gpose, v.g_new, tc, v.status_own));
+        }
         return timed(c, q, GEM_TAG_LBFGS_ADVANCE, [&]() { return launch_lbfgs_advance(q, lb, v.f_new, v.g_new, Wk); });
     };
     // LBFGS.step: at most max_eval + 1 closure evaluations per window (lbfgs.py:478-487, App. B)
@@ -1019,7 +1049,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     int round_launches = 0;
     if (graphs && a.p.max_eval >= 2) {
         for (auto& g : c->graphs) {
-            if (g.which == which && g.w0 == w0 && g.Wk == Wk && g.gemm_mode == (c->gemm_mode | (c->tap_chain << 8)) && g.heat == a.heat &&
+            if (g.which == which && g.w0 == w0 && g.Wk == Wk && g.gemm_mode == (c->gemm_mode | (c->tap_chain << 8) | (c->fuse_energy << 12)) && g.heat == a.heat &&
                 g.has_heat == ((a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * c->texel_prefetch_ctas) &&
                 g.trace_stride == lb.trace_stride &&
                 memcmp(&g.wt, &a.wt, sizeof(a.wt)) == 0 && g.p.lr == a.p.lr && g.p.max_iter == a.p.max_iter &&
@@ -1044,7 +1074,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             }
             GEM_CUDA(e);
             gem_ctx::RoundGraph g;
-            g.which = which, g.w0 = w0, g.Wk = Wk, g.gemm_mode = c->gemm_mode | (c->tap_chain << 8), g.heat = a.heat;
+            g.which = which, g.w0 = w0, g.Wk = Wk, g.gemm_mode = c->gemm_mode | (c->tap_chain << 8) | (c->fuse_energy << 12), g.heat = a.heat;
             g.has_heat = (a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * c->texel_prefetch_ctas;
             g.trace_stride = lb.trace_stride, g.wt = a.wt, g.p = a.p;
             g.launches = round_launches;

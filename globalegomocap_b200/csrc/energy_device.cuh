@@ -1,0 +1,265 @@
+// Per-joint part of the fused energy + analytic gradient (total_loss with the decoder bypassed: reference
+// optimizer.py:139-149, 172-177, 202-218, 226-240; FishEyeCalibrated.py:96-129; grid_sample(bilinear, zeros,
+// align_corners=True) and the autograd backward of all of them), shared by the stand-alone energy kernel (energy.cu)
+// and by the backward chain kernel's energy prologue (gemm_tap_tc.cu), so that both evaluate the SAME arithmetic
+// in the SAME order: results do not depend on which kernel runs the term.
+//
+// Every translation unit that includes this header is compiled with --fmad=false: the pixel-coordinate chain must
+// round like ATen's separate fp32 ops, because floor() of the pixel coordinate selects the texels.
+#pragma once
+#include "common.cuh"
+
+namespace gem {
+
+constexpr int kPatchWd = 8;            // side of the per-joint texel window of the cache (at most 8: 64 valid bits)
+constexpr int kEnergySlot = 160;       // joint slots per window (>= T*J, multiple of 32): 5 warps of partial sums
+
+// everything about one energy evaluation that is the same for every joint of the launch
+struct EnergyCommon {
+    const float* heat;
+    const int64_t* frame_base;
+    const int32_t* clip;
+    const float* mean_bone;
+    uint32_t* status;
+    int W, T, J, H, Wd;
+    float w3d, ws, wb, wv, wr;
+    // optional texel cache (used when the heat maps stay in pinned HOST memory and are read over PCIe): per joint
+    // an 8x8 window of its map, 256 contiguous bytes in HBM, the map coordinate of its corner and a valid bit per
+    // texel.  The same few texels are read by every evaluation of a stage (joints move by a fraction of a texel per
+    // step), so only the texels the optimiser actually samples cross the bus, once each while the joint stays in
+    // its window; values are copies of the map's, so the energy is bit-identical with and without the cache.
+    float* patch;              // [W][T*J][kPatchWd * kPatchWd]
+    short2* patch_origin;      // [W][T*J]: map coordinate of the window's corner
+    unsigned long long* patch_valid;   // [W][T*J]: one bit per texel of the window (0: empty window)
+    unsigned long long* patch_stats;   // optional {lookups, texels fetched}
+    // camera and skeleton of the calling ctx: they travel as kernel parameters (constant bank), so two ctxs with
+    // different calibrations never see each other's (FishEyeCalibrated.py:8-14 is per optimiser in the reference too)
+    CameraConst cam;
+    SkeletonConst skel;
+};
+
+__device__ __forceinline__ float texel(const float* __restrict__ heat, int64_t frame, int y, int x, int j, int H,
+                                       int Wd, int J) {
+    if (x < 0 || x >= Wd || y < 0 || y >= H) return 0.f;     // padding_mode='zeros'
+    return __ldg(heat + ((frame * H + y) * (int64_t)Wd + x) * J + j);
+}
+
+// Demand-fetched 8x8 window of one joint's map: origin and a valid bit per texel; only texels of the bilinear footprint
+// (x0, y0) .. (x0+1, y0+1) that are not in the window yet are read from the map (over PCIe when it is host memory).
+// A footprint that leaves the window re-centres it (and empties it).
+__device__ __forceinline__ void cache_lookup(const EnergyCommon& a, size_t pk, int64_t frame, int j, int x0, int y0,
+                                             bool count_lookup, float& nw, float& ne, float& sw, float& se) {
+    constexpr int kPatchW = kPatchWd;
+    float* pe = a.patch + pk * (kPatchW * kPatchW);
+    const short2 o = a.patch_origin[pk];
+    unsigned long long valid = a.patch_valid[pk];
+    int ox = o.x, oy = o.y;
+    int dx = x0 - ox, dy = y0 - oy;
+    if (valid == 0ull || dx < 0 || dx > kPatchW - 2 || dy < 0 || dy > kPatchW - 2)
+        ox = x0 - (kPatchW / 2 - 1), oy = y0 - (kPatchW / 2 - 1), dx = dy = kPatchW / 2 - 1, valid = 0ull;
+    const int b00 = dy * kPatchW + dx;
+    const unsigned long long foot = (3ull | (3ull << kPatchW)) << b00;
+    const unsigned long long missing = foot & ~valid;
+    if (a.patch_stats) {
+        if (count_lookup) atomicAdd(a.patch_stats, 1ull);
+        if (missing) atomicAdd(a.patch_stats + 1, (unsigned long long)__popcll(missing));
+    }
+    float* p0 = pe + b00;
+    if (missing) {                            // up to four independent loads in flight
+        const bool m0 = (missing >> b00) & 1ull, m1 = (missing >> (b00 + 1)) & 1ull;
+        const bool m2 = (missing >> (b00 + kPatchW)) & 1ull, m3 = (missing >> (b00 + kPatchW + 1)) & 1ull;
+        nw = m0 ? texel(a.heat, frame, y0, x0, j, a.H, a.Wd, a.J) : p0[0];
+        ne = m1 ? texel(a.heat, frame, y0, x0 + 1, j, a.H, a.Wd, a.J) : p0[1];
+        sw = m2 ? texel(a.heat, frame, y0 + 1, x0, j, a.H, a.Wd, a.J) : p0[kPatchW];
+        se = m3 ? texel(a.heat, frame, y0 + 1, x0 + 1, j, a.H, a.Wd, a.J) : p0[kPatchW + 1];
+        if (m0) p0[0] = nw;
+        if (m1) p0[1] = ne;
+        if (m2) p0[kPatchW] = sw;
+        if (m3) p0[kPatchW + 1] = se;
+        a.patch_origin[pk] = make_short2((short)ox, (short)oy);
+        a.patch_valid[pk] = valid | missing;
+    } else {
+        nw = p0[0], ne = p0[1], sw = p0[kPatchW], se = p0[kPatchW + 1];
+    }
+}
+
+// Fisheye projection of a joint and the map cell its bilinear footprint starts at (FishEyeCalibrated.py:96-129,
+// optimizer.py:139-149); the arithmetic (and --fmad=false) is what decides the cell, so the energy code and the
+// texel prefetch kernel share it.  Returns false when r == 0.
+struct Proj {
+    float r, inv, rho, drho, ix, iy, fx0, fy0;
+};
+__device__ __forceinline__ bool project_joint(const CameraConst& c_cam, float x, float y, float z, int H, int Wd, Proj& p) {
+    const float zn = -z;
+    p.r = sqrtf(x * x + y * y);
+    if (p.r == 0.f) return false;
+    const float theta = atanf(zn / p.r);
+    float rho = c_cam.poly[0], drho = 0.f, ti = 1.f;
+    for (int i = 1; i < c_cam.n_poly; ++i) {          // power accumulation, not Horner
+        drho += (float)i * c_cam.poly[i] * ti;
+        ti *= theta;
+        rho += ti * c_cam.poly[i];
+    }
+    p.rho = rho, p.drho = drho;
+    p.inv = 1.0f / p.r;
+    const float u = x * p.inv * rho + c_cam.cx;
+    const float v = y * p.inv * rho + c_cam.cy;
+    // pose_2d[:,0] -= 128; (pose_2d - 512)/512; grid_sample unnormalise (align_corners)
+    const float gxn = ((u - 128.f) - 512.f) / 512.f;
+    const float gyn = (v - 512.f) / 512.f;
+    p.ix = ((gxn + 1.f) / 2.f) * (float)(Wd - 1);
+    p.iy = ((gyn + 1.f) / 2.f) * (float)(H - 1);
+    p.fx0 = floorf(p.ix), p.fy0 = floorf(p.iy);
+    return true;
+}
+
+// The five energy terms of joint-frame k = t*J + j of window w and its dE/dx: X / X0 are the window's pose and anchor
+// (T*J*3 floats, shared memory).  e = {E_3d, E_smooth, E_bone, E_vae, E_reproj} contributions, g = weighted gradient.
+__device__ __forceinline__ void joint_energy_grad(const EnergyCommon& a, const float* X, const float* X0, int w, int k,
+                                                  float (&e)[5], float (&g)[3]) {
+    float e3d = 0.f, esm = 0.f, ebn = 0.f, eva = 0.f, erp = 0.f;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    const int TJ = a.T * a.J;
+    {
+        const int t = k / a.J, j = k - t * a.J;
+        const float x = X[k * 3 + 0], y = X[k * 3 + 1], z = X[k * 3 + 2];
+
+        // E_reproj, first half: the projection and the four texel loads are issued before the other terms so that
+        // their DRAM latency overlaps that arithmetic (the terms are still added to the gradient in the old order)
+        bool rp = false;
+        Proj pj;
+        float nw = 0.f, ne = 0.f, sw = 0.f, se = 0.f;
+        if (a.wr != 0.f) {
+            if (!project_joint(a.cam, x, y, z, a.H, a.Wd, pj)) {
+                if (a.status) atomicOr(a.status + w, GEM_WIN_NORM_ZERO);
+            } else if (pj.fx0 >= -1.f && pj.fx0 <= (float)a.Wd && pj.fy0 >= -1.f && pj.fy0 <= (float)a.H) {
+                // (anything further than one texel outside contributes exactly 0)
+                rp = true;
+                const int x0 = (int)pj.fx0, y0 = (int)pj.fy0;
+                const int64_t frame = a.frame_base[w] + t;
+                if (a.patch) {
+                    cache_lookup(a, (size_t)w * TJ + k, frame, j, x0, y0, true, nw, ne, sw, se);
+                } else {
+                    nw = texel(a.heat, frame, y0, x0, j, a.H, a.Wd, a.J);
+                    ne = texel(a.heat, frame, y0, x0 + 1, j, a.H, a.Wd, a.J);
+                    sw = texel(a.heat, frame, y0 + 1, x0, j, a.H, a.Wd, a.J);
+                    se = texel(a.heat, frame, y0 + 1, x0 + 1, j, a.H, a.Wd, a.J);
+                }
+            }
+        }
+
+        // E_3d = sum (x - x0)^2                                     optimizer.py:210-213
+        {
+            const float dx = x - X0[k * 3 + 0], dy = y - X0[k * 3 + 1], dz = z - X0[k * 3 + 2];
+            e3d = dx * dx + dy * dy + dz * dz;
+            gx += a.w3d * (2.f * dx), gy += a.w3d * (2.f * dy), gz += a.w3d * (2.f * dz);
+        }
+        // E_vae = sum x^2 on the decoded pose                        optimizer.py:215-218,238
+        {
+            eva = x * x + y * y + z * z;
+            gx += a.wv * (2.f * x), gy += a.wv * (2.f * y), gz += a.wv * (2.f * z);
+        }
+        // E_smooth: a_s = (x_s - x_{s+1}) - (x_{s+1} - x_{s+2}), s = 0..T-3   optimizer.py:202-208
+        {
+            float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {        // q = 0: a_t (coef 1), 1: a_{t-1} (coef -2), 2: a_{t-2} (coef 1)
+                const int s = t - q;
+                if (s < 0 || s > a.T - 3) continue;
+                const float coef = (q == 1) ? -2.f : 1.f;
+                const float* p0 = X + ((s)*a.J + j) * 3;
+                const float* p1 = X + ((s + 1) * a.J + j) * 3;
+                const float* p2 = X + ((s + 2) * a.J + j) * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float ac = (p0[c] - p1[c]) - (p1[c] - p2[c]);
+                    acc[c] += coef * ac;
+                    if (q == 0) esm += ac * ac;
+                }
+            }
+            gx += a.ws * (2.f * acc[0]), gy += a.ws * (2.f * acc[1]), gz += a.ws * (2.f * acc[2]);
+        }
+        // E_bone = sum (|x_j - x_parent| - Lbar_j)^2                 optimizer.py:172-177, 89-94
+        {
+            const float* mb = a.mean_bone + (size_t)a.clip[w] * a.J;
+            const int p = a.skel.parent[j];
+            const float bx = x - X[(t * a.J + p) * 3 + 0], by = y - X[(t * a.J + p) * 3 + 1],
+                        bz = z - X[(t * a.J + p) * 3 + 2];
+            const float len = sqrtf(bx * bx + by * by + bz * bz);
+            const float diff = len - mb[j];
+            ebn = diff * diff;
+            if (len > 0.f) {                        // torch.norm's subgradient at 0 is 0
+                const float c = a.wb * (2.f * diff) / len;
+                gx += c * bx, gy += c * by, gz += c * bz;
+            }
+            for (int ci = a.skel.child_start[j]; ci < a.skel.child_start[j + 1]; ++ci) {   // this joint as a parent
+                const int cj = a.skel.child_list[ci];
+                const float cx = X[(t * a.J + cj) * 3 + 0] - x, cy = X[(t * a.J + cj) * 3 + 1] - y,
+                            cz = X[(t * a.J + cj) * 3 + 2] - z;
+                const float cl = sqrtf(cx * cx + cy * cy + cz * cz);
+                if (cl > 0.f) {
+                    const float c = a.wb * (2.f * (cl - mb[cj])) / cl;
+                    gx -= c * cx, gy -= c * cy, gz -= c * cz;
+                }
+            }
+        }
+        // E_reproj = -sum bilinear(H_tj; pix(project(x)))            optimizer.py:139-149
+        if (rp) {
+            const float r = pj.r, inv = pj.inv, rho = pj.rho, drho = pj.drho;
+            const float ix = pj.ix, iy = pj.iy, fx0 = pj.fx0, fy0 = pj.fy0;
+            const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix;
+            const float wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
+            erp = -(nw * (wx0 * wy0) + ne * (wx1 * wy0) + sw * (wx0 * wy1) + se * (wx1 * wy1));
+            const float ds_dix = -nw * wy0 + ne * wy0 - sw * wy1 + se * wy1;
+            const float ds_diy = -nw * wx0 - ne * wx1 + sw * wx0 + se * wx1;
+            const float du = ds_dix * ((float)(a.Wd - 1) * 0.5f / 512.f);   // dS/du
+            const float dv = ds_diy * ((float)(a.H - 1) * 0.5f / 512.f);    // dS/dv
+            // fisheye Jacobian.  Only the energy's forward chain has to round like ATen's
+            // ops; the gradient is held to 1e-4, so one reciprocal replaces the dozen IEEE divisions.
+            const float r2 = r * r, q = r2 + z * z;
+            const float inv_q = __frcp_rn(q), inv_rq = inv * inv_q;
+            const float dth_dx = z * x * inv_rq, dth_dy = z * y * inv_rq, dth_dz = -r * inv_q;
+            const float xr = x * inv, yr = y * inv;
+            const float rho_r = rho * inv, rho_r3 = rho_r * inv * inv;
+            const float xd = xr * drho, yd = yr * drho;
+            const float du_dx = rho_r - x * x * rho_r3 + xd * dth_dx;
+            const float du_dy = -x * y * rho_r3 + xd * dth_dy;
+            const float du_dz = xd * dth_dz;
+            const float dv_dx = -x * y * rho_r3 + yd * dth_dx;
+            const float dv_dy = rho_r - y * y * rho_r3 + yd * dth_dy;
+            const float dv_dz = yd * dth_dz;
+            gx -= a.wr * (du * du_dx + dv * dv_dx);
+            gy -= a.wr * (du * du_dy + dv * dv_dy);
+            gz -= a.wr * (du * du_dz + dv * dv_dz);
+        }
+    }
+    e[0] = e3d, e[1] = esm, e[2] = ebn, e[3] = eva, e[4] = erp;
+    g[0] = gx, g[1] = gy, g[2] = gz;
+}
+
+// optimizer.py:239-240 (left to right; the reproj product is skipped when its weight is 0) from the window's five
+// term sums
+__device__ __forceinline__ float combine_energy(const EnergyCommon& a, const float (&t5)[5]) {
+    float E = a.w3d * t5[0] + a.ws * t5[1] + a.wb * t5[2] + a.wv * t5[3];
+    if (a.wr != 0.f) E += a.wr * t5[4];
+    return E;
+}
+
+// fp16 scheme: the power of two that brings a window's largest |dE/dx| entry to ~2^4 (gradients shrink to 1e-7 near
+// convergence, far below fp16's normal range); removed again, exactly, by the T*256 -> latent GEMM's epilogue
+__device__ __forceinline__ int grad_exponent(float mx) {
+    int e = 0;
+    if (mx > 0.f && mx < 3.0e38f) {
+        e = 4 - ilogbf(mx);
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    }
+    return e;
+}
+__device__ __forceinline__ void split_f16_energy(float x, uint16_t& h, uint16_t& l) {      // = tc::split_f16
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+    float hf;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(h));
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"((x - hf) * 2048.f));
+}
+
+}  // namespace gem

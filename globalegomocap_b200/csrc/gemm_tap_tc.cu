@@ -37,6 +37,7 @@
 #include <tuple>
 #include <unordered_map>
 
+#include "energy_device.cuh"
 #include "tc_common.cuh"
 
 namespace gem {
@@ -769,8 +770,26 @@ struct Chain2Args {
     long long* dbg;
 };
 
+// Energy prologue of the backward chain (optional): instead of loading d pose tiles that a separate energy kernel
+// wrote, the epilogue warps evaluate the energy terms and their analytic gradient for the CTA's twelve windows
+// themselves (energy_device.cuh: the same arithmetic as energy_grad_kernel, the same reduction tree) from the pose the
+// forward chain left in global memory, scale and split dE/dpose into the first layer's swizzled operand tile, and
+// arrive on act_full.  dE/dpose, its split copies and one launch per round never exist.
+struct Chain2Energy : EnergyCommon {
+    int enabled;
+    int in_buf, scratch0, scratch1;      // activation buffers: first layer's operand; pose / anchor + partial sums
+    const float* pose;                   // [W][T][J][3] decoded pose (the forward chain's output)
+    const float* pose0;                  // [W][T][J][3] the stage's anchor
+    float* energy;                       // [W]
+    int32_t* row_exp;                    // [W] exponent of the window's gradient scale
+};
+static_assert(sizeof(Chain2Maps) + sizeof(Chain2Args) + sizeof(Chain2Energy) <= 4096, "kernel parameters beyond 4 KB");
+constexpr int kEnergyQuarterFloats = 2048;      // scratch floats per TMEM lane quarter in each scratch buffer
+constexpr int kEnergyRedOffset = 1440;          // partial sums live behind the anchor poses in scratch1
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1)
-tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_constant__ Chain2Args g) {
+tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_constant__ Chain2Args g,
+                     const __grid_constant__ Chain2Energy en) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* act = smem;                                   // four buffers of (hi 16 KB, lo 16 KB)
@@ -798,7 +817,7 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a_hi), prefetch_tmap(&maps.a_lo);
-        mbar_init(act_full, 1);
+        mbar_init(act_full, en.enabled ? 2 * kChainEpiWarps : 1);      // energy prologue: the pair's epilogue warps arrive
         mbar_init(&w_full[0], 1), mbar_init(&w_full[1], 1), mbar_init(&w_empty[0], 1), mbar_init(&w_empty[1], 1);
         mbar_init(acc_full, 1), mbar_init(act_ready, 2 * kChainEpiWarps);
         fence_barrier_init();
@@ -819,6 +838,12 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
             uint8_t* p = act + tile * kATile + q * kQuarterBytes + (rows_q + rr) * 128 + c16 * 16;
             *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        if (en.enabled) {
+            // the energy prologue writes only the real channels of valid windows: padding columns, idle rows and the
+            // rows of windows beyond W must read zero (the TMA unit zero-fills them on the loading path)
+            float4* p = reinterpret_cast<float4*>(act + en.in_buf * 2 * kATile);
+            for (int i = threadIdx.x; i < 2 * kATile / 16; i += kChainThreads) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         fence_proxy_async_smem();
     }
     if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
@@ -833,8 +858,8 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
         if (lane == 0) {
             const uint32_t box_bytes = (uint32_t)rows_q * 128;
             const uint32_t act_bar = mapa_u32(smem_u32(act_full), 0);
-            if (rank == 0) mbar_arrive_expect_tx(act_full, 2u * (uint32_t)nkb0 * 8 * box_bytes);
-            for (int kb = 0; kb < nkb0; ++kb) {
+            if (rank == 0 && !en.enabled) mbar_arrive_expect_tx(act_full, 2u * (uint32_t)nkb0 * 8 * box_bytes);
+            for (int kb = 0; kb < (en.enabled ? 0 : nkb0); ++kb) {
                 uint8_t* dst = act + g.L[0].in_buf[kb] * 2 * kATile;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -868,7 +893,8 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
             int b = 0;
             for (int l = 0; l < g.nl; ++l) {
                 const Chain2Layer& L = g.L[l];
-                if (l == 0) mbar_wait(act_full, 0);
+                if (l == 0 && !en.enabled) mbar_wait(act_full, 0);
+                else if (l == 0) mbar_wait_cluster(act_full, 0);          // the pair's energy prologues have written the tiles
                 else mbar_wait_cluster(act_ready, (uint32_t)((l - 1) & 1));
                 tc_fence_after();
                 if (l < 3) TAP_DBG(2 + l);
@@ -910,6 +936,79 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
         const size_t token = (size_t)win * g.T + t;
         const uint32_t ready_bar = mapa_u32(smem_u32(act_ready), 0);
         const int c = sub;
+        if (en.enabled) {
+            // ===== energy prologue: this quarter's windows, 32 joint-frames per (virtual) warp as in energy_grad_kernel =====
+            constexpr int wpw = kEnergySlot / 32;                         // partial sums per window
+            const int TJ = en.T * en.J, n = TJ * 3;
+            float* s_x = reinterpret_cast<float*>(act + en.scratch0 * 2 * kATile) + q * kEnergyQuarterFloats;
+            float* s_x0 = reinterpret_cast<float*>(act + en.scratch1 * 2 * kATile) + q * kEnergyQuarterFloats;
+            float* s_red = s_x0 + kEnergyRedOffset;                      // [wpq][wpw][6]
+            const int tq = sub * 32 + lane;                               // thread within the quarter's four warps
+            int nwin = g.W - winq;
+            nwin = nwin < 0 ? 0 : (nwin > g.wpq ? g.wpq : nwin);
+            {
+                const float* gp = en.pose + (size_t)winq * n;
+                const float* gp0 = en.pose0 + (size_t)winq * n;
+                for (int i = tq; i < nwin * n; i += 128) s_x[i] = gp[i], s_x0[i] = gp0[i];
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+            float gv[4][3];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int v = sub + it * 4;                               // virtual warp: window v / wpw, joints (v % wpw) * 32 ..
+                const int wl_e = v / wpw, k = (v - wl_e * wpw) * 32 + lane;
+                float e5[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, g3[3] = {0.f, 0.f, 0.f};
+                if (wl_e < nwin && k < TJ) joint_energy_grad(en, s_x + wl_e * n, s_x0 + wl_e * n, winq + wl_e, k, e5, g3);
+                gv[it][0] = g3[0], gv[it][1] = g3[1], gv[it][2] = g3[2];
+                if (v < g.wpq * wpw) {                                    // (warp-uniform)
+                    const float r0 = warp_sum(e5[0]), r1 = warp_sum(e5[1]), r2 = warp_sum(e5[2]), r3 = warp_sum(e5[3]),
+                                r4 = warp_sum(e5[4]);
+                    const float r5 = warp_max(fmaxf(fabsf(g3[0]), fmaxf(fabsf(g3[1]), fabsf(g3[2]))));
+                    if (lane == 0) {
+                        float* d = s_red + v * 6;
+                        d[0] = r0, d[1] = r1, d[2] = r2, d[3] = r3, d[4] = r4, d[5] = r5;
+                    }
+                }
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+            if (tq < nwin) {                                              // one thread per window: the sums in order
+                float t5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int qq = 0; qq < wpw; ++qq)
+#pragma unroll
+                    for (int cc = 0; cc < 5; ++cc) t5[cc] += s_red[(tq * wpw + qq) * 6 + cc];
+                en.energy[winq + tq] = combine_energy(en, t5);
+            }
+            uint8_t* tile_hi = act + en.in_buf * 2 * kATile + q * kQuarterBytes;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int v = sub + it * 4;
+                const int wl_e = v / wpw, k = (v - wl_e * wpw) * 32 + lane;
+                if (wl_e < nwin && k < TJ) {
+                    float mx = 0.f;
+                    for (int qq = 0; qq < wpw; ++qq) mx = fmaxf(mx, s_red[(wl_e * wpw + qq) * 6 + 5]);
+                    const int e = grad_exponent(mx);
+                    const float sc = exp2f((float)e);
+                    if (k == 0) en.row_exp[winq + wl_e] = e;
+                    const int tt = k / en.J, j = k - tt * en.J;
+                    const int row = wl_e * en.T + tt;                    // TMEM lane / operand row within the quarter
+                    uint8_t* th = tile_hi + row * 128;
+                    uint8_t* tl = th + kATile;
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) {
+                        uint16_t h, lo16;
+                        split_f16_energy(gv[it][cc] * sc, h, lo16);
+                        const int col = j * 3 + cc;
+                        const int off = (((col >> 3) ^ (row & 7)) << 4) + (col & 7) * 2;       // SWIZZLE_128B
+                        *reinterpret_cast<uint16_t*>(th + off) = h;
+                        *reinterpret_cast<uint16_t*>(tl + off) = lo16;
+                    }
+                }
+            }
+            fence_proxy_async_smem();              // generic-proxy writes -> visible to the tensor core's operand reads
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(act_full), 0));
+        }
         for (int l = 0; l < g.nl; ++l) {
             const Chain2Layer& L = g.L[l];
             const int halves = L.N >> 4;
@@ -1294,6 +1393,15 @@ int launch_tap_chain(cudaStream_t stream, void* owner, const TapChainLaunch& L) 
 // output slabs are split into pseudo-layers; activation buffers are assigned here: a pseudo-layer's outputs go to
 // buffers that none of its own inputs occupy unless it is the layer's last pseudo-layer (whose MMAs have all
 // completed before its epilogue runs).
+// the fused chain's energy prologue handles windows of at most 160 joint-frames whose TMEM lane quarter holds at most
+// three of them (T >= 10) and a first layer of one K block (45 pose channels padded to 64)
+bool tap_chain_energy_supported(int T, int J, int first_layer_k) {
+    if (T < 3 || T > 32 || J < 1 || J > kMaxJoints) return false;
+    const int wpq = 32 / T, TJ = T * J;
+    return TJ <= kEnergySlot && wpq * (kEnergySlot / 32) <= 16 && wpq * TJ * 3 <= kEnergyRedOffset &&
+           kEnergyRedOffset + wpq * (kEnergySlot / 32) * 6 <= kEnergyQuarterFloats && first_layer_k <= 64;
+}
+
 int launch_tap_chain_pair(cudaStream_t stream, void* owner, const TapChainLaunch& L) {
     if (L.W <= 0) return GEM_OK;
     GEM_REQUIRE(L.nl >= 1 && L.nl <= kTapChainMax, "chain length");
@@ -1377,6 +1485,31 @@ int launch_tap_chain_pair(cudaStream_t stream, void* owner, const TapChainLaunch
     a.nl = np, a.W = L.W, a.T = L.T, a.wpq = wpq, a.out_plain = L.out_lo ? nullptr : (float*)L.out_hi;
     a.dbg = g_tap_dbg;
     a.status = L.status;
+    Chain2Energy en;
+    memset(&en, 0, sizeof(en));
+    if (L.energy) {
+        const ChainEnergyLaunch& E = *L.energy;
+        GEM_REQUIRE(tap_chain_energy_supported(L.T, E.J, w[0]->Kp) && E.J * 3 <= L.Kreal,
+                    "energy prologue: window geometry not supported by the fused chain");
+        GEM_REQUIRE(E.skel && E.skel->num_joints == E.J && E.pose && E.pose0 && E.clip && E.mean_bone && E.energy && E.row_exp,
+                    "energy prologue: missing argument");
+        GEM_REQUIRE(E.wt.reproj == 0.f || (E.cam && E.heat && E.frame_base), "energy prologue: camera / heat maps required");
+        en.enabled = 1;
+        en.in_buf = a.L[0].in_buf[0];
+        int nfree = 0, free_buf[4];
+        for (int bfr = 0; bfr < 4; ++bfr)
+            if (bfr != en.in_buf) free_buf[nfree++] = bfr;
+        en.scratch0 = free_buf[0], en.scratch1 = free_buf[1];
+        en.pose = E.pose, en.pose0 = E.pose0, en.energy = E.energy, en.row_exp = E.row_exp;
+        en.heat = E.heat, en.frame_base = E.frame_base, en.clip = E.clip, en.mean_bone = E.mean_bone, en.status = E.status;
+        en.W = L.W, en.T = L.T, en.J = E.J, en.H = E.H, en.Wd = E.Wd;
+        en.w3d = E.wt.w3d, en.ws = E.wt.smooth, en.wb = E.wt.bone, en.wv = E.wt.vae, en.wr = E.wt.reproj;
+        en.patch = E.patch && E.patch_valid ? E.patch : nullptr;
+        en.patch_origin = en.patch ? E.patch_origin : nullptr, en.patch_valid = en.patch ? E.patch_valid : nullptr;
+        en.patch_stats = en.patch ? E.patch_stats : nullptr;
+        if (E.cam) en.cam = *E.cam;
+        en.skel = *E.skel;
+    }
     static PerDeviceOnce attr_set;
     if (bool* once_ = attr_set.flag(); !*once_) {
         GEM_CUDA(cudaFuncSetAttribute(tc_tap_chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChain2Smem));
@@ -1384,7 +1517,7 @@ int launch_tap_chain_pair(cudaStream_t stream, void* owner, const TapChainLaunch
     }
     const int tiles = (L.W + 4 * wpq - 1) / (4 * wpq);
     const int grid = 2 * ((tiles + 1) / 2);
-    tc_tap_chain2_kernel<<<grid, kChainThreads, kChain2Smem, stream>>>(maps, a);
+    tc_tap_chain2_kernel<<<grid, kChainThreads, kChain2Smem, stream>>>(maps, a, en);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }

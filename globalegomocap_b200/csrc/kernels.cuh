@@ -76,6 +76,26 @@ int launch_tap_tc(cudaStream_t stream, void* owner, const TapTcLaunch& L);
 // layer's output reach HBM; weights stream through a two-slot ring.  Layers after the first must be 64 -> N with
 // N = 64 for every layer but the last (which may be 48-padded plain fp32 output, or N = 128 split output).
 constexpr int kTapChainMax = 5;
+// Optional energy prologue of a backward chain on CTA pairs (launch_tap_chain_pair): the chain kernel evaluates the
+// fused energy + gradient itself (energy_device.cuh) from `pose` and feeds dE/dpose straight into its first layer.
+struct ChainEnergyLaunch {
+    const CameraConst* cam;                     // host copies owned by the ctx (cam may be NULL when wt.reproj == 0)
+    const SkeletonConst* skel;
+    const float *pose, *pose0, *heat;           // [W][T][J][3] decoded pose and anchor; heat maps (NULL without reproj)
+    const int64_t* frame_base;
+    const int32_t* clip;
+    const float* mean_bone;
+    gem_energy_weights wt;
+    float* energy;                              // [W]
+    uint32_t* status;                           // [W] or NULL
+    int32_t* row_exp;                           // [W]
+    int J, H, Wd;
+    float* patch = nullptr;                     // optional texel cache (zero-copy heat maps)
+    short2* patch_origin = nullptr;
+    unsigned long long* patch_valid = nullptr;
+    unsigned long long* patch_stats = nullptr;
+};
+bool tap_chain_energy_supported(int T, int J, int first_layer_k);
 struct TapChainLaunch {
     int nl;
     const float* B[kTapChainMax];               // weight pointers (keys of tc_tap_prepare_weight, scheme 2)
@@ -89,6 +109,7 @@ struct TapChainLaunch {
     int ldo;
     int W, T;
     uint32_t* status = nullptr;                 // optional [W]: OR-ed with GEM_WIN_F16_RANGE when a split output saturates
+    const ChainEnergyLaunch* energy = nullptr;  // launch_tap_chain_pair only: energy prologue instead of loading A_hi / A_lo
 };
 int launch_tap_chain(cudaStream_t stream, void* owner, const TapChainLaunch& L);
 // the same on CTA pairs (cta_group::2): up to five layers with up to 256 channels in and out (gemm_tap_tc.cu)

@@ -72,8 +72,13 @@ def reference_on_cuda(tmp_path_factory):
     if not os.path.exists(os.path.join(repo, "baseline", "_ref", "optimizer.py")):
         return None
     out = {}
+    cache = os.environ.get("GEM_REF_CUDA_CACHE")           # optional directory: reuse the runs across pytest invocations
     for tag, tf32 in (("fp32", 0), ("stock", -1)):
-        path = str(tmp_path_factory.mktemp("refcuda") / f"ref_{tag}.npz")
+        path = (os.path.join(cache, f"ref_cuda_{tag}.npz") if cache else
+                str(tmp_path_factory.mktemp("refcuda") / f"ref_{tag}.npz"))
+        if cache and os.path.exists(path):
+            out[tag] = np.load(path)
+            continue
         res = subprocess.run([sys.executable, os.path.join(repo, "tests", "reference_runs.py"), "--out", path, "--tf32", str(tf32)],
                              capture_output=True, text=True, timeout=1500)
         assert res.returncode == 0, res.stderr[-2000:]
@@ -102,7 +107,8 @@ def test_cuda_deviations_stay_within_the_references_self_noise(setup, reference_
         assert int(res["status"].sum()) == 0
         tr, pose, ev = res["trace"].cpu().numpy(), res["pose"].cpu().numpy(), res["func_evals"].cpu().numpy()
         ours, leads = _against_ref1("this library (CUDA) vs reference 1 CPU thread", g, max_iter, stage, tr, ev, pose, cub, cols)
-        assert min(leads) >= 2, (stage, leads)                 # the first two evaluations agree for every window
+        # the first two evaluations agree for every window (some global-stage solves stop after their first one)
+        early = [(w, l) for w, l in enumerate(leads) if l < min(2, int(g[f"mi{max_iter}_n_eval"][0, stage, w]))]
         rows = [ours, ps.reference_self_noise(g, max_iter, stage)]
         yard = None
         if reference_on_cuda is not None:
@@ -114,9 +120,10 @@ def test_cuda_deviations_stay_within_the_references_self_noise(setup, reference_
                 rows.append(row)
             yard = rows[2]                                      # the strict yardstick: the reference's own fp32 CUDA path
         table += rows
-        checks.append((stage, ours, rows[1], yard))
+        checks.append((stage, ours, rows[1], yard, early))
     print("\nmax_iter", max_iter, "(local stage rows, then global stage rows)\n" + ps.format_table(table))
-    for stage, ours, ref_threads, yard in checks:
+    for stage, ours, ref_threads, yard, early in checks:
+        assert not early, (max_iter, stage, early)
         # every early divergence is an ill-conditioned interpolation in the reference's own trace
         assert ours["unexplained"] <= max(ref_threads["unexplained"], 2), (max_iter, stage, ours["unexplained"])
         if yard is None:
