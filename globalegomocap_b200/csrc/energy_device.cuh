@@ -113,40 +113,51 @@ __device__ __forceinline__ bool project_joint(const CameraConst& c_cam, float x,
     return true;
 }
 
+// First half of a joint's reprojection term: the projection and the four texel loads of its bilinear footprint.  Kept
+// apart from the arithmetic so that callers can have the loads of several joints in flight before they consume any
+// (the chain kernel's prologue evaluates four joints per thread); the stand-alone kernel calls both halves back to back.
+struct JointTexels {
+    Proj pj;
+    float nw, ne, sw, se;
+    bool rp;
+};
+__device__ __forceinline__ void joint_gather(const EnergyCommon& a, const float* X, int w, int k, JointTexels& jt) {
+    jt.rp = false;
+    jt.nw = jt.ne = jt.sw = jt.se = 0.f;
+    if (a.wr == 0.f) return;
+    const int t = k / a.J, j = k - t * a.J;
+    const float x = X[k * 3 + 0], y = X[k * 3 + 1], z = X[k * 3 + 2];
+    if (!project_joint(a.cam, x, y, z, a.H, a.Wd, jt.pj)) {
+        if (a.status) atomicOr(a.status + w, GEM_WIN_NORM_ZERO);
+    } else if (jt.pj.fx0 >= -1.f && jt.pj.fx0 <= (float)a.Wd && jt.pj.fy0 >= -1.f && jt.pj.fy0 <= (float)a.H) {
+        // (anything further than one texel outside contributes exactly 0)
+        jt.rp = true;
+        const int x0 = (int)jt.pj.fx0, y0 = (int)jt.pj.fy0;
+        const int64_t frame = a.frame_base[w] + t;
+        if (a.patch) {
+            cache_lookup(a, (size_t)w * (a.T * a.J) + k, frame, j, x0, y0, true, jt.nw, jt.ne, jt.sw, jt.se);
+        } else {
+            jt.nw = texel(a.heat, frame, y0, x0, j, a.H, a.Wd, a.J);
+            jt.ne = texel(a.heat, frame, y0, x0 + 1, j, a.H, a.Wd, a.J);
+            jt.sw = texel(a.heat, frame, y0 + 1, x0, j, a.H, a.Wd, a.J);
+            jt.se = texel(a.heat, frame, y0 + 1, x0 + 1, j, a.H, a.Wd, a.J);
+        }
+    }
+}
+
 // The five energy terms of joint-frame k = t*J + j of window w and its dE/dx: X / X0 are the window's pose and anchor
-// (T*J*3 floats, shared memory).  e = {E_3d, E_smooth, E_bone, E_vae, E_reproj} contributions, g = weighted gradient.
-__device__ __forceinline__ void joint_energy_grad(const EnergyCommon& a, const float* X, const float* X0, int w, int k,
-                                                  float (&e)[5], float (&g)[3]) {
+// (T*J*3 floats, shared memory), jt the joint's gathered texels.  e = {E_3d, E_smooth, E_bone, E_vae, E_reproj}
+// contributions, g = weighted gradient.
+__device__ __forceinline__ void joint_terms(const EnergyCommon& a, const float* X, const float* X0, int w, int k,
+                                            const JointTexels& jt, float (&e)[5], float (&g)[3]) {
     float e3d = 0.f, esm = 0.f, ebn = 0.f, eva = 0.f, erp = 0.f;
     float gx = 0.f, gy = 0.f, gz = 0.f;
-    const int TJ = a.T * a.J;
     {
         const int t = k / a.J, j = k - t * a.J;
         const float x = X[k * 3 + 0], y = X[k * 3 + 1], z = X[k * 3 + 2];
-
-        // E_reproj, first half: the projection and the four texel loads are issued before the other terms so that
-        // their DRAM latency overlaps that arithmetic (the terms are still added to the gradient in the old order)
-        bool rp = false;
-        Proj pj;
-        float nw = 0.f, ne = 0.f, sw = 0.f, se = 0.f;
-        if (a.wr != 0.f) {
-            if (!project_joint(a.cam, x, y, z, a.H, a.Wd, pj)) {
-                if (a.status) atomicOr(a.status + w, GEM_WIN_NORM_ZERO);
-            } else if (pj.fx0 >= -1.f && pj.fx0 <= (float)a.Wd && pj.fy0 >= -1.f && pj.fy0 <= (float)a.H) {
-                // (anything further than one texel outside contributes exactly 0)
-                rp = true;
-                const int x0 = (int)pj.fx0, y0 = (int)pj.fy0;
-                const int64_t frame = a.frame_base[w] + t;
-                if (a.patch) {
-                    cache_lookup(a, (size_t)w * TJ + k, frame, j, x0, y0, true, nw, ne, sw, se);
-                } else {
-                    nw = texel(a.heat, frame, y0, x0, j, a.H, a.Wd, a.J);
-                    ne = texel(a.heat, frame, y0, x0 + 1, j, a.H, a.Wd, a.J);
-                    sw = texel(a.heat, frame, y0 + 1, x0, j, a.H, a.Wd, a.J);
-                    se = texel(a.heat, frame, y0 + 1, x0 + 1, j, a.H, a.Wd, a.J);
-                }
-            }
-        }
+        const bool rp = jt.rp;
+        const Proj& pj = jt.pj;
+        const float nw = jt.nw, ne = jt.ne, sw = jt.sw, se = jt.se;
 
         // E_3d = sum (x - x0)^2                                     optimizer.py:210-213
         {
@@ -235,6 +246,13 @@ __device__ __forceinline__ void joint_energy_grad(const EnergyCommon& a, const f
     }
     e[0] = e3d, e[1] = esm, e[2] = ebn, e[3] = eva, e[4] = erp;
     g[0] = gx, g[1] = gy, g[2] = gz;
+}
+
+__device__ __forceinline__ void joint_energy_grad(const EnergyCommon& a, const float* X, const float* X0, int w, int k,
+                                                  float (&e)[5], float (&g)[3]) {
+    JointTexels jt;
+    joint_gather(a, X, w, k, jt);
+    joint_terms(a, X, X0, w, k, jt, e, g);
 }
 
 // optimizer.py:239-240 (left to right; the reproj product is skipped when its weight is 0) from the window's five

@@ -947,26 +947,66 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
             int nwin = g.W - winq;
             nwin = nwin < 0 ? 0 : (nwin > g.wpq ? g.wpq : nwin);
             {
+                // the quarter's windows are one contiguous run of floats (8-byte aligned: T*J*3 is even here, else scalar);
+                // all loads are issued before the first store so that one memory latency covers them
                 const float* gp = en.pose + (size_t)winq * n;
                 const float* gp0 = en.pose0 + (size_t)winq * n;
-                for (int i = tq; i < nwin * n; i += 128) s_x[i] = gp[i], s_x0[i] = gp0[i];
+                const int total = nwin * n;
+                if ((n & 1) == 0) {
+                    constexpr int kMaxV = (kEnergyRedOffset / 2 + 127) / 128;          // float2 loads per thread
+                    float2 a[kMaxV], b[kMaxV];
+#pragma unroll
+                    for (int u = 0; u < kMaxV; ++u) {
+                        const int i = tq + u * 128;
+                        a[u] = b[u] = make_float2(0.f, 0.f);
+                        if (2 * i < total) {
+                            a[u] = __ldg(reinterpret_cast<const float2*>(gp) + i);
+                            b[u] = __ldg(reinterpret_cast<const float2*>(gp0) + i);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kMaxV; ++u) {
+                        const int i = tq + u * 128;
+                        if (2 * i < total) {
+                            reinterpret_cast<float2*>(s_x)[i] = a[u];
+                            reinterpret_cast<float2*>(s_x0)[i] = b[u];
+                        }
+                    }
+                } else {
+                    for (int i = tq; i < total; i += 128) s_x[i] = gp[i], s_x0[i] = gp0[i];
+                }
             }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
             float gv[4][3];
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const int v = sub + it * 4;                               // virtual warp: window v / wpw, joints (v % wpw) * 32 ..
-                const int wl_e = v / wpw, k = (v - wl_e * wpw) * 32 + lane;
-                float e5[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, g3[3] = {0.f, 0.f, 0.f};
-                if (wl_e < nwin && k < TJ) joint_energy_grad(en, s_x + wl_e * n, s_x0 + wl_e * n, winq + wl_e, k, e5, g3);
-                gv[it][0] = g3[0], gv[it][1] = g3[1], gv[it][2] = g3[2];
-                if (v < g.wpq * wpw) {                                    // (warp-uniform)
-                    const float r0 = warp_sum(e5[0]), r1 = warp_sum(e5[1]), r2 = warp_sum(e5[2]), r3 = warp_sum(e5[3]),
-                                r4 = warp_sum(e5[4]);
-                    const float r5 = warp_max(fmaxf(fabsf(g3[0]), fmaxf(fabsf(g3[1]), fabsf(g3[2]))));
-                    if (lane == 0) {
-                        float* d = s_red + v * 6;
-                        d[0] = r0, d[1] = r1, d[2] = r2, d[3] = r3, d[4] = r4, d[5] = r5;
+            for (int half = 0; half < 2; ++half) {
+                // two joints per thread at a time: both joints' texel loads are in flight before either is consumed
+                JointTexels jt[2];
+                int kk[2], ww[2];
+                bool on[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int v = sub + (2 * half + u) * 4;               // virtual warp: window v / wpw, joints (v % wpw) * 32 ..
+                    ww[u] = v / wpw, kk[u] = (v - ww[u] * wpw) * 32 + lane;
+                    on[u] = ww[u] < nwin && kk[u] < TJ;
+                    jt[u].rp = false;
+                    if (on[u]) joint_gather(en, s_x + ww[u] * n, winq + ww[u], kk[u], jt[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int it = 2 * half + u;
+                    const int v = sub + it * 4;
+                    float e5[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, g3[3] = {0.f, 0.f, 0.f};
+                    if (on[u]) joint_terms(en, s_x + ww[u] * n, s_x0 + ww[u] * n, winq + ww[u], kk[u], jt[u], e5, g3);
+                    gv[it][0] = g3[0], gv[it][1] = g3[1], gv[it][2] = g3[2];
+                    if (v < g.wpq * wpw) {                                // (warp-uniform)
+                        const float r0 = warp_sum(e5[0]), r1 = warp_sum(e5[1]), r2 = warp_sum(e5[2]), r3 = warp_sum(e5[3]),
+                                    r4 = warp_sum(e5[4]);
+                        const float r5 = warp_max(fmaxf(fabsf(g3[0]), fmaxf(fabsf(g3[1]), fabsf(g3[2]))));
+                        if (lane == 0) {
+                            float* d = s_red + v * 6;
+                            d[0] = r0, d[1] = r1, d[2] = r2, d[3] = r3, d[4] = r4, d[5] = r5;
+                        }
                     }
                 }
             }

@@ -11,10 +11,13 @@ final window pose.  Two runs of the same problem are compared by
 
 A divergence is *explained* when the reference's own trace shows that the trial point of the first
 diverging evaluation (or one of the three before it) came out of a `_cubic_interpolate` call
-(torch/optim/lbfgs.py:12-37) whose result moves by more than 1e-4 relative when the newer loss value
-changes by at most two fp32 ulps — the bisection / extrapolation-bound branch flip of the
-discriminant d1^2 - g1*g2 (tests/golden/make_golden_dist.py records the
-perturbed results).  Divergences that first show after `LATE_EVAL` evaluations are accumulated
+(torch/optim/lbfgs.py:12-37) whose result moves by more than 1e-4 relative under the perturbations two
+independent fp32 implementations of the closure show against each other — the newer loss value off by up
+to PROBE_ULPS fp32 ulps (this library's teacher-forced energy is within 5.3e-7 of the reference's, the
+reference's own CUDA path within 3.5e-7 of its CPU path), a directional derivative off by 2^-18 relative
+(different summation order of a 2048-element dot product) — i.e. the bisection / extrapolation-bound branch
+flip of the discriminant d1^2 - g1*g2 (tests/golden/make_golden_dist.py records the
+calls' arguments, the probes re-run oracle/lbfgs_np.py's restatement of the interpolation on them).  Divergences that first show after `LATE_EVAL` evaluations are accumulated
 round-off (the reference against itself shows the same), not a single decision.
 """
 from __future__ import annotations
@@ -23,8 +26,20 @@ import numpy as np
 
 E_TOL = 1e-4
 JOINT_TOL_MM = 0.5
-SENS_TOL = 1e-4          # relative change of the interpolated step under a <= 2 ulp change of the loss
+SENS_TOL = 1e-4          # relative change of the interpolated step under the probes
+PROBE_ULPS = 8           # loss perturbation (fp32 ulps)
+PROBE_GREL = 2.0 ** -18  # relative perturbation of a directional derivative
 LATE_EVAL = 8            # first divergence at or after this evaluation: accumulated round-off
+ONSET_TOL = 2e-6         # relative energy difference that marks the ONSET of a divergence: four times the closure's
+                         # implementation noise (5e-7); the 1e-4 bar is typically crossed a few evaluations later
+
+
+def onset_of(E_a, n_a, E_b, n_b):
+    """First evaluation at which run b's energy leaves run a's by more than ONSET_TOL (n if never)."""
+    n = int(min(n_a, n_b))
+    a, b = np.asarray(E_a[:n], np.float64), np.asarray(E_b[:n], np.float64)
+    bad = np.nonzero(np.abs(a - b) / np.abs(np.asarray(E_a[:int(n_a)], np.float64)).max() > ONSET_TOL)[0]
+    return int(bad[0]) if len(bad) else n
 
 
 def compare_runs(E_a, n_a, pose_a, E_b, n_b, pose_b):
@@ -50,28 +65,55 @@ def cubic_rows(g, max_iter):
     return out, cols
 
 
-def cubic_sensitivity(rows, cols, k):
-    """Largest relative change of an interpolated step under a <= 2 ulp change of the loss, over the calls
-    that produced the trial points of evaluations k-3 .. k."""
+def _probe(r, cols):
+    """Largest relative change of one recorded call's result under the probes."""
+    from oracle.lbfgs_np import _cubic_interpolate
+    F = np.float32
+    x1, f1, g1, x2, f2, g2 = (float(r[cols[c]]) for c in ("x1", "f1", "g1", "x2", "f2", "g2"))
+    lo, hi = float(r[cols["lo"]]), float(r[cols["hi"]])
+    bounds = None if np.isnan(lo) else (F(lo), F(hi))
+    t0 = float(r[cols["t"]])
+    if t0 == 0:
+        return 0.0
+
+    def run(f2_, g1_, g2_):
+        with np.errstate(all="ignore"):
+            return float(_cubic_interpolate(F(x1) if x1 != 0 else 0.0, f1, F(g1_), F(x2), f2_, F(g2_), bounds))
+
     best = 0.0
-    for r in rows:
-        ev = int(r[cols["eval_index"]])
-        if k - 3 <= ev <= k:
-            t = r[cols["t"]]
-            pert = r[[cols["t_m2ulp"], cols["t_m1ulp"], cols["t_p1ulp"], cols["t_p2ulp"]]]
-            if np.isfinite(pert).any() and t != 0:
-                best = max(best, float(np.nanmax(np.abs(pert - t)) / abs(t)))
+    for k in range(1, PROBE_ULPS + 1):
+        for sgn in (-1.0, 1.0):
+            f2p = float(F(f2) + sgn * k * np.spacing(np.abs(F(f2))))
+            best = max(best, abs(run(f2p, g1, g2) - t0) / abs(t0))
+    for sgn in (-1.0, 1.0):
+        best = max(best, abs(run(f2, g1, g2 * (1 + sgn * PROBE_GREL)) - t0) / abs(t0))
+        best = max(best, abs(run(f2, g1 * (1 + sgn * PROBE_GREL), g2) - t0) / abs(t0))
+    pert = r[[cols["t_m2ulp"], cols["t_m1ulp"], cols["t_p1ulp"], cols["t_p2ulp"]]]         # recorded with torch's own types
+    if np.isfinite(pert).any():
+        best = max(best, float(np.nanmax(np.abs(pert - t0)) / abs(t0)))
     return best
 
 
-def classify(lead, n_a, n_b, rows, cols):
-    """'' (no divergence), 'cubic' (ill-conditioned interpolation), 'late' (accumulated round-off) or
-    'unexplained'."""
+def cubic_sensitivity(rows, cols, k):
+    """Largest relative change of an interpolated step under the probes, over the calls that produced the trial
+    points of evaluations k-2 .. k."""
+    best = 0.0
+    for r in rows:
+        ev = int(r[cols["eval_index"]])
+        if k - 2 <= ev <= k:
+            best = max(best, _probe(r, cols))
+    return best
+
+
+def classify(lead, n_a, n_b, rows, cols, onset=None):
+    """'' (no divergence), 'cubic' (the divergence sets in at an ill-conditioned interpolation), 'late' (accumulated
+    round-off) or 'unexplained'.  onset: evaluation at which the energies first part by ONSET_TOL (default: lead)."""
     if lead == min(n_a, n_b) and n_a == n_b:
         return ""
-    if cubic_sensitivity(rows, cols, lead) > SENS_TOL:
+    k = lead if onset is None else min(onset, lead)
+    if cubic_sensitivity(rows, cols, k) > SENS_TOL:
         return "cubic"
-    if lead >= LATE_EVAL:
+    if k >= LATE_EVAL:
         return "late"
     return "unexplained"
 
@@ -95,7 +137,8 @@ def reference_self_noise(g, max_iter, stage):
         lead, d, s = compare_runs(E[0, stage, w], ne[0, stage, w], P[0, stage, w], E[1, stage, w], ne[1, stage, w],
                                   P[1, stage, w])
         mm.append(d), strict.append(s)
-        kinds.append(classify(lead, int(ne[0, stage, w]), int(ne[1, stage, w]), rows[(stage, w)], cols))
+        kinds.append(classify(lead, int(ne[0, stage, w]), int(ne[1, stage, w]), rows[(stage, w)], cols,
+                              onset_of(E[0, stage, w], ne[0, stage, w], E[1, stage, w], ne[1, stage, w])))
     return summarize(f"reference {int(g['threads'][1])} threads vs 1 thread", mm, strict, kinds,
                      ne[1, stage].astype(int) - ne[0, stage].astype(int))
 
