@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgem_b200.so")
+LIB_PATH = os.environ.get("GEM_B200_LIB") or os.path.join(HERE, "libgem_b200.so")     # (env: a build variant under test)
 
 
 class GemError(RuntimeError):

@@ -28,7 +28,8 @@ struct gem_ctx {
     int device = 0;
     int Wmax = 0, n = 0, T = 0, J = 0, H = 0, Wd = 0, m = 0;
     int gemm_mode = 0;
-    int fuse_energy = 1;                         // mode 3 + CTA-pair chains: the backward chain evaluates the energy itself (GEM_FUSE_ENERGY)
+    int fuse_energy = 0;                         // opt-in (GEM_FUSE_ENERGY=1): the backward chain on CTA pairs evaluates the energy
+                                                 // itself; measured 0.5 ms per step SLOWER than the separate kernel
     int tap_chain = 2;                           // mode 3: 0 one launch per k=3 layer, 1 the four K<=128 layers of each direction
                                                  // in one launch, 2 all five on CTA pairs (cta_group::2) in one launch
     bool have_camera = false, have_skeleton = false;
@@ -964,6 +965,7 @@ struct StageCall {
     uint32_t* status;
     bool status_or = false;     // OR this stage's status bits into `status` instead of overwriting it
     bool texel_cache;           // read the maps through the per-joint texel cache
+    bool host_maps = false;     // the maps are host memory read over PCIe: texel prefetch kernel, more slices
 };
 
 __global__ void or_status_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int n) {
@@ -971,16 +973,23 @@ __global__ void or_status_kernel(uint32_t* __restrict__ dst, const uint32_t* __r
     if (i < n) dst[i] |= src[i];
 }
 
-// The texel cache pays when the maps are read over PCIe from (pinned / registered) host memory
-static bool want_texel_cache(const gem_ctx* c, const void* heat, float reproj) {
-    if (!heat || reproj == 0.f || c->texel_cache == 0) return false;
-    if (c->texel_cache == 1) return true;
+// The texel cache pays when the maps are read over PCIe from (pinned / registered) host memory, and on device-resident
+// maps once the energy kernel is bound by its DRAM traffic (every 4-byte texel of the HWC maps costs a 32-byte
+// sector, 64 bytes of DRAM burst): from kTexelCacheMinWindows windows on.  Below that the kernel is latency-bound and
+// the cache changes nothing (measured at 1870 windows).
+constexpr int kTexelCacheMinWindows = 8192;
+static bool is_host_memory(const void* p) {
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, heat) != cudaSuccess) {
+    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
     return at.type == cudaMemoryTypeHost;
+}
+static bool want_texel_cache(const gem_ctx* c, const void* heat, float reproj, int W) {
+    if (!heat || reproj == 0.f || c->texel_cache == 0) return false;
+    if (c->texel_cache == 1) return true;
+    return is_host_memory(heat) || W >= kTexelCacheMinWindows;
 }
 
 static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, int w0, int Wk, bool graphs) {
@@ -1013,7 +1022,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     // one closure round: decode -> fused energy/gradient -> decoder bwd-data -> L-BFGS advance
     auto enqueue_round = [&]() -> int {
         GEM_TRY(decode_impl(c, q, which, Wk, v, lb.ZT, v.pose, tc ? lb.ZT_hi : nullptr, tc ? lb.ZT_lo : nullptr, v.status_own));
-        if (a.texel_cache && c->texel_prefetch_ctas > 0)
+        if (a.host_maps && c->texel_prefetch_ctas > 0)
             // zero-copy maps: the wait for PCIe happens in a few CTAs, not in energy CTAs parked on every SM
             GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
                 return launch_texel_prefetch(q, &c->cam, Wk, c->T, c->J, c->H, c->Wd, v.pose, a.heat, v.fb_own, v.patch, v.patch_origin,
@@ -1051,7 +1060,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     if (graphs && a.p.max_eval >= 2) {
         for (auto& g : c->graphs) {
             if (g.which == which && g.w0 == w0 && g.Wk == Wk && g.gemm_mode == (c->gemm_mode | (c->tap_chain << 8) | (c->fuse_energy << 12)) && g.heat == a.heat &&
-                g.has_heat == ((a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * c->texel_prefetch_ctas) &&
+                g.has_heat == ((a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas : 0)) &&
                 g.trace_stride == lb.trace_stride &&
                 memcmp(&g.wt, &a.wt, sizeof(a.wt)) == 0 && g.p.lr == a.p.lr && g.p.max_iter == a.p.max_iter &&
                 g.p.max_eval == a.p.max_eval && g.p.tolerance_grad == a.p.tolerance_grad &&
@@ -1076,7 +1085,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             GEM_CUDA(e);
             gem_ctx::RoundGraph g;
             g.which = which, g.w0 = w0, g.Wk = Wk, g.gemm_mode = c->gemm_mode | (c->tap_chain << 8) | (c->fuse_energy << 12), g.heat = a.heat;
-            g.has_heat = (a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * c->texel_prefetch_ctas;
+            g.has_heat = (a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas : 0);
             g.trace_stride = lb.trace_stride, g.wt = a.wt, g.p = a.p;
             g.launches = round_launches;
             e = cudaGraphInstantiate(&g.exec, graph, 0);
@@ -1224,9 +1233,10 @@ int gem_solve_stage(gem_ctx* c, void* stream, int which, int W, const float* pos
     a.which = which, a.pose0 = pose0_d, a.heat = heat_d, a.frame_base = frame_base_d, a.clip = clip_d;
     a.mean_bone = mean_bone_d, a.eps = eps_d, a.eps_stride = (size_t)c->n, a.wt = *wt, a.p = *params_h;
     a.pose_out = pose_out_d, a.trace = energy_trace_d, a.n_iter = n_iter_d, a.func_evals = func_evals_d, a.status = status_d;
-    a.texel_cache = want_texel_cache(c, heat_d, wt->reproj);
+    a.texel_cache = want_texel_cache(c, heat_d, wt->reproj, W);
+    a.host_maps = a.texel_cache && is_host_memory(heat_d);
     const bool graphs = c->use_graphs && !c->prof_on;
-    const std::vector<int> w0 = slice_bounds(c, W, a.texel_cache, c->gemm_mode >= 1 && !c->tap_tc[which]);
+    const std::vector<int> w0 = slice_bounds(c, W, a.host_maps, c->gemm_mode >= 1 && !c->tap_tc[which]);
     Fork f;
     GEM_TRY(fork_slices(c, s, w0, graphs, &f));
     for (size_t k = 0; k + 1 < w0.size(); ++k) GEM_TRY(enqueue_stage_slice(c, f.cs[k], a, w0[k], w0[k + 1] - w0[k], graphs));
@@ -1254,14 +1264,15 @@ int gem_solve_windows(gem_ctx* c, void* stream, int W, const float* pose0_d, con
     a.which = 0, a.pose0 = pose0_d, a.heat = heat_d, a.frame_base = frame_base_d, a.clip = clip_d;
     a.mean_bone = mean_bone_d, a.eps = eps_d, a.eps_stride = 2 * (size_t)c->n, a.wt = *wt_local, a.p = *params_h;
     a.pose_out = local_pose_d, a.trace = nullptr, a.n_iter = n_iter_d, a.func_evals = func_evals_d, a.status = status_d;
-    a.texel_cache = want_texel_cache(c, heat_d, wt_local->reproj);
+    a.texel_cache = want_texel_cache(c, heat_d, wt_local->reproj, W);
+    a.host_maps = a.texel_cache && is_host_memory(heat_d);
     b = a;
-    b.texel_cache = false;
+    b.texel_cache = false, b.host_maps = false;
     b.which = 1, b.pose0 = rel_f32_d, b.heat = nullptr, b.frame_base = nullptr, b.eps = eps_d + c->n, b.wt = *wt_global;
     b.pose_out = global_pose_d, b.status_or = true;      // (status_d keeps the local stage's bits, the global stage ORs its own in)
     b.n_iter = n_iter_d ? n_iter_d + W : nullptr, b.func_evals = func_evals_d ? func_evals_d + W : nullptr;
     const bool graphs = c->use_graphs && !c->prof_on;
-    const std::vector<int> w0 = slice_bounds(c, W, a.texel_cache, c->gemm_mode >= 1 && !(c->tap_tc[0] && c->tap_tc[1]));
+    const std::vector<int> w0 = slice_bounds(c, W, a.host_maps, c->gemm_mode >= 1 && !(c->tap_tc[0] && c->tap_tc[1]));
     Fork f;
     GEM_TRY(fork_slices(c, s, w0, graphs, &f));
     const size_t P = (size_t)c->T * c->J * 3;

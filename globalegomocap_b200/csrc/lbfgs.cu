@@ -82,6 +82,9 @@ constexpr int kPer = 4 * kChunks;
 #ifndef GEM_LBFGS_RING
 #define GEM_LBFGS_RING 4
 #endif
+#ifndef GEM_LBFGS_L2HINT
+#define GEM_LBFGS_L2HINT 0  // 1: history rows of the recursion's first loop are loaded evict_last (the second loop re-reads
+#endif                      //    them in reverse order), those of the second loop evict_first
 constexpr int kRing = GEM_LBFGS_RING;   // rows (n floats each) of the (y, s) history in flight per CTA
 constexpr int kMaxHist = 64;
 
@@ -574,7 +577,12 @@ __device__ __forceinline__ void lbfgs_advance_window(const LbfgsBuffers& b, cons
             while (issued < limit) {
                 const int slot = (int)((rows_done + (uint32_t)issued) % kRing);
                 mbar_arrive_expect_tx(&full_bar[slot], row_bytes);
+#if GEM_LBFGS_L2HINT
+                bulk_g2s_hint(ring + (size_t)slot * n, row_src(issued), row_bytes, &full_bar[slot],
+                              issued < 2 * kr ? l2_policy_evict_last() : l2_policy_evict_first());
+#else
                 bulk_g2s(ring + (size_t)slot * n, row_src(issued), row_bytes, &full_bar[slot]);
+#endif
                 ++issued;
             }
         };
