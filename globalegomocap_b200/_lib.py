@@ -52,6 +52,7 @@ _SIGNATURES = {
     "gem_solve_windows": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, C.POINTER(EnergyWeights),
                                     C.POINTER(EnergyWeights), C.POINTER(LbfgsParams), _P, _P, _P, _P, _P, _P, _P]),
     "gem_ctx_set_texel_cache": (C.c_int, [_P, _I]),
+    "gem_ctx_set_heat_layout": (C.c_int, [_P, _I]),
     "gem_ctx_texel_cache_stats": (C.c_int, [_P, _I, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "gem_ctx_launch_count": (C.c_int64, [_P]),
     "gem_ctx_set_profiling": (C.c_int, [_P, _I]),

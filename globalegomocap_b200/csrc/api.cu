@@ -28,6 +28,7 @@ struct gem_ctx {
     int device = 0;
     int Wmax = 0, n = 0, T = 0, J = 0, H = 0, Wd = 0, m = 0;
     int gemm_mode = 0;
+    int heat_planar = 0;                         // heat-map layout: 0 = [frames][H][W][J] (pickle), 1 = [frames][J][H][W]
     int fuse_energy = 0;                         // opt-in (GEM_FUSE_ENERGY=1): the backward chain on CTA pairs evaluates the energy
                                                  // itself; measured 0.5 ms per step SLOWER than the separate kernel
     int tap_chain = 2;                           // mode 3: 0 one launch per k=3 layer, 1 the four K<=128 layers of each direction
@@ -337,6 +338,13 @@ int gem_debug_gemm_pair(int mode) {
 int gem_ctx_set_chunks(gem_ctx* c, int n_chunks) {
     GEM_REQUIRE(c != nullptr && n_chunks >= 0 && n_chunks <= 16, "n_chunks must be in [0, 16] (0 = automatic)");
     c->n_chunks = n_chunks;
+    return GEM_OK;
+}
+
+int gem_ctx_set_heat_layout(gem_ctx* c, int planar) {
+    GEM_REQUIRE(c != nullptr && (planar == 0 || planar == 1), "layout must be 0 (HWC) or 1 (planar CHW)");
+    GEM_REQUIRE(!planar || c->Wd % 4 == 0, "planar heat maps need a width that is a multiple of 4");
+    c->heat_planar = planar;
     return GEM_OK;
 }
 
@@ -839,7 +847,8 @@ int gem_energy_grad(gem_ctx* c, void* stream, int W, const float* pose_d, const 
     return timed(c, (cudaStream_t)stream, GEM_TAG_ENERGY, [&]() {
         return launch_energy_grad((cudaStream_t)stream, c->have_camera ? &c->cam : nullptr, &c->skel, W, c->T, c->J, c->H,
                                   c->Wd, pose_d, pose0_d, heat_d,
-                                  frame_base_d, clip_d, mean_bone_d, *wt, energy_d, terms_d, grad_d, status_d);
+                                  frame_base_d, clip_d, mean_bone_d, *wt, energy_d, terms_d, grad_d, status_d, nullptr, nullptr,
+                                  0, nullptr, nullptr, nullptr, 0, nullptr, nullptr, c->heat_planar);
     });
 }
 
@@ -1027,7 +1036,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
                 return launch_texel_prefetch(q, &c->cam, Wk, c->T, c->J, c->H, c->Wd, v.pose, a.heat, v.fb_own, v.patch, v.patch_origin,
                                              v.patch_valid, c->patch_stats_on ? c->patch_stats : nullptr,
-                                             c->texel_prefetch_ctas);
+                                             c->texel_prefetch_ctas, c->heat_planar);
             }));
         if (fused) {
             // the backward chain evaluates the energy in its prologue: no energy launch, no d pose in memory
@@ -1035,7 +1044,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             en.cam = c->have_camera ? &c->cam : nullptr, en.skel = &c->skel;
             en.pose = v.pose, en.pose0 = v.pose0_own, en.heat = a.heat, en.frame_base = v.fb_own, en.clip = v.clip_own;
             en.mean_bone = v.mb_own, en.wt = a.wt, en.energy = v.f_new, en.status = v.status_own, en.row_exp = v.row_exp;
-            en.J = c->J, en.H = c->H, en.Wd = c->Wd;
+            en.J = c->J, en.H = c->H, en.Wd = c->Wd, en.planar = c->heat_planar;
             if (a.texel_cache) {
                 en.patch = v.patch, en.patch_origin = v.patch_origin, en.patch_valid = v.patch_valid;
                 en.patch_stats = c->patch_stats_on ? c->patch_stats : nullptr;
@@ -1047,7 +1056,8 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
                                           v.pose0_own, a.heat, v.fb_own, v.clip_own,
                                           v.mb_own, a.wt, v.f_new, nullptr, v.gpose, v.status_own, tc ? v.gp_hi : nullptr,
                                           v.gp_lo, pose_pad(c), a.texel_cache ? v.patch : nullptr, v.patch_origin,
-                                          c->patch_stats_on ? c->patch_stats : nullptr, c->gemm_mode == 3, v.row_exp, v.patch_valid);
+                                          c->patch_stats_on ? c->patch_stats : nullptr, c->gemm_mode == 3, v.row_exp, v.patch_valid,
+                                          c->heat_planar);
             }));
             GEM_TRY(decode_vjp_impl(c, q, which, Wk, v, v.gpose, v.g_new, tc, v.status_own));
         }
@@ -1060,7 +1070,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     if (graphs && a.p.max_eval >= 2) {
         for (auto& g : c->graphs) {
             if (g.which == which && g.w0 == w0 && g.Wk == Wk && g.gemm_mode == (c->gemm_mode | (c->tap_chain << 8) | (c->fuse_energy << 12)) && g.heat == a.heat &&
-                g.has_heat == ((a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas : 0)) &&
+                g.has_heat == ((a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas : 0) + 4096 * c->heat_planar) &&
                 g.trace_stride == lb.trace_stride &&
                 memcmp(&g.wt, &a.wt, sizeof(a.wt)) == 0 && g.p.lr == a.p.lr && g.p.max_iter == a.p.max_iter &&
                 g.p.max_eval == a.p.max_eval && g.p.tolerance_grad == a.p.tolerance_grad &&
@@ -1085,7 +1095,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             GEM_CUDA(e);
             gem_ctx::RoundGraph g;
             g.which = which, g.w0 = w0, g.Wk = Wk, g.gemm_mode = c->gemm_mode | (c->tap_chain << 8) | (c->fuse_energy << 12), g.heat = a.heat;
-            g.has_heat = (a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas : 0);
+            g.has_heat = (a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas : 0) + 4096 * c->heat_planar;
             g.trace_stride = lb.trace_stride, g.wt = a.wt, g.p = a.p;
             g.launches = round_launches;
             e = cudaGraphInstantiate(&g.exec, graph, 0);

@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(512) texel_prefetch_kernel(const __grid_consta
         if (!project_joint(a.cam, x, y, z, a.H, a.Wd, p)) continue;
         if (!(p.fx0 >= -1.f && p.fx0 <= (float)a.Wd && p.fy0 >= -1.f && p.fy0 <= (float)a.H)) continue;
         float nw, ne, sw, se;
-        cache_lookup(a, i, a.frame_base[w] + t, j, (int)p.fx0, (int)p.fy0, false, nw, ne, sw, se);
+        if (a.planar) cache_lookup_planar(a, i, a.frame_base[w] + t, j, (int)p.fx0, (int)p.fy0, false, nw, ne, sw, se);
+        else cache_lookup(a, i, a.frame_base[w] + t, j, (int)p.fx0, (int)p.fy0, false, nw, ne, sw, se);
     }
 }
 
@@ -210,8 +211,9 @@ int launch_energy_grad(cudaStream_t stream, const CameraConst* cam, const Skelet
                        const float* mean_bone, const gem_energy_weights& wt, float* energy, float* terms,
                        float* grad, uint32_t* status, float* gp_hi, float* gp_lo, int pp, float* patch,
                        short2* patch_origin, unsigned long long* patch_stats, int gp_f16, int32_t* row_exp,
-                       unsigned long long* patch_valid) {
+                       unsigned long long* patch_valid, int planar) {
     if (W <= 0) return GEM_OK;
+    GEM_REQUIRE(!planar || Wd % 4 == 0, "planar heat maps need a width that is a multiple of 4");
     GEM_REQUIRE(skel != nullptr && skel->num_joints == J, "skeleton not set for this joint count");
     GEM_REQUIRE(wt.reproj == 0.f || cam != nullptr, "camera not set");
     GEM_REQUIRE(T * J <= kSlot, "T*J must be <= 160");
@@ -231,7 +233,7 @@ int launch_energy_grad(cudaStream_t stream, const CameraConst* cam, const Skelet
     a.patch_valid = a.patch ? patch_valid : nullptr;
     GEM_REQUIRE(!gp_hi || (gp_lo && pp >= J * 3 && T * pp <= (gp_f16 ? 2 : 1) * kSplitMax && (T * pp) % 4 == 0),
                 "bad split gradient layout");
-    a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd;
+    a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd, a.planar = planar ? 1 : 0;
     a.w3d = wt.w3d, a.ws = wt.smooth, a.wb = wt.bone, a.wv = wt.vae, a.wr = wt.reproj;
     const size_t pair_bytes = (size_t)kWinPerCta * T * J * 3 * sizeof(float);
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
@@ -246,15 +248,16 @@ int launch_energy_grad(cudaStream_t stream, const CameraConst* cam, const Skelet
 // fetches, into the joints' cache windows, the texels the energy evaluation of `pose` will sample (zero-copy maps)
 int launch_texel_prefetch(cudaStream_t stream, const CameraConst* cam, int W, int T, int J, int H, int Wd, const float* pose,
                           const float* heat, const int64_t* frame_base, float* patch, short2* patch_origin,
-                          unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas) {
+                          unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas, int planar) {
     if (W <= 0) return GEM_OK;
+    GEM_REQUIRE(!planar || Wd % 4 == 0, "planar heat maps need a width that is a multiple of 4");
     GEM_REQUIRE(cam && heat && frame_base && patch && patch_origin && patch_valid, "texel prefetch needs the camera, the maps and the cache");
     EnergyArgs a;
     memset(&a, 0, sizeof(a));
     a.cam = *cam;
     a.pose = pose, a.heat = heat, a.frame_base = frame_base;
     a.patch = patch, a.patch_origin = patch_origin, a.patch_valid = patch_valid, a.patch_stats = patch_stats;
-    a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd;
+    a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd, a.planar = planar ? 1 : 0;
     const size_t total = (size_t)W * T * J;
     int grid = (int)((total + 511) / 512);
     if (grid > ctas) grid = ctas;

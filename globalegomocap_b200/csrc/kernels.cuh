@@ -11,10 +11,10 @@ int launch_energy_grad(cudaStream_t stream, const CameraConst* cam, const Skelet
                        const gem_energy_weights& wt, float* energy, float* terms, float* grad, uint32_t* status,
                        float* gp_hi = nullptr, float* gp_lo = nullptr, int pp = 0, float* patch = nullptr,
                        short2* patch_origin = nullptr, unsigned long long* patch_stats = nullptr, int gp_f16 = 0,
-                       int32_t* row_exp = nullptr, unsigned long long* patch_valid = nullptr);
+                       int32_t* row_exp = nullptr, unsigned long long* patch_valid = nullptr, int planar = 0);
 int launch_texel_prefetch(cudaStream_t stream, const CameraConst* cam, int W, int T, int J, int H, int Wd, const float* pose,
                           const float* heat, const int64_t* frame_base, float* patch, short2* patch_origin,
-                          unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas);
+                          unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas, int planar = 0);
 constexpr int kPatchW = 8;      // side of the per-joint texel window of the energy kernel's cache (at most 8: 64 valid bits)
 
 enum { EPI_NONE = 0, EPI_LRELU = 1, EPI_MASK = 2 };
@@ -90,6 +90,7 @@ struct ChainEnergyLaunch {
     uint32_t* status;                           // [W] or NULL
     int32_t* row_exp;                           // [W]
     int J, H, Wd;
+    int planar = 0;                             // heat-map layout (gem_ctx_set_heat_layout)
     float* patch = nullptr;                     // optional texel cache (zero-copy heat maps)
     short2* patch_origin = nullptr;
     unsigned long long* patch_valid = nullptr;

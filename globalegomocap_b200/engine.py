@@ -51,6 +51,7 @@ class Engine:
                                       num_joints, self.H, self.Wd, max_history))
         self._vae = {}
         self._keep = []
+        self.heat_planar = False
 
     # ------------------------------------------------------------------ housekeeping
     def close(self):
@@ -111,6 +112,13 @@ class Engine:
         """-1 auto (on when the heat maps are pinned host memory), 0 off, 1 on; results are unaffected."""
         check(self.lib.gem_ctx_set_texel_cache(self._ctx, int(mode)))
 
+    def set_heat_layout(self, planar: bool):
+        """False: heat maps are [frames, H, W, J] (the pickle's layout); True: planar [frames, J, H, W]
+        (include/gem_b200.h: gem_ctx_set_heat_layout).  Results are bit-identical in both layouts."""
+        if bool(planar) != self.heat_planar:
+            check(self.lib.gem_ctx_set_heat_layout(self._ctx, int(bool(planar))))
+            self.heat_planar = bool(planar)
+
     def texel_cache_stats(self, enable: bool):
         """(lookups, texels fetched from the map) counted since the previous call; switches the counting on or off."""
         a, b = C.c_uint64(0), C.c_uint64(0)
@@ -132,9 +140,10 @@ class Engine:
         resolution / joint count, or a window that runs past the last frame, must not reach the kernel."""
         if heat is None:
             return
-        if tuple(heat.shape[-3:]) != (self.H, self.Wd, self.J):
-            raise GemError(f"heat maps are {tuple(heat.shape[-3:])}, the engine was created for "
-                           f"{(self.H, self.Wd, self.J)} (H, W, joints)")
+        want = (self.J, self.H, self.Wd) if self.heat_planar else (self.H, self.Wd, self.J)
+        if tuple(heat.shape[-3:]) != want:
+            raise GemError(f"heat maps are {tuple(heat.shape[-3:])}, the engine expects {want} "
+                           f"({'joints, H, W: planar layout' if self.heat_planar else 'H, W, joints'})")
         if frame_base is None or (isinstance(frame_base, torch.Tensor) and frame_base.is_cuda):
             return          # device-resident indices were range-checked by whoever built them (WindowBatch does)
         fb = np.asarray(frame_base)

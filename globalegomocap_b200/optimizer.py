@@ -171,8 +171,10 @@ def _pinned(name, shape, np_dtype):
 
 class ClipSet(list):
     """The clips of one call: a list of per-clip dicts of (pinned) host tensors, plus `heat_all`, the ONE pinned tensor
-    [total frames, H, W, J] every clip's heat maps are a view of (what the zero-copy path reads in place)."""
+    [total frames, H, W, J] (planar: [total frames, J, H, W]) every clip's heat maps are a view of — what the zero-copy
+    path reads in place."""
     heat_all = None
+    planar = False
 
 
 def _unpickle(data_id):
@@ -180,10 +182,15 @@ def _unpickle(data_id):
         return pickle.load(f)
 
 
-def load_clips(data_ids, pinned=True):
+def load_clips(data_ids, pinned=True, planar=True):
     """'<data_id>/test_data.pkl' of every clip (optimizer.py:315-324; extra keys are ignored) unpickled and landed
     ONCE in page-locked host memory: each per-frame list is stacked straight into its slice of one pinned buffer
-    per key, so the solver can read the heat maps where they are (or DMA them) without another host copy."""
+    per key, so the solver can read the heat maps where they are (or DMA them) without another host copy.
+
+    planar (default): the heat maps are stacked as [frames, J, H, W] — the permutation the reference applies to every
+    window before grid_sample (optimizer.py:251), done here once while the frames are copied anyway.  With planar maps
+    the x-neighbours of a bilinear footprint share a sector, which is what makes the zero-copy path cheap (a third of
+    the PCIe requests); planar=False keeps the pickle's [frames, H, W, J]."""
     raws = [_unpickle(d) for d in data_ids]
     n_frames = [len(r["estimated_local_skeleton"]) for r in raws]
     offs = np.concatenate([[0], np.cumsum(n_frames)]).astype(np.int64)
@@ -195,6 +202,9 @@ def load_clips(data_ids, pinned=True):
                 continue
             raise KeyError("test_data.pkl lacks the key {!r}".format(key))
         shape = tuple(np.asarray(next(r[key][0] for r in raws if len(r[key]))).shape) if total else ()
+        to_planar = planar and key == "heatmap_list" and len(shape) == 3
+        if to_planar:
+            shape = (shape[2], shape[0], shape[1])
         dt = _CLIP_DTYPES[key]
         buf = _pinned("clip_" + key, (total,) + shape, dt) if pinned else torch.from_numpy(np.empty((total,) + shape, dt))
         view = buf.numpy()
@@ -203,7 +213,11 @@ def load_clips(data_ids, pinned=True):
             if len(frames) != n_frames[i]:
                 raise ValueError("{}: {} has {} frames, expected {}".format(data_ids[i], key, len(frames), n_frames[i]))
             dst = view[offs[i]:offs[i + 1]]
-            if n_frames[i]:
+            if n_frames[i] and to_planar:
+                # HWC frames -> planar slice: torch's strided copy runs on all host threads (numpy's on one)
+                src = np.asarray(frames) if isinstance(frames, np.ndarray) else np.stack(frames)
+                torch.from_numpy(dst).copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=dt)).permute(0, 3, 1, 2))
+            elif n_frames[i]:
                 if isinstance(frames, np.ndarray):
                     np.copyto(dst, frames, casting="same_kind")
                 else:
@@ -211,6 +225,7 @@ def load_clips(data_ids, pinned=True):
             clips[i][key] = buf[offs[i]:offs[i + 1]]
         if key == "heatmap_list":
             clips.heat_all = buf
+            clips.planar = bool(to_planar)
     return clips
 
 
@@ -249,12 +264,15 @@ def solve_clips(clips, camera_model_path, vae_weight=0.0, gmm_weight=0.0, smooth
     if outputs not in ("all", "optimized"):
         raise ValueError("outputs must be 'all' or 'optimized'")
     prebuilt = isinstance(clips, WindowBatch)
+    planar = bool(getattr(clips, "planar", False))
     if prebuilt:
         batch_W = clips.W
         heat_shape = tuple(clips.heat.shape[-3:])
     else:
         batch_W = sum(_n_windows(len(c["estimated_local_skeleton"])) for c in clips)
         heat_shape = tuple(np.shape(clips[0]["heatmap_list"])[-3:]) if len(clips) else (64, 64, 15)
+    if planar:
+        heat_shape = (heat_shape[1], heat_shape[2], heat_shape[0])           # (J, H, W) -> (H, W, J)
     eng = engine if engine is not None else shared_engine(batch_W, max(max_iter - 1, 1), heat_hw=heat_shape[:2],
                                                           num_joints=heat_shape[2])
     eng.set_camera_json(camera_model_path) if isinstance(camera_model_path, str) else eng.set_camera(*camera_model_path)
@@ -272,13 +290,13 @@ def solve_clips(clips, camera_model_path, vae_weight=0.0, gmm_weight=0.0, smooth
         if ingest == "zero_copy" and not zero_copy_ok:
             raise ValueError("ingest='zero_copy' needs the clips' heat maps in one pinned host tensor (load_clips)")
         if zero_copy_ok and ingest in ("auto", "zero_copy"):
-            batch = WindowBatch(eng, clips, host_heat=heat_all)
+            batch = WindowBatch(eng, clips, host_heat=heat_all, planar=planar)
         else:
             host_side = len(clips) > 0 and not (isinstance(clips[0]["heatmap_list"], torch.Tensor) and
                                                 clips[0]["heatmap_list"].is_cuda)
             if host_side and copy_stream is None:
                 copy_stream = _copy_stream(eng.device)
-            batch = WindowBatch(eng, clips, copy_stream=copy_stream if host_side else None)
+            batch = WindowBatch(eng, clips, copy_stream=copy_stream if host_side else None, planar=planar)
     sol = seq_opt.solve(batch, eps=eps)
     if batch.ready_events:
         eng.set_slices(None)

@@ -63,8 +63,11 @@ class WindowBatch:
     back) the maps are not copied at all: the energy kernel reads them over PCIe through its texel cache, so
     only the texels the optimiser samples ever cross the bus."""
 
-    def __init__(self, engine: Engine, clips, copy_stream=None, min_piece_windows=96, host_heat=None):
+    def __init__(self, engine: Engine, clips, copy_stream=None, min_piece_windows=96, host_heat=None, planar=False):
+        # planar: the clips' heat maps (and host_heat) are [frames, J, H, W] instead of the pickle's [frames, H, W, J]
+        # (optimizer.load_clips(planar=True)); SequenceOptimizer.solve tells the engine
         dev = engine.device
+        self.planar = bool(planar)
         self.n_frames = [len(c["estimated_local_skeleton"]) for c in clips]
         self.starts = [window_starts(n, engine.T, OVERLAP) for n in self.n_frames]
         self.n_windows = [len(s) for s in self.starts]
@@ -206,6 +209,7 @@ class SequenceOptimizer:
         """Runs both stages for every window of ``batch``; returns per-window device tensors."""
         eng = self.engine
         W = batch.W
+        eng.set_heat_layout(getattr(batch, "planar", False))
         if eps is None:
             eps = torch.randn(W, 2, eng.n, device=eng.device, dtype=torch.float32)
         eps = eng._dev(eps, torch.float32)

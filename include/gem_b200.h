@@ -128,6 +128,14 @@ int gem_ctx_set_slices(gem_ctx* ctx, int n, const int32_t* first_window_h);
  * optimisation of the first clips overlaps the host-to-device copy of the later ones. */
 int gem_ctx_set_ready_events(gem_ctx* ctx, int n, const int32_t* first_window_h, void* const* events_h);
 
+/* Layout of every heat_d argument: 0 (default) = [frames][H][Wd][J], the pickle's HWC layout, gathered in place;
+ * 1 = planar [frames][J][H][Wd] — what the reference itself permutes each window's maps to before grid_sample
+ * (optimizer.py:251).  In the planar layout the x-neighbours of a bilinear footprint share a 32-byte sector: half
+ * the DRAM sectors per sample on resident maps, and the zero-copy texel cache fetches aligned float4 units (one PCIe
+ * request per four texels of a map row; about a third of the requests per stage).  Values are the same: results
+ * are bit-identical in both layouts.  Needs Wd % 4 == 0.  gem_lift_skeleton always takes HWC maps. */
+int gem_ctx_set_heat_layout(gem_ctx* ctx, int planar);
+
 /* heat_d may be pinned (or registered) HOST memory: the energy kernel then reads the maps over PCIe through a
  * per-joint 8x8 texel window in HBM (256 bytes per joint and a valid bit per texel: a texel is fetched the first time
  * the bilinear footprint needs it; the window is re-centred, empty, when the footprint leaves it), so only the few
@@ -135,7 +143,7 @@ int gem_ctx_set_ready_events(gem_ctx* ctx, int n, const int32_t* first_window_h,
  * results are bit-identical.  mode -1 (default): cache on exactly when heat_d is host memory; 0 off; 1 on. */
 int gem_ctx_set_texel_cache(gem_ctx* ctx, int mode);
 /* synchronises; returns the cache's lookups (one per joint per evaluation) and the texels it fetched from the map
- * (one 32-byte sector each) counted since the previous call while counting was enabled, then clears them and sets
+ * (one 32-byte sector each; with planar maps: the float4 requests) counted since the previous call while counting was enabled, then clears them and sets
  * counting on/off */
 int gem_ctx_texel_cache_stats(gem_ctx* ctx, int enable, uint64_t* lookups_h, uint64_t* texels_fetched_h);
 

@@ -210,8 +210,13 @@ def test_main_batch_ingest_modes_are_bit_identical(workdir, monkeypatch, vae_wei
     clips = gem.load_clips(names)
     assert clips.heat_all.is_pinned()
     eng = gem.shared_engine(W, 3)
-    resident = WindowBatch(eng, [{k: v.cuda() for k, v in c.items()} for c in clips])
+    assert clips.planar                                      # load_clips stacks the maps planar ([frames, J, H, W]) by default
+    resident = WindowBatch(eng, [{k: v.cuda() for k, v in c.items()} for c in clips], planar=True)
     res = gem.solve_clips(resident, eps=eps, **kw)
+    hwc = gem.load_clips(names, planar=False)                # the pickle's own layout gives the same bits
+    res_hwc = gem.solve_clips(WindowBatch(eng, [{k: v.cuda() for k, v in c.items()} for c in hwc]), eps=eps, **kw)
+    for a, b in zip(res["merged"], res_hwc["merged"]):
+        assert torch.equal(a["final_optimized_seq"], b["final_optimized_seq"])
     opt_only = gem.solve_clips(resident, eps=eps, outputs="optimized", **kw)
     torch.cuda.synchronize()
     for i in range(3):

@@ -78,8 +78,13 @@ def test_load_clips_lands_every_clip_in_one_staging_buffer(tmp_path):
         with open(d / "test_data.pkl", "wb") as f:
             pickle.dump(raw, f)
         dirs.append(str(d))
-    cs = gem.load_clips(dirs)
-    assert isinstance(cs, gem.ClipSet) and len(cs) == 2
+    planar = gem.load_clips(dirs)                            # default: heat maps land as [frames, J, H, W]
+    assert planar.planar and tuple(planar.heat_all.shape) == (18 + 26, 15, 64, 64)
+    for c, got in zip(clips, planar):
+        assert np.array_equal(got["heatmap_list"].numpy(), c["heatmap_list"].transpose(0, 3, 1, 2))
+        assert np.array_equal(got["gt_global_skeleton"].numpy(), c["gt_global_skeleton"])
+    cs = gem.load_clips(dirs, planar=False)
+    assert isinstance(cs, gem.ClipSet) and len(cs) == 2 and not cs.planar
     assert tuple(cs.heat_all.shape) == (18 + 26, 64, 64, 15) and cs.heat_all.dtype == torch.float32
     off = 0
     for c, got in zip(clips, cs):
