@@ -81,13 +81,18 @@ class WindowBatch:
         self.window_offsets = np.concatenate([[0], np.cumsum(self.n_windows)]).astype(np.int64)
         self.ready_events, self.ready_first_windows = [], []
 
-        # small host-built index tensors first: a pageable H2D copy issued after the big heat-map copies would
-        # queue behind them on the copy engine
-        self.frame_base = torch.as_tensor(fb, device=dev)
-        self.clip_idx = torch.as_tensor(clip_idx, device=dev)
-        parents = torch.as_tensor(KINEMATIC_PARENTS, device=dev)
-        t_idx = self.frame_base[:, None] + torch.arange(engine.T, device=dev)[None, :]      # [W,T] frame ids
-        self.frame_idx = t_idx
+        # The window index tensors depend only on the clips' lengths: built once per (lengths, device) and kept with the
+        # engine.  A pageable host-to-device copy per call would also synchronise the host with everything already
+        # enqueued, so that consecutive calls could not overlap their host-side preparation with the previous solve.
+        cache = engine.__dict__.setdefault("_index_cache", {})
+        key = (tuple(self.n_frames), engine.T, str(dev))
+        if key not in cache:
+            if len(cache) > 16:
+                cache.clear()
+            frame_base = torch.as_tensor(fb, device=dev)
+            cache[key] = (frame_base, torch.as_tensor(clip_idx, device=dev), torch.as_tensor(KINEMATIC_PARENTS, device=dev),
+                          frame_base[:, None] + torch.arange(engine.T, device=dev)[None, :])      # [W,T] frame ids
+        self.frame_base, self.clip_idx, parents, self.frame_idx = cache[key]
 
         total = int(offs[-1])
 

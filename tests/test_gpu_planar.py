@@ -49,7 +49,7 @@ def test_solves_are_bit_identical_and_pcie_requests_drop(vae_weights, camera):
     eng = Engine(max_windows=W)
     eng.set_camera(*camera)
     eng.set_vae(0, vae_weights[0])
-    out, fetched = {}, {}
+    out, fetched, looked = {}, {}, {}
     for name, heat, is_planar in (("hwc resident", hwc.cuda(), False), ("planar resident", planar.cuda(), True),
                                   ("hwc zero-copy", hwc.pin_memory(), False), ("planar zero-copy", planar.pin_memory(), True)):
         eng.set_heat_layout(is_planar)
@@ -57,11 +57,13 @@ def test_solves_are_bit_identical_and_pcie_requests_drop(vae_weights, camera):
         r = eng.solve_stage(0, x0, heat, np.asarray(starts, np.int64), np.zeros(W, np.int32), mb, eps, energy_weights(*W_LOCAL),
                             lbfgs_params(max_iter=6), want_trace=True)
         torch.cuda.synchronize()
-        lookups, fetched[name] = eng.texel_cache_stats(False)
+        looked[name], fetched[name] = eng.texel_cache_stats(False)
         out[name] = (r["pose"].clone(), torch.nan_to_num(r["trace"], nan=-7.0), r["func_evals"].clone())
     for name in out:
         for u, v in zip(out[name], out["hwc resident"]):
             assert torch.equal(u, v), name
-    print("PCIe requests, HWC:", fetched["hwc zero-copy"], "planar:", fetched["planar zero-copy"])
+    print("cache lookups:", looked, "PCIe requests:", fetched)
+    assert looked["hwc resident"] == looked["planar resident"] == 0           # small batches of resident maps: no cache
+    assert looked["hwc zero-copy"] == looked["planar zero-copy"] > 0
     assert 0 < fetched["planar zero-copy"] < 0.6 * fetched["hwc zero-copy"]
     eng.close()
