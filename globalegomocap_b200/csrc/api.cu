@@ -83,6 +83,7 @@ struct gem_ctx {
     unsigned long long* patch_stats = nullptr;   // {lookups, texels fetched}, counted while patch_stats_on
     bool patch_stats_on = false;
     int texel_cache = -1;                        // -1 auto (on when the maps are host memory), 0 off, 1 on
+    int texel_keep = 0;                          // measurement only (GEM_TEXEL_KEEP=1): stages do not empty the texel windows
     int texel_prefetch_ctas = 4;                 // CTAs of the texel prefetch kernel (0: the energy kernel fetches itself)
     int trace_cap = 0;                           // columns of trace_own
     bool use_graphs = true;
@@ -259,6 +260,7 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     if (c->n_chunks > 16) c->n_chunks = 16;
     if (const char* env = getenv("GEM_GRAPHS")) c->use_graphs = env[0] != '0';
     if (const char* env = getenv("GEM_TEXEL_CACHE")) c->texel_cache = atoi(env);
+    if (const char* env = getenv("GEM_TEXEL_KEEP")) c->texel_keep = atoi(env) != 0;
     if (const char* env = getenv("GEM_TEXEL_PREFETCH_CTAS")) c->texel_prefetch_ctas = atoi(env) > 0 ? atoi(env) : 0;
     // default skeleton: the reference's 15-joint kinematic tree (optimizer.py:34)
     if (num_joints == 15) {
@@ -809,14 +811,16 @@ __global__ void stage_inputs_kernel(int w_abs0, int TJ3, int J, const float* __r
                                     const int32_t* __restrict__ clip, const float* __restrict__ mean_bone,
                                     float* __restrict__ pose0_own, int64_t* __restrict__ fb_own,
                                     int32_t* __restrict__ clip_own, float* __restrict__ mb_own,
-                                    uint32_t* __restrict__ status_own, unsigned long long* __restrict__ patch_valid, int TJ) {
+                                    uint32_t* __restrict__ status_own, unsigned long long* __restrict__ patch_valid, int TJ,
+                                    int keep_patch) {
     // all pointers are the slice's (window blockIdx.x of the slice); mb_own is the ctx-wide table indexed by the
     // absolute window w_abs0 + blockIdx.x, which is what the staged clip index points at
     const int w = blockIdx.x;
     for (int i = threadIdx.x; i < TJ3; i += blockDim.x) pose0_own[(size_t)w * TJ3 + i] = pose0[(size_t)w * TJ3 + i];
     if (threadIdx.x < J) mb_own[(size_t)(w_abs0 + w) * J + threadIdx.x] = mean_bone[(size_t)clip[w] * J + threadIdx.x];
     // a new stage reads new maps: every joint's cached texel patch is stale
-    for (int i = threadIdx.x; i < TJ; i += blockDim.x) patch_valid[(size_t)w * TJ + i] = 0ull;      // empty window
+    if (!keep_patch)
+        for (int i = threadIdx.x; i < TJ; i += blockDim.x) patch_valid[(size_t)w * TJ + i] = 0ull;      // empty window
     if (threadIdx.x == 0) {
         fb_own[w] = fb ? fb[w] : 0;
         clip_own[w] = w_abs0 + w;
@@ -1019,7 +1023,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     if (a.trace) GEM_CUDA(cudaMemsetAsync(v.trace_own, 0xff, (size_t)Wk * c->trace_cap * sizeof(float), q));   // NaN
     stage_inputs_kernel<<<Wk, 128, 0, q>>>(w0, TJ3, c->J, a.pose0 + w0 * P, a.frame_base ? a.frame_base + w0 : nullptr,
                                            a.clip + w0, a.mean_bone, v.pose0_own, v.fb_own, v.clip_own, v.mb_own,
-                                           v.status_own, v.patch_valid, c->T * c->J);
+                                           v.status_own, v.patch_valid, c->T * c->J, c->texel_keep);
     GEM_CHECK_LAUNCH();
     c->launches += 1;
     // z0 = mu + eps * std                                   optimizer.py:255-259

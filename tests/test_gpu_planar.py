@@ -44,14 +44,21 @@ def test_solves_are_bit_identical_and_pcie_requests_drop(vae_weights, camera):
     x0 = np.stack([est[s:s + 10] for s in starts]).astype(np.float32)
     mb = syn.mean_bone_length(est)
     eps = np.random.default_rng(9).standard_normal((W, 2048)).astype(np.float32)
-    hwc = torch.from_numpy(clip["heatmap_list"])
+    hwc = torch.from_numpy(np.ascontiguousarray(clip["heatmap_list"]))
     planar = hwc.permute(0, 3, 1, 2).contiguous()
+
+    def pinned(t):
+        p = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        p.copy_(t)
+        assert p.is_pinned() and p.is_contiguous()
+        return p
+
     eng = Engine(max_windows=W)
     eng.set_camera(*camera)
     eng.set_vae(0, vae_weights[0])
     out, fetched, looked = {}, {}, {}
     for name, heat, is_planar in (("hwc resident", hwc.cuda(), False), ("planar resident", planar.cuda(), True),
-                                  ("hwc zero-copy", hwc.pin_memory(), False), ("planar zero-copy", planar.pin_memory(), True)):
+                                  ("hwc zero-copy", pinned(hwc), False), ("planar zero-copy", pinned(planar), True)):
         eng.set_heat_layout(is_planar)
         eng.texel_cache_stats(True)
         r = eng.solve_stage(0, x0, heat, np.asarray(starts, np.int64), np.zeros(W, np.int32), mb, eps, energy_weights(*W_LOCAL),
