@@ -50,9 +50,12 @@ def test_product_has_no_cpu_fallback():
 
 
 def test_product_never_imports_the_oracle():
+    """Neither the oracle nor the reference harness (baseline/) is reachable from the product package or the CLI."""
+    assert not re.search(r"^\s*(from|import)\s+(oracle|baseline)\b", open(os.path.join(REPO, "optimize_whole_sequence.py")).read(),
+                         flags=re.M)
     pkg = os.path.join(REPO, "globalegomocap_b200")
     for root, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert not re.search(r"^\s*(from|import)\s+(oracle|baseline)\b", text, flags=re.M), f
