@@ -377,7 +377,7 @@ def main():
             d = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in c.items()
                  if k not in ("gt_global_skeleton", "heatmap_list", "mean_bone_length")}
             if "mean_bone_length" in c:
-                d["mean_bone_length"] = c["mean_bone_length"]
+                d["mean_bone_length"] = torch.from_numpy(np.ascontiguousarray(c["mean_bone_length"])).pin_memory()
             d["heatmap_list"] = heat_all[offs[i]:offs[i + 1]]
             d["heatmap_list"].copy_(torch.from_numpy(np.ascontiguousarray(c["heatmap_list"])))
             clips.append(d)

@@ -1154,9 +1154,26 @@ static std::vector<int> slice_bounds(const gem_ctx* c, int W, bool zero_copy, bo
         w0.push_back(W);
         return w0;
     }
-    // automatic: 4 slices; 8 when the maps are read over PCIe (more slices hide more of the transfers)
-    int n = c->prof_on ? 1 : (c->n_chunks > 0 ? c->n_chunks : (zero_copy ? 8 : 4));
-    const int kAlign = 12, kMinChunk = 96;
+    // automatic: up to 4 slices; up to 8 when the maps are read over PCIe (more slices hide more of the transfers).
+    // The GEMMs run 256-row CTA-pair tiles (a row = a window): among the admissible slice counts take the one whose
+    // slices pad to the fewest tile rows in total, the larger count on ties (468 windows: 2 slices of 234, not 4 of 117
+    // that would each fill less than half a tile: DESIGN.md section 7).
+    const int kAlign = 12, kMinChunk = 96, kTile = 256;
+    int n;
+    if (c->prof_on) {
+        n = 1;
+    } else if (c->n_chunks > 0) {
+        n = c->n_chunks;
+    } else {
+        const int n_max = zero_copy ? 8 : 4;
+        const int k_max = n_max < W / kMinChunk ? n_max : (W / kMinChunk > 1 ? W / kMinChunk : 1);
+        auto padded = [&](int k) { return (long)k * (((W + k - 1) / k + kTile - 1) / kTile) * kTile; };
+        long least = padded(1);
+        for (int k = 2; k <= k_max; ++k) least = padded(k) < least ? padded(k) : least;
+        n = 1;
+        for (int k = 2; k <= k_max; ++k)          // concurrency is worth ~20 % of a step: accept up to 25 % more tile rows for it
+            if (4 * padded(k) <= 5 * least) n = k;
+    }
     if (n > W / kMinChunk) n = W / kMinChunk;
     if (n < 1) n = 1;
     w0.assign(n + 1, W);

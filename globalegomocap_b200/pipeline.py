@@ -162,9 +162,12 @@ class WindowBatch:
         # sequence brings the whole sequence's lengths along ("mean_bone_length", computed before sharding)
         est32 = self.est.to(torch.float32)
         bone = torch.linalg.vector_norm(est32 - est32[:, parents, :], dim=-1)   # [F,15]
-        self.mean_bone = torch.stack([
-            torch.as_tensor(np.asarray(clips[i]["mean_bone_length"], dtype=np.float32), device=dev)
-            if "mean_bone_length" in clips[i] else bone[offs[i]:offs[i + 1]].mean(0) for i in range(len(clips))])
+        def given(i):
+            mb = clips[i]["mean_bone_length"]          # (a pinned tensor crosses without synchronising the host)
+            mb = mb if isinstance(mb, torch.Tensor) else torch.as_tensor(np.asarray(mb, dtype=np.float32))
+            return mb.to(device=dev, dtype=torch.float32, non_blocking=True)
+        self.mean_bone = torch.stack([given(i) if "mean_bone_length" in clips[i] else bone[offs[i]:offs[i + 1]].mean(0)
+                                      for i in range(len(clips))])
 
     def replicate(self, R):
         """Every window R times (independent solves from their own noise that share the clips' inputs in HBM):
