@@ -633,8 +633,9 @@ int make_map(CUtensorMap* map, const void* base, bool f16, uint64_t rows, uint64
                : make_map_f32(map, static_cast<const float*>(base), 2, dims, strides, box);
 }
 
-constexpr int kNumBN = 4;
-constexpr int kBNs[kNumBN] = {112, 128, 144, 160};
+constexpr int kNumBN = 6;
+constexpr int kBNs[kNumBN] = {64, 96, 112, 128, 144, 160};      // (64 and 96: CTA-pair kernel only, small batches)
+constexpr int kFirstWideBN = 2;
 struct WeightSplit {
     void *hi = nullptr, *lo = nullptr;                 // K-major [N][K], fp32 (TF32 scheme) or fp16
     int K = 0, N = 0;
@@ -808,10 +809,10 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
     // least padded tiling wins).  Beyond: the fewest waves x columns over the 148 SMs (sign words need
     // 32-column alignment).
     const int mt = (g.M + BM - 1) / BM;
-    int best = 1;
+    int best = 3;                                  // 128
     if ((long)mt * (g.N / 128) > kNumSMs) {
         long best_cost = -1;
-        for (int i = 0; i < kNumBN; ++i) {
+        for (int i = kFirstWideBN; i < kNumBN; ++i) {
             if (g.C_sign && kBNs[i] % 32 != 0) continue;
             const long tiles = (long)mt * ((g.N + kBNs[i] - 1) / kBNs[i]);
             const long cost = ((tiles + kNumSMs - 1) / kNumSMs) * kBNs[i];
@@ -819,7 +820,7 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
         }
     }
     if (const char* env = getenv("GEM_GEMM_BN")) {
-        for (int i = 0; i < kNumBN; ++i)
+        for (int i = kFirstWideBN; i < kNumBN; ++i)
             if (atoi(env) == kBNs[i] && !(g.C_sign && kBNs[i] % 32 != 0)) best = i;
     }
     // fp16 scheme: CTA pairs (cta_group::2) unless GEM_GEMM_PAIR=0; 160-wide tiles (the lowest shared-memory traffic
@@ -830,11 +831,31 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
     }();
     const int pair_mode = g_gemm_pair >= 0 ? g_gemm_pair : pair_env;
     if (f16 && pair_mode && !(a.C_lo && !a.out16)) {      // (fp32 hi/lo outputs need the one-CTA kernel's larger staging area)
+        // 160-wide tiles have the lowest shared-memory traffic per MMA.  A small batch (a slice of a few hundred windows:
+        // strong scaling, a real 30-clip dataset) leaves most SMs without a tile; GEM_GEMM_NARROW=1 then takes the
+        // narrowest tile (64 / 96 / 128 columns) that still fits the machine in one wave.  Bit-identical, but measured
+        // to gain only 3-7 % of the GEMM at 236 windows (34.5 -> 32 us per launch: the tile's K loop is bound by its
+        // operand loads, not by the MMAs) and nothing at 372 / 472 windows: off by default.
         int bn = 160;
+        const long pairs_m = (g.M + 2 * BM - 1) / (2 * BM);
+        static const int narrow_env = []() {
+            const char* env = getenv("GEM_GEMM_NARROW");
+            return env ? atoi(env) : 0;
+        }();
+        if (narrow_env) {
+            const int cand[3] = {64, 96, 128};
+            for (int c : cand)
+                if (pairs_m * ((g.N + c - 1) / c) <= kNumSMs / 2) {
+                    bn = c;
+                    break;
+                }
+        }
         if (const char* env = getenv("GEM_GEMM_BN")) bn = atoi(env);
-        if (bn == 128) return launch_pair_bn<128>(stream, map_a_hi, map_a_lo, wit->second, 1, a);
-        if (bn == 144) return launch_pair_bn<144>(stream, map_a_hi, map_a_lo, wit->second, 2, a);
-        return launch_pair_bn<160>(stream, map_a_hi, map_a_lo, wit->second, 3, a);
+        if (bn == 64) return launch_pair_bn<64>(stream, map_a_hi, map_a_lo, wit->second, 0, a);
+        if (bn == 96) return launch_pair_bn<96>(stream, map_a_hi, map_a_lo, wit->second, 1, a);
+        if (bn == 128) return launch_pair_bn<128>(stream, map_a_hi, map_a_lo, wit->second, 3, a);
+        if (bn == 144) return launch_pair_bn<144>(stream, map_a_hi, map_a_lo, wit->second, 4, a);
+        return launch_pair_bn<160>(stream, map_a_hi, map_a_lo, wit->second, 5, a);
     }
     return f16 ? launch_scheme<true>(kBNs[best], stream, map_a_hi, map_a_lo, wit->second, best, a)
                : launch_scheme<false>(kBNs[best], stream, map_a_hi, map_a_lo, wit->second, best, a);
