@@ -671,12 +671,10 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(args, {"windows_total": windows_total, "windows_per_gpu": W,
-                                                 "closure_evaluations_last_step": evals,
-                                                 "lbfgs_iterations_last_step": n_iter,
-                                                 "rounds_per_step": rounds, "gemm_mode": args.gemm_mode,
-                                                 "value_api": "globalegomocap_b200.optimizer.solve_clips(WindowBatch resident in HBM, "
-                                                              "outputs='optimized')"}),
+                "config": workload_config(args, None),          # (identical in both arms: the workload, nothing about the run)
+                "run": {"windows_total": windows_total, "windows_per_gpu": W, "closure_evaluations_last_step": evals,
+                        "lbfgs_iterations_last_step": n_iter, "rounds_per_step": rounds, "gemm_mode": args.gemm_mode,
+                        "value_api": "globalegomocap_b200.optimizer.solve_clips(WindowBatch resident in HBM, outputs='optimized')"},
                 "clocks": clocks, "e2e": e2e,
                 "e2e_zero_copy": e2e_modes.get("zero_copy"), "e2e_upload": e2e_modes.get("upload"),
                 "e2e_with_unpickle": unpickle,
