@@ -787,9 +787,15 @@ static_assert(sizeof(Chain2Maps) + sizeof(Chain2Args) + sizeof(Chain2Energy) <= 
 constexpr int kEnergyQuarterFloats = 2048;      // scratch floats per TMEM lane quarter in each scratch buffer
 constexpr int kEnergyRedOffset = 1440;          // partial sums live behind the anchor poses in scratch1
 
+// kEnergy: the variant with the energy prologue compiled in (its per-joint code is 6 k instructions; the plain
+// chain stays at its 4 k, which its instruction-cache behaviour depends on: stall_no_inst was 18 % of the samples with
+// both in one kernel)
+template <bool kEnergy>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kChainThreads, 1)
 tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_constant__ Chain2Args g,
-                     const __grid_constant__ Chain2Energy en) {
+                     const __grid_constant__ Chain2Energy en_arg) {
+    const Chain2Energy& en = en_arg;
+    const bool en_on = kEnergy && en_arg.enabled;      // (folds to false at compile time in the plain variant)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* act = smem;                                   // four buffers of (hi 16 KB, lo 16 KB)
@@ -817,7 +823,7 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a_hi), prefetch_tmap(&maps.a_lo);
-        mbar_init(act_full, en.enabled ? 2 * kChainEpiWarps : 1);      // energy prologue: the pair's epilogue warps arrive
+        mbar_init(act_full, en_on ? 2 * kChainEpiWarps : 1);      // energy prologue: the pair's epilogue warps arrive
         mbar_init(&w_full[0], 1), mbar_init(&w_full[1], 1), mbar_init(&w_empty[0], 1), mbar_init(&w_empty[1], 1);
         mbar_init(acc_full, 1), mbar_init(act_ready, 2 * kChainEpiWarps);
         fence_barrier_init();
@@ -838,7 +844,7 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
             uint8_t* p = act + tile * kATile + q * kQuarterBytes + (rows_q + rr) * 128 + c16 * 16;
             *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (en.enabled) {
+        if (en_on) {
             // the energy prologue writes only the real channels of valid windows: padding columns, idle rows and the
             // rows of windows beyond W must read zero (the TMA unit zero-fills them on the loading path)
             float4* p = reinterpret_cast<float4*>(act + en.in_buf * 2 * kATile);
@@ -858,8 +864,8 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
         if (lane == 0) {
             const uint32_t box_bytes = (uint32_t)rows_q * 128;
             const uint32_t act_bar = mapa_u32(smem_u32(act_full), 0);
-            if (rank == 0 && !en.enabled) mbar_arrive_expect_tx(act_full, 2u * (uint32_t)nkb0 * 8 * box_bytes);
-            for (int kb = 0; kb < (en.enabled ? 0 : nkb0); ++kb) {
+            if (rank == 0 && !en_on) mbar_arrive_expect_tx(act_full, 2u * (uint32_t)nkb0 * 8 * box_bytes);
+            for (int kb = 0; kb < (en_on ? 0 : nkb0); ++kb) {
                 uint8_t* dst = act + g.L[0].in_buf[kb] * 2 * kATile;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -893,7 +899,7 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
             int b = 0;
             for (int l = 0; l < g.nl; ++l) {
                 const Chain2Layer& L = g.L[l];
-                if (l == 0 && !en.enabled) mbar_wait(act_full, 0);
+                if (l == 0 && !en_on) mbar_wait(act_full, 0);
                 else if (l == 0) mbar_wait_cluster(act_full, 0);          // the pair's energy prologues have written the tiles
                 else mbar_wait_cluster(act_ready, (uint32_t)((l - 1) & 1));
                 tc_fence_after();
@@ -936,7 +942,7 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
         const size_t token = (size_t)win * g.T + t;
         const uint32_t ready_bar = mapa_u32(smem_u32(act_ready), 0);
         const int c = sub;
-        if (en.enabled) {
+        if constexpr (kEnergy) if (en_on) {
             // ===== energy prologue: this quarter's windows, 32 joint-frames per (virtual) warp as in energy_grad_kernel =====
             constexpr int wpw = kEnergySlot / 32;                         // partial sums per window
             const int TJ = en.T * en.J, n = TJ * 3;
@@ -1552,12 +1558,14 @@ int launch_tap_chain_pair(cudaStream_t stream, void* owner, const TapChainLaunch
     }
     static PerDeviceOnce attr_set;
     if (bool* once_ = attr_set.flag(); !*once_) {
-        GEM_CUDA(cudaFuncSetAttribute(tc_tap_chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChain2Smem));
+        GEM_CUDA(cudaFuncSetAttribute(tc_tap_chain2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChain2Smem));
+        GEM_CUDA(cudaFuncSetAttribute(tc_tap_chain2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChain2Smem));
         *once_ = true;
     }
     const int tiles = (L.W + 4 * wpq - 1) / (4 * wpq);
     const int grid = 2 * ((tiles + 1) / 2);
-    tc_tap_chain2_kernel<<<grid, kChainThreads, kChain2Smem, stream>>>(maps, a, en);
+    if (en.enabled) tc_tap_chain2_kernel<true><<<grid, kChainThreads, kChain2Smem, stream>>>(maps, a, en);
+    else tc_tap_chain2_kernel<false><<<grid, kChainThreads, kChain2Smem, stream>>>(maps, a, en);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }
