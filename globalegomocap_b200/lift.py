@@ -28,16 +28,37 @@ def load_camera_c2w(path):
     return np.asarray(cal["polynomialC2W"], dtype=np.float64), float(intr[0][2]), float(intr[1][2])
 
 
-def skeleton_resize(points_3d, bone_length):
-    """`Skeleton._skeleton_resize` (utils/skeleton.py:123-135), float64; bone_length in millimetres."""
-    pts = np.array(points_3d, dtype=np.float64)
-    vec = pts - pts[KINEMATIC_PARENTS, :]
-    est = np.linalg.norm(vec, axis=1)
-    multi = np.concatenate(([0.0], np.asarray(bone_length, dtype=np.float64)[1:] / est[1:]))
-    resized = vec * multi[:, None] / 1000
-    for i in range(pts.shape[0]):
-        pts[i, :] = pts[KINEMATIC_PARENTS[i], :] + resized[i, :]
+def _tree_levels(parents):
+    """Joints grouped by their depth in the kinematic tree (the root, which is its own parent, is depth 0)."""
+    parents = list(parents)
+    depth = [0] * len(parents)
+    for j, p in enumerate(parents):            # parents precede their children in the reference's joint order
+        depth[j] = 0 if p == j else depth[p] + 1
+    return [np.asarray([j for j, d in enumerate(depth) if d == lvl]) for lvl in range(1, max(depth) + 1)]
+
+
+def rescale_bones(joints, bone_length_mm, parents=KINEMATIC_PARENTS):
+    """Every bone of every pose rescaled to a given length, the tree re-grown from the root
+    (`Skeleton._skeleton_resize`, utils/skeleton.py:123-135): joints [..., J, 3] float64 in metres, bone_length_mm [J]
+    in millimetres (entry 0 unused).  One vectorised update per tree depth, over all poses at once; a joint is its
+    parent's NEW position plus its own rescaled bone, added in the reference's order, so the result is the
+    reference's to the last bit."""
+    pts = np.array(joints, dtype=np.float64)
+    par = np.asarray(parents)
+    bone = pts - pts[..., par, :]
+    length = np.linalg.norm(bone, axis=-1)
+    target = np.asarray(bone_length_mm, dtype=np.float64)
+    scale = np.zeros_like(length)
+    scale[..., 1:] = target[1:] / length[..., 1:]
+    bone = bone * scale[..., None] / 1000
+    for level in _tree_levels(parents):
+        pts[..., level, :] = pts[..., par[level], :] + bone[..., level, :]
     return pts
+
+
+def skeleton_resize(points_3d, bone_length):
+    """`Skeleton._skeleton_resize` for one pose or a stack of poses (see rescale_bones)."""
+    return rescale_bones(points_3d, bone_length)
 
 
 def lift_skeletons(heatmaps, depths, poly_c2w, cx, cy, bone_length=None, device=None, upscale=16, pad_x=128,
@@ -66,7 +87,7 @@ def lift_skeletons(heatmaps, depths, poly_c2w, cx, cy, bone_length=None, device=
                                     C.c_void_p(preds.data_ptr()), C.c_void_p(maxvals.data_ptr()), None))
     out = points.cpu().numpy()
     if bone_length is not None:
-        out = np.stack([skeleton_resize(o, bone_length) for o in out])
+        out = rescale_bones(out, bone_length)
     if return_preds:
         return out, preds.cpu().numpy(), maxvals.cpu().numpy()
     return out

@@ -59,24 +59,16 @@ def _align_sequence(est, gt):
 
 
 def resize_to_mean_bones(joints):
-    """Skeleton._skeleton_resize with the mean3D bone lengths (utils/skeleton.py:127-139):
-    every bone is rescaled to the mean length, walking the kinematic tree from the root."""
-    bone_len = np.linalg.norm(MEAN3D_MM - MEAN3D_MM[PARENTS], axis=1)
-    vec = joints - joints[PARENTS]
-    est_len = np.linalg.norm(vec, axis=1)
-    mult = np.concatenate(([0.0], bone_len[1:] / est_len[1:]))
-    vec = vec * mult[:, None] / 1000
-    out = np.array(joints, dtype=np.float64)
-    for i in range(out.shape[0]):
-        out[i] = out[PARENTS[i]] + vec[i]
-    return out
+    """Poses [..., 15, 3] with every bone rescaled to the mean skeleton's length (`Skeleton.skeleton_resize_single`,
+    utils/skeleton.py:118-122 with mean3D.mat's lengths)."""
+    from .lift import rescale_bones
+    return rescale_bones(joints, np.linalg.norm(MEAN3D_MM - MEAN3D_MM[PARENTS], axis=1), PARENTS)
 
 
 def _align_per_pose_host(est, gt, resize):
     est, gt = np.array(est, dtype=np.float64), np.array(gt, dtype=np.float64)
     if resize:
-        est = np.stack([resize_to_mean_bones(p) for p in est])
-        gt = np.stack([resize_to_mean_bones(p) for p in gt])
+        est, gt = resize_to_mean_bones(est), resize_to_mean_bones(gt)
     out = np.zeros_like(est)
     for i in range(est.shape[0]):
         c, R, t = umeyama(est[i], gt[i])
