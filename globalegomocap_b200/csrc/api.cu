@@ -1058,7 +1058,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
                 return launch_energy_grad(q, c->have_camera ? &c->cam : nullptr, &c->skel, Wk, c->T, c->J, c->H, c->Wd, v.pose,
                                           v.pose0_own, a.heat, v.fb_own, v.clip_own,
-                                          v.mb_own, a.wt, v.f_new, nullptr, v.gpose, v.status_own, tc ? v.gp_hi : nullptr,
+                                          v.mb_own, a.wt, v.f_new, nullptr, tc ? nullptr : v.gpose, v.status_own, tc ? v.gp_hi : nullptr,
                                           v.gp_lo, pose_pad(c), a.texel_cache ? v.patch : nullptr, v.patch_origin,
                                           c->patch_stats_on ? c->patch_stats : nullptr, c->gemm_mode == 3, v.row_exp, v.patch_valid,
                                           c->heat_planar);
