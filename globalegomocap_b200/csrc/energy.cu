@@ -65,169 +65,152 @@ __global__ void __launch_bounds__(512) texel_prefetch_kernel(const __grid_consta
     }
 }
 
-// Persistent and double-buffered: a CTA walks over window pairs (pair, pair + gridDim.x, ...); the next pair's pose /
-// anchor tiles are requested from the TMA engine before the current pair is evaluated, and the current pair's results
-// leave by bulk stores that the next iteration does not wait for.  A pair's arithmetic and reduction order are exactly
-// those of the one-pair-per-CTA kernel of round 1 (results are bit-identical); what changes is that only a CTA's first
-// pair exposes the launch / barrier-init / first-load latency chain.
+// (Round 2 also measured a persistent, double-buffered variant — CTAs walking over window pairs with the next pair's
+// tiles in flight and stores not waited for, bit-identical: 27.7 us against 27.8 us at 1870 windows, 1.02 ms against
+// 0.95 ms at 100 980.  The kernel is bound by instruction issue — about 500 instructions per joint with --fmad=false,
+// IEEE divisions / square roots and the eleven-term polynomial — not by the load latency that pipelining hides.)
 __global__ void __launch_bounds__(kThreads, 4) energy_grad_kernel(const __grid_constant__ EnergyArgs a) {
-    constexpr int kTile = kWinPerCta * kSlot * 3;
-    __shared__ __align__(16) float s_x[2][kTile];
-    __shared__ __align__(16) float s_x0[2][kTile];
-    __shared__ __align__(16) float s_g[2][kTile];
+    __shared__ __align__(16) float s_x[kWinPerCta * kSlot * 3];
+    __shared__ __align__(16) float s_x0[kWinPerCta * kSlot * 3];
+    __shared__ __align__(16) float s_g[kWinPerCta * kSlot * 3];
     __shared__ float s_red[kThreads / 32][6];
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ __align__(16) float s_gh[2][kWinPerCta * kSplitMax];
-    __shared__ __align__(16) float s_gl[2][kWinPerCta * kSplitMax];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(16) float s_gh[kWinPerCta * kSplitMax];
+    __shared__ __align__(16) float s_gl[kWinPerCta * kSplitMax];
 
     const int tid = threadIdx.x;
     const int TJ = a.T * a.J;
     const int n = TJ * 3;                         // floats per window
-    const int npairs = (a.W + kWinPerCta - 1) / kWinPerCta;
-    const uint32_t tile_bytes = (uint32_t)(kWinPerCta * n * sizeof(float));
-    // a pair takes the bulk path when both of its windows exist (windows are contiguous: one copy covers both)
-    auto is_bulk = [&](int pair) { return a.use_bulk && pair * kWinPerCta + kWinPerCta <= a.W; };
-    auto request = [&](int pair, int b) {         // thread 0
-        if (!is_bulk(pair)) return;
-        mbar_arrive_expect_tx(&s_bar[b], 2 * tile_bytes);
-        bulk_g2s(s_x[b], a.pose + (size_t)pair * kWinPerCta * n, tile_bytes, &s_bar[b]);
-        bulk_g2s(s_x0[b], a.pose0 + (size_t)pair * kWinPerCta * n, tile_bytes, &s_bar[b]);
-    };
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1), mbar_init(&s_bar[1], 1);
-        fence_barrier_init();
-    }
-    __syncthreads();
-    if (tid == 0 && (int)blockIdx.x < npairs) request(blockIdx.x, 0);
+    const int w0 = blockIdx.x * kWinPerCta;
+    const int nwin = min(kWinPerCta, a.W - w0);
+    const bool bulk = a.use_bulk && nwin == kWinPerCta;
 
+    // ---- stage pose / anchor tiles -----------------------------------------------------------
+    if (bulk) {
+        // windows are contiguous in memory: one bulk copy covers both (2*n*4 bytes, 16-B multiple)
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(kWinPerCta * n * sizeof(float));
+            mbar_arrive_expect_tx(&s_bar, 2 * bytes);
+            bulk_g2s(s_x, a.pose + (size_t)w0 * n, bytes, &s_bar);
+            bulk_g2s(s_x0, a.pose0 + (size_t)w0 * n, bytes, &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+    } else {
+        for (int i = tid; i < nwin * n; i += kThreads) {
+            s_x[i] = a.pose[(size_t)w0 * n + i];
+            s_x0[i] = a.pose0[(size_t)w0 * n + i];
+        }
+        __syncthreads();
+    }
+    // with the bulk path both windows sit back to back (stride n); keep the same packing otherwise
     const int wl = tid / kSlot;                   // window slot inside the CTA
     const int k = tid - wl * kSlot;               // joint-frame index t*J + j
-    int it = 0;
-    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x, ++it) {
-        const int b = it & 1;
-        const int w0 = pair * kWinPerCta;
-        const int nwin = min(kWinPerCta, a.W - w0);
-        const bool bulk = is_bulk(pair);
-        // every thread has finished the previous iteration: its tiles (buffer b ^ 1) may be refilled, its partial sums
-        // overwritten, and thread 0 has seen the bulk stores of two iterations ago read their staging buffers (b)
-        __syncthreads();
-        if (tid == 0 && pair + (int)gridDim.x < npairs) request(pair + gridDim.x, b ^ 1);
+    const bool active = wl < nwin && k < TJ;
+    const int w = w0 + wl;
+    const float* X = s_x + wl * n;
+    const float* X0 = s_x0 + wl * n;
 
-        // ---- this pair's pose / anchor tiles ---------------------------------------------------
-        if (bulk) {
-            mbar_wait(&s_bar[b], (uint32_t)((it >> 1) & 1));
-        } else {
-            for (int i = tid; i < nwin * n; i += kThreads) {
-                s_x[b][i] = a.pose[(size_t)w0 * n + i];
-                s_x0[b][i] = a.pose0[(size_t)w0 * n + i];
-            }
-            __syncthreads();
+    float e3d = 0.f, esm = 0.f, ebn = 0.f, eva = 0.f, erp = 0.f;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (active) {
+        float e5[5], g3[3];
+        joint_energy_grad(a, X, X0, w, k, e5, g3);        // energy_device.cuh: shared with the chain kernel's prologue
+        e3d = e5[0], esm = e5[1], ebn = e5[2], eva = e5[3], erp = e5[4];
+        gx = g3[0], gy = g3[1], gz = g3[2];
+    }
+    if (wl < kWinPerCta && k < TJ) {
+        if (a.grad) {
+            float* G = s_g + wl * n;
+            G[k * 3 + 0] = gx, G[k * 3 + 1] = gy, G[k * 3 + 2] = gz;
         }
-        // with the bulk path both windows sit back to back (stride n); keep the same packing otherwise
-        const bool active = wl < nwin && k < TJ;
-        const int w = w0 + wl;
-        const float* X = s_x[b] + wl * n;
-        const float* X0 = s_x0[b] + wl * n;
-
-        float e3d = 0.f, esm = 0.f, ebn = 0.f, eva = 0.f, erp = 0.f;
-        float gx = 0.f, gy = 0.f, gz = 0.f;
-        if (active) {
-            float e5[5], g3[3];
-            joint_energy_grad(a, X, X0, w, k, e5, g3);    // energy_device.cuh: shared with the chain kernel's prologue
-            e3d = e5[0], esm = e5[1], ebn = e5[2], eva = e5[3], erp = e5[4];
-            gx = g3[0], gy = g3[1], gz = g3[2];
-        }
-        if (wl < kWinPerCta && k < TJ) {
-            if (a.grad) {
-                float* G = s_g[b] + wl * n;
-                G[k * 3 + 0] = gx, G[k * 3 + 1] = gy, G[k * 3 + 2] = gz;
-            }
-            if (a.gp_hi && !a.gp_f16) {
-                const int t = k / a.J, j = k - t * a.J;
-                const int o = wl * a.T * a.pp + t * a.pp + j * 3;
-                const float g3[3] = {gx, gy, gz};
+        if (a.gp_hi && !a.gp_f16) {
+            const int t = k / a.J, j = k - t * a.J;
+            const int o = wl * a.T * a.pp + t * a.pp + j * 3;
+            const float g3[3] = {gx, gy, gz};
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float h = __uint_as_float(__float_as_uint(g3[c]) & 0xFFFFE000u);
-                    s_gh[b][o + c] = h, s_gl[b][o + c] = g3[c] - h;
-                }
-                if (j == 0)
-                    for (int c = a.J * 3; c < a.pp; ++c)
-                        s_gh[b][wl * a.T * a.pp + t * a.pp + c] = 0.f, s_gl[b][wl * a.T * a.pp + t * a.pp + c] = 0.f;
+            for (int c = 0; c < 3; ++c) {
+                const float h = __uint_as_float(__float_as_uint(g3[c]) & 0xFFFFE000u);
+                s_gh[o + c] = h, s_gl[o + c] = g3[c] - h;
             }
-        }
-
-        // ---- per-window energy reduction: shuffle inside each warp, then kSlot/32 partials --------
-        const float r0 = warp_sum(e3d), r1 = warp_sum(esm), r2 = warp_sum(ebn), r3 = warp_sum(eva), r4 = warp_sum(erp);
-        const float r5 = warp_max(fmaxf(fabsf(gx), fmaxf(fabsf(gy), fabsf(gz))));      // (inactive threads hold zeros)
-        if ((tid & 31) == 0) {
-            float* d = s_red[tid >> 5];
-            d[0] = r0, d[1] = r1, d[2] = r2, d[3] = r3, d[4] = r4, d[5] = r5;
-        }
-        if (bulk) fence_proxy_async_smem();           // make the staged tiles visible to the bulk-copy engine
-        __syncthreads();
-
-        if (tid < kWinPerCta && tid < nwin) {
-            constexpr int wpw = kSlot / 32;
-            float t5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int q = 0; q < wpw; ++q)
-#pragma unroll
-                for (int c = 0; c < 5; ++c) t5[c] += s_red[tid * wpw + q][c];
-            const int ww = w0 + tid;
-            if (a.terms) {
-#pragma unroll
-                for (int c = 0; c < 5; ++c) a.terms[(size_t)ww * 5 + c] = t5[c];
-            }
-            a.energy[ww] = combine_energy(a, t5);
-        }
-        int ns = a.T * a.pp;                           // floats per window of the split tile
-        if (a.gp_hi && a.gp_f16) {
-            // fp16 scheme: scale the window by 2^e (max entry -> ~2^4), split, stage as uint16
-            constexpr int wpw = kSlot / 32;
-            if (wl < kWinPerCta && k < TJ) {
-                float mx = 0.f;
-                for (int q = 0; q < wpw; ++q) mx = fmaxf(mx, s_red[wl * wpw + q][5]);
-                const int e = grad_exponent(mx);
-                const float sc = exp2f((float)e);
-                if (k == 0 && wl < nwin) a.row_exp[w] = e;
-                const int t = k / a.J, j = k - t * a.J;
-                uint16_t* gh = reinterpret_cast<uint16_t*>(s_gh[b]) + wl * a.T * a.pp + t * a.pp;
-                uint16_t* gl = reinterpret_cast<uint16_t*>(s_gl[b]) + wl * a.T * a.pp + t * a.pp;
-                const float g3[3] = {gx * sc, gy * sc, gz * sc};
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    uint16_t h, l;
-                    split_f16_energy(g3[c], h, l);
-                    gh[j * 3 + c] = h, gl[j * 3 + c] = l;
-                }
-                if (j == 0)
-                    for (int c = a.J * 3; c < a.pp; ++c) gh[c] = 0, gl[c] = 0;
-            }
-            if (bulk) fence_proxy_async_smem();
-            __syncthreads();
-            ns = ns / 2;                               // staged as 16-bit: the copies below count 4-byte words
-        }
-        if (bulk) {
-            if (tid == 0) {
-                if (a.grad) bulk_s2g(a.grad + (size_t)w0 * n, s_g[b], tile_bytes);
-                if (a.gp_hi) {
-                    bulk_s2g(a.gp_hi + (size_t)w0 * ns, s_gh[b], (uint32_t)(kWinPerCta * ns * sizeof(float)));
-                    bulk_s2g(a.gp_lo + (size_t)w0 * ns, s_gl[b], (uint32_t)(kWinPerCta * ns * sizeof(float)));
-                }
-                bulk_commit();
-                bulk_wait_read1();                     // the PREVIOUS iteration's stores have read their staging buffers
-            }
-        } else {
-            if (a.grad)
-                for (int i = tid; i < nwin * n; i += kThreads) a.grad[(size_t)w0 * n + i] = s_g[b][i];
-            if (a.gp_hi)
-                for (int i = tid; i < nwin * ns; i += kThreads) {
-                    a.gp_hi[(size_t)w0 * ns + i] = s_gh[b][i];
-                    a.gp_lo[(size_t)w0 * ns + i] = s_gl[b][i];
-                }
+            if (j == 0)
+                for (int c = a.J * 3; c < a.pp; ++c) s_gh[wl * a.T * a.pp + t * a.pp + c] = 0.f, s_gl[wl * a.T * a.pp + t * a.pp + c] = 0.f;
         }
     }
-    if (tid == 0) bulk_wait_read0();                   // shared memory must outlive the last stores' reads
+
+    // ---- per-window energy reduction: shuffle inside each warp, then kSlot/32 partials --------
+    const float r0 = warp_sum(e3d), r1 = warp_sum(esm), r2 = warp_sum(ebn), r3 = warp_sum(eva), r4 = warp_sum(erp);
+    const float r5 = warp_max(fmaxf(fabsf(gx), fmaxf(fabsf(gy), fabsf(gz))));      // (inactive threads hold zeros)
+    if ((tid & 31) == 0) {
+        float* d = s_red[tid >> 5];
+        d[0] = r0, d[1] = r1, d[2] = r2, d[3] = r3, d[4] = r4, d[5] = r5;
+    }
+    if (bulk) fence_proxy_async_smem();           // make s_g visible to the bulk-copy engine
+    __syncthreads();
+
+    if (tid < kWinPerCta && tid < nwin) {
+        constexpr int wpw = kSlot / 32;
+        float t5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int q = 0; q < wpw; ++q)
+#pragma unroll
+            for (int c = 0; c < 5; ++c) t5[c] += s_red[tid * wpw + q][c];
+        const int ww = w0 + tid;
+        if (a.terms) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) a.terms[(size_t)ww * 5 + c] = t5[c];
+        }
+        a.energy[ww] = combine_energy(a, t5);
+    }
+    int ns = a.T * a.pp;                           // floats per window of the split tile
+    if (a.gp_hi && a.gp_f16) {
+        // fp16 scheme: scale the window by 2^e (max entry -> ~2^4), split, stage as uint16
+        constexpr int wpw = kSlot / 32;
+        if (wl < kWinPerCta && k < TJ) {
+            float mx = 0.f;
+            for (int q = 0; q < wpw; ++q) mx = fmaxf(mx, s_red[wl * wpw + q][5]);
+            const int e = grad_exponent(mx);
+            const float sc = exp2f((float)e);
+            if (k == 0 && wl < nwin) a.row_exp[w] = e;
+            const int t = k / a.J, j = k - t * a.J;
+            uint16_t* gh = reinterpret_cast<uint16_t*>(s_gh) + wl * a.T * a.pp + t * a.pp;
+            uint16_t* gl = reinterpret_cast<uint16_t*>(s_gl) + wl * a.T * a.pp + t * a.pp;
+            const float g3[3] = {gx * sc, gy * sc, gz * sc};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint16_t h, l;
+                split_f16_energy(g3[c], h, l);
+                gh[j * 3 + c] = h, gl[j * 3 + c] = l;
+            }
+            if (j == 0)
+                for (int c = a.J * 3; c < a.pp; ++c) gh[c] = 0, gl[c] = 0;
+        }
+        if (bulk) fence_proxy_async_smem();
+        __syncthreads();
+        ns = ns / 2;                               // staged as 16-bit: the copies below count 4-byte words
+    }
+    if (bulk) {
+        if (tid == 0) {
+            if (a.grad) bulk_s2g(a.grad + (size_t)w0 * n, s_g, (uint32_t)(kWinPerCta * n * sizeof(float)));
+            if (a.gp_hi) {
+                bulk_s2g(a.gp_hi + (size_t)w0 * ns, s_gh, (uint32_t)(kWinPerCta * ns * sizeof(float)));
+                bulk_s2g(a.gp_lo + (size_t)w0 * ns, s_gl, (uint32_t)(kWinPerCta * ns * sizeof(float)));
+            }
+            bulk_commit();
+            bulk_wait_read0();
+        }
+    } else {
+        if (a.grad)
+            for (int i = tid; i < nwin * n; i += kThreads) a.grad[(size_t)w0 * n + i] = s_g[i];
+        if (a.gp_hi)
+            for (int i = tid; i < nwin * ns; i += kThreads) {
+                a.gp_hi[(size_t)w0 * ns + i] = s_gh[i];
+                a.gp_lo[(size_t)w0 * ns + i] = s_gl[i];
+            }
+    }
 }
 
 int launch_energy_grad(cudaStream_t stream, const CameraConst* cam, const SkeletonConst* skel, int W, int T, int J, int H,
@@ -264,8 +247,7 @@ int launch_energy_grad(cudaStream_t stream, const CameraConst* cam, const Skelet
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     a.use_bulk = (pair_bytes % 16 == 0) && al16(pose) && al16(pose0) && al16(grad) &&
                  (!gp_hi || (al16(gp_hi) && al16(gp_lo)));
-    const int npairs = (W + kWinPerCta - 1) / kWinPerCta;
-    const int grid = npairs < 4 * kNumSMs ? npairs : 4 * kNumSMs;          // four CTAs per SM, each walking over pairs
+    const int grid = (W + kWinPerCta - 1) / kWinPerCta;
     energy_grad_kernel<<<grid, kThreads, 0, stream>>>(a);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
