@@ -112,13 +112,15 @@ def parse_args():
                          "3 fp16 scheme everywhere")
     ap.add_argument("--cpu-windows", type=int, default=12, help="windows per timed CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--chunks", type=int, default=-1, help="window slices run concurrently per stage (-1 library default)")
-    ap.add_argument("--e2e-mode", default="zero_copy", choices=["zero_copy", "upload"],
+    ap.add_argument("--e2e-mode", default="zero_copy", choices=["zero_copy", "upload", "resident_maps"],
                     help="how the e2e headline moves the heat maps (declared up front; the other mode is reported beside it)")
     ap.add_argument("--heat-layout", default="planar", choices=["planar", "hwc"],
                     help="layout of the staged heat maps: planar [frames, J, H, W] (what optimizer.load_clips produces by "
                          "default) or the pickle's hwc [frames, H, W, J]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-host", action="store_true",
+                    help="after the e2e measurement: cProfile of three e2e steps (GPU idle at each step's start) to stderr")
     ap.add_argument("--no-unpickle", action="store_true", help="skip the e2e_with_unpickle figure (main_batch on a real pickle)")
     return ap.parse_args()
 
@@ -423,7 +425,10 @@ def main():
             t0 = torch.cuda.Event(enable_timing=True)
             t0.record()
             # every input starts in pinned host memory; the result ends in pinned host memory
-            out = gem.solve_clips(clips, ingest=mode, **solve_kw)
+            if mode == "resident_maps":      # diagnostic: heat maps already in HBM, everything else from pinned host memory
+                out = gem.solve_clips(clips_dev_maps, ingest="upload", **solve_kw)
+            else:
+                out = gem.solve_clips(clips, ingest=mode, **solve_kw)
             h1 = time.perf_counter()
             t_solve = torch.cuda.Event(enable_timing=True)
             t_solve.record()
@@ -497,6 +502,13 @@ def main():
         small = sum(t.numel() * t.element_size() for c in clips for k, t in c.items()
                     if k != "heatmap_list" and isinstance(t, torch.Tensor))
         order = [args.e2e_mode] + [m for m in ("zero_copy", "upload") if m != args.e2e_mode]
+        if args.e2e_mode == "resident_maps":
+            clips_dev_maps = gem.ClipSet()
+            clips_dev_maps.planar = planar
+            for c in clips:
+                d = dict(c)
+                d["heatmap_list"] = c["heatmap_list"].to(dev)
+                clips_dev_maps.append(d)
         for mode in order:
             step = make_step_e2e(mode)
             for _ in range(2):
@@ -516,12 +528,37 @@ def main():
                 lookups, fetched = eng.texel_cache_stats(False)
                 entry["h2d_bytes_per_step"] = int(small + fetched * 32)
                 entry["texel_cache"] = {"lookups": lookups, "texels_fetched": fetched}
-                entry["mode"] = ("zero-copy heat maps: pinned host memory read over PCIe by the energy kernel through a per-joint "
-                                 "texel cache; h2d bytes = small arrays + one 32-byte sector per texel the cache fetched")
+                entry["mode"] = ("zero-copy heat maps: pinned host memory read over PCIe through a per-joint texel window in HBM "
+                                 "(planar maps: whole 64-byte window rows, fetched by a few CTAs from the miss list a probe kernel "
+                                 "writes); h2d bytes = small arrays + 32 bytes per sector fetched (texels_fetched counts sectors)")
             else:
                 entry["h2d_bytes_per_step"] = int(h2d_bytes)
                 entry["mode"] = "explicit piecewise upload of every input on a copy stream, overlapped with the solve"
             e2e_modes[mode] = entry
+        if args.profile_host and rank == 0:
+            # per-tag kernel time of one e2e step on ONE stream (event pair around every launch), next to the resident pass
+            step = make_step_e2e(args.e2e_mode)
+            ms_e, prof_e, _, _ = timed(step, 1, profile=True)
+            sys.stderr.write("e2e step with per-launch events: %.2f ms; per tag (launches, ms): %s\n" % (
+                ms_e, {t: (n, round(v, 3)) for t, (n, v) in sorted(prof_e.items())}))
+            sys.stderr.write("resident step with per-launch events: per tag (launches, ms): %s\n" % (
+                {t: (n, round(v, 3)) for t, (n, v) in sorted(prof.items())}))
+            import cProfile
+            import pstats
+            step = make_step_e2e(args.e2e_mode)
+            pr = cProfile.Profile()
+            walls = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                h0 = time.perf_counter()
+                pr.enable()
+                step()
+                pr.disable()
+                h1 = time.perf_counter()
+                torch.cuda.synchronize()
+                walls.append(((h1 - h0) * 1e3, (time.perf_counter() - h0) * 1e3))
+            sys.stderr.write("host profile of e2e steps (ms: host call, until GPU idle): %s\n" % walls)
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
         e2e = dict(e2e_modes[args.e2e_mode])
         e2e["declared_mode"] = args.e2e_mode
         e2e["pcie_h2d_GBps_rank0"] = e2e["h2d_bytes_per_step"] / max(e2e["ms_per_step"], 1e-9) / 1e6

@@ -76,15 +76,26 @@ struct gem_ctx {
     int64_t* fb_own = nullptr;
     int32_t* clip_own = nullptr;
     uint32_t* status_own = nullptr;
-    // energy kernel's texel cache (heat maps read from pinned host memory): [W][T*J][16] + origins, and counters
+    // energy kernel's texel cache (heat maps read from pinned host memory): [W][T*J][kPatchFloats] + origins + valid
+    // masks, allocated by the first call that needs them (ensure_texel_cache); and counters
     float* patch = nullptr;
     short2* patch_origin = nullptr;
     unsigned long long* patch_valid = nullptr;   // one bit per texel of a joint's window
     unsigned long long* patch_stats = nullptr;   // {lookups, texels fetched}, counted while patch_stats_on
+    uint2* miss_list = nullptr;                  // planar maps: joints whose footprint the probe kernel found missing [W][T*J]
+    uint32_t* miss_count = nullptr;              // [W][2]: {entries, fetch CTAs done} of the slice that starts at the window
     bool patch_stats_on = false;
     int texel_cache = -1;                        // -1 auto (on when the maps are host memory), 0 off, 1 on
     int texel_keep = 0;                          // measurement only (GEM_TEXEL_KEEP=1): stages do not empty the texel windows
-    int texel_prefetch_ctas = 4;                 // CTAs of the texel prefetch kernel (0: the energy kernel fetches itself)
+    int texel_prefetch_ctas = 8;                 // CTAs of the texel fetch / prefetch kernel (0: the energy kernel fetches itself)
+    int texel_prefetch_threads = 512;            // threads per CTA of the texel prefetch kernel
+    int texel_probe = 1;                         // planar maps: probe + fetch launches instead of the one prefetch kernel (GEM_TEXEL_PROBE=0)
+    // a stage's FIRST round misses on every joint: its fetches are issued slice after slice (each slice's fetch waits
+    // for the previous slice's), with more CTAs and only the footprint's rows, so that the first slices compute while
+    // the later ones still wait for the bus - instead of all slices sharing the bus and finishing together
+    int texel_cold_chain = 1, texel_cold_ctas = 32, texel_cold_rows = 2, texel_rows = 4;
+    std::vector<cudaEvent_t> cold_ev;            // one per slice of the running call
+    int cold_used = 0;                           // events of cold_ev recorded by the running call
     int trace_cap = 0;                           // columns of trace_own
     bool use_graphs = true;
     struct RoundGraph {
@@ -170,6 +181,24 @@ static int ctx_alloc(gem_ctx* c, T** p, size_t count) {
     return GEM_OK;
 }
 
+// The texel cache's buffers (1 KB per joint-frame with 16 x 16 windows) exist only in ctxs that read maps through it.
+static int ensure_texel_cache(gem_ctx* c) {
+    if (c->patch) return GEM_OK;
+    const size_t Weven = ((size_t)c->Wmax + 1) & ~(size_t)1, joints = Weven * c->T * c->J;
+    float* patch = nullptr;
+    int rc = ctx_alloc(c, &patch, joints * kPatchFloats);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->patch_origin, joints);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->patch_valid, joints);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->miss_list, joints);
+    if (rc == GEM_OK) rc = ctx_alloc(c, &c->miss_count, 2 * Weven);
+    if (rc != GEM_OK) return rc;
+    GEM_CUDA(cudaMemset(c->patch_valid, 0, joints * sizeof(unsigned long long)));
+    GEM_CUDA(cudaMemset(c->patch_origin, 0, joints * sizeof(short2)));
+    GEM_CUDA(cudaMemset(c->miss_count, 0, 2 * Weven * sizeof(uint32_t)));
+    c->patch = patch;
+    return GEM_OK;
+}
+
 #define GEM_TRY(expr)            \
     do {                         \
         int _rc = (expr);        \
@@ -227,9 +256,6 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     if (rc == GEM_OK) rc = ctx_alloc(c, &c->fb_own, W);
     if (rc == GEM_OK) rc = ctx_alloc(c, &c->clip_own, W);
     if (rc == GEM_OK) rc = ctx_alloc(c, &c->status_own, W);
-    A(&c->patch, Weven * seq_len * num_joints * (kPatchW * kPatchW));
-    if (rc == GEM_OK) rc = ctx_alloc(c, &c->patch_origin, Weven * seq_len * num_joints);
-    if (rc == GEM_OK) rc = ctx_alloc(c, &c->patch_valid, Weven * seq_len * num_joints);
     if (rc == GEM_OK) rc = ctx_alloc(c, &c->patch_stats, 2);
     if (rc == GEM_OK && cudaMemset(c->patch_stats, 0, 2 * sizeof(unsigned long long)) != cudaSuccess) rc = GEM_ERR_CUDA;
     LbfgsBuffers& b = c->lb;
@@ -262,6 +288,12 @@ int gem_ctx_create(gem_ctx** out, int device, int max_windows, int latent_dim, i
     if (const char* env = getenv("GEM_TEXEL_CACHE")) c->texel_cache = atoi(env);
     if (const char* env = getenv("GEM_TEXEL_KEEP")) c->texel_keep = atoi(env) != 0;
     if (const char* env = getenv("GEM_TEXEL_PREFETCH_CTAS")) c->texel_prefetch_ctas = atoi(env) > 0 ? atoi(env) : 0;
+    if (const char* env = getenv("GEM_TEXEL_PREFETCH_THREADS")) c->texel_prefetch_threads = atoi(env);
+    if (const char* env = getenv("GEM_TEXEL_PROBE")) c->texel_probe = env[0] != '0';
+    if (const char* env = getenv("GEM_TEXEL_COLD_CHAIN")) c->texel_cold_chain = env[0] != '0';
+    if (const char* env = getenv("GEM_TEXEL_COLD_CTAS")) c->texel_cold_ctas = atoi(env) > 0 ? atoi(env) : 1;
+    if (const char* env = getenv("GEM_TEXEL_COLD_ROWS")) c->texel_cold_rows = atoi(env);
+    if (const char* env = getenv("GEM_TEXEL_ROWS")) c->texel_rows = atoi(env);
     // default skeleton: the reference's 15-joint kinematic tree (optimizer.py:34)
     if (num_joints == 15) {
         static const int32_t parents[15] = {0, 0, 1, 2, 0, 4, 5, 1, 7, 8, 9, 4, 11, 12, 13};
@@ -282,6 +314,7 @@ int gem_ctx_destroy(gem_ctx* c) {
     drop_graphs(c);
     for (cudaStream_t st : c->streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : c->join_ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : c->cold_ev) cudaEventDestroy(ev);
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     tc_gemm_release(c);
     tc_tap_release(c);
@@ -579,6 +612,8 @@ struct Slice {
     float* patch;
     short2* patch_origin;
     unsigned long long* patch_valid;
+    uint2* miss_list;
+    uint32_t* miss_count;
     LbfgsBuffers lb;
 };
 static Slice slice_of(gem_ctx* c, int w0) {
@@ -605,8 +640,12 @@ static Slice slice_of(gem_ctx* c, int w0) {
     v.pose0_own = c->pose0_own + v.tok0 * P, v.mb_own = c->mb_own;     // (mean bones are indexed by absolute window)
     v.trace_own = c->trace_own + (size_t)w0 * c->trace_cap;
     v.fb_own = c->fb_own + w0, v.clip_own = c->clip_own + w0, v.status_own = c->status_own + w0;
-    v.patch = c->patch + v.tok0 * c->J * (kPatchW * kPatchW), v.patch_origin = c->patch_origin + v.tok0 * c->J;
-    v.patch_valid = c->patch_valid + v.tok0 * c->J;
+    v.patch = nullptr, v.patch_origin = nullptr, v.patch_valid = nullptr, v.miss_list = nullptr, v.miss_count = nullptr;
+    if (c->patch) {                                   // (ensure_texel_cache)
+        v.patch = c->patch + v.tok0 * c->J * kPatchFloats, v.patch_origin = c->patch_origin + v.tok0 * c->J;
+        v.patch_valid = c->patch_valid + v.tok0 * c->J;
+        v.miss_list = c->miss_list + v.tok0 * c->J, v.miss_count = c->miss_count + 2 * (size_t)w0;
+    }
     v.lb = c->lb;
     LbfgsBuffers& b = v.lb;
     const size_t on = (size_t)w0 * n;
@@ -812,15 +851,16 @@ __global__ void stage_inputs_kernel(int w_abs0, int TJ3, int J, const float* __r
                                     float* __restrict__ pose0_own, int64_t* __restrict__ fb_own,
                                     int32_t* __restrict__ clip_own, float* __restrict__ mb_own,
                                     uint32_t* __restrict__ status_own, unsigned long long* __restrict__ patch_valid, int TJ,
-                                    int keep_patch) {
+                                    int keep_patch, uint32_t* __restrict__ miss_count) {
     // all pointers are the slice's (window blockIdx.x of the slice); mb_own is the ctx-wide table indexed by the
     // absolute window w_abs0 + blockIdx.x, which is what the staged clip index points at
     const int w = blockIdx.x;
     for (int i = threadIdx.x; i < TJ3; i += blockDim.x) pose0_own[(size_t)w * TJ3 + i] = pose0[(size_t)w * TJ3 + i];
     if (threadIdx.x < J) mb_own[(size_t)(w_abs0 + w) * J + threadIdx.x] = mean_bone[(size_t)clip[w] * J + threadIdx.x];
     // a new stage reads new maps: every joint's cached texel patch is stale
-    if (!keep_patch)
+    if (!keep_patch && patch_valid)
         for (int i = threadIdx.x; i < TJ; i += blockDim.x) patch_valid[(size_t)w * TJ + i] = 0ull;      // empty window
+    if (miss_count && w == 0 && threadIdx.x < 2) miss_count[threadIdx.x] = 0u;     // (an aborted call may have left entries)
     if (threadIdx.x == 0) {
         fb_own[w] = fb ? fb[w] : 0;
         clip_own[w] = w_abs0 + w;
@@ -1023,7 +1063,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     if (a.trace) GEM_CUDA(cudaMemsetAsync(v.trace_own, 0xff, (size_t)Wk * c->trace_cap * sizeof(float), q));   // NaN
     stage_inputs_kernel<<<Wk, 128, 0, q>>>(w0, TJ3, c->J, a.pose0 + w0 * P, a.frame_base ? a.frame_base + w0 : nullptr,
                                            a.clip + w0, a.mean_bone, v.pose0_own, v.fb_own, v.clip_own, v.mb_own,
-                                           v.status_own, v.patch_valid, c->T * c->J, c->texel_keep);
+                                           v.status_own, v.patch_valid, c->T * c->J, c->texel_keep, v.miss_count);
     GEM_CHECK_LAUNCH();
     c->launches += 1;
     // z0 = mu + eps * std                                   optimizer.py:255-259
@@ -1033,14 +1073,35 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     const bool tc = use_tc_chain(c, which, Wk);
     const bool fused = fused_energy_ok(c, which, Wk);
     // one closure round: decode -> fused energy/gradient -> decoder bwd-data -> L-BFGS advance
+    bool first_round = true;                     // (round 0 is launched directly, never captured)
     auto enqueue_round = [&]() -> int {
         GEM_TRY(decode_impl(c, q, which, Wk, v, lb.ZT, v.pose, tc ? lb.ZT_hi : nullptr, tc ? lb.ZT_lo : nullptr, v.status_own));
-        if (a.host_maps && c->texel_prefetch_ctas > 0)
+        if (a.host_maps && c->texel_prefetch_ctas > 0 && c->heat_planar && c->texel_probe) {
+            // zero-copy planar maps: a probe over all joints lists the misses, a few CTAs fetch them over PCIe
+            const bool cold = first_round && c->texel_cold_chain && !c->texel_keep;
+            if (cold && c->cold_used > 0) GEM_CUDA(cudaStreamWaitEvent(q, c->cold_ev[c->cold_used - 1], 0));
+            c->launches += 1;
+            GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
+                return launch_texel_probe_fetch(q, &c->cam, Wk, c->T, c->J, c->H, c->Wd, v.pose, a.heat, v.fb_own, v.patch,
+                                                v.patch_origin, v.patch_valid, c->patch_stats_on ? c->patch_stats : nullptr,
+                                                cold ? c->texel_cold_ctas : c->texel_prefetch_ctas, c->texel_prefetch_threads,
+                                                v.miss_count, v.miss_list, cold ? c->texel_cold_rows : c->texel_rows);
+            }));
+            if (cold) {
+                if ((size_t)c->cold_used == c->cold_ev.size()) {
+                    cudaEvent_t ev;
+                    GEM_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                    c->cold_ev.push_back(ev);
+                }
+                GEM_CUDA(cudaEventRecord(c->cold_ev[c->cold_used++], q));
+            }
+            first_round = false;
+        } else if (a.host_maps && c->texel_prefetch_ctas > 0)
             // zero-copy maps: the wait for PCIe happens in a few CTAs, not in energy CTAs parked on every SM
             GEM_TRY(timed(c, q, GEM_TAG_ENERGY, [&]() {
                 return launch_texel_prefetch(q, &c->cam, Wk, c->T, c->J, c->H, c->Wd, v.pose, a.heat, v.fb_own, v.patch, v.patch_origin,
                                              v.patch_valid, c->patch_stats_on ? c->patch_stats : nullptr,
-                                             c->texel_prefetch_ctas, c->heat_planar);
+                                             c->texel_prefetch_ctas, c->heat_planar, c->texel_prefetch_threads);
             }));
         if (fused) {
             // the backward chain evaluates the energy in its prologue: no energy launch, no d pose in memory
@@ -1074,7 +1135,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     if (graphs && a.p.max_eval >= 2) {
         for (auto& g : c->graphs) {
             if (g.which == which && g.w0 == w0 && g.Wk == Wk && g.gemm_mode == (c->gemm_mode | (c->tap_chain << 8) | (c->fuse_energy << 12)) && g.heat == a.heat &&
-                g.has_heat == ((a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas : 0) + 4096 * c->heat_planar) &&
+                g.has_heat == ((a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas + 512 * (c->texel_prefetch_threads / 32) : 0) + (1 << 20) * c->heat_planar + (1 << 21) * c->texel_probe) &&
                 g.trace_stride == lb.trace_stride &&
                 memcmp(&g.wt, &a.wt, sizeof(a.wt)) == 0 && g.p.lr == a.p.lr && g.p.max_iter == a.p.max_iter &&
                 g.p.max_eval == a.p.max_eval && g.p.tolerance_grad == a.p.tolerance_grad &&
@@ -1099,7 +1160,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             GEM_CUDA(e);
             gem_ctx::RoundGraph g;
             g.which = which, g.w0 = w0, g.Wk = Wk, g.gemm_mode = c->gemm_mode | (c->tap_chain << 8) | (c->fuse_energy << 12), g.heat = a.heat;
-            g.has_heat = (a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas : 0) + 4096 * c->heat_planar;
+            g.has_heat = (a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas + 512 * (c->texel_prefetch_threads / 32) : 0) + (1 << 20) * c->heat_planar + (1 << 21) * c->texel_probe;
             g.trace_stride = lb.trace_stride, g.wt = a.wt, g.p = a.p;
             g.launches = round_launches;
             e = cudaGraphInstantiate(&g.exec, graph, 0);
@@ -1189,6 +1250,7 @@ struct Fork {
 // slice k runs on its own stream, after everything already on the caller's stream `s` and after the ready
 // events that cover its windows (gem_ctx_set_ready_events; consumed by this call)
 static int fork_slices(gem_ctx* c, cudaStream_t s, const std::vector<int>& w0, bool graphs, Fork* f) {
+    c->cold_used = 0;
     const int n = (int)w0.size() - 1;
     f->forked = n > 1 || graphs || !c->ready.empty();      // (the caller's stream may be the legacy one: not capturable)
     f->cs.assign(n, s);
@@ -1266,6 +1328,7 @@ int gem_solve_stage(gem_ctx* c, void* stream, int which, int W, const float* pos
     a.pose_out = pose_out_d, a.trace = energy_trace_d, a.n_iter = n_iter_d, a.func_evals = func_evals_d, a.status = status_d;
     a.texel_cache = want_texel_cache(c, heat_d, wt->reproj, W);
     a.host_maps = a.texel_cache && is_host_memory(heat_d);
+    if (a.texel_cache) GEM_TRY(ensure_texel_cache(c));
     const bool graphs = c->use_graphs && !c->prof_on;
     const std::vector<int> w0 = slice_bounds(c, W, a.host_maps, c->gemm_mode >= 1 && !c->tap_tc[which]);
     Fork f;
@@ -1297,6 +1360,7 @@ int gem_solve_windows(gem_ctx* c, void* stream, int W, const float* pose0_d, con
     a.pose_out = local_pose_d, a.trace = nullptr, a.n_iter = n_iter_d, a.func_evals = func_evals_d, a.status = status_d;
     a.texel_cache = want_texel_cache(c, heat_d, wt_local->reproj, W);
     a.host_maps = a.texel_cache && is_host_memory(heat_d);
+    if (a.texel_cache) GEM_TRY(ensure_texel_cache(c));
     b = a;
     b.texel_cache = false, b.host_maps = false;
     b.which = 1, b.pose0 = rel_f32_d, b.heat = nullptr, b.frame_base = nullptr, b.eps = eps_d + c->n, b.wt = *wt_global;

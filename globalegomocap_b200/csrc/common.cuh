@@ -147,4 +147,21 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
+// ---- per-joint texel window of the energy kernel's cache (energy_device.cuh) ------------------------------------------
+constexpr int kPatchWd = 8;            // side of the per-joint texel window of the HWC cache (at most 8: 64 valid bits)
+#ifndef GEM_PLANAR_W
+#define GEM_PLANAR_W 16
+#endif
+#ifndef GEM_PLANAR_H
+#define GEM_PLANAR_H 16
+#endif
+#ifndef GEM_PLANAR_ALIGN
+#define GEM_PLANAR_ALIGN 8
+#endif
+constexpr int kPlanarW = GEM_PLANAR_W, kPlanarH = GEM_PLANAR_H, kPlanarAlign = GEM_PLANAR_ALIGN;
+constexpr int kPatchFloats = kPlanarW * kPlanarH > kPatchWd * kPatchWd ? kPlanarW * kPlanarH : kPatchWd * kPatchWd;
+static_assert(kPlanarW % kPlanarAlign == 0 && kPlanarW >= 2 * kPlanarAlign && (kPlanarAlign == 4 || kPlanarAlign == 8 || kPlanarAlign == 16),
+              "window width / alignment");
+static_assert(kPlanarH <= 64 && kPlanarW <= 32, "one valid bit per window row; a row is fetched by at most 8 lanes");
+
 }  // namespace gem

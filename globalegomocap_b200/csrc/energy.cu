@@ -52,7 +52,7 @@ struct EnergyArgs : EnergyCommon {
 __global__ void __launch_bounds__(512) texel_prefetch_kernel(const __grid_constant__ EnergyArgs a) {
     const int TJ = a.T * a.J;
     const size_t total = (size_t)a.W * TJ;
-    for (size_t i = (size_t)blockIdx.x * 512 + threadIdx.x; i < total; i += (size_t)gridDim.x * 512) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int w = (int)(i / TJ), k = (int)(i - (size_t)w * TJ);
         const int t = k / a.J, j = k - t * a.J;
         const float x = a.pose[i * 3 + 0], y = a.pose[i * 3 + 1], z = a.pose[i * 3 + 2];
@@ -62,6 +62,63 @@ __global__ void __launch_bounds__(512) texel_prefetch_kernel(const __grid_consta
         float nw, ne, sw, se;
         if (a.planar) cache_lookup_planar(a, i, a.frame_base[w] + t, j, (int)p.fx0, (int)p.fy0, false, nw, ne, sw, se);
         else cache_lookup(a, i, a.frame_base[w] + t, j, (int)p.fx0, (int)p.fy0, false, nw, ne, sw, se);
+    }
+}
+
+// Planar maps, two launches instead of one: the PROBE (one thread per joint, every SM, no bus traffic: projection and
+// a look at the joint's window) appends the joints whose footprint is not in their window to a miss list; the FETCH
+// kernel (a few CTAs) walks only that list - a few per cent of the joints in a typical round - and fetches whole window
+// rows, kPlanarW / 4 lanes per row, so that a row is ONE request on the bus (energy_device.cuh: planar_fetch_rows).  The list's order varies from run to run, its
+// contents do not, and the fetched values are copies of the map's.
+__global__ void __launch_bounds__(128) texel_probe_kernel(const __grid_constant__ EnergyArgs a, uint32_t* __restrict__ count,
+                                                          uint2* __restrict__ list) {
+    const int TJ = a.T * a.J;
+    const size_t total = (size_t)a.W * TJ;
+    const size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
+    bool miss = false;
+    int x0 = 0, y0 = 0;
+    if (i < total) {
+        const float x = a.pose[i * 3 + 0], y = a.pose[i * 3 + 1], z = a.pose[i * 3 + 2];
+        Proj p;
+        if (project_joint(a.cam, x, y, z, a.H, a.Wd, p) &&
+            (p.fx0 >= -1.f && p.fx0 <= (float)a.Wd && p.fy0 >= -1.f && p.fy0 <= (float)a.H)) {
+            x0 = (int)p.fx0, y0 = (int)p.fy0;
+            miss = planar_window_miss(a, i, x0, y0);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, miss);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (miss) list[base + __popc(m & ((1u << lane) - 1u))] = make_uint2((uint32_t)i, ((uint32_t)(uint16_t)(short)x0) | ((uint32_t)(uint16_t)(short)y0 << 16));
+}
+
+template <int kRows>
+__global__ void __launch_bounds__(512) texel_fetch_kernel(const __grid_constant__ EnergyArgs a, uint32_t* __restrict__ count,
+                                                          const uint2* __restrict__ list) {
+    constexpr int kPlanarFetchLanes = kRows * (kPlanarW / 4);               // lanes that share one fetch event
+    static_assert(kRows % 2 == 0 && kPlanarFetchLanes <= 32 && 32 % kPlanarFetchLanes == 0, "a fetch event is handled inside one warp");
+    const int TJ = a.T * a.J;
+    const uint32_t n = *reinterpret_cast<volatile uint32_t*>(count);
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gl = (int)(tid % kPlanarFetchLanes);                          // lane within the event's group
+    const unsigned group_mask = (unsigned)(((1ull << kPlanarFetchLanes) - 1ull) << ((threadIdx.x & 31) - gl));
+    const uint32_t groups = gridDim.x * blockDim.x / kPlanarFetchLanes;
+    for (uint32_t e = tid / kPlanarFetchLanes; e < n; e += groups) {
+        const uint2 m = list[e];
+        const size_t pk = m.x;
+        const int x0 = (short)(m.y & 0xffffu), y0 = (short)(m.y >> 16);
+        const int w = (int)(pk / TJ), k = (int)(pk - (size_t)w * TJ);
+        const int t = k / a.J, j = k - t * a.J;
+        planar_fetch_rows<kRows>(a, pk, a.frame_base[w] + t, j, x0, y0, gl, group_mask);
+    }
+    // the last CTA to finish empties the list for the next round (every CTA has read n by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(count + 1, 1u) == gridDim.x - 1) count[0] = 0u, count[1] = 0u;
     }
 }
 
@@ -256,8 +313,9 @@ int launch_energy_grad(cudaStream_t stream, const CameraConst* cam, const Skelet
 // fetches, into the joints' cache windows, the texels the energy evaluation of `pose` will sample (zero-copy maps)
 int launch_texel_prefetch(cudaStream_t stream, const CameraConst* cam, int W, int T, int J, int H, int Wd, const float* pose,
                           const float* heat, const int64_t* frame_base, float* patch, short2* patch_origin,
-                          unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas, int planar) {
+                          unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas, int planar, int threads) {
     if (W <= 0) return GEM_OK;
+    GEM_REQUIRE(threads >= 32 && threads <= 512 && threads % 32 == 0, "texel prefetch: 32..512 threads per CTA");
     GEM_REQUIRE(!planar || Wd % 4 == 0, "planar heat maps need a width that is a multiple of 4");
     GEM_REQUIRE(cam && heat && frame_base && patch && patch_origin && patch_valid, "texel prefetch needs the camera, the maps and the cache");
     EnergyArgs a;
@@ -267,9 +325,37 @@ int launch_texel_prefetch(cudaStream_t stream, const CameraConst* cam, int W, in
     a.patch = patch, a.patch_origin = patch_origin, a.patch_valid = patch_valid, a.patch_stats = patch_stats;
     a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd, a.planar = planar ? 1 : 0;
     const size_t total = (size_t)W * T * J;
-    int grid = (int)((total + 511) / 512);
+    int grid = (int)((total + threads - 1) / threads);
     if (grid > ctas) grid = ctas;
-    texel_prefetch_kernel<<<grid, 512, 0, stream>>>(a);
+    texel_prefetch_kernel<<<grid, threads, 0, stream>>>(a);
+    GEM_CHECK_LAUNCH();
+    return GEM_OK;
+}
+
+// planar maps: probe (all joints) + fetch (the probe's miss list); miss_count = {entries, CTAs done}, both zero on entry
+int launch_texel_probe_fetch(cudaStream_t stream, const CameraConst* cam, int W, int T, int J, int H, int Wd, const float* pose,
+                             const float* heat, const int64_t* frame_base, float* patch, short2* patch_origin,
+                             unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas, int threads,
+                             uint32_t* miss_count, uint2* miss_list, int rows) {
+    if (W <= 0) return GEM_OK;
+    GEM_REQUIRE(Wd % 4 == 0, "planar heat maps need a width that is a multiple of 4");
+    GEM_REQUIRE(cam && heat && frame_base && patch && patch_origin && patch_valid && miss_count && miss_list,
+                "texel prefetch needs the camera, the maps, the cache and the miss list");
+    GEM_REQUIRE(ctas >= 1 && threads >= 32 && threads <= 512 && threads % 32 == 0, "texel fetch: 32..512 threads per CTA");
+    GEM_REQUIRE(H < 32767 && Wd < 32767, "map side beyond the miss list's 16-bit coordinates");
+    EnergyArgs a;
+    memset(&a, 0, sizeof(a));
+    a.cam = *cam;
+    a.pose = pose, a.heat = heat, a.frame_base = frame_base;
+    a.patch = patch, a.patch_origin = patch_origin, a.patch_valid = patch_valid, a.patch_stats = patch_stats;
+    a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd, a.planar = 1;
+    const size_t total = (size_t)W * T * J;
+    texel_probe_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(a, miss_count, miss_list);
+    GEM_CHECK_LAUNCH();
+    constexpr int kMaxRows = 32 / (kPlanarW / 4);                           // rows one warp can fetch per event
+    if (rows >= 8 && kMaxRows >= 8) texel_fetch_kernel<(kMaxRows >= 8 ? 8 : 2)><<<ctas, threads, 0, stream>>>(a, miss_count, miss_list);
+    else if (rows >= 4 && kMaxRows >= 4) texel_fetch_kernel<(kMaxRows >= 4 ? 4 : 2)><<<ctas, threads, 0, stream>>>(a, miss_count, miss_list);
+    else texel_fetch_kernel<2><<<ctas, threads, 0, stream>>>(a, miss_count, miss_list);
     GEM_CHECK_LAUNCH();
     return GEM_OK;
 }

@@ -11,7 +11,6 @@
 
 namespace gem {
 
-constexpr int kPatchWd = 8;            // side of the per-joint texel window of the cache (at most 8: 64 valid bits)
 constexpr int kEnergySlot = 160;       // joint slots per window (>= T*J, multiple of 32): 5 warps of partial sums
 
 // everything about one energy evaluation that is the same for every joint of the launch
@@ -53,7 +52,7 @@ __device__ __forceinline__ float texel(const float* __restrict__ heat, int64_t f
 __device__ __forceinline__ void cache_lookup(const EnergyCommon& a, size_t pk, int64_t frame, int j, int x0, int y0,
                                              bool count_lookup, float& nw, float& ne, float& sw, float& se) {
     constexpr int kPatchW = kPatchWd;
-    float* pe = a.patch + pk * (kPatchW * kPatchW);
+    float* pe = a.patch + pk * kPatchFloats;
     const short2 o = a.patch_origin[pk];
     unsigned long long valid = a.patch_valid[pk];
     int ox = o.x, oy = o.y;
@@ -86,55 +85,102 @@ __device__ __forceinline__ void cache_lookup(const EnergyCommon& a, size_t pk, i
     }
 }
 
-// The same window over PLANAR maps: a map row is contiguous, so the fetch unit is an aligned float4 (four x-neighbours,
-// one request over PCIe instead of four) and the window's origin is aligned to 4 texels in x.  A joint that wanders
-// over a 5 x 5 texel area costs ~8 requests per stage instead of ~23.  Requires Wd % 4 == 0.
+// The window over PLANAR maps.  A map row is contiguous, and a read of pinned host memory costs the same whether it
+// brings 16 or 128 contiguous bytes (tools/pcie_gather_bench.cu: ~16 M requests/s per SM, ~150 M/s per GPU, at any size
+// up to a 128-byte line), so the fetch unit is a whole window ROW: kPlanarW texels (64 B), origin aligned to
+// kPlanarAlign texels in x, one valid bit per row.  Rows are fetched by texel_fetch_kernel (energy.cu), kPlanarW / 4
+// lanes per row so that a row is one request; the per-thread path below is the fallback when nothing prefetched
+// (resident maps with the cache forced on).  Requires Wd % 4 == 0.
+__device__ __forceinline__ void planar_recentre(int x0, int y0, int& ox, int& oy) {
+    // x0 - ox lands in [W/2 - A/2, W/2 + A/2 - 1], y0 - oy = H/2 - 1
+    ox = (x0 - (kPlanarW / 2 - kPlanarAlign / 2)) & ~(kPlanarAlign - 1), oy = y0 - (kPlanarH / 2 - 1);
+}
+__device__ __forceinline__ bool planar_outside(unsigned long long valid, int dx, int dy) {
+    return valid == 0ull || dx < 0 || dx > kPlanarW - 2 || dy < 0 || dy > kPlanarH - 2;
+}
+// true when the footprint at (x0, y0) is not in the joint's window: empty window, outside it, or a row not fetched yet
+__device__ __forceinline__ bool planar_window_miss(const EnergyCommon& a, size_t pk, int x0, int y0) {
+    const short2 o = a.patch_origin[pk];
+    const unsigned long long valid = a.patch_valid[pk];
+    const int dx = x0 - o.x, dy = y0 - o.y;
+    if (planar_outside(valid, dx, dy)) return true;
+    return ((3ull << dy) & ~valid) != 0ull;
+}
+
 __device__ __forceinline__ void cache_lookup_planar(const EnergyCommon& a, size_t pk, int64_t frame, int j, int x0, int y0,
                                                     bool count_lookup, float& nw, float& ne, float& sw, float& se) {
-    constexpr int kPatchW = kPatchWd;
-    float* pe = a.patch + pk * (kPatchW * kPatchW);
+    float* pe = a.patch + pk * kPatchFloats;
     const short2 o = a.patch_origin[pk];
     unsigned long long valid = a.patch_valid[pk];
     int ox = o.x, oy = o.y;
     int dx = x0 - ox, dy = y0 - oy;
-    if (valid == 0ull || dx < 0 || dx > kPatchW - 2 || dy < 0 || dy > kPatchW - 2) {
-        ox = (x0 - 2) & ~3, oy = y0 - (kPatchW / 2 - 1), valid = 0ull;     // x0 - ox in [2, 5]
-        dx = x0 - ox, dy = y0 - oy;
+    if (planar_outside(valid, dx, dy)) {
+        planar_recentre(x0, y0, ox, oy);
+        valid = 0ull, dx = x0 - ox, dy = y0 - oy;
     }
-    const int b00 = dy * kPatchW + dx;
-    const unsigned long long foot = (3ull | (3ull << kPatchW)) << b00;
-    const unsigned long long missing = foot & ~valid;
-    unsigned long long fetched_bits = 0ull;
+    const unsigned long long need = (3ull << dy) & ~valid;
     int requests = 0;
-    if (missing) {
+    if (need) {                                   // fallback: this thread reads the missing rows itself, unit by unit
         const float* plane = a.heat + (frame * a.J + j) * (int64_t)a.H * a.Wd;
-#pragma unroll
         for (int r = 0; r < 2; ++r) {
-#pragma unroll
-            for (int uu = 0; uu < 2; ++uu) {
-                const int u = (dx + uu) >> 2;                          // float4 unit of the window row (0 or 1)
-                if (uu == 1 && u == (dx >> 2)) continue;               // both footprint columns in the same unit
-                const unsigned long long ubits = 0xFull << ((dy + r) * kPatchW + 4 * u);
-                if (!(missing & ubits)) continue;
-                const int y = oy + dy + r, xs = ox + 4 * u;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);            // padding_mode='zeros' outside the map
-                if (y >= 0 && y < a.H && xs >= 0 && xs < a.Wd) {
-                    v = __ldg(reinterpret_cast<const float4*>(plane + (int64_t)y * a.Wd + xs));
-                    ++requests;
-                }
-                *reinterpret_cast<float4*>(pe + (dy + r) * kPatchW + 4 * u) = v;
-                fetched_bits |= ubits;
+            if (!((need >> (dy + r)) & 1ull)) continue;
+            const int y = oy + dy + r;
+#pragma unroll 1
+            for (int u = 0; u < kPlanarW / 4; ++u) {
+                const int xs = ox + 4 * u;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);           // padding_mode='zeros' outside the map
+                if (y >= 0 && y < a.H && xs >= 0 && xs < a.Wd) v = __ldg(reinterpret_cast<const float4*>(plane + (int64_t)y * a.Wd + xs));
+                *reinterpret_cast<float4*>(pe + (dy + r) * kPlanarW + 4 * u) = v;
             }
+            if (y >= 0 && y < a.H) requests += kPlanarW * 4 / 32;     // counted in 32-byte sectors
         }
         a.patch_origin[pk] = make_short2((short)ox, (short)oy);
-        a.patch_valid[pk] = valid | fetched_bits;
+        a.patch_valid[pk] = valid | need;
     }
     if (a.patch_stats) {
         if (count_lookup) atomicAdd(a.patch_stats, 1ull);
         if (requests) atomicAdd(a.patch_stats + 1, (unsigned long long)requests);
     }
-    const float* p0 = pe + b00;
-    nw = p0[0], ne = p0[1], sw = p0[kPatchW], se = p0[kPatchW + 1];
+    const float* p0 = pe + dy * kPlanarW + dx;
+    nw = p0[0], ne = p0[1], sw = p0[kPlanarW], se = p0[kPlanarW + 1];
+}
+
+// One fetch event of texel_fetch_kernel, executed by a group of kRows * kPlanarW / 4 lanes (lane `gl` of the group): the
+// footprint's two rows and (kRows - 2) / 2 rows above and below, kPlanarW / 4 lanes per row.
+template <int kRows>
+__device__ __forceinline__ void planar_fetch_rows(const EnergyCommon& a, size_t pk, int64_t frame, int j, int x0, int y0, int gl,
+                                                  unsigned group_mask) {
+    constexpr int kLanesPerRow = kPlanarW / 4;
+    float* pe = a.patch + pk * kPatchFloats;
+    const short2 o = a.patch_origin[pk];
+    unsigned long long valid = a.patch_valid[pk];
+    __syncwarp(group_mask);                       // every lane has read the window's state before lane 0 rewrites it
+    int ox = o.x, oy = o.y;
+    int dx = x0 - ox, dy = y0 - oy;
+    if (planar_outside(valid, dx, dy)) {
+        planar_recentre(x0, y0, ox, oy);
+        valid = 0ull, dx = x0 - ox, dy = y0 - oy;
+    }
+    const int r = gl / kLanesPerRow, u = gl - r * kLanesPerRow;
+    const int row = dy - (kRows - 2) / 2 + r;
+    int lo = dy - (kRows - 2) / 2, hi = lo + kRows - 1;
+    lo = lo < 0 ? 0 : lo, hi = hi > kPlanarH - 1 ? kPlanarH - 1 : hi;
+    const unsigned long long span = ((2ull << hi) - 1ull) & ~((1ull << lo) - 1ull);
+    const unsigned long long need = span & ~valid;
+    if (row >= 0 && row < kPlanarH && ((need >> row) & 1ull)) {
+        const int y = oy + row, xs = ox + 4 * u;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);                   // padding_mode='zeros' outside the map
+        if (y >= 0 && y < a.H && xs >= 0 && xs < a.Wd) {
+            const float* plane = a.heat + (frame * a.J + j) * (int64_t)a.H * a.Wd;
+            v = __ldg(reinterpret_cast<const float4*>(plane + (int64_t)y * a.Wd + xs));
+        }
+        *reinterpret_cast<float4*>(pe + row * kPlanarW + 4 * u) = v;
+        if (a.patch_stats && u == 0 && y >= 0 && y < a.H) atomicAdd(a.patch_stats + 1, (unsigned long long)(kPlanarW * 4 / 32));
+    }
+    if (gl == 0) {
+        a.patch_origin[pk] = make_short2((short)ox, (short)oy);
+        a.patch_valid[pk] = valid | need;
+    }
 }
 
 // Fisheye projection of a joint and the map cell its bilinear footprint starts at (FishEyeCalibrated.py:96-129,

@@ -14,8 +14,13 @@ int launch_energy_grad(cudaStream_t stream, const CameraConst* cam, const Skelet
                        int32_t* row_exp = nullptr, unsigned long long* patch_valid = nullptr, int planar = 0);
 int launch_texel_prefetch(cudaStream_t stream, const CameraConst* cam, int W, int T, int J, int H, int Wd, const float* pose,
                           const float* heat, const int64_t* frame_base, float* patch, short2* patch_origin,
-                          unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas, int planar = 0);
-constexpr int kPatchW = 8;      // side of the per-joint texel window of the energy kernel's cache (at most 8: 64 valid bits)
+                          unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas, int planar = 0,
+                          int threads = 512);
+int launch_texel_probe_fetch(cudaStream_t stream, const CameraConst* cam, int W, int T, int J, int H, int Wd, const float* pose,
+                             const float* heat, const int64_t* frame_base, float* patch, short2* patch_origin,
+                             unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas, int threads,
+                             uint32_t* miss_count, uint2* miss_list, int rows);
+constexpr int kPatchW = kPatchWd;
 
 enum { EPI_NONE = 0, EPI_LRELU = 1, EPI_MASK = 2 };
 struct TapGemmArgs {
