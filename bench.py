@@ -114,9 +114,9 @@ def parse_args():
     ap.add_argument("--chunks", type=int, default=-1, help="window slices run concurrently per stage (-1 library default)")
     ap.add_argument("--e2e-mode", default="zero_copy", choices=["zero_copy", "upload", "resident_maps"],
                     help="how the e2e headline moves the heat maps (declared up front; the other mode is reported beside it)")
-    ap.add_argument("--heat-layout", default="planar", choices=["planar", "hwc"],
-                    help="layout of the staged heat maps: planar [frames, J, H, W] (what optimizer.load_clips produces by "
-                         "default) or the pickle's hwc [frames, H, W, J]")
+    ap.add_argument("--heat-layout", default="tiled", choices=["tiled", "planar", "hwc"],
+                    help="layout of the staged heat maps: tiled [frames, J, H/4, W/8, 4, 8] (optimizer.load_clips(planar='tiled'): one "
+                         "128-byte line per 4 x 8 tile), planar [frames, J, H, W], or the pickle's hwc [frames, H, W, J]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-host", action="store_true",
@@ -321,8 +321,10 @@ def workload_config(args, extra):
                        + ", 15 joints, 64x64x15 HWC fp32 heatmaps, random-init motion VAEs (local + global), "
                        f"windows of 10 frames stride 8, L-BFGS max_iter={args.max_iter} both stages",
            "sequences": n_seq, "frames_per_sequence": frames, "replicate": rep, "max_iter": args.max_iter,
-           "heat_layout": getattr(args, "heat_layout", "planar") + (" ([frames, J, H, W]: optimizer.load_clips' staging layout)"
-                                                                    if getattr(args, "heat_layout", "planar") == "planar" else " ([frames, H, W, J]: the pickle's)"),
+           "heat_layout": getattr(args, "heat_layout", "tiled") + {
+               "planar": " ([frames, J, H, W]: optimizer.load_clips' staging layout)",
+               "tiled": " ([frames, J, H/4, W/8, 4, 8]: optimizer.load_clips(planar='tiled'), one 128-byte line per 4 x 8 tile)",
+               "hwc": " ([frames, H, W, J]: the pickle's)"}[getattr(args, "heat_layout", "tiled")],
            "scaling_mode": args.scaling,
            "cache": "inputs (heat maps 0.74 GB and L-BFGS state 0.18 GB per sequence) are larger than L2 (126 MB); no flush needed"}
     if extra:
@@ -340,7 +342,7 @@ def main():
     import torch.distributed as dist
     from globalegomocap_b200 import optimizer as gem
     from globalegomocap_b200 import synthetic as syn
-    from globalegomocap_b200.engine import Engine
+    from globalegomocap_b200.engine import Engine, tile_heat, untile_heat
     from globalegomocap_b200.pipeline import WindowBatch
     from globalegomocap_b200.vae_prep import PreparedVae
 
@@ -367,14 +369,16 @@ def main():
     offs = np.concatenate([[0], np.cumsum(n_frames)])
     host_gb = offs[-1] * 64 * 64 * 15 * 4 / 1e9
     do_e2e = not args.no_e2e and rep == 1 and host_gb <= 8.0
-    planar = args.heat_layout == "planar"
+    planar = {"hwc": 0, "planar": 1, "tiled": 2}[args.heat_layout]
     clips = gem.ClipSet()
     clips.planar = planar
     if planar:                                   # what optimizer.load_clips does while it stacks the pickle's frames
         for c in clips_np:
-            c["heatmap_list"] = np.ascontiguousarray(c["heatmap_list"].transpose(0, 3, 1, 2))
+            maps = torch.from_numpy(c["heatmap_list"]).permute(0, 3, 1, 2)
+            c["heatmap_list"] = (tile_heat(maps) if planar == 2 else maps).contiguous().numpy()
     if do_e2e:
-        heat_all = torch.empty((int(offs[-1]),) + ((15, 64, 64) if planar else (64, 64, 15)), dtype=torch.float32).pin_memory()
+        heat_all = torch.empty((int(offs[-1]),) + {0: (64, 64, 15), 1: (15, 64, 64), 2: (15, 16, 8, 4, 8)}[planar],
+                               dtype=torch.float32).pin_memory()
         for i, c in enumerate(clips_np):
             d = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in c.items()
                  if k not in ("gt_global_skeleton", "heatmap_list", "mean_bone_length")}
@@ -529,8 +533,9 @@ def main():
                 entry["h2d_bytes_per_step"] = int(small + fetched * 32)
                 entry["texel_cache"] = {"lookups": lookups, "texels_fetched": fetched}
                 entry["mode"] = ("zero-copy heat maps: pinned host memory read over PCIe through a per-joint texel window in HBM "
-                                 "(planar maps: whole 64-byte window rows, fetched by a few CTAs from the miss list a probe kernel "
-                                 "writes); h2d bytes = small arrays + 32 bytes per sector fetched (texels_fetched counts sectors)")
+                                 "(tiled maps: one 128-byte request per 4 x 8 tile; planar maps: whole 64-byte window rows; both "
+                                 "fetched by a few CTAs from the miss list a probe kernel writes); h2d bytes = small arrays + "
+                                 "32 bytes per sector fetched (texels_fetched counts sectors)")
             else:
                 entry["h2d_bytes_per_step"] = int(h2d_bytes)
                 entry["mode"] = "explicit piecewise upload of every input on a copy stream, overlapped with the solve"
@@ -571,7 +576,9 @@ def main():
         work = tempfile.mkdtemp(prefix="gem_bench_pkl_")
         clip0 = {k: v for k, v in clips_np[0].items() if k in gem.CLIP_KEYS}
         if planar:
-            clip0["heatmap_list"] = np.ascontiguousarray(clip0["heatmap_list"].transpose(0, 2, 3, 1))      # the pickle's own layout
+            maps0 = torch.from_numpy(clip0["heatmap_list"])
+            maps0 = untile_heat(maps0) if planar == 2 else maps0
+            clip0["heatmap_list"] = maps0.permute(0, 2, 3, 1).contiguous().numpy()      # the pickle's own layout
         syn.write_clip_pickle(clip0, os.path.join(work, "seq0"))
         kw = dict(camera_model_path=syn.DEFAULT_CAMERA_JSON, vae_weight=0.0, gmm_weight=0.0, smoothness_weight=0.001,
                   bone_length_weight=0.01, weight_3d=0.01, reproj_weight=0.01, final_smooth=True, max_iter=args.max_iter,
@@ -667,7 +674,8 @@ def main():
             import ctypes as C
             from globalegomocap_b200.lift import load_camera_c2w
             poly_c2w, lcx, lcy = load_camera_c2w(syn.DEFAULT_CAMERA_JSON)
-            lheat = resident.heat.permute(0, 2, 3, 1).contiguous() if planar else resident.heat     # the lift reads the pickle's HWC
+            lheat = untile_heat(resident.heat) if planar == 2 else resident.heat
+            lheat = lheat.permute(0, 2, 3, 1).contiguous() if planar else lheat     # the lift reads the pickle's HWC
             nf, lh, lw, lj = lheat.shape
             ldepth = torch.rand((nf, lj), dtype=torch.float64, device=dev) + 0.5
             lpts = torch.empty((nf, lj, 3), dtype=torch.float64, device=dev)

@@ -28,7 +28,7 @@ struct gem_ctx {
     int device = 0;
     int Wmax = 0, n = 0, T = 0, J = 0, H = 0, Wd = 0, m = 0;
     int gemm_mode = 0;
-    int heat_planar = 0;                         // heat-map layout: 0 = [frames][H][W][J] (pickle), 1 = [frames][J][H][W]
+    int heat_planar = 0;                         // heat-map layout: 0 = [frames][H][W][J] (pickle), 1 = [frames][J][H][W], 2 = tiled
     int fuse_energy = 0;                         // opt-in (GEM_FUSE_ENERGY=1): the backward chain on CTA pairs evaluates the energy
                                                  // itself; measured 0.5 ms per step SLOWER than the separate kernel
     int tap_chain = 2;                           // mode 3: 0 one launch per k=3 layer, 1 the four K<=128 layers of each direction
@@ -377,8 +377,9 @@ int gem_ctx_set_chunks(gem_ctx* c, int n_chunks) {
 }
 
 int gem_ctx_set_heat_layout(gem_ctx* c, int planar) {
-    GEM_REQUIRE(c != nullptr && (planar == 0 || planar == 1), "layout must be 0 (HWC) or 1 (planar CHW)");
+    GEM_REQUIRE(c != nullptr && planar >= 0 && planar <= 2, "layout must be 0 (HWC), 1 (planar CHW) or 2 (tiled CHW)");
     GEM_REQUIRE(!planar || c->Wd % 4 == 0, "planar heat maps need a width that is a multiple of 4");
+    GEM_REQUIRE(planar != 2 || (c->Wd % kTileW == 0 && c->H % kTileH == 0), "tiled heat maps need H % 4 == 0 and W % 8 == 0");
     c->heat_planar = planar;
     return GEM_OK;
 }
@@ -1085,7 +1086,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
                 return launch_texel_probe_fetch(q, &c->cam, Wk, c->T, c->J, c->H, c->Wd, v.pose, a.heat, v.fb_own, v.patch,
                                                 v.patch_origin, v.patch_valid, c->patch_stats_on ? c->patch_stats : nullptr,
                                                 cold ? c->texel_cold_ctas : c->texel_prefetch_ctas, c->texel_prefetch_threads,
-                                                v.miss_count, v.miss_list, cold ? c->texel_cold_rows : c->texel_rows);
+                                                v.miss_count, v.miss_list, cold ? c->texel_cold_rows : c->texel_rows, c->heat_planar);
             }));
             if (cold) {
                 if ((size_t)c->cold_used == c->cold_ev.size()) {
@@ -1135,7 +1136,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
     if (graphs && a.p.max_eval >= 2) {
         for (auto& g : c->graphs) {
             if (g.which == which && g.w0 == w0 && g.Wk == Wk && g.gemm_mode == (c->gemm_mode | (c->tap_chain << 8) | (c->fuse_energy << 12)) && g.heat == a.heat &&
-                g.has_heat == ((a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas + 512 * (c->texel_prefetch_threads / 32) : 0) + (1 << 20) * c->heat_planar + (1 << 21) * c->texel_probe) &&
+                g.has_heat == ((a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas + 512 * (c->texel_prefetch_threads / 32) : 0) + (1 << 20) * c->heat_planar + (1 << 22) * c->texel_probe) &&
                 g.trace_stride == lb.trace_stride &&
                 memcmp(&g.wt, &a.wt, sizeof(a.wt)) == 0 && g.p.lr == a.p.lr && g.p.max_iter == a.p.max_iter &&
                 g.p.max_eval == a.p.max_eval && g.p.tolerance_grad == a.p.tolerance_grad &&
@@ -1160,7 +1161,7 @@ static int enqueue_stage_slice(gem_ctx* c, cudaStream_t q, const StageCall& a, i
             GEM_CUDA(e);
             gem_ctx::RoundGraph g;
             g.which = which, g.w0 = w0, g.Wk = Wk, g.gemm_mode = c->gemm_mode | (c->tap_chain << 8) | (c->fuse_energy << 12), g.heat = a.heat;
-            g.has_heat = (a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas + 512 * (c->texel_prefetch_threads / 32) : 0) + (1 << 20) * c->heat_planar + (1 << 21) * c->texel_probe;
+            g.has_heat = (a.wt.reproj != 0.f) + 2 * (int)a.texel_cache + 4 * (int)c->patch_stats_on + 8 * (a.host_maps ? c->texel_prefetch_ctas + 512 * (c->texel_prefetch_threads / 32) : 0) + (1 << 20) * c->heat_planar + (1 << 22) * c->texel_probe;
             g.trace_stride = lb.trace_stride, g.wt = a.wt, g.p = a.p;
             g.launches = round_launches;
             e = cudaGraphInstantiate(&g.exec, graph, 0);

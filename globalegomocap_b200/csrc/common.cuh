@@ -163,5 +163,7 @@ constexpr int kPatchFloats = kPlanarW * kPlanarH > kPatchWd * kPatchWd ? kPlanar
 static_assert(kPlanarW % kPlanarAlign == 0 && kPlanarW >= 2 * kPlanarAlign && (kPlanarAlign == 4 || kPlanarAlign == 8 || kPlanarAlign == 16),
               "window width / alignment");
 static_assert(kPlanarH <= 64 && kPlanarW <= 32, "one valid bit per window row; a row is fetched by at most 8 lanes");
+constexpr int kTileW = 8, kTileH = 4, kTileFloats = kTileW * kTileH;      // tiled maps (layout 2): one 128-byte line per tile
+static_assert(kPlanarW == 2 * kTileW && kPlanarH == 4 * kTileH, "the tiled window is 2 x 4 tiles");
 
 }  // namespace gem

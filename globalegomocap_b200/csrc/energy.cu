@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(512) texel_prefetch_kernel(const __grid_consta
         if (!project_joint(a.cam, x, y, z, a.H, a.Wd, p)) continue;
         if (!(p.fx0 >= -1.f && p.fx0 <= (float)a.Wd && p.fy0 >= -1.f && p.fy0 <= (float)a.H)) continue;
         float nw, ne, sw, se;
-        if (a.planar) cache_lookup_planar(a, i, a.frame_base[w] + t, j, (int)p.fx0, (int)p.fy0, false, nw, ne, sw, se);
+        if (a.planar == 2) cache_lookup_tiled(a, i, a.frame_base[w] + t, j, (int)p.fx0, (int)p.fy0, false, nw, ne, sw, se);
+        else if (a.planar) cache_lookup_planar(a, i, a.frame_base[w] + t, j, (int)p.fx0, (int)p.fy0, false, nw, ne, sw, se);
         else cache_lookup(a, i, a.frame_base[w] + t, j, (int)p.fx0, (int)p.fy0, false, nw, ne, sw, se);
     }
 }
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(128) texel_probe_kernel(const __grid_constant_
         if (project_joint(a.cam, x, y, z, a.H, a.Wd, p) &&
             (p.fx0 >= -1.f && p.fx0 <= (float)a.Wd && p.fy0 >= -1.f && p.fy0 <= (float)a.H)) {
             x0 = (int)p.fx0, y0 = (int)p.fy0;
-            miss = planar_window_miss(a, i, x0, y0);
+            miss = a.planar == 2 ? tiled_window_miss(a, i, x0, y0) : planar_window_miss(a, i, x0, y0);
         }
     }
     const unsigned m = __ballot_sync(0xffffffffu, miss);
@@ -115,6 +116,31 @@ __global__ void __launch_bounds__(512) texel_fetch_kernel(const __grid_constant_
         planar_fetch_rows<kRows>(a, pk, a.frame_base[w] + t, j, x0, y0, gl, group_mask);
     }
     // the last CTA to finish empties the list for the next round (every CTA has read n by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(count + 1, 1u) == gridDim.x - 1) count[0] = 0u, count[1] = 0u;
+    }
+}
+
+// tiled maps: eight lanes per fetch event, a 128-byte tile per load instruction of the group (energy_device.cuh:
+// tiled_fetch_event)
+__global__ void __launch_bounds__(512) texel_fetch_tiles_kernel(const __grid_constant__ EnergyArgs a, uint32_t* __restrict__ count,
+                                                                const uint2* __restrict__ list) {
+    const int TJ = a.T * a.J;
+    const uint32_t n = *reinterpret_cast<volatile uint32_t*>(count);
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t groups = gridDim.x * blockDim.x / 8;
+    const int l = (int)(threadIdx.x & 7);
+    const unsigned group_mask = 0xffu << ((threadIdx.x & 31) - l);
+    for (uint32_t e = tid / 8; e < n; e += groups) {
+        const uint2 m = list[e];
+        const size_t pk = m.x;
+        const int x0 = (short)(m.y & 0xffffu), y0 = (short)(m.y >> 16);
+        const int w = (int)(pk / TJ), k = (int)(pk - (size_t)w * TJ);
+        const int t = k / a.J, j = k - t * a.J;
+        tiled_fetch_event(a, pk, a.frame_base[w] + t, j, x0, y0, l, group_mask);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -277,7 +303,8 @@ int launch_energy_grad(cudaStream_t stream, const CameraConst* cam, const Skelet
                        short2* patch_origin, unsigned long long* patch_stats, int gp_f16, int32_t* row_exp,
                        unsigned long long* patch_valid, int planar) {
     if (W <= 0) return GEM_OK;
-    GEM_REQUIRE(!planar || Wd % 4 == 0, "planar heat maps need a width that is a multiple of 4");
+    GEM_REQUIRE(planar >= 0 && planar <= 2 && (!planar || Wd % 4 == 0), "planar heat maps need a width that is a multiple of 4");
+    GEM_REQUIRE(planar != 2 || (Wd % kTileW == 0 && H % kTileH == 0), "tiled heat maps need H % 4 == 0 and W % 8 == 0");
     GEM_REQUIRE(skel != nullptr && skel->num_joints == J, "skeleton not set for this joint count");
     GEM_REQUIRE(wt.reproj == 0.f || cam != nullptr, "camera not set");
     GEM_REQUIRE(T * J <= kSlot, "T*J must be <= 160");
@@ -298,7 +325,7 @@ int launch_energy_grad(cudaStream_t stream, const CameraConst* cam, const Skelet
     a.patch_valid = a.patch ? patch_valid : nullptr;
     GEM_REQUIRE(!gp_hi || (gp_lo && pp >= J * 3 && T * pp <= (gp_f16 ? 2 : 1) * kSplitMax && (T * pp) % 4 == 0),
                 "bad split gradient layout");
-    a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd, a.planar = planar ? 1 : 0;
+    a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd, a.planar = planar;
     a.w3d = wt.w3d, a.ws = wt.smooth, a.wb = wt.bone, a.wv = wt.vae, a.wr = wt.reproj;
     const size_t pair_bytes = (size_t)kWinPerCta * T * J * 3 * sizeof(float);
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
@@ -316,14 +343,15 @@ int launch_texel_prefetch(cudaStream_t stream, const CameraConst* cam, int W, in
                           unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas, int planar, int threads) {
     if (W <= 0) return GEM_OK;
     GEM_REQUIRE(threads >= 32 && threads <= 512 && threads % 32 == 0, "texel prefetch: 32..512 threads per CTA");
-    GEM_REQUIRE(!planar || Wd % 4 == 0, "planar heat maps need a width that is a multiple of 4");
+    GEM_REQUIRE(planar >= 0 && planar <= 2 && (!planar || Wd % 4 == 0), "planar heat maps need a width that is a multiple of 4");
+    GEM_REQUIRE(planar != 2 || (Wd % kTileW == 0 && H % kTileH == 0), "tiled heat maps need H % 4 == 0 and W % 8 == 0");
     GEM_REQUIRE(cam && heat && frame_base && patch && patch_origin && patch_valid, "texel prefetch needs the camera, the maps and the cache");
     EnergyArgs a;
     memset(&a, 0, sizeof(a));
     a.cam = *cam;
     a.pose = pose, a.heat = heat, a.frame_base = frame_base;
     a.patch = patch, a.patch_origin = patch_origin, a.patch_valid = patch_valid, a.patch_stats = patch_stats;
-    a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd, a.planar = planar ? 1 : 0;
+    a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd, a.planar = planar;
     const size_t total = (size_t)W * T * J;
     int grid = (int)((total + threads - 1) / threads);
     if (grid > ctas) grid = ctas;
@@ -336,9 +364,11 @@ int launch_texel_prefetch(cudaStream_t stream, const CameraConst* cam, int W, in
 int launch_texel_probe_fetch(cudaStream_t stream, const CameraConst* cam, int W, int T, int J, int H, int Wd, const float* pose,
                              const float* heat, const int64_t* frame_base, float* patch, short2* patch_origin,
                              unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas, int threads,
-                             uint32_t* miss_count, uint2* miss_list, int rows) {
+                             uint32_t* miss_count, uint2* miss_list, int rows, int layout) {
     if (W <= 0) return GEM_OK;
+    GEM_REQUIRE(layout == 1 || layout == 2, "probe + fetch read planar (1) or tiled (2) maps");
     GEM_REQUIRE(Wd % 4 == 0, "planar heat maps need a width that is a multiple of 4");
+    GEM_REQUIRE(layout != 2 || (Wd % kTileW == 0 && H % kTileH == 0), "tiled heat maps need H % 4 == 0 and W % 8 == 0");
     GEM_REQUIRE(cam && heat && frame_base && patch && patch_origin && patch_valid && miss_count && miss_list,
                 "texel prefetch needs the camera, the maps, the cache and the miss list");
     GEM_REQUIRE(ctas >= 1 && threads >= 32 && threads <= 512 && threads % 32 == 0, "texel fetch: 32..512 threads per CTA");
@@ -348,12 +378,13 @@ int launch_texel_probe_fetch(cudaStream_t stream, const CameraConst* cam, int W,
     a.cam = *cam;
     a.pose = pose, a.heat = heat, a.frame_base = frame_base;
     a.patch = patch, a.patch_origin = patch_origin, a.patch_valid = patch_valid, a.patch_stats = patch_stats;
-    a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd, a.planar = 1;
+    a.W = W, a.T = T, a.J = J, a.H = H, a.Wd = Wd, a.planar = layout;
     const size_t total = (size_t)W * T * J;
     texel_probe_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(a, miss_count, miss_list);
     GEM_CHECK_LAUNCH();
     constexpr int kMaxRows = 32 / (kPlanarW / 4);                           // rows one warp can fetch per event
-    if (rows >= 8 && kMaxRows >= 8) texel_fetch_kernel<(kMaxRows >= 8 ? 8 : 2)><<<ctas, threads, 0, stream>>>(a, miss_count, miss_list);
+    if (layout == 2) texel_fetch_tiles_kernel<<<ctas, threads, 0, stream>>>(a, miss_count, miss_list);
+    else if (rows >= 8 && kMaxRows >= 8) texel_fetch_kernel<(kMaxRows >= 8 ? 8 : 2)><<<ctas, threads, 0, stream>>>(a, miss_count, miss_list);
     else if (rows >= 4 && kMaxRows >= 4) texel_fetch_kernel<(kMaxRows >= 4 ? 4 : 2)><<<ctas, threads, 0, stream>>>(a, miss_count, miss_list);
     else texel_fetch_kernel<2><<<ctas, threads, 0, stream>>>(a, miss_count, miss_list);
     GEM_CHECK_LAUNCH();

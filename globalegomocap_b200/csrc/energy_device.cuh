@@ -21,7 +21,7 @@ struct EnergyCommon {
     const float* mean_bone;
     uint32_t* status;
     int W, T, J, H, Wd;
-    int planar;                // heat-map layout: 0 = [frames][H][Wd][J] (the pickle's HWC), 1 = [frames][J][H][Wd] (planar:
+    int planar;                // heat-map layout: 2 = tiled (below), 0 = [frames][H][Wd][J] (the pickle's HWC), 1 = [frames][J][H][Wd] (planar:
                                // what the reference itself permutes every window to, optimizer.py:251; x-neighbours share a sector)
     float w3d, ws, wb, wv, wr;
     // optional texel cache (used when the heat maps stay in pinned HOST memory and are read over PCIe): per joint
@@ -42,6 +42,8 @@ struct EnergyCommon {
 __device__ __forceinline__ float texel(const float* __restrict__ heat, int64_t frame, int y, int x, int j, int H,
                                        int Wd, int J, int planar = 0) {
     if (x < 0 || x >= Wd || y < 0 || y >= H) return 0.f;     // padding_mode='zeros'
+    if (planar == 2)       // tiled: [H/4][Wd/8] tiles of 4 rows x 8 texels
+        return __ldg(heat + (frame * J + j) * (int64_t)H * Wd + ((int64_t)(y >> 2) * (Wd >> 3) + (x >> 3)) * 32 + (y & 3) * 8 + (x & 7));
     if (planar) return __ldg(heat + ((frame * J + j) * H + y) * (int64_t)Wd + x);
     return __ldg(heat + ((frame * H + y) * (int64_t)Wd + x) * J + j);
 }
@@ -183,6 +185,113 @@ __device__ __forceinline__ void planar_fetch_rows(const EnergyCommon& a, size_t 
     }
 }
 
+// The window over TILED maps (layout 2: every map stored as [H/4][Wd/8] tiles of 4 rows x 8 texels, one 128-byte line
+// each).  The bus charges per request, not per byte (section 4 of DESIGN.md), and a row-major map can only offer one
+// row per request; a tile brings 4 x 8 texels of the joint's neighbourhood in ONE request, so a bilinear footprint
+// costs 1.4 requests on average (1, 2 or 4 tiles) instead of 2 rows, and the joint's later positions mostly fall into
+// tiles that are already there.  The window is the same 16 x 16 texels of HBM (row-major), its origin aligned to the
+// tile grid, with one valid bit per tile (2 across, 4 down).  Requires H % 4 == 0 and Wd % 8 == 0.
+__device__ __forceinline__ void tiled_recentre(int x0, int y0, int& ox, int& oy) {
+    ox = (x0 - 4) & ~(kTileW - 1), oy = (y0 - 6) & ~(kTileH - 1);           // x0 - ox in [4, 11], y0 - oy in [6, 9]
+}
+// bits of the window's tiles the footprint at window coordinates (dx, dy) touches
+__device__ __forceinline__ unsigned tiled_foot(int dx, int dy) {
+    const unsigned cols = (1u << (dx >> 3)) | (1u << ((dx + 1) >> 3));
+    return (cols << (2 * (dy >> 2))) | (cols << (2 * ((dy + 1) >> 2)));
+}
+__device__ __forceinline__ bool tiled_window_miss(const EnergyCommon& a, size_t pk, int x0, int y0) {
+    const short2 o = a.patch_origin[pk];
+    const unsigned long long valid = a.patch_valid[pk];
+    const int dx = x0 - o.x, dy = y0 - o.y;
+    if (planar_outside(valid, dx, dy)) return true;
+    return (tiled_foot(dx, dy) & ~(unsigned)valid) != 0u;
+}
+// address of the tile that holds map texel (y, x) (both multiples of the tile size here), or NULL outside the map
+__device__ __forceinline__ const float* tile_ptr(const EnergyCommon& a, int64_t frame, int j, int y, int x) {
+    if (y < 0 || y >= a.H || x < 0 || x >= a.Wd) return nullptr;           // a tile is wholly inside or wholly outside
+    const float* map = a.heat + (frame * a.J + j) * (int64_t)a.H * a.Wd;
+    return map + ((int64_t)(y / kTileH) * (a.Wd / kTileW) + x / kTileW) * kTileFloats;
+}
+// per-thread path (nothing prefetched: resident maps, or the probe was switched off)
+__device__ __forceinline__ void cache_lookup_tiled(const EnergyCommon& a, size_t pk, int64_t frame, int j, int x0, int y0,
+                                                   bool count_lookup, float& nw, float& ne, float& sw, float& se) {
+    float* pe = a.patch + pk * kPatchFloats;
+    const short2 o = a.patch_origin[pk];
+    unsigned long long valid = a.patch_valid[pk];
+    int ox = o.x, oy = o.y;
+    int dx = x0 - ox, dy = y0 - oy;
+    if (planar_outside(valid, dx, dy)) {
+        tiled_recentre(x0, y0, ox, oy);
+        valid = 0ull, dx = x0 - ox, dy = y0 - oy;
+    }
+    const unsigned need = tiled_foot(dx, dy) & ~(unsigned)valid;
+    int requests = 0;
+    if (need) {
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+            if (!((need >> q) & 1u)) continue;
+            const int ty = q >> 1, tx = q & 1;
+            const float* src = tile_ptr(a, frame, j, oy + ty * kTileH, ox + tx * kTileW);
+            requests += src ? kTileFloats * 4 / 32 : 0;                      // counted in 32-byte sectors
+#pragma unroll 1
+            for (int l = 0; l < 8; ++l) {
+                const float4 v = src ? __ldg(reinterpret_cast<const float4*>(src) + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(pe + (ty * kTileH + (l >> 1)) * kPlanarW + tx * kTileW + (l & 1) * 4) = v;
+            }
+        }
+        a.patch_origin[pk] = make_short2((short)ox, (short)oy);
+        a.patch_valid[pk] = valid | need;
+    }
+    if (a.patch_stats) {
+        if (count_lookup) atomicAdd(a.patch_stats, 1ull);
+        if (requests) atomicAdd(a.patch_stats + 1, (unsigned long long)requests);
+    }
+    const float* p0 = pe + dy * kPlanarW + dx;
+    nw = p0[0], ne = p0[1], sw = p0[kPlanarW], se = p0[kPlanarW + 1];
+}
+// One fetch event of texel_fetch_tiles_kernel, executed by a group of eight lanes (lane l of the group = one float4 of a
+// tile's 128 bytes: row l / 2, half l % 2, so a tile is ONE request): the loads of the (up to) four tiles of the
+// footprint are all issued before the first store.
+__device__ __forceinline__ void tiled_fetch_event(const EnergyCommon& a, size_t pk, int64_t frame, int j, int x0, int y0, int l,
+                                                  unsigned group_mask) {
+    float* pe = a.patch + pk * kPatchFloats;
+    const short2 o = a.patch_origin[pk];
+    unsigned long long valid = a.patch_valid[pk];
+    __syncwarp(group_mask);                       // every lane has read the window's state before lane 0 rewrites it
+    int ox = o.x, oy = o.y;
+    int dx = x0 - ox, dy = y0 - oy;
+    if (planar_outside(valid, dx, dy)) {
+        tiled_recentre(x0, y0, ox, oy);
+        valid = 0ull, dx = x0 - ox, dy = y0 - oy;
+    }
+    const unsigned need = tiled_foot(dx, dy) & ~(unsigned)valid;
+    float4 v[4];
+    bool take[4];
+    int ty[4], tx[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        ty[q] = ((q >> 1) ? (dy + 1) : dy) >> 2, tx[q] = ((q & 1) ? (dx + 1) : dx) >> 3;
+        // the second row / column of tiles only when the footprint really crosses into it (else it repeats the first)
+        const bool distinct = (!(q >> 1) || ty[q] != (dy >> 2)) && (!(q & 1) || tx[q] != (dx >> 3));
+        take[q] = distinct && ((need >> (ty[q] * 2 + tx[q])) & 1u);
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);   // padding_mode='zeros' outside the map
+        if (take[q]) {
+            const float* src = tile_ptr(a, frame, j, oy + ty[q] * kTileH, ox + tx[q] * kTileW);
+            if (src) {
+                v[q] = __ldg(reinterpret_cast<const float4*>(src) + l);
+                if (a.patch_stats && l == 0) atomicAdd(a.patch_stats + 1, (unsigned long long)(kTileFloats * 4 / 32));
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (take[q]) *reinterpret_cast<float4*>(pe + (ty[q] * kTileH + (l >> 1)) * kPlanarW + tx[q] * kTileW + (l & 1) * 4) = v[q];
+    if (l == 0) {
+        a.patch_origin[pk] = make_short2((short)ox, (short)oy);
+        a.patch_valid[pk] = valid | need;
+    }
+}
+
 // Fisheye projection of a joint and the map cell its bilinear footprint starts at (FishEyeCalibrated.py:96-129,
 // optimizer.py:139-149); the arithmetic (and --fmad=false) is what decides the cell, so the energy code and the
 // texel prefetch kernel share it.  Returns false when r == 0.
@@ -234,7 +343,9 @@ __device__ __forceinline__ void joint_gather(const EnergyCommon& a, const float*
         jt.rp = true;
         const int x0 = (int)jt.pj.fx0, y0 = (int)jt.pj.fy0;
         const int64_t frame = a.frame_base[w] + t;
-        if (a.patch && a.planar) {
+        if (a.patch && a.planar == 2) {
+            cache_lookup_tiled(a, (size_t)w * (a.T * a.J) + k, frame, j, x0, y0, true, jt.nw, jt.ne, jt.sw, jt.se);
+        } else if (a.patch && a.planar) {
             cache_lookup_planar(a, (size_t)w * (a.T * a.J) + k, frame, j, x0, y0, true, jt.nw, jt.ne, jt.sw, jt.se);
         } else if (a.patch) {
             cache_lookup(a, (size_t)w * (a.T * a.J) + k, frame, j, x0, y0, true, jt.nw, jt.ne, jt.sw, jt.se);

@@ -1548,7 +1548,7 @@ int launch_tap_chain_pair(cudaStream_t stream, void* owner, const TapChainLaunch
         en.scratch0 = free_buf[0], en.scratch1 = free_buf[1];
         en.pose = E.pose, en.pose0 = E.pose0, en.energy = E.energy, en.row_exp = E.row_exp;
         en.heat = E.heat, en.frame_base = E.frame_base, en.clip = E.clip, en.mean_bone = E.mean_bone, en.status = E.status;
-        en.W = L.W, en.T = L.T, en.J = E.J, en.H = E.H, en.Wd = E.Wd, en.planar = E.planar ? 1 : 0;
+        en.W = L.W, en.T = L.T, en.J = E.J, en.H = E.H, en.Wd = E.Wd, en.planar = E.planar;
         en.w3d = E.wt.w3d, en.ws = E.wt.smooth, en.wb = E.wt.bone, en.wv = E.wt.vae, en.wr = E.wt.reproj;
         en.patch = E.patch && E.patch_valid ? E.patch : nullptr;
         en.patch_origin = en.patch ? E.patch_origin : nullptr, en.patch_valid = en.patch ? E.patch_valid : nullptr;

@@ -19,7 +19,7 @@ int launch_texel_prefetch(cudaStream_t stream, const CameraConst* cam, int W, in
 int launch_texel_probe_fetch(cudaStream_t stream, const CameraConst* cam, int W, int T, int J, int H, int Wd, const float* pose,
                              const float* heat, const int64_t* frame_base, float* patch, short2* patch_origin,
                              unsigned long long* patch_valid, unsigned long long* patch_stats, int ctas, int threads,
-                             uint32_t* miss_count, uint2* miss_list, int rows);
+                             uint32_t* miss_count, uint2* miss_list, int rows, int layout);
 constexpr int kPatchW = kPatchWd;
 
 enum { EPI_NONE = 0, EPI_LRELU = 1, EPI_MASK = 2 };

@@ -35,6 +35,43 @@ class _DevPtr:
                                          "version": 2, "strides": None}
 
 
+def heat_layout_code(layout) -> int:
+    """0 (HWC, the pickle's), 1 (planar) or 2 (tiled) from a bool, an int or a name."""
+    if isinstance(layout, str):
+        return {"hwc": 0, "planar": 1, "tiled": 2}[layout]
+    code = int(layout)
+    if code not in (0, 1, 2):
+        raise ValueError("heat layout must be 0 / 'hwc', 1 / 'planar' or 2 / 'tiled'")
+    return code
+
+
+def heat_dims(shape, layout):
+    """(H, W, J) of heat maps whose per-frame shape ends `shape`, in the given layout."""
+    code = heat_layout_code(layout)
+    if code == 0:
+        return int(shape[-3]), int(shape[-2]), int(shape[-1])
+    if code == 1:
+        return int(shape[-2]), int(shape[-1]), int(shape[-3])
+    return int(shape[-4]) * 4, int(shape[-3]) * 8, int(shape[-5])
+
+
+def tile_heat(planar_maps):
+    """[..., H, W] maps -> [..., H/4, W/8, 4, 8] (the tiled layout's per-map order), a strided view."""
+    *lead, H, W = planar_maps.shape
+    if H % 4 or W % 8:
+        raise ValueError("tiled heat maps need H % 4 == 0 and W % 8 == 0")
+    n = len(lead)
+    v = planar_maps.reshape(*lead, H // 4, 4, W // 8, 8)
+    return v.permute(*range(n), n, n + 2, n + 1, n + 3)
+
+
+def untile_heat(tiled_maps):
+    """[..., H/4, W/8, 4, 8] -> [..., H, W] (a copy)."""
+    *lead, th, tw, r, c = tiled_maps.shape
+    n = len(lead)
+    return tiled_maps.permute(*range(n), n, n + 2, n + 1, n + 3).reshape(*lead, th * r, tw * c)
+
+
 class Engine:
     def __init__(self, max_windows, device=None, latent_dim=2048, seq_len=10, num_joints=15, heat_hw=(64, 64),
                  max_history=24):
@@ -51,7 +88,7 @@ class Engine:
                                       num_joints, self.H, self.Wd, max_history))
         self._vae = {}
         self._keep = []
-        self.heat_planar = False
+        self.heat_planar = 0            # heat-map layout code (heat_layout_code)
 
     # ------------------------------------------------------------------ housekeeping
     def close(self):
@@ -112,12 +149,15 @@ class Engine:
         """-1 auto (on when the heat maps are pinned host memory), 0 off, 1 on; results are unaffected."""
         check(self.lib.gem_ctx_set_texel_cache(self._ctx, int(mode)))
 
-    def set_heat_layout(self, planar: bool):
-        """False: heat maps are [frames, H, W, J] (the pickle's layout); True: planar [frames, J, H, W]
-        (include/gem_b200.h: gem_ctx_set_heat_layout).  Results are bit-identical in both layouts."""
-        if bool(planar) != self.heat_planar:
-            check(self.lib.gem_ctx_set_heat_layout(self._ctx, int(bool(planar))))
-            self.heat_planar = bool(planar)
+    def set_heat_layout(self, planar):
+        """False / 0 / "hwc": heat maps are [frames, H, W, J] (the pickle's layout); True / 1 / "planar": [frames, J, H, W];
+        2 / "tiled": [frames, J, H/4, W/8, 4, 8], every map as tiles of 4 rows x 8 texels (one 128-byte line each: what the
+        zero-copy path fetches per PCIe request) (include/gem_b200.h: gem_ctx_set_heat_layout).  Results are
+        bit-identical in all layouts."""
+        code = heat_layout_code(planar)
+        if code != self.heat_planar:
+            check(self.lib.gem_ctx_set_heat_layout(self._ctx, code))
+            self.heat_planar = code
 
     def texel_cache_stats(self, enable: bool):
         """(lookups, texels fetched from the map) counted since the previous call; switches the counting on or off."""
@@ -140,10 +180,11 @@ class Engine:
         resolution / joint count, or a window that runs past the last frame, must not reach the kernel."""
         if heat is None:
             return
-        want = (self.J, self.H, self.Wd) if self.heat_planar else (self.H, self.Wd, self.J)
-        if tuple(heat.shape[-3:]) != want:
-            raise GemError(f"heat maps are {tuple(heat.shape[-3:])}, the engine expects {want} "
-                           f"({'joints, H, W: planar layout' if self.heat_planar else 'H, W, joints'})")
+        want = {0: (self.H, self.Wd, self.J), 1: (self.J, self.H, self.Wd),
+                2: (self.J, self.H // 4, self.Wd // 8, 4, 8)}[int(self.heat_planar)]
+        if tuple(heat.shape[-len(want):]) != want:
+            raise GemError(f"heat maps are {tuple(heat.shape[-len(want):])}, the engine expects {want} "
+                           f"({('H, W, joints', 'joints, H, W: planar layout', 'joints, H/4, W/8, 4, 8: tiled layout')[int(self.heat_planar)]})")
         if frame_base is None or (isinstance(frame_base, torch.Tensor) and frame_base.is_cuda):
             return          # device-resident indices were range-checked by whoever built them (WindowBatch does)
         fb = np.asarray(frame_base)

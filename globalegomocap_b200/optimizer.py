@@ -23,7 +23,7 @@ import pickle
 import numpy as np
 import torch
 
-from .engine import Engine, GemError, energy_weights, lbfgs_params
+from .engine import Engine, GemError, energy_weights, heat_dims, heat_layout_code, lbfgs_params, tile_heat
 from .metrics import calculate_errors
 from .pipeline import SequenceOptimizer
 from .vae_prep import PreparedVae
@@ -174,7 +174,7 @@ class ClipSet(list):
     [total frames, H, W, J] (planar: [total frames, J, H, W]) every clip's heat maps are a view of — what the zero-copy
     path reads in place."""
     heat_all = None
-    planar = False
+    planar = 0          # layout code of the heat maps: 0 the pickle's HWC, 1 planar, 2 tiled (engine.heat_layout_code)
 
 
 def _unpickle(data_id):
@@ -182,15 +182,19 @@ def _unpickle(data_id):
         return pickle.load(f)
 
 
-def load_clips(data_ids, pinned=True, planar=True):
+def load_clips(data_ids, pinned=True, planar="tiled"):
     """'<data_id>/test_data.pkl' of every clip (optimizer.py:315-324; extra keys are ignored) unpickled and landed
     ONCE in page-locked host memory: each per-frame list is stacked straight into its slice of one pinned buffer
     per key, so the solver can read the heat maps where they are (or DMA them) without another host copy.
 
-    planar (default): the heat maps are stacked as [frames, J, H, W] — the permutation the reference applies to every
-    window before grid_sample (optimizer.py:251), done here once while the frames are copied anyway.  With planar maps
-    the x-neighbours of a bilinear footprint share a sector, which is what makes the zero-copy path cheap (a third of
-    the PCIe requests); planar=False keeps the pickle's [frames, H, W, J]."""
+    planar=True: the heat maps are stacked as [frames, J, H, W] — the permutation the reference applies to every window
+    before grid_sample (optimizer.py:251), done here once while the frames are copied anyway.  With planar maps the
+    x-neighbours of a bilinear footprint share a sector, which is what makes the zero-copy path cheap;
+    planar="tiled" (or 2; the default, for maps with H % 4 == 0 and W % 8 == 0, else plain planar) goes one step
+    further and stores every map as [H/4, W/8] tiles of 4 rows x 8 texels, one 128-byte line each, so that ONE PCIe
+    request brings a joint's two-dimensional neighbourhood (the bus charges per request: DESIGN.md section 4);
+    planar=False keeps the pickle's [frames, H, W, J]."""
+    layout = heat_layout_code(planar)
     raws = [_unpickle(d) for d in data_ids]
     n_frames = [len(r["estimated_local_skeleton"]) for r in raws]
     offs = np.concatenate([[0], np.cumsum(n_frames)]).astype(np.int64)
@@ -202,8 +206,12 @@ def load_clips(data_ids, pinned=True, planar=True):
                 continue
             raise KeyError("test_data.pkl lacks the key {!r}".format(key))
         shape = tuple(np.asarray(next(r[key][0] for r in raws if len(r[key]))).shape) if total else ()
-        to_planar = planar and key == "heatmap_list" and len(shape) == 3
-        if to_planar:
+        to_planar = layout if key == "heatmap_list" and len(shape) == 3 else 0
+        if to_planar == 2 and (shape[0] % 4 or shape[1] % 8):
+            to_planar = 1                              # maps that do not tile: plain planar
+        if to_planar == 2:
+            shape = (shape[2], shape[0] // 4, shape[1] // 8, 4, 8)
+        elif to_planar:
             shape = (shape[2], shape[0], shape[1])
         dt = _CLIP_DTYPES[key]
         buf = _pinned("clip_" + key, (total,) + shape, dt) if pinned else torch.from_numpy(np.empty((total,) + shape, dt))
@@ -216,7 +224,8 @@ def load_clips(data_ids, pinned=True, planar=True):
             if n_frames[i] and to_planar:
                 # HWC frames -> planar slice: torch's strided copy runs on all host threads (numpy's on one)
                 src = np.asarray(frames) if isinstance(frames, np.ndarray) else np.stack(frames)
-                torch.from_numpy(dst).copy_(torch.from_numpy(np.ascontiguousarray(src, dtype=dt)).permute(0, 3, 1, 2))
+                src = torch.from_numpy(np.ascontiguousarray(src, dtype=dt)).permute(0, 3, 1, 2)
+                torch.from_numpy(dst).copy_(tile_heat(src) if to_planar == 2 else src)
             elif n_frames[i]:
                 if isinstance(frames, np.ndarray):
                     np.copyto(dst, frames, casting="same_kind")
@@ -225,13 +234,20 @@ def load_clips(data_ids, pinned=True, planar=True):
             clips[i][key] = buf[offs[i]:offs[i + 1]]
         if key == "heatmap_list":
             clips.heat_all = buf
-            clips.planar = bool(to_planar)
+            clips.planar = int(to_planar)
     return clips
 
 
 def load_clip(data_id, pinned=True):
     """'<data_id>/test_data.pkl' -> dict of (pinned) host tensors (optimizer.py:315-324); extra keys are ignored."""
     return load_clips([data_id], pinned=pinned)[0]
+
+
+def _shape_of(frames):
+    """Shape of a per-frame array / tensor / list of per-frame arrays without stacking the list."""
+    if hasattr(frames, "shape"):
+        return tuple(frames.shape)
+    return (len(frames),) + (tuple(np.shape(frames[0])) if len(frames) else ())
 
 
 def _n_windows(n_frames, seq_len=10, overlap=2):
@@ -264,15 +280,13 @@ def solve_clips(clips, camera_model_path, vae_weight=0.0, gmm_weight=0.0, smooth
     if outputs not in ("all", "optimized"):
         raise ValueError("outputs must be 'all' or 'optimized'")
     prebuilt = isinstance(clips, WindowBatch)
-    planar = bool(getattr(clips, "planar", False))
+    planar = heat_layout_code(getattr(clips, "planar", 0))
     if prebuilt:
         batch_W = clips.W
-        heat_shape = tuple(clips.heat.shape[-3:])
+        heat_shape = heat_dims(clips.heat.shape, planar)
     else:
         batch_W = sum(_n_windows(len(c["estimated_local_skeleton"])) for c in clips)
-        heat_shape = tuple(np.shape(clips[0]["heatmap_list"])[-3:]) if len(clips) else (64, 64, 15)
-    if planar:
-        heat_shape = (heat_shape[1], heat_shape[2], heat_shape[0])           # (J, H, W) -> (H, W, J)
+        heat_shape = heat_dims(_shape_of(clips[0]["heatmap_list"]), planar) if len(clips) else (64, 64, 15)
     eng = engine if engine is not None else shared_engine(batch_W, max(max_iter - 1, 1), heat_hw=heat_shape[:2],
                                                           num_joints=heat_shape[2])
     eng.set_camera_json(camera_model_path) if isinstance(camera_model_path, str) else eng.set_camera(*camera_model_path)

@@ -10,7 +10,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .engine import KINEMATIC_PARENTS, Engine, energy_weights, lbfgs_params
+from .engine import KINEMATIC_PARENTS, Engine, energy_weights, heat_layout_code, lbfgs_params
 
 SEQ_LEN = 10
 OVERLAP = 2
@@ -64,10 +64,17 @@ class WindowBatch:
     only the texels the optimiser samples ever cross the bus."""
 
     def __init__(self, engine: Engine, clips, copy_stream=None, min_piece_windows=96, host_heat=None, planar=False):
-        # planar: the clips' heat maps (and host_heat) are [frames, J, H, W] instead of the pickle's [frames, H, W, J]
-        # (optimizer.load_clips(planar=True)); SequenceOptimizer.solve tells the engine
+        # planar: layout of the clips' heat maps (and of host_heat): False / 0 the pickle's [frames, H, W, J], True / 1
+        # [frames, J, H, W], 2 / "tiled" [frames, J, H/4, W/8, 4, 8] (optimizer.load_clips); SequenceOptimizer.solve tells
+        # the engine
         dev = engine.device
-        self.planar = bool(planar)
+        self.planar = heat_layout_code(planar)     # 0 HWC, 1 planar, 2 tiled
+        if len(clips):
+            h0 = clips[0]["heatmap_list"] if host_heat is None else host_heat
+            ndim = h0.ndim if hasattr(h0, "ndim") else (1 + np.ndim(h0[0]) if len(h0) else (6 if self.planar == 2 else 4))
+            if ndim != (6 if self.planar == 2 else 4):
+                raise ValueError("heat maps with {} dimensions do not fit the declared layout {} ([frames, H, W, J], "
+                                 "[frames, J, H, W] or tiled [frames, J, H/4, W/8, 4, 8])".format(ndim, self.planar))
         self.n_frames = [len(c["estimated_local_skeleton"]) for c in clips]
         self.starts = [window_starts(n, engine.T, OVERLAP) for n in self.n_frames]
         self.n_windows = [len(s) for s in self.starts]

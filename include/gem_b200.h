@@ -130,21 +130,27 @@ int gem_ctx_set_ready_events(gem_ctx* ctx, int n, const int32_t* first_window_h,
 
 /* Layout of every heat_d argument: 0 (default) = [frames][H][Wd][J], the pickle's HWC layout, gathered in place;
  * 1 = planar [frames][J][H][Wd] — what the reference itself permutes each window's maps to before grid_sample
- * (optimizer.py:251).  In the planar layout the x-neighbours of a bilinear footprint share a 32-byte sector: half
- * the DRAM sectors per sample on resident maps, and the zero-copy texel cache fetches aligned float4 units (one PCIe
- * request per four texels of a map row; about a third of the requests per stage).  Values are the same: results
- * are bit-identical in both layouts.  Needs Wd % 4 == 0.  gem_lift_skeleton always takes HWC maps. */
+ * (optimizer.py:251); 2 = tiled [frames][J][H/4][Wd/8][4][8]: every map as tiles of 4 rows x 8 texels, one 128-byte
+ * line per tile.  In the planar layout the x-neighbours of a bilinear footprint share a 32-byte sector (half the DRAM
+ * sectors per sample on resident maps) and the zero-copy texel window fetches whole 64-byte rows; in the tiled layout
+ * one PCIe request brings a joint's 4 x 8 neighbourhood (reads of host memory are charged per request, not per byte:
+ * half the requests of the planar layout again).  Values are the same: results are bit-identical in all layouts.
+ * Layout 1 needs Wd % 4 == 0, layout 2 H % 4 == 0 and Wd % 8 == 0.  gem_lift_skeleton always takes HWC maps. */
 int gem_ctx_set_heat_layout(gem_ctx* ctx, int planar);
 
 /* heat_d may be pinned (or registered) HOST memory: the energy kernel then reads the maps over PCIe through a
- * per-joint 8x8 texel window in HBM (256 bytes per joint and a valid bit per texel: a texel is fetched the first time
- * the bilinear footprint needs it; the window is re-centred, empty, when the footprint leaves it), so only the few
- * per cent of the maps the optimiser ever samples cross the bus and no up-front copy is needed.  Values are copies:
- * results are bit-identical.  mode -1 (default): cache on exactly when heat_d is host memory; 0 off; 1 on. */
+ * per-joint texel window in HBM (HWC maps: 8 x 8 texels with a valid bit per texel; planar maps: 16 x 16 with a valid
+ * bit per 64-byte row; tiled maps: 16 x 16 with a valid bit per 4 x 8 tile.  A unit is fetched the first time a
+ * bilinear footprint needs it — for planar and tiled maps by a probe kernel that lists the joints with a missing
+ * footprint and a few fetch CTAs that walk that list before every energy evaluation; the window is re-centred,
+ * empty, when the footprint leaves it), so only the few per cent of the maps the optimiser ever samples cross the
+ * bus and no up-front copy is needed.  The window buffers (1 KB per joint-frame) are allocated by the first call that
+ * uses them.  Values are copies: results are bit-identical.  mode -1 (default): cache on exactly when heat_d is host
+ * memory; 0 off; 1 on. */
 int gem_ctx_set_texel_cache(gem_ctx* ctx, int mode);
 /* synchronises; returns the cache's lookups (one per joint per evaluation) and the texels it fetched from the map
- * (one 32-byte sector each; with planar maps: the float4 requests) counted since the previous call while counting was enabled, then clears them and sets
- * counting on/off */
+ * (counted in 32-byte sectors: one per texel with HWC maps, two per window row with planar maps, four per tile with
+ * tiled maps) since the previous call while counting was enabled, then clears them and sets counting on/off */
 int gem_ctx_texel_cache_stats(gem_ctx* ctx, int enable, uint64_t* lookups_h, uint64_t* texels_fetched_h);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */

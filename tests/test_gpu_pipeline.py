@@ -210,8 +210,10 @@ def test_main_batch_ingest_modes_are_bit_identical(workdir, monkeypatch, vae_wei
     clips = gem.load_clips(names)
     assert clips.heat_all.is_pinned()
     eng = gem.shared_engine(W, 3)
-    assert clips.planar                                      # load_clips stacks the maps planar ([frames, J, H, W]) by default
-    resident = WindowBatch(eng, [{k: v.cuda() for k, v in c.items()} for c in clips], planar=True)
+    assert clips.planar == 2                                 # load_clips tiles the maps ([frames, J, H/4, W/8, 4, 8]) by default
+    with pytest.raises(ValueError):                          # tiled maps declared planar
+        WindowBatch(eng, [{k: v.cuda() for k, v in c.items()} for c in clips], planar=True)
+    resident = WindowBatch(eng, [{k: v.cuda() for k, v in c.items()} for c in clips], planar=clips.planar)
     res = gem.solve_clips(resident, eps=eps, **kw)
     hwc = gem.load_clips(names, planar=False)                # the pickle's own layout gives the same bits
     res_hwc = gem.solve_clips(WindowBatch(eng, [{k: v.cuda() for k, v in c.items()} for c in hwc]), eps=eps, **kw)

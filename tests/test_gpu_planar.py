@@ -1,6 +1,7 @@
-"""Planar heat maps ([frames, J, H, W], gem_ctx_set_heat_layout) against the pickle's HWC layout: the same texel values
-reach the same arithmetic, so energies, gradients and whole solves are bit-identical; over PCIe the planar texel cache
-needs about a third of the requests.  Needs a B200: `pytest -m gpu`."""
+"""Planar ([frames, J, H, W]) and tiled ([frames, J, H/4, W/8, 4, 8]) heat maps (gem_ctx_set_heat_layout) against the
+pickle's HWC layout: the same texel values reach the same arithmetic, so energies, gradients and whole solves are
+bit-identical; over PCIe the planar window needs fewer requests than the HWC one, the tiled one fewer again.
+Needs a B200: `pytest -m gpu`."""
 import numpy as np
 import pytest
 import torch
@@ -14,7 +15,7 @@ W_LOCAL = (0.01 / 10000, 0.001 / 100, 0.01, 0.0, 0.01)
 
 def test_energy_and_gradient_are_bit_identical_in_both_layouts(golden_dir, clip58, camera):
     import os
-    from globalegomocap_b200.engine import Engine, energy_weights
+    from globalegomocap_b200.engine import Engine, energy_weights, tile_heat
     g = np.load(os.path.join(golden_dir, "energy.npz"))
     names = [str(n) for n in g["names"] if str(n).startswith("all__")]
     xs = np.stack([g[f"{n}__x"] for n in names])
@@ -29,9 +30,14 @@ def test_energy_and_gradient_are_bit_identical_in_both_layouts(golden_dir, clip5
     args = (xs, x0, None, fb, np.zeros(len(names), np.int32), g["mean_bone_length"], w)
     a = eng.energy_grad(args[0], args[1], heat, *args[3:])
     eng.set_heat_layout(True)
-    b = eng.energy_grad(args[0], args[1], np.ascontiguousarray(heat.transpose(0, 3, 1, 2)), *args[3:])
-    for u, v in zip(a, b):
-        assert torch.equal(u, v)
+    planar = np.ascontiguousarray(heat.transpose(0, 3, 1, 2))
+    b = eng.energy_grad(args[0], args[1], planar, *args[3:])
+    eng.set_heat_layout("tiled")            # [frames, J, H/4, W/8, 4, 8]: the same texels behind another address
+    c = eng.energy_grad(args[0], args[1], tile_heat(torch.from_numpy(planar)).contiguous(), *args[3:])
+    for u, v, t in zip(a, b, c):
+        assert torch.equal(u, v) and torch.equal(u, t)
+    with pytest.raises(Exception):          # planar-shaped maps while the engine expects tiles
+        eng.energy_grad(args[0], args[1], planar, *args[3:])
     eng.close()
 
 
@@ -57,9 +63,13 @@ def test_solves_are_bit_identical_and_pcie_requests_drop(vae_weights, camera):
     eng.set_camera(*camera)
     eng.set_vae(0, vae_weights[0])
     out, fetched, looked = {}, {}, {}
+    from globalegomocap_b200.engine import tile_heat
+    tiled = tile_heat(planar).contiguous()
     for name, heat, is_planar in (("hwc resident", hwc.cuda(), False), ("planar resident", planar.cuda(), True),
                                   ("hwc zero-copy", pinned(hwc), False), ("planar zero-copy", pinned(planar), True),
-                                  ("planar resident, cache forced", planar.cuda(), True)):
+                                  ("planar resident, cache forced", planar.cuda(), True),
+                                  ("tiled resident", tiled.cuda(), 2), ("tiled zero-copy", pinned(tiled), 2),
+                                  ("tiled resident, cache forced", tiled.cuda(), 2)):
         eng.set_heat_layout(is_planar)
         eng.set_texel_cache(1 if "forced" in name else -1)        # forced: the energy kernel's own per-thread row fetch
         eng.texel_cache_stats(True)
@@ -78,4 +88,7 @@ def test_solves_are_bit_identical_and_pcie_requests_drop(vae_weights, camera):
     # HWC: one request per texel.  Planar: whole window rows (16 texels = two 32-byte sectors, ONE request each; the
     # counter is in sectors), and a miss also brings in the rows next to the footprint's
     assert 0 < fetched["planar zero-copy"] / 2 < 0.8 * fetched["hwc zero-copy"]
+    # tiled: one request = one 4 x 8 tile (four sectors): fewer requests again
+    assert looked["tiled resident"] == 0 and looked["tiled zero-copy"] == looked["tiled resident, cache forced"] == looked["planar zero-copy"]
+    assert 0 < fetched["tiled zero-copy"] / 4 < 0.8 * fetched["planar zero-copy"] / 2
     eng.close()

@@ -78,11 +78,21 @@ def test_load_clips_lands_every_clip_in_one_staging_buffer(tmp_path):
         with open(d / "test_data.pkl", "wb") as f:
             pickle.dump(raw, f)
         dirs.append(str(d))
-    planar = gem.load_clips(dirs)                            # default: heat maps land as [frames, J, H, W]
-    assert planar.planar and tuple(planar.heat_all.shape) == (18 + 26, 15, 64, 64)
+    assert gem.load_clips(dirs).planar == 2                  # default: tiled (64 x 64 maps tile)
+    planar = gem.load_clips(dirs, planar=True)               # heat maps land as [frames, J, H, W]
+    assert planar.planar == 1 and tuple(planar.heat_all.shape) == (18 + 26, 15, 64, 64)
     for c, got in zip(clips, planar):
         assert np.array_equal(got["heatmap_list"].numpy(), c["heatmap_list"].transpose(0, 3, 1, 2))
         assert np.array_equal(got["gt_global_skeleton"].numpy(), c["gt_global_skeleton"])
+    tiled = gem.load_clips(dirs, planar="tiled")             # [frames, J, H/4, W/8, 4, 8]: 4 x 8 tiles of every map
+    assert tiled.planar == 2 and tuple(tiled.heat_all.shape) == (18 + 26, 15, 16, 8, 4, 8)
+    from globalegomocap_b200.engine import heat_dims, untile_heat
+    assert heat_dims(tiled.heat_all.shape, 2) == (64, 64, 15)
+    for c, got in zip(clips, tiled):
+        assert np.array_equal(untile_heat(got["heatmap_list"]).numpy(), c["heatmap_list"].transpose(0, 3, 1, 2))
+        y, x = 37, 29                                        # a texel's address inside its map
+        flat = got["heatmap_list"].reshape(len(c["heatmap_list"]), 15, -1).numpy()
+        assert np.array_equal(flat[:, :, ((y >> 2) * 8 + (x >> 3)) * 32 + (y & 3) * 8 + (x & 7)], c["heatmap_list"][:, y, x, :])
     cs = gem.load_clips(dirs, planar=False)
     assert isinstance(cs, gem.ClipSet) and len(cs) == 2 and not cs.planar
     assert tuple(cs.heat_all.shape) == (18 + 26, 64, 64, 15) and cs.heat_all.dtype == torch.float32
