@@ -747,7 +747,13 @@ tc_tap_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
 // the w_empty / acc_full barriers of both CTAs.
 constexpr int kChain2Max = 6;
 constexpr int kChain2WSlot = 3 * 96 * 128;                     // 36,864 B: three half slabs of 96 rows x 128 B
-constexpr size_t kChain2Smem = 8 * kATile + 2 * kChain2WSlot + 1024 /*align slack*/ + 256 /*barriers*/;
+// shared memory: n_act activation buffers (hi + lo tile each) and n_slots weight slots: 4 + 2 (200 KB), or - when the
+// first layer's K blocks stream through two buffers and no later layer needs more - 2 + 4 (208 KB): four weight
+// blocks in flight instead of two
+constexpr int kChain2SlotsMax = 4;
+constexpr size_t kChain2Smem = (8 * kATile + 2 * kChain2WSlot > 4 * kATile + 4 * kChain2WSlot ? 8 * kATile + 2 * kChain2WSlot
+                                                                                             : 4 * kATile + 4 * kChain2WSlot) +
+                               1024 /*align slack*/ + 256 /*barriers*/;
 
 struct Chain2Layer {
     const float* bias;           // full-layer bias [N] or NULL
@@ -765,6 +771,8 @@ struct Chain2Maps {
 struct Chain2Args {
     Chain2Layer L[kChain2Max];
     int nl, W, T, wpq;
+    int n_act, n_slots;          // activation buffers (2 or 4) and weight ring slots (4 or 2)
+    int stream0;                 // the first layer's K blocks stream through buffers 0 / 1 (loop order: K block outer, slab inner)
     float* out_plain;
     uint32_t* status;            // optional [W]: GEM_WIN_F16_RANGE is OR-ed in when a split activation saturates
     long long* dbg;
@@ -798,15 +806,18 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
     const bool en_on = kEnergy && en_arg.enabled;      // (folds to false at compile time in the plain variant)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* act = smem;                                   // four buffers of (hi 16 KB, lo 16 KB)
-    uint8_t* wring = smem + 8 * kATile;                    // two half-block slots
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wring + 2 * kChain2WSlot);
-    uint64_t* act_full = bars;                             // leader: both CTAs' first-layer activation tiles landed
-    uint64_t* w_full = bars + 1;                           // [2] leader: both halves of a weight block landed
-    uint64_t* w_empty = bars + 3;                          // [2] each CTA (multicast commit)
-    uint64_t* acc_full = bars + 5;                         // each CTA (multicast commit), phase = pseudo-layer
-    uint64_t* act_ready = bars + 6;                        // leader: 32 epilogue warps of the pair, phase = pseudo-layer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint8_t* act = smem;                                   // n_act buffers of (hi 16 KB, lo 16 KB)
+    uint8_t* wring = smem + (size_t)g.n_act * 2 * kATile;  // n_slots half-block slots
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wring + (size_t)g.n_slots * kChain2WSlot);
+    uint64_t* act_full = bars;                             // [2] leader: both CTAs' first-layer activation tiles landed
+                                                           //     (streaming: per buffer, phase = use of the buffer)
+    uint64_t* act_empty = bars + 2;                        // [2] each CTA (multicast commit): streaming buffer consumed
+    uint64_t* w_full = bars + 4;                           // [n_slots] leader: both halves of a weight block landed
+    uint64_t* w_empty = bars + 4 + kChain2SlotsMax;        // [n_slots] each CTA (multicast commit)
+    uint64_t* acc_full = bars + 4 + 2 * kChain2SlotsMax;   // each CTA (multicast commit), phase = pseudo-layer
+    uint64_t* act_ready = acc_full + 1;                    // leader: 32 epilogue warps of the pair, phase = pseudo-layer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + 1);
+    const int nslots = g.n_slots;
     __shared__ float sbias[kChain2Max * 128];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -824,7 +835,8 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&maps.a_hi), prefetch_tmap(&maps.a_lo);
         mbar_init(act_full, en_on ? 2 * kChainEpiWarps : 1);      // energy prologue: the pair's epilogue warps arrive
-        mbar_init(&w_full[0], 1), mbar_init(&w_full[1], 1), mbar_init(&w_empty[0], 1), mbar_init(&w_empty[1], 1);
+        mbar_init(&act_full[1], 1), mbar_init(&act_empty[0], 1), mbar_init(&act_empty[1], 1);
+        for (int i = 0; i < kChain2SlotsMax; ++i) mbar_init(&w_full[i], 1), mbar_init(&w_empty[i], 1);
         mbar_init(acc_full, 1), mbar_init(act_ready, 2 * kChainEpiWarps);
         fence_barrier_init();
     }
@@ -837,7 +849,7 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
     // idle rows of each quarter are never written by TMA: clear them once so the first layer's MMA reads zeros
     {
         const int idle = 32 - rows_q;
-        const int total = 8 * 4 * idle * 8;                    // 16-byte slots in the eight tiles
+        const int total = 2 * g.n_act * 4 * idle * 8;          // 16-byte slots in the activation tiles
         for (int i = threadIdx.x; i < total; i += kChainThreads) {
             const int tile = i / (4 * idle * 8), r = i % (4 * idle * 8);
             const int q = r / (idle * 8), rr = (r % (idle * 8)) / 8, c16 = r % 8;
@@ -864,33 +876,50 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
         if (lane == 0) {
             const uint32_t box_bytes = (uint32_t)rows_q * 128;
             const uint32_t act_bar = mapa_u32(smem_u32(act_full), 0);
-            if (rank == 0 && !en_on) mbar_arrive_expect_tx(act_full, 2u * (uint32_t)nkb0 * 8 * box_bytes);
-            for (int kb = 0; kb < (en_on ? 0 : nkb0); ++kb) {
-                uint8_t* dst = act + g.L[0].in_buf[kb] * 2 * kATile;
+            const bool stream0 = g.stream0 && !en_on;
+            auto load_act = [&](int kb, int buf, uint32_t bar) {
+                uint8_t* dst = act + buf * 2 * kATile;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    tma_load_3d_pair(dst + q * kQuarterBytes, &maps.a_hi, kb * 64, 0, win0 + q * g.wpq, act_bar);
-                    tma_load_3d_pair(dst + kATile + q * kQuarterBytes, &maps.a_lo, kb * 64, 0, win0 + q * g.wpq, act_bar);
+                    tma_load_3d_pair(dst + q * kQuarterBytes, &maps.a_hi, kb * 64, 0, win0 + q * g.wpq, bar);
+                    tma_load_3d_pair(dst + kATile + q * kQuarterBytes, &maps.a_lo, kb * 64, 0, win0 + q * g.wpq, bar);
                 }
-            }
-            for (int l = 0; l < g.nl; ++l) prefetch_tmap(&maps.w[g.L[l].wmap][0]);
+            };
             int b = 0;
-            for (int l = 0; l < g.nl; ++l) {
-                const Chain2Layer& L = g.L[l];
+            auto load_weights = [&](const Chain2Layer& L, int i, int kb) {
                 const int half = 3 * L.ncta / 2;                           // slab rows per CTA
                 const uint32_t bt = (uint32_t)half * 128;
-                for (int i = 0; i < L.ny; ++i)
-                    for (int kb = 0; kb < L.num_kb; ++kb, ++b) {
-                        const int slot = b & 1;
-                        mbar_wait(&w_empty[slot], (uint32_t)(((b >> 1) & 1) ^ 1));
-                        uint8_t* dst = wring + slot * kChain2WSlot;
-                        if (rank == 0) mbar_arrive_expect_tx(&w_full[slot], 2u * 3u * bt);
-                        const uint32_t bar = mapa_u32(smem_u32(&w_full[slot]), 0);
-                        const int row = (L.y0 + i) * 3 * L.ncta + (int)rank * half;
-                        tma_load_2d_pair(dst, &maps.w[L.wmap][0], kb * 64, row, bar);
-                        tma_load_2d_pair(dst + bt, &maps.w[L.wmap][1], kb * 64, row, bar);
-                        tma_load_2d_pair(dst + 2 * bt, &maps.w[L.wmap][2], kb * 64, row, bar);
+                const int slot = b % nslots;
+                mbar_wait(&w_empty[slot], (uint32_t)(((b / nslots) & 1) ^ 1));
+                uint8_t* dst = wring + slot * kChain2WSlot;
+                if (rank == 0) mbar_arrive_expect_tx(&w_full[slot], 2u * 3u * bt);
+                const uint32_t bar = mapa_u32(smem_u32(&w_full[slot]), 0);
+                const int row = (L.y0 + i) * 3 * L.ncta + (int)rank * half;
+                tma_load_2d_pair(dst, &maps.w[L.wmap][0], kb * 64, row, bar);
+                tma_load_2d_pair(dst + bt, &maps.w[L.wmap][1], kb * 64, row, bar);
+                tma_load_2d_pair(dst + 2 * bt, &maps.w[L.wmap][2], kb * 64, row, bar);
+                ++b;
+            };
+            if (!stream0) {
+                if (rank == 0 && !en_on) mbar_arrive_expect_tx(act_full, 2u * (uint32_t)nkb0 * 8 * box_bytes);
+                for (int kb = 0; kb < (en_on ? 0 : nkb0); ++kb) load_act(kb, g.L[0].in_buf[kb], act_bar);
+            }
+            for (int l = 0; l < g.nl; ++l) prefetch_tmap(&maps.w[g.L[l].wmap][0]);
+            for (int l = 0; l < g.nl; ++l) {
+                const Chain2Layer& L = g.L[l];
+                if (l == 0 && stream0) {
+                    // K block outer, slab inner: the activation K blocks stream through buffers 0 / 1
+                    for (int kb = 0; kb < L.num_kb; ++kb) {
+                        const int ab = kb & 1, use = kb >> 1;
+                        if (use > 0) mbar_wait(&act_empty[ab], (uint32_t)((use - 1) & 1));
+                        if (rank == 0) mbar_arrive_expect_tx(&act_full[ab], 2u * 8 * box_bytes);
+                        load_act(kb, ab, mapa_u32(smem_u32(&act_full[ab]), 0));
+                        for (int i = 0; i < L.ny; ++i) load_weights(L, i, kb);
                     }
+                    continue;
+                }
+                for (int i = 0; i < L.ny; ++i)
+                    for (int kb = 0; kb < L.num_kb; ++kb) load_weights(L, i, kb);
             }
         }
     } else if (warp == 1) {
@@ -899,7 +928,8 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
             int b = 0;
             for (int l = 0; l < g.nl; ++l) {
                 const Chain2Layer& L = g.L[l];
-                if (l == 0 && !en_on) mbar_wait(act_full, 0);
+                if (l == 0 && g.stream0 && !en_on) {}                     // (waits per K block below)
+                else if (l == 0 && !en_on) mbar_wait(act_full, 0);
                 else if (l == 0) mbar_wait_cluster(act_full, 0);          // the pair's energy prologues have written the tiles
                 else mbar_wait_cluster(act_ready, (uint32_t)((l - 1) & 1));
                 tc_fence_after();
@@ -907,25 +937,37 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
                 const int np = 3 * L.ncta;
                 const uint32_t bt = (uint32_t)(np / 2) * 128;
                 const uint32_t idesc = instr_desc_f16(2 * kRows, np);
-                for (int i = 0; i < L.ny; ++i) {
+                auto block = [&](int i, int kb, int buf) {
                     const uint32_t acc = tmem_base + (uint32_t)(((l + i) & 1) * 192);
-                    for (int kb = 0; kb < L.num_kb; ++kb, ++b) {
-                        const int slot = b & 1;
-                        mbar_wait(&w_full[slot], (uint32_t)((b >> 1) & 1));
-                        tc_fence_after();
-                        const uint8_t* in = act + L.in_buf[kb] * 2 * kATile;
-                        const uint32_t wb = smem_u32(wring + slot * kChain2WSlot);
-                        const uint64_t a_hi = make_smem_desc(smem_u32(in)), a_lo = make_smem_desc(smem_u32(in + kATile));
-                        const uint64_t b_hi = make_smem_desc(wb), b_lo = make_smem_desc(wb + bt), b_hs = make_smem_desc(wb + 2 * bt);
+                    const int slot = b % nslots;
+                    mbar_wait(&w_full[slot], (uint32_t)((b / nslots) & 1));
+                    tc_fence_after();
+                    const uint8_t* in = act + buf * 2 * kATile;
+                    const uint32_t wb = smem_u32(wring + slot * kChain2WSlot);
+                    const uint64_t a_hi = make_smem_desc(smem_u32(in)), a_lo = make_smem_desc(smem_u32(in + kATile));
+                    const uint64_t b_hi = make_smem_desc(wb), b_lo = make_smem_desc(wb + bt), b_hs = make_smem_desc(wb + 2 * bt);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                            umma_f16_pair(acc, a_lo + adv, b_hs + adv, idesc, (kb > 0) || (k != 0));      // small terms first
-                            umma_f16_pair(acc, a_hi + adv, b_lo + adv, idesc, 1);
-                            umma_f16_pair(acc, a_hi + adv, b_hi + adv, idesc, 1);
-                        }
-                        umma_commit_pair(&w_empty[slot], 3);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                        umma_f16_pair(acc, a_lo + adv, b_hs + adv, idesc, (kb > 0) || (k != 0));      // small terms first
+                        umma_f16_pair(acc, a_hi + adv, b_lo + adv, idesc, 1);
+                        umma_f16_pair(acc, a_hi + adv, b_hi + adv, idesc, 1);
                     }
+                    umma_commit_pair(&w_empty[slot], 3);
+                    ++b;
+                };
+                if (l == 0 && g.stream0 && !en_on) {
+                    // K block outer, slab inner (every accumulator still sums its K blocks in ascending order)
+                    for (int kb = 0; kb < L.num_kb; ++kb) {
+                        const int ab = kb & 1;
+                        mbar_wait(&act_full[ab], (uint32_t)((kb >> 1) & 1));
+                        tc_fence_after();
+                        for (int i = 0; i < L.ny; ++i) block(i, kb, ab);
+                        umma_commit_pair(&act_empty[ab], 3);           // the buffer may take the K block after next
+                    }
+                } else {
+                    for (int i = 0; i < L.ny; ++i)
+                        for (int kb = 0; kb < L.num_kb; ++kb) block(i, kb, L.in_buf[kb]);
                 }
                 umma_commit_pair(acc_full, 3);
             }
@@ -1488,46 +1530,57 @@ int launch_tap_chain_pair(cudaStream_t stream, void* owner, const TapChainLaunch
     if (!L.out_lo) maps.o_hi = maps.a_hi, maps.o_lo = maps.a_lo;      // unused by the kernel
     for (int l = 0; l < kChain2Max; ++l) maps.w[l][0] = maps.w[l][1] = maps.w[l][2] = maps.a_hi;
     Chain2Args a;
-    memset(&a, 0, sizeof(a));
-    // buffer plan
-    int cur[4], ncur = w[0]->Kp / 64;                 // buffers holding the current layer's input K blocks
-    for (int i = 0; i < ncur; ++i) cur[i] = i;
     int np = 0;
-    for (int l = 0; l < L.nl; ++l) {
-        maps.w[l][0] = w[l]->map_hi2, maps.w[l][1] = w[l]->map_lo2, maps.w[l][2] = w[l]->map_hs2;
-        const bool last = l == L.nl - 1;
-        const int gridy = w[l]->gridy;
-        int next[4], nnext = 0;
-        for (int y0 = 0; y0 < gridy; y0 += 2) {
-            GEM_REQUIRE(np < kChain2Max, "too many pseudo-layers in the chain");
-            Chain2Layer& c = a.L[np++];
-            c.bias = L.bias[l], c.aux_bits = L.aux_bits[l], c.sign_out = L.sign_out[l];
-            c.ncta = w[l]->ncta, c.y0 = y0, c.ny = gridy - y0 < 2 ? gridy - y0 : 2;
-            c.num_kb = w[l]->Kp / 64, c.N = w[l]->N, c.epi = L.epi[l], c.wmap = l;
-            c.out_kind = last ? (L.out_lo ? 1 : 2) : 0;
-            for (int i = 0; i < c.num_kb; ++i) c.in_buf[i] = (unsigned char)cur[i];
-            const bool last_pseudo = y0 + 2 >= gridy;
-            for (int i = 0; i < c.ny; ++i) {
-                // a free buffer: not an input (unless this is the layer's last pseudo-layer), not an output kept for
-                // the next layer, not one a TMA store of an earlier pseudo-layer of this layer may still be reading
-                int pick = -1;
-                for (int bfr = 0; bfr < 4 && pick < 0; ++bfr) {
-                    bool used = false;
-                    for (int k = 0; k < nnext; ++k) used |= next[k] == bfr;
-                    if (!last_pseudo)
-                        for (int k = 0; k < ncur; ++k) used |= cur[k] == bfr;
-                    for (int k = 0; k < i; ++k) used |= c.stage_buf[k] == bfr;
-                    if (!used) pick = bfr;
+    // buffer plan over nbuf activation buffers.  stream: the first layer's K blocks pass through buffers 0 / 1 while its
+    // MMAs run (they are dead once its accumulators are complete, so its outputs may take them)
+    auto plan = [&](int nbuf, bool stream) -> bool {
+        memset(&a, 0, sizeof(a));
+        np = 0;
+        int cur[4], ncur = w[0]->Kp / 64;             // buffers holding the current layer's input K blocks
+        for (int i = 0; i < ncur; ++i) cur[i] = stream ? (i & 1) : i;
+        if (!stream && ncur > nbuf) return false;
+        for (int l = 0; l < L.nl; ++l) {
+            maps.w[l][0] = w[l]->map_hi2, maps.w[l][1] = w[l]->map_lo2, maps.w[l][2] = w[l]->map_hs2;
+            const bool last = l == L.nl - 1;
+            const int gridy = w[l]->gridy;
+            if (l == 0 && stream && gridy > 2) return false;           // (one pseudo-layer: both slabs accumulate per K block)
+            int next[4], nnext = 0;
+            for (int y0 = 0; y0 < gridy; y0 += 2) {
+                if (np >= kChain2Max) return false;
+                Chain2Layer& c = a.L[np++];
+                c.bias = L.bias[l], c.aux_bits = L.aux_bits[l], c.sign_out = L.sign_out[l];
+                c.ncta = w[l]->ncta, c.y0 = y0, c.ny = gridy - y0 < 2 ? gridy - y0 : 2;
+                c.num_kb = w[l]->Kp / 64, c.N = w[l]->N, c.epi = L.epi[l], c.wmap = l;
+                c.out_kind = last ? (L.out_lo ? 1 : 2) : 0;
+                for (int i = 0; i < c.num_kb; ++i) c.in_buf[i] = (unsigned char)cur[i];
+                const bool last_pseudo = y0 + 2 >= gridy;
+                for (int i = 0; i < c.ny; ++i) {
+                    // a free buffer: not an input (unless this is the layer's last pseudo-layer), not an output kept for
+                    // the next layer, not one a TMA store of an earlier pseudo-layer of this layer may still be reading
+                    int pick = -1;
+                    for (int bfr = 0; bfr < nbuf && pick < 0; ++bfr) {
+                        bool used = false;
+                        for (int k = 0; k < nnext; ++k) used |= next[k] == bfr;
+                        if (!last_pseudo)
+                            for (int k = 0; k < ncur; ++k) used |= cur[k] == bfr;
+                        for (int k = 0; k < i; ++k) used |= c.stage_buf[k] == bfr;
+                        if (!used) pick = bfr;
+                    }
+                    if (pick < 0) return false;
+                    c.stage_buf[i] = (unsigned char)pick;
+                    next[nnext++] = pick;
                 }
-                GEM_REQUIRE(pick >= 0, "no free activation buffer for the chain");
-                c.stage_buf[i] = (unsigned char)pick;
-                next[nnext++] = pick;
             }
+            if (nnext > 4) return false;
+            for (int i = 0; i < nnext; ++i) cur[i] = next[i];
+            ncur = nnext;
         }
-        GEM_REQUIRE(nnext <= 4, "layer output does not fit the activation buffers");
-        for (int i = 0; i < nnext; ++i) cur[i] = next[i];
-        ncur = nnext;
-    }
+        a.n_act = nbuf, a.n_slots = nbuf == 2 ? 4 : 2, a.stream0 = stream ? 1 : 0;
+        return true;
+    };
+    static const bool stream_ok = [] { const char* e = getenv("GEM_CHAIN_STREAM"); return !e || e[0] != '0'; }();
+    const bool want_stream = stream_ok && !L.energy && w[0]->Kp / 64 == 4;
+    if (!(want_stream && plan(2, true))) GEM_REQUIRE(plan(4, false), "no free activation buffer for the chain");
     a.nl = np, a.W = L.W, a.T = L.T, a.wpq = wpq, a.out_plain = L.out_lo ? nullptr : (float*)L.out_hi;
     a.dbg = g_tap_dbg;
     a.status = L.status;

@@ -1,10 +1,9 @@
-timeout 600 python -m pytest tests/test_gpu_planar.py -q -m gpu > gpurun_out/probe_tests.log 2>&1; echo tests rc $?
-B="timeout 300 python bench.py --no-cpu-baseline --no-unpickle --steps 10 --warmup 5 --heat-layout tiled"
-run() { name=$1; shift; env "$@" $B > gpurun_out/e2e_t_$name.json 2>gpurun_out/e2e_t_$name.err; }
-run pf8 X=1
-run pf4 GEM_TEXEL_PREFETCH_CTAS=4
-run pf16 GEM_TEXEL_PREFETCH_CTAS=16
-run pf8c16 GEM_TEXEL_COLD_CTAS=16
-run pf8c64 GEM_TEXEL_COLD_CTAS=64
-run pf8t256 GEM_TEXEL_PREFETCH_THREADS=256
+timeout 600 python -m pytest tests/test_gpu_tc_gemm.py tests/test_gpu_kernels.py tests/test_gpu_fused_energy.py tests/test_gpu_pipeline.py -x -q -m gpu > gpurun_out/chain_tests.log 2>&1; echo tests rc $?
+timeout 120 python tools/dbg_chain.py 468 > gpurun_out/dbg_chain_468_stream.txt 2>&1
+GEM_CHAIN_STREAM=0 timeout 120 python tools/dbg_chain.py 468 > gpurun_out/dbg_chain_468_nostream.txt 2>&1
+B="timeout 300 python bench.py --no-cpu-baseline --no-unpickle --no-e2e --steps 10 --warmup 5"
+$B > gpurun_out/chain_stream.json 2>gpurun_out/chain_stream.err
+GEM_CHAIN_STREAM=0 $B > gpurun_out/chain_nostream.json 2>gpurun_out/chain_nostream.err
+$B > gpurun_out/chain_stream2.json 2>gpurun_out/chain_stream2.err
+GEM_CHAIN_STREAM=0 $B > gpurun_out/chain_nostream2.json 2>gpurun_out/chain_nostream2.err
 echo done
