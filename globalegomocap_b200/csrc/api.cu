@@ -369,6 +369,10 @@ int gem_debug_gemm_pair(int mode) {
     gem::g_gemm_pair = mode;
     return GEM_OK;
 }
+int gem_debug_energy_fixed(int mode) {      // 0: the runtime-shape energy kernel for every launch, 1: compile-time shape where it applies, -1: default
+    gem::g_energy_fixed = mode;
+    return GEM_OK;
+}
 
 int gem_ctx_set_chunks(gem_ctx* c, int n_chunks) {
     GEM_REQUIRE(c != nullptr && n_chunks >= 0 && n_chunks <= 16, "n_chunks must be in [0, 16] (0 = automatic)");

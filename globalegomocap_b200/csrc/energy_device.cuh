@@ -39,6 +39,20 @@ struct EnergyCommon {
     SkeletonConst skel;
 };
 
+// Problem shape as seen by the per-joint code.  ShapeDyn reads the launch's runtime values; ShapeFix carries them as
+// compile-time constants (the reference's own configuration: 10 frames x 15 joints, 64 x 64 maps, 11 or 14 polynomial
+// coefficients), which turns the divisions by J into multiplications, the texel addresses into shifts and unrolls the
+// polynomial.  Same operations on the same values in the same order: results do not depend on the policy.
+struct ShapeDyn {
+    int T, J, H, Wd, n_poly;
+    __device__ __forceinline__ explicit ShapeDyn(const EnergyCommon& a) : T(a.T), J(a.J), H(a.H), Wd(a.Wd), n_poly(a.cam.n_poly) {}
+};
+template <int kT, int kJ, int kH, int kW, int kNP>
+struct ShapeFix {
+    static constexpr int T = kT, J = kJ, H = kH, Wd = kW, n_poly = kNP;
+    __device__ __forceinline__ explicit ShapeFix(const EnergyCommon&) {}
+};
+
 __device__ __forceinline__ float texel(const float* __restrict__ heat, int64_t frame, int y, int x, int j, int H,
                                        int Wd, int J, int planar = 0) {
     if (x < 0 || x >= Wd || y < 0 || y >= H) return 0.f;     // padding_mode='zeros'
@@ -298,13 +312,16 @@ __device__ __forceinline__ void tiled_fetch_event(const EnergyCommon& a, size_t 
 struct Proj {
     float r, inv, rho, drho, ix, iy, fx0, fy0;
 };
-__device__ __forceinline__ bool project_joint(const CameraConst& c_cam, float x, float y, float z, int H, int Wd, Proj& p) {
+__device__ __forceinline__ bool project_joint(const CameraConst& c_cam, float x, float y, float z, int H, int Wd, Proj& p,
+                                              int n_poly = -1) {
+    if (n_poly < 0) n_poly = c_cam.n_poly;
     const float zn = -z;
     p.r = sqrtf(x * x + y * y);
     if (p.r == 0.f) return false;
     const float theta = atanf(zn / p.r);
     float rho = c_cam.poly[0], drho = 0.f, ti = 1.f;
-    for (int i = 1; i < c_cam.n_poly; ++i) {          // power accumulation, not Horner
+#pragma unroll
+    for (int i = 1; i < n_poly; ++i) {                // power accumulation, not Horner
         drho += (float)i * c_cam.poly[i] * ti;
         ti *= theta;
         rho += ti * c_cam.poly[i];
@@ -330,30 +347,51 @@ struct JointTexels {
     float nw, ne, sw, se;
     bool rp;
 };
-__device__ __forceinline__ void joint_gather(const EnergyCommon& a, const float* X, int w, int k, JointTexels& jt) {
+template <class S>
+__device__ __forceinline__ void joint_gather(const EnergyCommon& a, const S& sh, const float* X, int w, int k, JointTexels& jt) {
     jt.rp = false;
     jt.nw = jt.ne = jt.sw = jt.se = 0.f;
     if (a.wr == 0.f) return;
-    const int t = k / a.J, j = k - t * a.J;
+    const int t = k / sh.J, j = k - t * sh.J;
     const float x = X[k * 3 + 0], y = X[k * 3 + 1], z = X[k * 3 + 2];
-    if (!project_joint(a.cam, x, y, z, a.H, a.Wd, jt.pj)) {
+    if (!project_joint(a.cam, x, y, z, sh.H, sh.Wd, jt.pj, sh.n_poly)) {
         if (a.status) atomicOr(a.status + w, GEM_WIN_NORM_ZERO);
-    } else if (jt.pj.fx0 >= -1.f && jt.pj.fx0 <= (float)a.Wd && jt.pj.fy0 >= -1.f && jt.pj.fy0 <= (float)a.H) {
+    } else if (jt.pj.fx0 >= -1.f && jt.pj.fx0 <= (float)sh.Wd && jt.pj.fy0 >= -1.f && jt.pj.fy0 <= (float)sh.H) {
         // (anything further than one texel outside contributes exactly 0)
         jt.rp = true;
         const int x0 = (int)jt.pj.fx0, y0 = (int)jt.pj.fy0;
         const int64_t frame = a.frame_base[w] + t;
         if (a.patch && a.planar == 2) {
-            cache_lookup_tiled(a, (size_t)w * (a.T * a.J) + k, frame, j, x0, y0, true, jt.nw, jt.ne, jt.sw, jt.se);
+            cache_lookup_tiled(a, (size_t)w * (sh.T * sh.J) + k, frame, j, x0, y0, true, jt.nw, jt.ne, jt.sw, jt.se);
         } else if (a.patch && a.planar) {
-            cache_lookup_planar(a, (size_t)w * (a.T * a.J) + k, frame, j, x0, y0, true, jt.nw, jt.ne, jt.sw, jt.se);
+            cache_lookup_planar(a, (size_t)w * (sh.T * sh.J) + k, frame, j, x0, y0, true, jt.nw, jt.ne, jt.sw, jt.se);
         } else if (a.patch) {
-            cache_lookup(a, (size_t)w * (a.T * a.J) + k, frame, j, x0, y0, true, jt.nw, jt.ne, jt.sw, jt.se);
+            cache_lookup(a, (size_t)w * (sh.T * sh.J) + k, frame, j, x0, y0, true, jt.nw, jt.ne, jt.sw, jt.se);
         } else {
-            jt.nw = texel(a.heat, frame, y0, x0, j, a.H, a.Wd, a.J, a.planar);
-            jt.ne = texel(a.heat, frame, y0, x0 + 1, j, a.H, a.Wd, a.J, a.planar);
-            jt.sw = texel(a.heat, frame, y0 + 1, x0, j, a.H, a.Wd, a.J, a.planar);
-            jt.se = texel(a.heat, frame, y0 + 1, x0 + 1, j, a.H, a.Wd, a.J, a.planar);
+            // one 64-bit base per map (or frame), 32-bit offsets inside it
+            const int H = sh.H, Wd = sh.Wd, J = sh.J;
+            const bool xl = x0 >= 0 && x0 < Wd, xr = x0 + 1 >= 0 && x0 + 1 < Wd;           // padding_mode='zeros'
+            const bool yt = y0 >= 0 && y0 < H, yb = y0 + 1 >= 0 && y0 + 1 < H;
+            if (a.planar == 2) {           // tiled: [H/4][Wd/8] tiles of 4 rows x 8 texels
+                const float* map = a.heat + (frame * J + j) * (int64_t)(H * Wd);
+                auto at = [&](int yy, int xx) { return __ldg(map + (((yy >> 2) * (Wd >> 3) + (xx >> 3)) * 32 + (yy & 3) * 8 + (xx & 7))); };
+                jt.nw = (xl && yt) ? at(y0, x0) : 0.f;
+                jt.ne = (xr && yt) ? at(y0, x0 + 1) : 0.f;
+                jt.sw = (xl && yb) ? at(y0 + 1, x0) : 0.f;
+                jt.se = (xr && yb) ? at(y0 + 1, x0 + 1) : 0.f;
+            } else if (a.planar) {
+                const float* map = a.heat + (frame * J + j) * (int64_t)(H * Wd);
+                jt.nw = (xl && yt) ? __ldg(map + (y0 * Wd + x0)) : 0.f;
+                jt.ne = (xr && yt) ? __ldg(map + (y0 * Wd + x0 + 1)) : 0.f;
+                jt.sw = (xl && yb) ? __ldg(map + ((y0 + 1) * Wd + x0)) : 0.f;
+                jt.se = (xr && yb) ? __ldg(map + ((y0 + 1) * Wd + x0 + 1)) : 0.f;
+            } else {
+                const float* map = a.heat + frame * (int64_t)(H * Wd * J) + j;
+                jt.nw = (xl && yt) ? __ldg(map + (y0 * Wd + x0) * J) : 0.f;
+                jt.ne = (xr && yt) ? __ldg(map + (y0 * Wd + x0 + 1) * J) : 0.f;
+                jt.sw = (xl && yb) ? __ldg(map + ((y0 + 1) * Wd + x0) * J) : 0.f;
+                jt.se = (xr && yb) ? __ldg(map + ((y0 + 1) * Wd + x0 + 1) * J) : 0.f;
+            }
         }
     }
 }
@@ -361,12 +399,13 @@ __device__ __forceinline__ void joint_gather(const EnergyCommon& a, const float*
 // The five energy terms of joint-frame k = t*J + j of window w and its dE/dx: X / X0 are the window's pose and anchor
 // (T*J*3 floats, shared memory), jt the joint's gathered texels.  e = {E_3d, E_smooth, E_bone, E_vae, E_reproj}
 // contributions, g = weighted gradient.
-__device__ __forceinline__ void joint_terms(const EnergyCommon& a, const float* X, const float* X0, int w, int k,
+template <class S>
+__device__ __forceinline__ void joint_terms(const EnergyCommon& a, const S& sh, const float* X, const float* X0, int w, int k,
                                             const JointTexels& jt, float (&e)[5], float (&g)[3]) {
     float e3d = 0.f, esm = 0.f, ebn = 0.f, eva = 0.f, erp = 0.f;
     float gx = 0.f, gy = 0.f, gz = 0.f;
     {
-        const int t = k / a.J, j = k - t * a.J;
+        const int t = k / sh.J, j = k - t * sh.J;
         const float x = X[k * 3 + 0], y = X[k * 3 + 1], z = X[k * 3 + 2];
         const bool rp = jt.rp;
         const Proj& pj = jt.pj;
@@ -385,18 +424,25 @@ __device__ __forceinline__ void joint_terms(const EnergyCommon& a, const float* 
         }
         // E_smooth: a_s = (x_s - x_{s+1}) - (x_{s+1} - x_{s+2}), s = 0..T-3   optimizer.py:202-208
         {
+            // the five frames t-2 .. t+2 of this joint, each read once (rows outside the window are never used)
+            float v[5][3];
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                const int f = t - 2 + m;
+                const bool in = (m == 2) || (f >= 0 && f < sh.T);
+                const float* pf = X + (k + (in ? (m - 2) * sh.J : 0)) * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[m][c] = (m == 2) ? (c == 0 ? x : (c == 1 ? y : z)) : pf[c];
+            }
             float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < 3; ++q) {        // q = 0: a_t (coef 1), 1: a_{t-1} (coef -2), 2: a_{t-2} (coef 1)
                 const int s = t - q;
-                if (s < 0 || s > a.T - 3) continue;
+                if (s < 0 || s > sh.T - 3) continue;
                 const float coef = (q == 1) ? -2.f : 1.f;
-                const float* p0 = X + ((s)*a.J + j) * 3;
-                const float* p1 = X + ((s + 1) * a.J + j) * 3;
-                const float* p2 = X + ((s + 2) * a.J + j) * 3;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float ac = (p0[c] - p1[c]) - (p1[c] - p2[c]);
+                    const float ac = (v[2 - q][c] - v[3 - q][c]) - (v[3 - q][c] - v[4 - q][c]);
                     acc[c] += coef * ac;
                     if (q == 0) esm += ac * ac;
                 }
@@ -407,8 +453,8 @@ __device__ __forceinline__ void joint_terms(const EnergyCommon& a, const float* 
         {
             const float* mb = a.mean_bone + (size_t)a.clip[w] * a.J;
             const int p = a.skel.parent[j];
-            const float bx = x - X[(t * a.J + p) * 3 + 0], by = y - X[(t * a.J + p) * 3 + 1],
-                        bz = z - X[(t * a.J + p) * 3 + 2];
+            const float* Xt = X + (k - j) * 3;                     // frame t's joints
+            const float bx = x - Xt[p * 3 + 0], by = y - Xt[p * 3 + 1], bz = z - Xt[p * 3 + 2];
             const float len = sqrtf(bx * bx + by * by + bz * bz);
             const float diff = len - mb[j];
             ebn = diff * diff;
@@ -418,8 +464,7 @@ __device__ __forceinline__ void joint_terms(const EnergyCommon& a, const float* 
             }
             for (int ci = a.skel.child_start[j]; ci < a.skel.child_start[j + 1]; ++ci) {   // this joint as a parent
                 const int cj = a.skel.child_list[ci];
-                const float cx = X[(t * a.J + cj) * 3 + 0] - x, cy = X[(t * a.J + cj) * 3 + 1] - y,
-                            cz = X[(t * a.J + cj) * 3 + 2] - z;
+                const float cx = Xt[cj * 3 + 0] - x, cy = Xt[cj * 3 + 1] - y, cz = Xt[cj * 3 + 2] - z;
                 const float cl = sqrtf(cx * cx + cy * cy + cz * cz);
                 if (cl > 0.f) {
                     const float c = a.wb * (2.f * (cl - mb[cj])) / cl;
@@ -436,8 +481,8 @@ __device__ __forceinline__ void joint_terms(const EnergyCommon& a, const float* 
             erp = -(nw * (wx0 * wy0) + ne * (wx1 * wy0) + sw * (wx0 * wy1) + se * (wx1 * wy1));
             const float ds_dix = -nw * wy0 + ne * wy0 - sw * wy1 + se * wy1;
             const float ds_diy = -nw * wx0 - ne * wx1 + sw * wx0 + se * wx1;
-            const float du = ds_dix * ((float)(a.Wd - 1) * 0.5f / 512.f);   // dS/du
-            const float dv = ds_diy * ((float)(a.H - 1) * 0.5f / 512.f);    // dS/dv
+            const float du = ds_dix * ((float)(sh.Wd - 1) * 0.5f / 512.f);  // dS/du
+            const float dv = ds_diy * ((float)(sh.H - 1) * 0.5f / 512.f);   // dS/dv
             // fisheye Jacobian.  Only the energy's forward chain has to round like ATen's
             // ops; the gradient is held to 1e-4, so one reciprocal replaces the dozen IEEE divisions.
             const float r2 = r * r, q = r2 + z * z;
@@ -461,11 +506,12 @@ __device__ __forceinline__ void joint_terms(const EnergyCommon& a, const float* 
     g[0] = gx, g[1] = gy, g[2] = gz;
 }
 
-__device__ __forceinline__ void joint_energy_grad(const EnergyCommon& a, const float* X, const float* X0, int w, int k,
+template <class S>
+__device__ __forceinline__ void joint_energy_grad(const EnergyCommon& a, const S& sh, const float* X, const float* X0, int w, int k,
                                                   float (&e)[5], float (&g)[3]) {
     JointTexels jt;
-    joint_gather(a, X, w, k, jt);
-    joint_terms(a, X, X0, w, k, jt, e, g);
+    joint_gather(a, sh, X, w, k, jt);
+    joint_terms(a, sh, X, X0, w, k, jt, e, g);
 }
 
 // optimizer.py:239-240 (left to right; the reproj product is skipped when its weight is 0) from the window's five

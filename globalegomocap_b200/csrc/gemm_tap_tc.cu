@@ -1038,14 +1038,14 @@ tc_tap_chain2_kernel(const __grid_constant__ Chain2Maps maps, const __grid_const
                     ww[u] = v / wpw, kk[u] = (v - ww[u] * wpw) * 32 + lane;
                     on[u] = ww[u] < nwin && kk[u] < TJ;
                     jt[u].rp = false;
-                    if (on[u]) joint_gather(en, s_x + ww[u] * n, winq + ww[u], kk[u], jt[u]);
+                    if (on[u]) joint_gather(en, ShapeDyn(en), s_x + ww[u] * n, winq + ww[u], kk[u], jt[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int it = 2 * half + u;
                     const int v = sub + it * 4;
                     float e5[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, g3[3] = {0.f, 0.f, 0.f};
-                    if (on[u]) joint_terms(en, s_x + ww[u] * n, s_x0 + ww[u] * n, winq + ww[u], kk[u], jt[u], e5, g3);
+                    if (on[u]) joint_terms(en, ShapeDyn(en), s_x + ww[u] * n, s_x0 + ww[u] * n, winq + ww[u], kk[u], jt[u], e5, g3);
                     gv[it][0] = g3[0], gv[it][1] = g3[1], gv[it][2] = g3[2];
                     if (v < g.wpq * wpw) {                                // (warp-uniform)
                         const float r0 = warp_sum(e5[0]), r1 = warp_sum(e5[1]), r2 = warp_sum(e5[2]), r3 = warp_sum(e5[3]),

@@ -649,8 +649,13 @@ struct KeyHash {
 };
 struct TcState {
     std::unordered_map<std::pair<const float*, int>, WeightSplit, KeyHash> weights;   // (caller's weight pointer, scheme)
-    void *a_hi = nullptr, *a_lo = nullptr;
-    size_t a_capacity = 0;                                    // bytes in each of a_hi / a_lo
+    // split copies of activations that arrive un-split (the layer-by-layer fallbacks, gem_gemm): one pair of buffers per
+    // STREAM, because a ctx's slices run concurrently on their own streams and each may be in one of these launches
+    struct Scratch {
+        void *hi = nullptr, *lo = nullptr;
+        size_t capacity = 0;                                  // bytes in each of hi / lo
+    };
+    std::unordered_map<cudaStream_t, Scratch> scratch;
 };
 std::mutex g_mu;
 std::unordered_map<void*, TcState*> g_states;                // one per workspace owner (ctx)
@@ -777,22 +782,28 @@ int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, s
     uint64_t pitch = (uint64_t)g.lda;
     if (!a_hi) {
         const size_t need = (size_t)g.M * g.K * esz;
-        if (need > st->a_capacity) {
+        TcState::Scratch* sc;
+        {
+            std::lock_guard<std::mutex> lk(g_mu);
+            sc = &st->scratch[stream];                        // (references into an unordered_map stay valid)
+        }
+        if (need > sc->capacity) {
             GEM_CUDA(cudaStreamSynchronize(stream));
-            if (st->a_hi) cudaFree(st->a_hi), cudaFree(st->a_lo);
-            GEM_CUDA(cudaMalloc(&st->a_hi, need));
-            GEM_CUDA(cudaMalloc(&st->a_lo, need));
-            st->a_capacity = need;
+            if (sc->hi) cudaFree(sc->hi), cudaFree(sc->lo);
+            sc->hi = sc->lo = nullptr, sc->capacity = 0;
+            GEM_CUDA(cudaMalloc(&sc->hi, need));
+            GEM_CUDA(cudaMalloc(&sc->lo, need));
+            sc->capacity = need;
         }
         const size_t n4 = (size_t)g.M * (g.K / 4);
         if (f16)
             split_f16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(g.A, g.lda, g.M, g.K, g.row_exp,
-                                                                            (uint16_t*)st->a_hi, (uint16_t*)st->a_lo, nullptr);
+                                                                            (uint16_t*)sc->hi, (uint16_t*)sc->lo, nullptr);
         else
-            split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(g.A, g.lda, g.M, g.K, (float*)st->a_hi,
-                                                                             (float*)st->a_lo);
+            split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(g.A, g.lda, g.M, g.K, (float*)sc->hi,
+                                                                             (float*)sc->lo);
         GEM_CHECK_LAUNCH();
-        a_hi = st->a_hi, a_lo = st->a_lo, pitch = (uint64_t)g.K;
+        a_hi = sc->hi, a_lo = sc->lo, pitch = (uint64_t)g.K;
     }
     CUtensorMap map_a_hi, map_a_lo;
     int rc = make_map(&map_a_hi, a_hi, f16, (uint64_t)g.M, (uint64_t)g.K, pitch);
@@ -943,7 +954,8 @@ void tc_gemm_release(void* owner) {
     if (it == g_states.end()) return;
     TcState* st = it->second;
     for (auto& kv : st->weights) cudaFree(kv.second.hi), cudaFree(kv.second.lo);
-    if (st->a_hi) cudaFree(st->a_hi), cudaFree(st->a_lo);
+    for (auto& kv : st->scratch)
+        if (kv.second.hi) cudaFree(kv.second.hi), cudaFree(kv.second.lo);
     delete st;
     g_states.erase(it);
 }

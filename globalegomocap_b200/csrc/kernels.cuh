@@ -45,6 +45,7 @@ int launch_tap_gemm_simt(cudaStream_t stream, const TapGemmArgs& g);
 // scheme: 1 = 3xTF32, 2 = fp16 hi + scaled fp16 lo (kind::f16, cross terms in their own accumulator)
 int launch_tap_gemm_tc(cudaStream_t stream, const TapGemmArgs& g, void* owner, size_t scheme);
 extern int g_gemm_pair;
+extern int g_energy_fixed;   // debug override of GEM_ENERGY_FIXED (gem_debug_energy_fixed): -1 = environment / default
 extern long long* g_gemm_dbg;
 int tc_gemm_prepare_weight(void* owner, cudaStream_t stream, const float* B, int ldb, int K, int N, int scheme = 1);
 int launch_split_f16(cudaStream_t stream, const float* A, int lda, int M, int K, const int32_t* row_exp, uint16_t* hi,

@@ -110,6 +110,48 @@ def test_energy_batch_independent_and_bulk_path_equal(engine, clip58):
         assert e == outs[0][0] and (gr == outs[0][1]).all()
 
 
+@pytest.mark.parametrize("layout", ["hwc", "planar", "tiled"])
+def test_energy_compile_time_shape_matches_runtime_shape(engine, clip58, layout):
+    """The energy kernel instantiated for the reference's configuration (10 x 15 joints, 64 x 64 maps, 11 polynomial
+    coefficients as compile-time constants: multiplications for the divisions by J, shifts for the texel addresses, an
+    unrolled polynomial) evaluates the same operations in the same order as the runtime-shape kernel: bit-identical
+    energies, terms and gradients in every heat-map layout, with joints at the map border and outside it."""
+    import ctypes as C
+    from globalegomocap_b200.engine import energy_weights
+    rng = np.random.default_rng(5)
+    W = 7
+    x0 = np.stack([clip58["estimated_local_skeleton"][8 * i:8 * i + 10] for i in range(W)]).astype(np.float32)
+    x = x0 + 0.02 * rng.standard_normal(x0.shape).astype(np.float32)
+    x[3] *= 1.8                                    # projections that leave the map
+    heat = np.ascontiguousarray(clip58["heatmap_list"][:8 * W + 10])
+    if layout == "planar":
+        heat_in = np.ascontiguousarray(heat.transpose(0, 3, 1, 2))
+    elif layout == "tiled":
+        n = heat.shape[0]
+        heat_in = np.ascontiguousarray(heat.transpose(0, 3, 1, 2).reshape(n, 15, 16, 4, 8, 8).transpose(0, 1, 2, 4, 3, 5))
+    else:
+        heat_in = heat
+    fb = np.arange(W, dtype=np.int64) * 8
+    mb = np.full(15, 0.25, np.float32)
+    w = energy_weights(0.01, 0.02, 0.05, 0.003, 0.04)
+    lib = engine.lib
+    lib.gem_debug_energy_fixed.argtypes = [C.c_int]
+    code = {"hwc": 0, "planar": 1, "tiled": 2}[layout]
+    out = {}
+    try:
+        engine.set_heat_layout(code)
+        for fixed in (0, 1):
+            lib.gem_debug_energy_fixed(fixed)
+            E, terms, grad, status = engine.energy_grad(x, x0, heat_in, fb, np.zeros(W, np.int32), mb, w)
+            out[fixed] = (E.cpu().numpy(), terms.cpu().numpy(), grad.cpu().numpy(), status.cpu().numpy())
+    finally:
+        lib.gem_debug_energy_fixed(-1)
+        engine.set_heat_layout(0)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    assert np.abs(out[1][2]).max() > 0
+
+
 def test_vae_decode_vjp_encode_match_reference(engine, golden_dir):
     g = np.load(os.path.join(golden_dir, "vae.npz"))
     pose = engine.decode(0, g["z"]).cpu().numpy()

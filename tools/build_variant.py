@@ -15,11 +15,26 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 from globalegomocap_b200 import build as B  # noqa: E402
 
-AFFECTED = ("api.cu", "energy.cu", "gemm_tap_tc.cu")
+
+
+def affected(defs):
+    """translation units (or the headers they include) that mention one of the macros"""
+    names = [d[2:].split("=")[0] for d in defs if d.startswith("-D")]
+    headers = {h: open(os.path.join(B.CSRC, h)).read() for h in os.listdir(B.CSRC) if h.endswith((".cuh", ".h"))}
+    hit_headers = {h for h, txt in headers.items() if any(n in txt for n in names)}
+    out = []
+    for src in B.SOURCES:
+        txt = open(os.path.join(B.CSRC, src)).read()
+        if any(n in txt for n in names) or any(f'"{h}"' in txt for h in hit_headers):
+            out.append(src)
+    return tuple(out)
+
 
 
 def main():
     name, defs = sys.argv[1], sys.argv[2:]
+    AFFECTED = affected(defs)
+    print("rebuilding", AFFECTED)
     B.build()
     out_dir = os.path.join(B.HERE, "_build_var", name)
     os.makedirs(out_dir, exist_ok=True)
