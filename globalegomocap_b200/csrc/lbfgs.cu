@@ -82,6 +82,9 @@ constexpr int kPer = 4 * kChunks;
 #ifndef GEM_LBFGS_RING
 #define GEM_LBFGS_RING 4
 #endif
+#ifndef GEM_LBFGS_SHARED_ADDR
+#define GEM_LBFGS_SHARED_ADDR 1   // 1: the recursion addresses its ring and barriers by 32-bit shared addresses held in registers
+#endif
 #ifndef GEM_LBFGS_L2HINT
 #define GEM_LBFGS_L2HINT 0  // 1: history rows of the recursion's first loop are loaded evict_last (the second loop re-reads
 #endif                      //    them in reverse order), those of the second loop evict_first
@@ -96,6 +99,42 @@ __device__ __forceinline__ void ld8(float (&r)[kPer], const float* __restrict__ 
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c < n4) v = *reinterpret_cast<const float4*>(p + 4 * c);
         r[4 * i + 0] = v.x, r[4 * i + 1] = v.y, r[4 * i + 2] = v.z, r[4 * i + 3] = v.w;
+    }
+}
+// the same from a 32-bit shared-window address (`addr` = this thread's first float4 of the row).  The history ring and
+// its barriers are addressed this way inside the recursion: through generic pointers every access re-derived the
+// shared window's base from two special registers (S2R), ~25 of the ~80 instructions a row costs a warp.
+__device__ __forceinline__ void lds8(float (&r)[kPer], uint32_t addr, int tid, int n4) {
+#pragma unroll
+    for (int i = 0; i < kChunks; ++i) {
+        const int c = tid + i * kLbThreads;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < n4)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(addr + (uint32_t)(i * kLbThreads * 16))
+                         : "memory");
+        r[4 * i + 0] = v.x, r[4 * i + 1] = v.y, r[4 * i + 2] = v.z, r[4 * i + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_addr, uint32_t parity) {      // mbar_wait (common.cuh) on a shared address
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar_addr), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if ((spin & 255u) == 255u) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ull) __trap();
+        }
     }
 }
 __device__ __forceinline__ void st8(float* __restrict__ p, const float (&r)[kPer], int tid, int n4) {
@@ -608,11 +647,19 @@ __device__ __forceinline__ void lbfgs_advance_window(const LbfgsBuffers& b, cons
         for (int i = 0; i < kPer; ++i) q[i] = -q[i];
         int r = 0;                                    // rows consumed from the ring
         float row[kPer];
+        uint32_t ring_s = smem_u32(ring) + (uint32_t)tid * 16u;            // this thread's first float4 of slot 0
+        uint32_t bars_s = smem_u32(full_bar);
+        asm volatile("" : "+r"(ring_s), "+r"(bars_s));                     // opaque: kept in registers, not re-derived per row
         auto next_row = [&]() {
             const uint32_t g = rows_done + (uint32_t)r;           // rows this group's ring has carried so far
-            const int slot = (int)(g % kRing);
+            const uint32_t slot = g % kRing;
+#if GEM_LBFGS_SHARED_ADDR
+            mbar_wait_s(bars_s + slot * 8u, (g / kRing) & 1u);
+            lds8(row, ring_s + slot * row_bytes, tid, n4);
+#else
             mbar_wait(&full_bar[slot], (g / kRing) & 1u);
             ld8(row, ring + (size_t)slot * n, tid, n4);
+#endif
             ++r;
         };
         if (pushed) {

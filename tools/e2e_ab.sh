@@ -1,7 +1,7 @@
-timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fused_energy.py tests/test_gpu_planar.py tests/test_gpu_pipeline.py tests/test_gpu_tc_gemm.py -x -q -m gpu > gpurun_out/en_tests.log 2>&1; echo tests rc $?
-B="timeout 300 python bench.py --no-cpu-baseline --no-unpickle --steps 10 --warmup 5"
-$B > gpurun_out/en_fixed.json 2>gpurun_out/en_fixed.err
-GEM_ENERGY_FIXED=0 $B > gpurun_out/en_dyn.json 2>gpurun_out/en_dyn.err
-$B > gpurun_out/en_fixed2.json 2>gpurun_out/en_fixed2.err
-GEM_ENERGY_FIXED=0 $B > gpurun_out/en_dyn2.json 2>gpurun_out/en_dyn2.err
+timeout 900 python -m pytest tests/test_gpu_lbfgs.py tests/test_gpu_pipeline.py tests/test_gpu_dist.py -x -q -m gpu > gpurun_out/lb2_tests.log 2>&1; echo tests rc $?
+B="timeout 300 python bench.py --no-cpu-baseline --no-unpickle --no-e2e --steps 10 --warmup 5"
+for v in base generic base generic; do
+  if [ $v = base ]; then unset GEM_B200_LIB; else export GEM_B200_LIB=$PWD/globalegomocap_b200/libgem_b200_$v.so; fi
+  $B > gpurun_out/lb2_$v.$RANDOM.json 2>>gpurun_out/lb2.err
+done
 echo done
