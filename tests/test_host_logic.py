@@ -107,6 +107,17 @@ def test_load_clips_lands_every_clip_in_one_staging_buffer(tmp_path):
         off += n
     one = gem.load_clip(dirs[1])
     assert np.array_equal(one["camera_pose_list"].numpy(), clips[1]["camera_pose_list"])
+    # the maps are stacked piece by piece on a few host threads: ragged pieces give the same buffer
+    chunk = gem._STACK_CHUNK
+    try:
+        gem._STACK_CHUNK = 5
+        for layout in ("tiled", True):
+            again = gem.load_clips(dirs, planar=layout)      # (the staging pool is reused: compare with the source)
+            for c, got in zip(clips, again):
+                maps = untile_heat(got["heatmap_list"]) if layout == "tiled" else got["heatmap_list"]
+                assert np.array_equal(maps.numpy(), c["heatmap_list"].transpose(0, 3, 1, 2))
+    finally:
+        gem._STACK_CHUNK = chunk
 
 
 def test_bench_workload_resolution_and_strong_shards():
