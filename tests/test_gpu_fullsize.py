@@ -10,7 +10,9 @@ the batch `bench.py` times — checked through properties that do not need the (
     `optimizer.py:370-423`: nothing may leak between windows);
   * the stitched sequences have the reference's length 8 W + 2 per clip (`optimizer.py:425-437`), and the SLAM round
     trip local -> first camera of the window -> global (`utils/utils.py:99-112`, `optimizer.py:302-308`), stitched over
-    the overlaps, returns camera_pose[f] . x_local[f] for every frame.
+    the overlaps, returns camera_pose[f] . x_local[f] for every frame;
+  * the 1e4-window sweep point of BASELINE configs[4] (11 220 windows: six replicas of every window in one batch)
+    reproduces the 1870-window batch replica by replica, bit for bit.
 
 Needs a B200: `pytest -m gpu`."""
 import numpy as np
@@ -112,3 +114,27 @@ def test_stitched_lengths_and_slam_round_trip(full):
         assert np.abs(est - direct).max() < 1e-9
         assert np.array_equal(m["final_gt_seq"].cpu().numpy(), c["gt_global_skeleton"][:n])
         assert torch.isfinite(m["final_optimized_seq"]).all()
+
+
+def test_sweep_point_of_1e4_windows_reproduces_the_1870_window_batch(full, vae_weights, camera):
+    """BASELINE configs[4] (`bench.py --windows 10000` tiles the workload the same way): every window solved six times
+    from the same noise in ONE batch of 11 220 windows — replicas share the clips' heat maps in HBM — gives, replica by
+    replica, the rows of the 1870-window solve bit for bit."""
+    from globalegomocap_b200.engine import Engine
+    from globalegomocap_b200.pipeline import WindowBatch
+    from globalegomocap_b200.vae_prep import PreparedVae
+    R = 6
+    eng = Engine(max_windows=W_TOTAL * R, max_history=24)
+    try:
+        prep = (PreparedVae(vae_weights[0], eng.device), PreparedVae(vae_weights[1], eng.device))
+        kw = dict(full["kw"], local_vae_path=prep[0], global_vae_path=prep[1], engine=eng, outputs="optimized")
+        batch = WindowBatch(eng, full["clips"]).replicate(R)
+        assert batch.W == W_TOTAL * R == 11220
+        out = full["gem"].solve_clips(batch, eps=full["eps"].repeat(R, 1, 1), **kw)
+        torch.cuda.synchronize()
+        for a, b in zip(_rows(out["sol"]), _rows(full["out"]["sol"])):
+            for r in range(R):
+                assert torch.equal(a[r * W_TOTAL:(r + 1) * W_TOTAL].cpu(), b.cpu()), r
+        assert len(out["merged"]) == N_SEQ * R
+    finally:
+        eng.close()
