@@ -50,3 +50,32 @@ def test_main_end_to_end_matches_reference(golden_dir, clip58, vae_weights, came
     assert mid_mm.max() < 60
     opt_mm = np.abs(out["opt_global"] - g["final_optimized_seq"]).max(axis=(1, 2)) * 1000
     assert np.median(opt_mm) < 0.5 and opt_mm.max() < 60, opt_mm
+
+
+def test_stitching_and_slam_transforms_match_the_reference_at_1000_frames(golden_dir):
+    """BASELINE configs[0] (tests/golden/main_1k_mi25.npz, the unmodified reference's `optimizer.main` on a 1000-frame
+    sequence): the un-optimised estimate goes local -> first camera of its window -> global and through the overlap
+    merge (optimizer.py:394-402, 425-437) — the oracle's restatement of that path reproduces the reference's 994
+    frames to round-off, and the ground truth passes through the merge unchanged."""
+    from globalegomocap_b200 import synthetic as syn
+    g = np.load(os.path.join(golden_dir, "main_1k_mi25.npz"))
+    clip = syn.make_clip(int(g["n_frames"]), seed=int(g["seed"]))
+    starts = pl.window_starts(len(clip["estimated_local_skeleton"]))
+    assert len(starts) == int(g["windows"]) == 124
+    est_w, gt_w = [], []
+    for s in starts:
+        cams = clip["camera_pose_list"][s:s + 10]
+        rel = pl.relative_global_pose(clip["estimated_local_skeleton"][s:s + 10], cams)
+        est_w.append(pl.to_global_pose(rel, cams))
+        gt_w.append(clip["gt_global_skeleton"][s:s + 10])
+    est = pl.merge_batches(np.stack(est_w))
+    assert est.shape == g["final_estimated_seq"].shape == (994, 15, 3)
+    np.testing.assert_allclose(est, g["final_estimated_seq"], rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(pl.merge_batches(np.stack(gt_w)), g["final_gt_seq"])
+    # the reference's two runs (eight threads, one thread) of the 25-iteration solve end tens of millimetres apart
+    # per frame while their printed metrics agree to 0.13 %: the spread the GPU test measures the CUDA path against
+    opt_mm = np.abs(g["final_optimized_seq_one_thread"] - g["final_optimized_seq"]).max(axis=(1, 2)) * 1000
+    assert 5.0 < np.median(opt_mm) < 100.0
+    worst = max(abs(float(np.mean(g["err1__" + k[5:]])) / float(np.mean(g[k])) - 1.0)
+                for k in g.files if k.startswith("err__") and "original" not in k)
+    assert worst < 0.005
