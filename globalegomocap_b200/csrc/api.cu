@@ -880,6 +880,7 @@ __global__ void stage_inputs_kernel(int w_abs0, int TJ3, int J, const float* __r
         return GEM_ERR_CAPACITY;                                                 \
     }                                                                            \
     GEM_REQUIRE((W) >= 0, "W must be >= 0");                                      \
+    if ((W) == 0) return GEM_OK; /* no windows: a no-op (empty buffers have no address to check) */ \
     GEM_CUDA(cudaSetDevice((c)->device))
 
 extern "C" {

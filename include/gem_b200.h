@@ -20,6 +20,8 @@
  *     calls do not synchronise unless stated.
  *   - one host thread per gem_ctx; one gem_ctx per device (multi-GPU = one process
  *     per GPU).
+ *   - sizes: a per-window call with W = 0 is a no-op that returns GEM_OK (its buffers
+ *     may be NULL); W above the ctx's max_windows returns GEM_ERR_CAPACITY.
  *   - window geometry: T frames x J joints x 3, pose tensors are [W][T][J][3] fp32,
  *     heatmaps are the pickle's HWC layout [frames][H][Wd][J] fp32 and are gathered
  *     in place (map of window w, frame t, joint j = frame_base[w]+t, channel j;

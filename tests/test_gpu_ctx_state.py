@@ -148,3 +148,46 @@ def test_heat_map_shape_is_validated(clip58, camera):
     with pytest.raises(GemError, match="frame"):
         eng.energy_grad(x, x, np.zeros((10, 64, 64, 15), np.float32), np.asarray([5], np.int64), np.zeros(1, np.int32), mbone, w)
     eng.close()
+
+
+def test_empty_and_too_short_inputs(tmp_path, clip58, vae_weights, camera, monkeypatch):
+    """Edge sizes: a call with zero windows is a no-op that reports success (every entry point); more windows than
+    the ctx was sized for is refused; a clip shorter than one window has no windows (`range(0, N - 10 + 1, 8)` is empty,
+    optimizer.py:370) — `solve_clips` stitches nothing for it beside the other clips' results, `main` refuses it
+    instead of failing inside the merge like the reference's empty `merge_batches` (optimizer.py:425-437)."""
+    from globalegomocap_b200 import optimizer as gem
+    from globalegomocap_b200.engine import Engine, GemError, energy_weights, lbfgs_params
+    from globalegomocap_b200.vae_prep import PreparedVae
+    eng = Engine(max_windows=8)
+    eng.set_camera(*camera)
+    eng.set_vae(0, vae_weights[0])
+    eng.set_vae(1, vae_weights[1])
+    heat = clip58["heatmap_list"][:10]
+    mbone = np.full(15, 0.25, np.float32)
+    w = energy_weights(*W_LOCAL)
+    x0 = np.zeros((0, 10, 15, 3), np.float32)
+    E, terms, grad, status = eng.energy_grad(x0, x0, heat, np.zeros(0, np.int64), np.zeros(0, np.int32), mbone, w)
+    assert E.shape == (0,) and grad.shape == (0, 10, 15, 3) and status.shape == (0,)
+    assert eng.decode(0, np.zeros((0, 2048), np.float32)).shape == (0, 10, 15, 3)
+    r = eng.solve_stage(0, x0, heat, np.zeros(0, np.int64), np.zeros(0, np.int32), mbone, np.zeros((0, 2048), np.float32), w,
+                        lbfgs_params(max_iter=3))
+    torch.cuda.synchronize()
+    assert r["pose"].shape == (0, 10, 15, 3)
+    too_many = np.zeros((9, 10, 15, 3), np.float32)
+    with pytest.raises(GemError, match="capacity"):
+        eng.energy_grad(too_many, too_many, heat, np.zeros(9, np.int64), np.zeros(9, np.int32), mbone, w)
+    # a 9-frame clip between two real ones
+    short = {k: v[:9] for k, v in clip58.items()}
+    one = {k: v[:10] for k, v in clip58.items()}
+    prep = (PreparedVae(vae_weights[0], eng.device), PreparedVae(vae_weights[1], eng.device))
+    eps = torch.randn(2, 2, 2048, generator=torch.Generator().manual_seed(1))
+    out = gem.solve_clips([one, short, one], camera, max_iter=2, eps=eps, local_vae_path=prep[0], global_vae_path=prep[1],
+                          engine=eng)
+    assert out["merged"][1] is None and out["batch"].W == 2
+    assert out["merged"][0]["final_optimized_seq"].shape == (10, 15, 3) == out["merged"][2]["final_optimized_seq"].shape
+    syn.write_clip_pickle(short, str(tmp_path / "short"))
+    with pytest.raises(ValueError, match="shorter than one window"):
+        gem.main(str(tmp_path / "short"), camera_model_path=syn.DEFAULT_CAMERA_JSON, vae_weight=0.0, gmm_weight=0.0,
+                 smoothness_weight=0.001, bone_length_weight=0.01, weight_3d=0.01, reproj_weight=0.01, engine=eng,
+                 local_vae_path=prep[0], global_vae_path=prep[1])
+    eng.close()
