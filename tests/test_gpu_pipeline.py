@@ -313,3 +313,34 @@ def test_main_on_the_1k_frame_sequence_matches_the_reference_run(workdir, golden
     assert np.median(opt_mm) < 1.5 * np.median(opt_self) and np.percentile(opt_mm, 90) < 1.5 * np.percentile(opt_self, 90)
     assert np.percentile(mid_mm, 90) < 1.5 * np.percentile(mid_self, 90) and mid_mm.max() < 2.0 * mid_self.max()
     assert worst < 3.0 * worst_self
+
+
+def test_save_pose_writes_the_references_result_pickle(workdir, monkeypatch):
+    """`save_pose=True` (optimizer.py:469-483): out/<dataset>/<sequence>/result_pose.pkl with the reference's four keys
+    and container types — lists of per-frame (15, 3) arrays, the optimised sequence an ndarray when `final_smooth` — holding
+    exactly the sequences `main` returns.  `save=True` / `visualization=True` (open3d meshes) are refused before any work."""
+    import pickle
+
+    from globalegomocap_b200 import optimizer as gem
+    monkeypatch.chdir(workdir)
+    kw = dict(camera_model_path=syn.DEFAULT_CAMERA_JSON, vae_weight=0.0, gmm_weight=0.0, smoothness_weight=0.001,
+              bone_length_weight=0.01, weight_3d=0.01, reproj_weight=0.01, max_iter=2)
+    for smooth in (True, False):
+        torch.manual_seed(3)
+        errors, est, mid_local, opt, gt = gem.main("data/synth/clip0", final_smooth=smooth, save_pose=True, **kw)
+        path = workdir / "out" / "synth" / "clip0" / "result_pose.pkl"
+        with open(path, "rb") as f:
+            saved = pickle.load(f)
+        assert sorted(saved) == ["estimated_pose", "gt_pose", "mid_optimized_pose", "optimized_pose"]
+        assert isinstance(saved["estimated_pose"], list) and isinstance(saved["gt_pose"], list)
+        assert isinstance(saved["mid_optimized_pose"], list) and saved["mid_optimized_pose"][0].shape == (15, 3)
+        assert isinstance(saved["optimized_pose"], np.ndarray if smooth else list)
+        assert np.array_equal(np.asarray(saved["estimated_pose"]), np.asarray(est))
+        assert np.array_equal(np.asarray(saved["optimized_pose"]), np.asarray(opt))
+        assert np.array_equal(np.asarray(saved["gt_pose"]), np.asarray(gt))
+        assert np.asarray(saved["mid_optimized_pose"]).shape == np.asarray(est).shape
+        os.remove(path)
+    for bad in (dict(save=True), dict(visualization=True)):
+        with pytest.raises(NotImplementedError):
+            gem.main("data/synth/clip0", **bad, **kw)
+    assert not (workdir / "out" / "synth" / "clip0" / "result_pose.pkl").exists()
