@@ -119,6 +119,7 @@ class BodyPoseOptimizer:
             fb = torch.arange(W, dtype=torch.int64) * self.seq_len
         if eps is None:
             eps = torch.randn(W, self.engine.n)               # one draw per stage call, SeqConvVAE.py:159-169
+        self.engine.set_heat_layout(0)                        # [.., H, Wd, 15] as in the pickle (a shared engine may have been switched)
         res = self.engine.solve_stage(0, poses, heat, fb, torch.zeros(W, dtype=torch.int32),
                                       self.mean_bone_length, eps, self._weights(),
                                       lbfgs_params(lr=self.lr, max_iter=self.max_iter), want_trace=want_trace)
@@ -133,6 +134,54 @@ class BodyPoseOptimizer:
             self.heatmap_seq = torch.as_tensor(np.asarray(heatmap_seq)).float()
         return res["pose"][0].cpu().numpy()
 
+    # ---- the reference's per-term methods (optimizer.py:89-94, 139-149, 172-177, 202-218): same names and arguments,
+    # each evaluated by the fused CUDA energy kernel (its un-weighted term sums) at the state the last optimize call left
+    def calculate_bone_length(self, skeleton):
+        """(T, 15*3) or (T, 15, 3) -> (T, 15) bone lengths; entry 0 is 0, the root being its own parent (optimizer.py:89-94)."""
+        sk = torch.as_tensor(skeleton).to(self.device).view(-1, 15, 3)
+        return torch.linalg.vector_norm(sk - sk[:, self.kinematic_parents, :], dim=-1)
+
+    def _terms(self, x, need_anchor=False, need_heat=False):
+        pose = torch.as_tensor(x).detach().float().reshape(1, self.seq_len, 15, 3)
+        if need_anchor and self.initial_pose is None:
+            raise GemError("pose_energy_3d needs the initial pose of a previous optimize_pose_seq_pytorch_LBFGS call")
+        if need_heat and self.heatmap_seq is None:
+            raise GemError("reprojection_energy_heatmap_fast needs the heat maps of a previous "
+                           "optimize_pose_seq_pytorch_LBFGS call (with reproj_weight != 0)")
+        anchor = self.initial_pose[None] if self.initial_pose is not None else pose
+        heat = fb = None
+        if need_heat:
+            heat, fb = self.heatmap_seq, torch.zeros(1, dtype=torch.int64)
+            self.engine.set_heat_layout(0)                      # this class holds the pickle's HWC maps
+        _, terms, _, status = self.engine.energy_grad(pose, anchor, heat, fb, torch.zeros(1, dtype=torch.int32),
+                                                      self.mean_bone_length,
+                                                      energy_weights(1.0, 1.0, 1.0, 1.0, 1.0 if need_heat else 0.0))
+        _raise_on_status(status)
+        return terms[0]                      # {E_3d, E_smooth, E_bone, E_vae, E_reproj}, un-weighted
+
+    def pose_energy_3d(self, x):
+        """sum (x - initial_pose)^2 (optimizer.py:210-213)."""
+        return self._terms(x, need_anchor=True)[0]
+
+    def smooth_accelerate(self, x):
+        """sum of squared second differences over the window's frames (optimizer.py:202-208)."""
+        return self._terms(x)[1]
+
+    def bone_length_energy(self, x):
+        """sum (|x_j - x_parent(j)| - mean_bone_length_j)^2 (optimizer.py:172-177)."""
+        return self._terms(x)[2]
+
+    def vae_energy(self, hidden_parameter):
+        """sum of squares of its argument — `total_loss` passes the DECODED POSE, not z (optimizer.py:215-218, 238)."""
+        v = torch.as_tensor(hidden_parameter).detach().float()
+        if v.numel() == self.seq_len * 45:
+            return self._terms(v)[3]
+        return torch.sum(torch.square(v.to(self.device)))       # any other shape: the one-liner itself
+
+    def reprojection_energy_heatmap_fast(self, pose):
+        """-sum of the heat maps sampled bilinearly at the fisheye projections of the joints (optimizer.py:139-149)."""
+        return self._terms(pose, need_heat=True)[4]
+
     def total_loss(self, hidden_parameter):
         """E(z) at the state left by the last optimize call (initial pose / heatmaps), optimizer.py:226-240."""
         if self.initial_pose is None:
@@ -142,6 +191,7 @@ class BodyPoseOptimizer:
         heat = fb = None
         if self.reproj_weight != 0:
             heat, fb = self.heatmap_seq, torch.zeros(1, dtype=torch.int64)
+            self.engine.set_heat_layout(0)
         E, _, _, status = self.engine.energy_grad(pose, self.initial_pose[None], heat, fb,
                                                   torch.zeros(1, dtype=torch.int32), self.mean_bone_length,
                                                   self._weights(), want_terms=False)

@@ -344,3 +344,51 @@ def test_save_pose_writes_the_references_result_pickle(workdir, monkeypatch):
         with pytest.raises(NotImplementedError):
             gem.main("data/synth/clip0", **bad, **kw)
     assert not (workdir / "out" / "synth" / "clip0" / "result_pose.pkl").exists()
+
+
+def test_per_term_methods_of_the_optimizer_class_match_reference(workdir, golden_dir, clip58, monkeypatch):
+    """`pose_energy_3d`, `smooth_accelerate`, `bone_length_energy`, `vae_energy`,
+    `reprojection_energy_heatmap_fast` and `calculate_bone_length` keep the reference's names and arguments
+    (optimizer.py:89-94, 139-149, 172-177, 202-218) and give the reference's values (golden per-term energies of 15
+    cases, 5e-6) at the state an optimize call leaves; their weighted sum is `total_loss`'s combination
+    (optimizer.py:239-240)."""
+    from globalegomocap_b200 import optimizer as gem
+    monkeypatch.chdir(workdir)
+    g = np.load(os.path.join(golden_dir, "energy.npz"))
+    opt = gem.BodyPoseOptimizer(camera_model_path=syn.DEFAULT_CAMERA_JSON,
+                                mean_skeleton=torch.from_numpy(clip58["estimated_local_skeleton"]).float(),
+                                vae_path=gem.LOCAL_VAE_PATH, latent_dim=2048, network_seq_len=10, seq_len=10,
+                                windows_size=1, overlap_size=2, lr=2, max_iter=2)
+    np.testing.assert_allclose(opt.mean_bone_length.cpu().numpy(), g["mean_bone_length"], rtol=1e-6)
+    bl = opt.calculate_bone_length(torch.from_numpy(clip58["estimated_local_skeleton"][:10]).float().view(10, 45))
+    assert tuple(bl.shape) == (10, 15) and float(bl[:, 0].abs().max()) == 0.0
+    names = [str(n) for n in g["names"] if str(n).startswith("all__")]
+    w = [float(v) for v in g["all__weights"]]                       # {w3d, smooth, bone, vae, reproj}
+    opt.set_weights(vae_weight=w[3], gmm_weight=0.0, smooth_weight=w[1], bone_length_weight=w[2], weight_3d=w[0],
+                    reproj_weight=w[4])
+    checked = 0
+    for n in names:
+        if n.endswith("edges") or n.endswith("dense_near"):
+            continue                                                # (cases on synthetic dense maps: test_gpu_kernels.py)
+        s = int(g[f"{n}__start"])
+        x = torch.from_numpy(g[f"{n}__x"]).float()
+        # the state optimize_pose_seq_pytorch_LBFGS leaves (optimizer.py:247-252)
+        opt.initial_pose = torch.from_numpy(clip58["estimated_local_skeleton"][s:s + 10]).float()
+        opt.heatmap_seq = torch.from_numpy(clip58["heatmap_list"][s:s + 10]).float()
+        got = {"e3d": opt.pose_energy_3d(x), "smooth": opt.smooth_accelerate(x), "bone": opt.bone_length_energy(x),
+               "vae": opt.vae_energy(x), "reproj": opt.reprojection_energy_heatmap_fast(x)}
+        for t, v in got.items():
+            ref = float(g[f"{n}__E_{t}"])
+            assert abs(float(v) - ref) <= 5e-6 * max(abs(ref), 1.0), (n, t, float(v), ref)
+        total = (w[0] * float(got["e3d"]) + w[1] * float(got["smooth"]) + w[2] * float(got["bone"]) + w[3] * float(got["vae"])
+                 + w[4] * float(got["reproj"]))
+        ref = float(g[f"{n}__E_total"])
+        assert abs(total - ref) <= 2e-5 * max(abs(ref), 1e-2), (n, total, ref)
+        checked += 1
+    assert checked >= 3
+    fresh = gem.BodyPoseOptimizer(camera_model_path=syn.DEFAULT_CAMERA_JSON,
+                                  mean_skeleton=torch.from_numpy(clip58["estimated_local_skeleton"]).float(),
+                                  vae_path=gem.LOCAL_VAE_PATH, latent_dim=2048, network_seq_len=10, seq_len=10, engine=opt.engine)
+    with pytest.raises(gem.GemError):
+        fresh.pose_energy_3d(x)                                     # no optimize call yet: no initial pose
+    assert float(fresh.vae_energy(torch.ones(1, 2048))) == 2048.0   # the one-liner on a latent-shaped argument
