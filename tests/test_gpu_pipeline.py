@@ -392,3 +392,42 @@ def test_per_term_methods_of_the_optimizer_class_match_reference(workdir, golden
     with pytest.raises(gem.GemError):
         fresh.pose_energy_3d(x)                                     # no optimize call yet: no initial pose
     assert float(fresh.vae_energy(torch.ones(1, 2048))) == 2048.0   # the one-liner on a latent-shaped argument
+
+
+def test_cli_summary_matches_the_references_cli(workdir):
+    """The reference's `optimize_whole_sequence.py` run UNMODIFIED on a three-clip dataset (tests/golden/make_golden_cli.py,
+    `torch.manual_seed(0)` set before it) against this repository's CLI with `--seed 0` on the same dataset, batched and
+    clip by clip: the same lines in the same order (clips in natural order), the un-optimised figures to round-off, the
+    optimised ones — 25 free-running iterations on 9 windows, statistical for the reference itself — within 3 %."""
+    import json
+    import re
+    with open(os.path.join(REPO, "tests", "golden", "cli_summary.json")) as f:
+        g = json.load(f)
+    root = workdir / "data" / "synth_cli"
+    for name, frames, seed in g["clips"]:
+        syn.write_clip_pickle(syn.make_clip(int(frames), seed=int(seed)), str(root / name))
+    env = dict(os.environ, PYTHONPATH=REPO)
+    for batch in ("True", "False"):
+        out = subprocess.run([sys.executable, os.path.join(REPO, "optimize_whole_sequence.py"), "--data_path", "data/synth_cli",
+                              "--camera", syn.DEFAULT_CAMERA_JSON, "--seed", str(g["seed"]), "--batch_clips", batch],
+                             cwd=workdir, env=env, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stderr[-2000:]
+        lines = [ln for ln in out.stdout.splitlines() if ln.startswith(("Average", "running data", "-----"))]
+        assert [ln.split(":")[0] for ln in lines] == [ln.split(":")[0] for ln in g["lines"]]
+        assert [ln for ln in lines if ln.startswith("running")] == [ln for ln in g["lines"] if ln.startswith("running")]
+        worst = 0.0
+        for ln in lines:
+            m = re.match(r"(Average [^:]+): (.*)$", ln)
+            if not m:
+                continue
+            ours, ref = float(m.group(2)), g["summary"][m.group(1)]
+            if "original" in m.group(1):
+                assert abs(ours - ref) <= 1e-9 * abs(ref), (ln, ref)
+            else:
+                worst = max(worst, abs(ours / ref - 1.0))
+        je = re.search(r"joints error is: \[([^\]]*)\]", out.stdout)
+        ours_je = np.array([float(t) for t in je.group(1).split()])
+        assert ours_je.shape == (15,)
+        worst_je = float(np.abs(ours_je / np.array(g["joints_error"]) - 1.0).max())
+        print("batch_clips", batch, "worst optimised summary deviation %.4f, worst per-joint error deviation %.4f" % (worst, worst_je))
+        assert worst < 0.03 and worst_je < 0.10
