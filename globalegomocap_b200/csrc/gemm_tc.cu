@@ -96,7 +96,7 @@ struct TcArgs {
 // Epilogue of one 128 x BN accumulator tile, run by kEpiWarps = 16 warps: a warp can only read the TMEM lane
 // quarter (warp % 4), so four warps share each quarter and deal its 16-column chunks round-robin.  (With one warp
 // per quarter the epilogue was a single dependent instruction stream per scheduler — ~460 instructions per chunk
-// at an IPC of 0.2 — and took 23k of a tile's 63k cycles; per-CTA timestamps, scratch/dbg_gemm.py.)
+// at an IPC of 0.2 — and took 23k of a tile's 63k cycles; per-CTA timestamps, tools/dbg_gemm.py.)
 // The accumulators' sum, bias and activation are formed one row per thread, staged in the (now idle) pipeline
 // memory and, after a named barrier over the quarter's four warps, written out along the rows: 16-byte vectors,
 // whole row segments per instruction instead of 32 row segments of 16 bytes.
